@@ -1,0 +1,249 @@
+// extern "C" boundary of libeinconv_b200.so: argument validation, kernel selection, workspace
+// accounting.  See include/einconv_b200.h for the contract of each entry point and the reference
+// call site it replaces.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "dispatch.cuh"
+
+namespace einconv {
+
+static thread_local char g_error[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t err, const char* what) {
+  set_error("%s: %s", what, cudaGetErrorString(err));
+  return EINCONV_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int make_dev_geom(const einconv_geom* g, DevGeom* out, bool need_c_out) {
+  EINCONV_CHECK_ARG(g != nullptr, "geometry is NULL");
+  EINCONV_CHECK_ARG(g->n_dims >= 1 && g->n_dims <= kMaxDims, "n_dims must be in [1, %d], got %d",
+                    kMaxDims, g->n_dims);
+  EINCONV_CHECK_ARG(g->groups >= 1, "groups must be >= 1, got %d", g->groups);
+  EINCONV_CHECK_ARG(g->batch >= 0 && g->batch < (1ll << 31), "bad batch size %lld", (long long)g->batch);
+  EINCONV_CHECK_ARG(g->c_in_g >= 0 && g->c_in_g < (1ll << 31), "bad c_in_g %lld", (long long)g->c_in_g);
+  if (need_c_out)
+    EINCONV_CHECK_ARG(g->c_out_g >= 0 && g->c_out_g < (1ll << 31), "bad c_out_g %lld", (long long)g->c_out_g);
+  DevGeom d{};
+  d.n_dims = g->n_dims;
+  d.groups = g->groups;
+  d.batch = (int)g->batch;
+  d.c_in_g = (int)g->c_in_g;
+  d.c_out_g = need_c_out ? (int)g->c_out_g : 0;
+  long long in_total = 1, out_total = 1, k_total = 1;
+  for (int i = 0; i < g->n_dims; ++i) {
+    EINCONV_CHECK_ARG(g->in[i] >= 0 && g->k[i] >= 1 && g->stride[i] >= 1 && g->dilation[i] >= 1 &&
+                          g->pad_left[i] >= 0 && g->out[i] >= 0,
+                      "invalid geometry in dimension %d (in=%d k=%d stride=%d dilation=%d pad=%d out=%d)",
+                      i, g->in[i], g->k[i], g->stride[i], g->dilation[i], g->pad_left[i], g->out[i]);
+    // every output must be able to reach its last tap without running past what padding allows;
+    // the right padding is implied by `out`, so only the left edge can be checked here.
+    d.in[i] = g->in[i];
+    d.k[i] = g->k[i];
+    d.stride[i] = g->stride[i];
+    d.dil[i] = g->dilation[i];
+    d.pad[i] = g->pad_left[i];
+    d.out[i] = g->out[i];
+    d.out_div[i] = FastDiv((uint32_t)g->out[i]);
+    d.k_div[i] = FastDiv((uint32_t)g->k[i]);
+    d.in_div[i] = FastDiv((uint32_t)g->in[i]);
+    in_total *= g->in[i];
+    out_total *= g->out[i];
+    k_total *= g->k[i];
+    EINCONV_CHECK_ARG(in_total < (1ll << 31) && out_total < (1ll << 31) && k_total < (1ll << 24),
+                      "spatial extent too large");
+  }
+  for (int i = g->n_dims; i < kMaxDims; ++i) {
+    d.in[i] = 1; d.k[i] = 1; d.stride[i] = 1; d.dil[i] = 1; d.pad[i] = 0; d.out[i] = 1;
+  }
+  d.in_total = (int)in_total;
+  d.out_total = (int)out_total;
+  d.k_total = (int)k_total;
+  *out = d;
+  return EINCONV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel selection
+// ---------------------------------------------------------------------------------------------
+enum class Path { FFMA, DEPTHWISE, TENSOR };
+
+static int resolve_math(int dtype, int math) {
+  if (math == EINCONV_MATH_AUTO)
+    return (dtype == EINCONV_BF16 || dtype == EINCONV_F16) ? EINCONV_MATH_HALF : EINCONV_MATH_FP32;
+  return math;
+}
+
+static Path select_path(int op, const DevGeom& g, int dtype, int math, int kernels) {
+  if (kernels == EINCONV_KERNELS_GENERIC) return Path::FFMA;
+  if ((op == EINCONV_OP_CONV_FWD || op == EINCONV_OP_CONV_INPUT_VJP) && depthwise_supported(g, dtype))
+    return Path::DEPTHWISE;
+  const int m = resolve_math(dtype, math);
+  if ((m == EINCONV_MATH_TF32 || m == EINCONV_MATH_HALF) && tc_supported(op, g, dtype, m))
+    return Path::TENSOR;
+  return Path::FFMA;
+}
+
+static int check_math(int dtype, int math) {
+  EINCONV_CHECK_ARG(math >= EINCONV_MATH_AUTO && math <= EINCONV_MATH_HALF, "unknown math mode %d", math);
+  EINCONV_CHECK_ARG(elem_size(dtype) > 0, "unknown dtype %d", dtype);
+  if (math == EINCONV_MATH_TF32 && dtype != EINCONV_F32) {
+    set_error("EINCONV_MATH_TF32 requires f32 tensors");
+    return EINCONV_ERR_UNSUPPORTED;
+  }
+  if (math == EINCONV_MATH_HALF && dtype != EINCONV_BF16 && dtype != EINCONV_F16) {
+    set_error("EINCONV_MATH_HALF requires bf16/f16 tensors");
+    return EINCONV_ERR_UNSUPPORTED;
+  }
+  return EINCONV_OK;
+}
+
+}  // namespace einconv
+
+using namespace einconv;
+
+extern "C" {
+
+int einconv_abi_version(void) { return EINCONV_ABI_VERSION; }
+
+const char* einconv_last_error(void) { return g_error; }
+
+int64_t einconv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype, int math,
+                                    int kernels) {
+  DevGeom g;
+  if (make_dev_geom(geom, &g, op != EINCONV_OP_UNFOLD && op != EINCONV_OP_FOLD)) return nullptr;
+  if (check_math(dtype, math)) return nullptr;
+  switch (op) {
+    case EINCONV_OP_UNFOLD: return "unfold_plane";
+    case EINCONV_OP_FOLD: return "fold_gather";
+    default: break;
+  }
+  switch (select_path(op, g, dtype, math, kernels)) {
+    case Path::DEPTHWISE: return "depthwise_stencil";
+    case Path::TENSOR: return tc_kernel_name(op, g, dtype, resolve_math(dtype, math));
+    default: return "ffma_gather_gemm";
+  }
+}
+
+int64_t einconv_workspace_bytes(int op, const einconv_geom* geom, int dtype, int math, int kernels) {
+  DevGeom g;
+  if (make_dev_geom(geom, &g, op != EINCONV_OP_UNFOLD && op != EINCONV_OP_FOLD)) return -1;
+  if (check_math(dtype, math)) return -1;
+  if (op == EINCONV_OP_UNFOLD || op == EINCONV_OP_FOLD) return 0;
+  const Path path = select_path(op, g, dtype, math, kernels);
+  if (path == Path::DEPTHWISE) return 0;
+  if (path == Path::TENSOR) return tc_workspace_bytes(op, g, dtype, resolve_math(dtype, math));
+  switch (op) {
+    case EINCONV_OP_CONV_WEIGHT_VJP:
+    case EINCONV_OP_KFC:
+    case EINCONV_OP_KFAC_REDUCE: return ffma_splitk_workspace(op, g, dtype, nullptr);
+    default: return 0;
+  }
+}
+
+int einconv_unfold(const void* x, const int64_t* x_strides_host, void* out, int dtype,
+                   const einconv_geom* g, void* stream) {
+  EINCONV_CHECK_ARG(x && out, "unfold: NULL tensor pointer");
+  return launch_unfold(x, x_strides_host, out, dtype, g, (cudaStream_t)stream);
+}
+
+int einconv_fold(const void* gu, void* gx, int dtype, const einconv_geom* g, void* stream) {
+  EINCONV_CHECK_ARG(gu && gx, "fold: NULL tensor pointer");
+  return launch_fold(gu, gx, dtype, g, (cudaStream_t)stream);
+}
+
+int einconv_conv_fwd(const void* x, const void* w, const void* bias, void* y, int dtype,
+                     const einconv_geom* geom, int math, int kernels, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+  EINCONV_CHECK_ARG(x && w && y, "conv_fwd: NULL tensor pointer");
+  DevGeom g;
+  int st = make_dev_geom(geom, &g, true);
+  if (st) return st;
+  if ((st = check_math(dtype, math))) return st;
+  if ((long long)g.batch * g.groups * g.c_out_g * g.out_total == 0) return EINCONV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (select_path(EINCONV_OP_CONV_FWD, g, dtype, math, kernels)) {
+    case Path::DEPTHWISE: return dw_conv_fwd(x, w, bias, y, dtype, g, s);
+    case Path::TENSOR:
+      return tc_conv_fwd(x, w, bias, y, dtype, g, resolve_math(dtype, math), workspace, workspace_bytes, s);
+    default: return ffma_conv_fwd(x, w, bias, y, dtype, g, s);
+  }
+}
+
+int einconv_conv_input_vjp(const void* w, const void* v, void* gx, int dtype,
+                           const einconv_geom* geom, int math, int kernels, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  EINCONV_CHECK_ARG(w && v && gx, "conv_input_vjp: NULL tensor pointer");
+  DevGeom g;
+  int st = make_dev_geom(geom, &g, true);
+  if (st) return st;
+  if ((st = check_math(dtype, math))) return st;
+  if ((long long)g.batch * g.groups * g.c_in_g * g.in_total == 0) return EINCONV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (select_path(EINCONV_OP_CONV_INPUT_VJP, g, dtype, math, kernels)) {
+    case Path::DEPTHWISE: return dw_conv_input_vjp(w, v, gx, dtype, g, s);
+    default: return ffma_conv_input_vjp(w, v, gx, dtype, g, s);
+  }
+}
+
+int einconv_conv_weight_vjp(const void* x, const void* v, void* gw, int dtype,
+                            const einconv_geom* geom, int math, int kernels, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  EINCONV_CHECK_ARG(x && v && gw, "conv_weight_vjp: NULL tensor pointer");
+  DevGeom g;
+  int st = make_dev_geom(geom, &g, true);
+  if (st) return st;
+  if ((st = check_math(dtype, math))) return st;
+  if ((long long)g.groups * g.c_out_g * g.c_in_g * g.k_total == 0) return EINCONV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (select_path(EINCONV_OP_CONV_WEIGHT_VJP, g, dtype, math, kernels)) {
+    case Path::TENSOR:
+      return tc_conv_weight_vjp(x, v, gw, dtype, g, resolve_math(dtype, math), workspace, workspace_bytes, s);
+    default: return ffma_conv_weight_vjp(x, v, gw, dtype, g, workspace, workspace_bytes, s);
+  }
+}
+
+int einconv_kfc(const void* x, void* out, int dtype, const einconv_geom* geom, double scale,
+                int math, int kernels, void* workspace, int64_t workspace_bytes, void* stream) {
+  EINCONV_CHECK_ARG(x && out, "kfc: NULL tensor pointer");
+  DevGeom g;
+  int st = make_dev_geom(geom, &g, false);
+  if (st) return st;
+  if ((st = check_math(dtype, math))) return st;
+  if ((long long)g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (select_path(EINCONV_OP_KFC, g, dtype, math, kernels)) {
+    case Path::TENSOR:
+      return tc_kfc(x, out, dtype, g, scale, resolve_math(dtype, math), workspace, workspace_bytes, s);
+    default: return ffma_kfc(x, out, dtype, g, scale, workspace, workspace_bytes, s);
+  }
+}
+
+int einconv_kfac_reduce(const void* x, void* out, int dtype, const einconv_geom* geom, double scale,
+                        int math, int kernels, void* workspace, int64_t workspace_bytes,
+                        void* stream) {
+  EINCONV_CHECK_ARG(x && out, "kfac_reduce: NULL tensor pointer");
+  DevGeom g;
+  int st = make_dev_geom(geom, &g, false);
+  if (st) return st;
+  if ((st = check_math(dtype, math))) return st;
+  if ((long long)g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
+  return ffma_kfac_reduce(x, out, dtype, g, scale, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// Shared device/host helpers for the einconv_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/einconv_b200.h"
+
+namespace einconv {
+
+constexpr int kMaxDims = EINCONV_MAX_DIMS;
+constexpr int kNumSMs = 148;  // B200
+
+// ---------------------------------------------------------------------------------------------
+// error reporting (thread-local message, C status codes)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t err, const char* what);
+void count_launch(int n = 1);
+
+#define EINCONV_CHECK_ARG(cond, ...)        \
+  do {                                      \
+    if (!(cond)) {                          \
+      ::einconv::set_error(__VA_ARGS__);    \
+      return EINCONV_ERR_INVALID;           \
+    }                                       \
+  } while (0)
+
+#define EINCONV_CHECK_LAUNCH(what)                                   \
+  do {                                                               \
+    cudaError_t err__ = cudaGetLastError();                          \
+    if (err__ != cudaSuccess) return ::einconv::cuda_fail(err__, what); \
+    ::einconv::count_launch();                                       \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Division by a runtime constant: q = (n * mul) >> 32 >> shift  (n < 2^31)
+// ---------------------------------------------------------------------------------------------
+struct FastDiv {
+  uint32_t div = 1, mul = 0, shift = 0;
+  FastDiv() = default;
+  explicit FastDiv(uint32_t d) : div(d) {
+    if (d <= 1) {
+      div = 1;
+      mul = 0;
+      shift = 0;
+      return;
+    }
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;  // ceil(log2 d)
+    shift = s - 1;
+    // mul = ceil(2^(32+shift) / d); fits in 32 bits for d >= 2 with shift = ceil(log2 d) - 1
+    uint64_t one = 1ull << (32 + shift);
+    mul = (uint32_t)((one + d - 1) / d);
+  }
+  __host__ __device__ __forceinline__ uint32_t quot(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+    return div == 1 ? n : (__umulhi(n, mul) >> shift);
+#else
+    return div == 1 ? n : (uint32_t)(((uint64_t)n * mul) >> 32 >> shift);
+#endif
+  }
+  __host__ __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = quot(n);
+    r = n - q * div;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Device-side geometry.  Spatial dimension d has
+//   in[d], k[d], stride[d], dil[d], pad[d] (left), out[d]
+// and the index law  i = stride * o + dil * k - pad   (conv_index_pattern.py:131-134).
+// ---------------------------------------------------------------------------------------------
+struct DevGeom {
+  int n_dims;
+  int groups;
+  int batch;
+  int c_in_g;
+  int c_out_g;
+  int in[kMaxDims];
+  int k[kMaxDims];
+  int stride[kMaxDims];
+  int dil[kMaxDims];
+  int pad[kMaxDims];
+  int out[kMaxDims];
+  int in_total;   // prod(in)
+  int out_total;  // prod(out)
+  int k_total;    // prod(k)
+  FastDiv out_div[kMaxDims];
+  FastDiv k_div[kMaxDims];
+  FastDiv in_div[kMaxDims];
+};
+
+// Validates and converts the ABI struct.  Returns 0 or a negative status (message set).
+int make_dev_geom(const einconv_geom* g, DevGeom* out, bool need_c_out);
+
+inline int64_t elem_size(int dtype) {
+  switch (dtype) {
+    case EINCONV_F32: return 4;
+    case EINCONV_BF16: return 2;
+    case EINCONV_F16: return 2;
+    case EINCONV_F64: return 8;
+    default: return 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dtype <-> compute type conversion
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+  using acc_t = float;
+  static __device__ __forceinline__ float load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, float v) { *p = v; }
+};
+template <> struct Cvt<double> {
+  using acc_t = double;
+  static __device__ __forceinline__ double load(const double* p) { return __ldg(p); }
+  static __device__ __forceinline__ void store(double* p, double v) { *p = v; }
+};
+template <> struct Cvt<__nv_bfloat16> {
+  using acc_t = float;
+  static __device__ __forceinline__ float load(const __nv_bfloat16* p) {
+    return __bfloat162float(__ldg(p));
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float v) {
+    *p = __float2bfloat16_rn(v);
+  }
+};
+template <> struct Cvt<__half> {
+  using acc_t = float;
+  static __device__ __forceinline__ float load(const __half* p) { return __half2float(__ldg(p)); }
+  static __device__ __forceinline__ void store(__half* p, float v) { *p = __float2half_rn(v); }
+};
+
+template <typename F>
+inline int dispatch_dtype(int dtype, F&& f) {
+  switch (dtype) {
+    case EINCONV_F32: return f((float*)nullptr);
+    case EINCONV_BF16: return f((__nv_bfloat16*)nullptr);
+    case EINCONV_F16: return f((__half*)nullptr);
+    case EINCONV_F64: return f((double*)nullptr);
+    default:
+      set_error("unknown dtype %d", dtype);
+      return EINCONV_ERR_INVALID;
+  }
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace einconv

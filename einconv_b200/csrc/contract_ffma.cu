@@ -1,0 +1,820 @@
+// Generic CUDA-core evaluation of the five contraction networks (forward, input VJP, weight VJP,
+// KFC, KFAC-reduce) for every geometry: arbitrary N, stride, padding, dilation, groups, and every
+// dtype (fp64 included).  One tiled FMA GEMM whose operands are *gathered on the fly* with the
+// index law i = s*o + d*k - p; nothing is unfolded in memory and no index pattern exists.
+//
+// This is the `simplify=False` / EINCONV_KERNELS_GENERIC path and the EINCONV_MATH_FP32 path (true
+// fp32 / fp64 accumulation, meeting the reference's rtol 1e-5 tolerances).  The tensor-core kernels
+// in tc_*.cu and the stencil kernels in depthwise.cu are the specialised fast paths.
+//
+// GEMM view of each network (g = group, handled by blockIdx.z; Kt = prod(k), Ot = prod(out)):
+//   forward     C[(b,o), co]      = sum_{(ci,k)} X~[(b,o),(ci,k)] * W[co,(ci,k)]     expressions/convNd_forward.py:48-55
+//   input VJP   C[(b,i), ci]      = sum_{(co,k)} V~[(b,i),(co,k)] * W[co,ci,k]       expressions/convNd_input_vjp.py:53-60
+//   weight VJP  C[co, (ci,k)]     = sum_{(b,o)}  V[b,co,o]        * X~[(b,o),(ci,k)] expressions/convNd_weight_vjp.py:51-58
+//   KFC         C[(ci,k),(ci',k')] = sum_{(b,o)} X~[(b,o),(ci,k)] * X~[(b,o),(ci',k')] expressions/convNd_kfc.py:75-90
+//   KFAC-red.   u[b,(ci,k)] = sum_o X~[(b,o),(ci,k)] ;  C = sum_b u u^T              expressions/convNd_kfac_reduce.py:77-92
+// where X~ is the (virtual) unfolded input and V~ the (virtual) scattered cotangent.
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace einconv {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+constexpr int PAD = 4;
+
+// ---------------------------------------------------------------------------------------------
+// Gather contexts.  ND = compile-time bound on the number of spatial dims handled in registers.
+// ---------------------------------------------------------------------------------------------
+template <int ND>
+struct PosCtx {      // an output position (b, o..) expressed in input coordinates
+  long long base;    // b * batch_stride + sum_d (s_d*o_d - p_d) * in_stride_d
+  int v[ND];         // s_d * o_d - p_d
+  bool valid;        // index inside the problem
+};
+template <int ND>
+struct TapCtx {      // a (channel, tap) pair
+  long long off;     // ch * channel_stride + sum_d dil_d*k_d * in_stride_d
+  int dk[ND];        // dil_d * k_d
+  bool valid;
+};
+
+// contiguous element strides of the input's spatial dims
+template <int ND>
+struct Strides {
+  int s[ND];
+};
+
+template <int ND>
+__device__ __forceinline__ PosCtx<ND> make_pos(const DevGeom& g, const Strides<ND>& st,
+                                               long long batch_stride, int idx, int total) {
+  // idx = b * out_total + oflat
+  PosCtx<ND> c;
+  c.valid = idx < total;
+  uint32_t rem = c.valid ? (uint32_t)idx : 0u;
+  long long base = 0;
+#pragma unroll
+  for (int d = ND - 1; d >= 0; --d) {
+    if (d < g.n_dims) {
+      uint32_t q, o;
+      g.out_div[d].divmod(rem, q, o);
+      rem = q;
+      c.v[d] = g.stride[d] * (int)o - g.pad[d];
+      base += (long long)c.v[d] * st.s[d];
+    } else {
+      c.v[d] = 0;
+    }
+  }
+  c.base = base + (long long)rem * batch_stride;  // rem == b
+  return c;
+}
+
+template <int ND>
+__device__ __forceinline__ TapCtx<ND> make_tap(const DevGeom& g, const Strides<ND>& st,
+                                               long long chan_stride, int idx, int total) {
+  // idx = ch * k_total + kflat
+  TapCtx<ND> c;
+  c.valid = idx < total;
+  uint32_t rem = c.valid ? (uint32_t)idx : 0u;
+  long long off = 0;
+#pragma unroll
+  for (int d = ND - 1; d >= 0; --d) {
+    if (d < g.n_dims) {
+      uint32_t q, k;
+      g.k_div[d].divmod(rem, q, k);
+      rem = q;
+      c.dk[d] = g.dil[d] * (int)k;
+      off += (long long)c.dk[d] * st.s[d];
+    } else {
+      c.dk[d] = 0;
+    }
+  }
+  c.off = off + (long long)rem * chan_stride;  // rem == channel
+  return c;
+}
+
+// x~[(b,o),(ch,k)] : forward gather
+template <typename T, int ND>
+__device__ __forceinline__ typename Cvt<T>::acc_t gather_fwd(const T* __restrict__ x,
+                                                             const DevGeom& g,
+                                                             const PosCtx<ND>& p,
+                                                             const TapCtx<ND>& t) {
+  bool ok = p.valid && t.valid;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    if (d < g.n_dims) {
+      const int i = p.v[d] + t.dk[d];
+      ok = ok && (i >= 0) && (i < g.in[d]);
+    }
+  }
+  return ok ? Cvt<T>::load(x + p.base + t.off) : typename Cvt<T>::acc_t(0);
+}
+
+// Input-VJP gather: V~[(b,i),(co,k)] = v[b, co, o] with o_d = (i_d + p_d - dil_d*k_d)/s_d if integral
+template <int ND>
+struct InPosCtx {   // an input position (b, i..)
+  int b;
+  int ip[ND];       // i_d + p_d
+  bool valid;
+};
+template <int ND>
+__device__ __forceinline__ InPosCtx<ND> make_inpos(const DevGeom& g, int idx, int total) {
+  InPosCtx<ND> c;
+  c.valid = idx < total;
+  uint32_t rem = c.valid ? (uint32_t)idx : 0u;
+#pragma unroll
+  for (int d = ND - 1; d >= 0; --d) {
+    if (d < g.n_dims) {
+      uint32_t q, i;
+      g.in_div[d].divmod(rem, q, i);
+      rem = q;
+      c.ip[d] = (int)i + g.pad[d];
+    } else {
+      c.ip[d] = 0;
+    }
+  }
+  c.b = (int)rem;
+  return c;
+}
+template <int ND>
+struct ChanTapCtx {  // (co, k..) for the input VJP
+  int ch;
+  int dk[ND];
+  bool valid;
+};
+template <int ND>
+__device__ __forceinline__ ChanTapCtx<ND> make_chantap(const DevGeom& g, int idx, int total) {
+  ChanTapCtx<ND> c;
+  c.valid = idx < total;
+  uint32_t rem = c.valid ? (uint32_t)idx : 0u;
+#pragma unroll
+  for (int d = ND - 1; d >= 0; --d) {
+    if (d < g.n_dims) {
+      uint32_t q, k;
+      g.k_div[d].divmod(rem, q, k);
+      rem = q;
+      c.dk[d] = g.dil[d] * (int)k;
+    } else {
+      c.dk[d] = 0;
+    }
+  }
+  c.ch = (int)rem;
+  return c;
+}
+template <typename T, int ND>
+__device__ __forceinline__ typename Cvt<T>::acc_t gather_bwd(const T* __restrict__ v,
+                                                             const DevGeom& g, int chan_base,
+                                                             int chan_total,
+                                                             const InPosCtx<ND>& p,
+                                                             const ChanTapCtx<ND>& t) {
+  bool ok = p.valid && t.valid;
+  long long oflat = 0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    if (d < g.n_dims) {
+      const int num = p.ip[d] - t.dk[d];
+      const int s = g.stride[d];
+      const int o = (s == 1) ? num : num / s;
+      ok = ok && (num >= 0) && (o * s == num) && (o < g.out[d]);
+      oflat = oflat * g.out[d] + o;
+    }
+  }
+  if (!ok) return typename Cvt<T>::acc_t(0);
+  const long long off = ((long long)p.b * chan_total + chan_base + t.ch) * g.out_total + oflat;
+  return Cvt<T>::load(v + off);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The GEMM core.  Prob supplies:
+//   static constexpr bool A_RED_FAST / B_RED_FAST   thread mapping of the tile loads: true = lanes
+//                                                    walk the reduction index, false = the row/col
+//   int M, N, K;  int k_splits;                       problem extents; blockIdx.z = group*k_splits + split
+//   RowA make_row_a(z, m) / RedA make_red_a(z, k) / acc load_a(row, red)     (same for b)
+//   void store(z, m, n, acc)
+// ---------------------------------------------------------------------------------------------
+template <typename Prob>
+__global__ void __launch_bounds__(NT) gather_gemm_kernel(const __grid_constant__ Prob prob) {
+  using acc_t = typename Prob::acc_t;
+  __shared__ acc_t As[2][BK][BM + PAD];
+  __shared__ acc_t Bs[2][BK][BN + PAD];
+
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int z = blockIdx.z;
+  const int split = z % prob.k_splits;
+  const int grp = z / prob.k_splits;
+
+  // reduction range of this split, in multiples of BK
+  const int k_chunks = (prob.K + BK - 1) / BK;
+  const int per_split = (k_chunks + prob.k_splits - 1) / prob.k_splits;
+  const int kc_begin = split * per_split;
+  const int kc_end = min(k_chunks, kc_begin + per_split);
+
+  // ---- thread -> tile element mapping for the loads (4 A and 4 B elements per thread)
+  // row-fast: row = tid % 64, red = tid / 64 + 4*j ;  red-fast: red = tid % 16, row = tid / 16 + 16*j
+  int a_row[4], a_red[4], b_row[4], b_red[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if constexpr (Prob::A_RED_FAST) { a_red[j] = tid % BK; a_row[j] = tid / BK + (NT / BK) * j; }
+    else                  { a_row[j] = tid % BM; a_red[j] = tid / BM + (NT / BM) * j; }
+    if constexpr (Prob::B_RED_FAST) { b_red[j] = tid % BK; b_row[j] = tid / BK + (NT / BK) * j; }
+    else                  { b_row[j] = tid % BN; b_red[j] = tid / BN + (NT / BN) * j; }
+  }
+
+  // contexts that stay fixed over the reduction loop
+  typename Prob::RowA rowa[Prob::A_RED_FAST ? 4 : 1];
+  typename Prob::RowB rowb[Prob::B_RED_FAST ? 4 : 1];
+#pragma unroll
+  for (int j = 0; j < (Prob::A_RED_FAST ? 4 : 1); ++j) rowa[j] = prob.make_row_a(grp, m0 + a_row[j]);
+#pragma unroll
+  for (int j = 0; j < (Prob::B_RED_FAST ? 4 : 1); ++j) rowb[j] = prob.make_row_b(grp, n0 + b_row[j]);
+
+  acc_t ra[4], rb[4];
+  auto fetch = [&](int kc) {
+    const int k0 = kc * BK;
+    if constexpr (Prob::A_RED_FAST) {
+      const auto red = prob.make_red_a(grp, k0 + a_red[0]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ra[j] = prob.load_a(rowa[j], red);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ra[j] = prob.load_a(rowa[0], prob.make_red_a(grp, k0 + a_red[j]));
+    }
+    if constexpr (Prob::B_RED_FAST) {
+      const auto red = prob.make_red_b(grp, k0 + b_red[0]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rb[j] = prob.load_b(rowb[j], red);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rb[j] = prob.load_b(rowb[0], prob.make_red_b(grp, k0 + b_red[j]));
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      As[buf][a_red[j]][a_row[j]] = ra[j];
+      Bs[buf][b_red[j]][b_row[j]] = rb[j];
+    }
+  };
+
+  const int tx = tid % 16;  // n direction
+  const int ty = tid / 16;  // m direction
+  acc_t acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = acc_t(0);
+
+  if (kc_begin < kc_end) {
+    fetch(kc_begin);
+    stash(0);
+    __syncthreads();
+    for (int kc = kc_begin; kc < kc_end; ++kc) {
+      const int buf = (kc - kc_begin) & 1;
+      if (kc + 1 < kc_end) fetch(kc + 1);
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        acc_t a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[buf][kk][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[buf][kk][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      }
+      if (kc + 1 < kc_end) {
+        stash(buf ^ 1);
+        __syncthreads();
+      }
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < prob.M && n < prob.N) prob.store(grp, split, m, n, acc[i][j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Problem definitions
+// ---------------------------------------------------------------------------------------------
+template <typename T, int ND>
+struct ProbBase {
+  using acc_t = typename Cvt<T>::acc_t;
+  DevGeom g;
+  Strides<ND> st;   // contiguous spatial strides of x
+  int M, N, K, k_splits;
+  int c_in_total, c_out_total;  // G*Cin_g, G*Cout_g
+};
+
+template <typename T, int ND>
+static void fill_base(ProbBase<T, ND>& p, const DevGeom& g) {
+  p.g = g;
+  int s = 1;
+  for (int d = ND - 1; d >= 0; --d) {
+    if (d < g.n_dims) {
+      p.st.s[d] = s;
+      s *= g.in[d];
+    } else {
+      p.st.s[d] = 0;
+    }
+  }
+  p.c_in_total = g.groups * g.c_in_g;
+  p.c_out_total = g.groups * g.c_out_g;
+  p.k_splits = 1;
+}
+
+// ---- forward --------------------------------------------------------------------------------
+template <typename T, int ND>
+struct FwdProb : ProbBase<T, ND> {
+  using acc_t = typename Cvt<T>::acc_t;
+  static constexpr bool A_RED_FAST = false;  // lanes walk output positions (contiguous in x)
+  static constexpr bool B_RED_FAST = true;   // lanes walk (ci,k) (contiguous in w)
+  using RowA = PosCtx<ND>;
+  using RedA = TapCtx<ND>;
+  struct RowB { long long off; bool valid; };
+  struct RedB { int k; bool valid; };
+  const T* x; const T* w; const T* bias; T* y;
+
+  __device__ RowA make_row_a(int grp, int m) const {
+    return make_pos<ND>(this->g, this->st, (long long)this->c_in_total * this->g.in_total, m, this->M);
+  }
+  __device__ RedA make_red_a(int grp, int k) const {
+    TapCtx<ND> t = make_tap<ND>(this->g, this->st, this->g.in_total, k, this->K);
+    t.off += (long long)grp * this->g.c_in_g * this->g.in_total;
+    return t;
+  }
+  __device__ acc_t load_a(const RowA& r, const RedA& t) const { return gather_fwd<T, ND>(x, this->g, r, t); }
+  __device__ RowB make_row_b(int grp, int n) const {
+    return {((long long)grp * this->g.c_out_g + n) * this->K, n < this->N};
+  }
+  __device__ RedB make_red_b(int grp, int k) const { return {k, k < this->K}; }
+  __device__ acc_t load_b(const RowB& r, const RedB& t) const {
+    return (r.valid && t.valid) ? Cvt<T>::load(w + r.off + t.k) : acc_t(0);
+  }
+  __device__ void store(int grp, int split, int m, int n, acc_t v) const {
+    const int b = m / this->g.out_total, o = m - b * this->g.out_total;
+    const int co = grp * this->g.c_out_g + n;
+    if (bias) v += Cvt<T>::load(bias + co);
+    Cvt<T>::store(y + ((long long)b * this->c_out_total + co) * this->g.out_total + o, v);
+  }
+};
+
+// ---- input VJP ------------------------------------------------------------------------------
+template <typename T, int ND>
+struct InVjpProb : ProbBase<T, ND> {
+  using acc_t = typename Cvt<T>::acc_t;
+  static constexpr bool A_RED_FAST = false;  // lanes walk input positions
+  static constexpr bool B_RED_FAST = true;   // lanes walk (co,k)
+  using RowA = InPosCtx<ND>;
+  using RedA = ChanTapCtx<ND>;
+  struct RowB { int ci; bool valid; };
+  struct RedB { long long off; bool valid; };
+  const T* w; const T* v; T* gx;
+
+  __device__ RowA make_row_a(int grp, int m) const { return make_inpos<ND>(this->g, m, this->M); }
+  __device__ RedA make_red_a(int grp, int k) const { return make_chantap<ND>(this->g, k, this->K); }
+  __device__ acc_t load_a(const RowA& r, const RedA& t) const {
+    // channel base of this group is folded in through a per-launch pointer offset (see launch)
+    return gather_bwd<T, ND>(v, this->g, 0, this->c_out_total, r, t);
+  }
+  __device__ RowB make_row_b(int grp, int n) const { return {n, n < this->N}; }
+  __device__ RedB make_red_b(int grp, int k) const {
+    // k = co * Kt + kflat  ->  w[(g*Cout_g + co), ci, kflat]
+    const int co = k / this->g.k_total, kf = k - co * this->g.k_total;
+    return {(((long long)grp * this->g.c_out_g + co) * this->g.c_in_g) * this->g.k_total + kf, k < this->K};
+  }
+  __device__ acc_t load_b(const RowB& r, const RedB& t) const {
+    return (r.valid && t.valid) ? Cvt<T>::load(w + t.off + (long long)r.ci * this->g.k_total) : acc_t(0);
+  }
+  __device__ void store(int grp, int split, int m, int n, acc_t val) const {
+    const int b = m / this->g.in_total, i = m - b * this->g.in_total;
+    Cvt<T>::store(gx + ((long long)b * this->c_in_total + grp * this->g.c_in_g + n) * this->g.in_total + i, val);
+  }
+};
+
+// ---- weight VJP (split-K) -------------------------------------------------------------------
+template <typename T, int ND>
+struct WVjpProb : ProbBase<T, ND> {
+  using acc_t = typename Cvt<T>::acc_t;
+  static constexpr bool A_RED_FAST = true;  // lanes walk (b,o) (contiguous in v)
+  static constexpr bool B_RED_FAST = true;  // lanes walk (b,o) (nearly contiguous in x)
+  struct RowA { long long off; bool valid; };
+  struct RedA { long long off; bool valid; };
+  using RowB = TapCtx<ND>;
+  using RedB = PosCtx<ND>;
+  const T* x; const T* v; acc_t* partial;  // [G][splits][M][N]
+
+  __device__ RowA make_row_a(int grp, int m) const {
+    return {((long long)grp * this->g.c_out_g + m) * this->g.out_total, m < this->M};
+  }
+  __device__ RedA make_red_a(int grp, int k) const {
+    const int b = k / this->g.out_total, o = k - b * this->g.out_total;
+    return {(long long)b * this->c_out_total * this->g.out_total + o, k < this->K};
+  }
+  __device__ acc_t load_a(const RowA& r, const RedA& t) const {
+    return (r.valid && t.valid) ? Cvt<T>::load(v + r.off + t.off) : acc_t(0);
+  }
+  __device__ RowB make_row_b(int grp, int n) const {
+    TapCtx<ND> t = make_tap<ND>(this->g, this->st, this->g.in_total, n, this->N);
+    t.off += (long long)grp * this->g.c_in_g * this->g.in_total;
+    return t;
+  }
+  __device__ RedB make_red_b(int grp, int k) const {
+    return make_pos<ND>(this->g, this->st, (long long)this->c_in_total * this->g.in_total, k, this->K);
+  }
+  __device__ acc_t load_b(const RowB& t, const RedB& r) const { return gather_fwd<T, ND>(x, this->g, r, t); }
+  __device__ void store(int grp, int split, int m, int n, acc_t val) const {
+    partial[(((long long)grp * this->k_splits + split) * this->M + m) * this->N + n] = val;
+  }
+};
+
+// ---- KFC (split-K) --------------------------------------------------------------------------
+template <typename T, int ND>
+struct KfcProb : ProbBase<T, ND> {
+  using acc_t = typename Cvt<T>::acc_t;
+  static constexpr bool A_RED_FAST = true;
+  static constexpr bool B_RED_FAST = true;
+  using RowA = TapCtx<ND>;
+  using RedA = PosCtx<ND>;
+  using RowB = TapCtx<ND>;
+  using RedB = PosCtx<ND>;
+  const T* x; acc_t* partial;  // [G][splits][A][A]
+
+  __device__ RowA make_row_a(int grp, int m) const {
+    TapCtx<ND> t = make_tap<ND>(this->g, this->st, this->g.in_total, m, this->M);
+    t.off += (long long)grp * this->g.c_in_g * this->g.in_total;
+    return t;
+  }
+  __device__ RedA make_red_a(int grp, int k) const {
+    return make_pos<ND>(this->g, this->st, (long long)this->c_in_total * this->g.in_total, k, this->K);
+  }
+  __device__ acc_t load_a(const RowA& t, const RedA& r) const { return gather_fwd<T, ND>(x, this->g, r, t); }
+  __device__ RowB make_row_b(int grp, int n) const { return make_row_a(grp, n); }
+  __device__ RedB make_red_b(int grp, int k) const { return make_red_a(grp, k); }
+  __device__ acc_t load_b(const RowB& t, const RedB& r) const { return gather_fwd<T, ND>(x, this->g, r, t); }
+  __device__ void store(int grp, int split, int m, int n, acc_t val) const {
+    partial[(((long long)grp * this->k_splits + split) * this->M + m) * this->N + n] = val;
+  }
+};
+
+// ---- u u^T for KFAC-reduce: C[g][a][a'] = sum_b u[b][g*A + a] * u[b][g*A + a'] -----------------
+template <typename T, int ND>
+struct OuterProb : ProbBase<T, ND> {
+  using acc_t = typename Cvt<T>::acc_t;
+  static constexpr bool A_RED_FAST = false;  // lanes walk a (contiguous in u)
+  static constexpr bool B_RED_FAST = false;
+  struct RowA { int a; bool valid; };
+  struct RedA { long long off; bool valid; };
+  using RowB = RowA;
+  using RedB = RedA;
+  const acc_t* u;   // [B][G*A]
+  acc_t* partial;   // [G][1][A][A]
+
+  __device__ RowA make_row_a(int grp, int m) const { return {grp * this->M + m, m < this->M}; }
+  __device__ RedA make_red_a(int grp, int k) const {
+    return {(long long)k * this->g.groups * this->M, k < this->K};
+  }
+  __device__ acc_t load_a(const RowA& r, const RedA& t) const {
+    return (r.valid && t.valid) ? u[t.off + r.a] : acc_t(0);
+  }
+  __device__ RowB make_row_b(int grp, int n) const { return make_row_a(grp, n); }
+  __device__ RedB make_red_b(int grp, int k) const { return make_red_a(grp, k); }
+  __device__ acc_t load_b(const RowB& r, const RedB& t) const { return load_a(r, t); }
+  __device__ void store(int grp, int split, int m, int n, acc_t val) const {
+    partial[(((long long)grp * this->k_splits + split) * this->M + m) * this->N + n] = val;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// split-K reduction + scale + cast:  out[i] = scale * sum_s partial[grp][s][i]
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(
+    const typename Cvt<T>::acc_t* __restrict__ partial, T* __restrict__ out, long long per_group,
+    int k_splits, int groups, double scale) {
+  using acc_t = typename Cvt<T>::acc_t;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per_group * groups) return;
+  const long long grp = idx / per_group, i = idx - grp * per_group;
+  const acc_t* src = partial + grp * k_splits * per_group + i;
+  acc_t s = acc_t(0);
+  for (int k = 0; k < k_splits; ++k) s += src[(long long)k * per_group];
+  Cvt<T>::store(out + idx, (acc_t)(s * (acc_t)scale));
+}
+
+// ---------------------------------------------------------------------------------------------
+// KFAC-reduce stage 1: u[b, c, k..] = sum_{o..} x[b, c, s*o + d*k - p]   (one pass over x, HBM-bound)
+//   sum_o prod_d [i_d = s_d*o_d + d_d*k_d - p_d]  ==  prod_d m_d(k_d, i_d),
+//   m_d(k, i) = 1 iff t = i + p_d - d_d*k >= 0, s_d | t, t/s_d < O_d,
+// so the window sums are separable: a warp reduces one input row (last dim) into K_w partial sums,
+// then adds them to every outer tap the row belongs to.  One CTA per (b, c) plane.
+// ---------------------------------------------------------------------------------------------
+constexpr int KW_MAX = 8;
+
+__device__ __forceinline__ bool tap_member(const DevGeom& g, int d, int i, int k) {
+  const int t = i + g.pad[d] - g.dil[d] * k;
+  if (t < 0) return false;
+  const int s = g.stride[d];
+  const int o = (s == 1) ? t : t / s;
+  return o * s == t && o < g.out[d];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) window_sum_kernel(const T* __restrict__ x,
+                                                         typename Cvt<T>::acc_t* __restrict__ u,
+                                                         const __grid_constant__ DevGeom g,
+                                                         int planes) {
+  using acc_t = typename Cvt<T>::acc_t;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  acc_t* acc = reinterpret_cast<acc_t*>(smem_raw);  // [k_total]
+  const int plane = blockIdx.x;
+  if (plane >= planes) return;
+  for (int t = threadIdx.x; t < g.k_total; t += blockDim.x) acc[t] = acc_t(0);
+  __syncthreads();
+
+  const int W = g.n_dims - 1;
+  const int in_w = g.in[W], k_w = g.k[W];
+  const int n_rows = g.in_total / in_w;
+  const int k_outer = g.k_total / k_w;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const T* src = x + (long long)plane * g.in_total;
+
+  if (k_w <= KW_MAX) {
+    for (int row = warp; row < n_rows; row += n_warps) {
+      acc_t part[KW_MAX];
+#pragma unroll
+      for (int kw = 0; kw < KW_MAX; ++kw) part[kw] = acc_t(0);
+      for (int iw = lane; iw < in_w; iw += 32) {
+        const acc_t val = Cvt<T>::load(src + (long long)row * in_w + iw);
+#pragma unroll
+        for (int kw = 0; kw < KW_MAX; ++kw)
+          if (kw < k_w && tap_member(g, W, iw, kw)) part[kw] += val;
+      }
+#pragma unroll
+      for (int kw = 0; kw < KW_MAX; ++kw) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part[kw] += __shfl_xor_sync(0xffffffffu, part[kw], off);
+      }
+      // outer coordinates of this row, then every outer tap combination it belongs to;
+      // lane l takes combinations l, l+32, ...
+      int i[kMaxDims];
+      {
+        uint32_t rem = (uint32_t)row;
+        for (int d = W - 1; d >= 0; --d) {
+          uint32_t q, r;
+          g.in_div[d].divmod(rem, q, r);
+          i[d] = (int)r;
+          rem = q;
+        }
+      }
+      for (int kq = lane; kq < k_outer; kq += 32) {
+        uint32_t krem = (uint32_t)kq;
+        bool ok = true;
+        for (int d = W - 1; d >= 0; --d) {
+          uint32_t q, kd;
+          g.k_div[d].divmod(krem, q, kd);
+          krem = q;
+          ok = ok && tap_member(g, d, i[d], (int)kd);
+        }
+        if (ok) {
+#pragma unroll
+          for (int kw = 0; kw < KW_MAX; ++kw)
+            if (kw < k_w) atomicAdd(&acc[kq * k_w + kw], part[kw]);
+        }
+      }
+    }
+  } else {
+    // wide kernels: per-pixel enumeration of taps
+    for (int idx = threadIdx.x; idx < g.in_total; idx += blockDim.x) {
+      uint32_t rem = (uint32_t)idx;
+      int i[kMaxDims];
+      for (int d = W; d >= 0; --d) {
+        uint32_t q, r;
+        g.in_div[d].divmod(rem, q, r);
+        i[d] = (int)r;
+        rem = q;
+      }
+      const acc_t val = Cvt<T>::load(src + idx);
+      for (int kf = 0; kf < g.k_total; ++kf) {
+        uint32_t krem = (uint32_t)kf;
+        bool ok = true;
+        for (int d = W; d >= 0; --d) {
+          uint32_t q, kd;
+          g.k_div[d].divmod(krem, q, kd);
+          krem = q;
+          ok = ok && tap_member(g, d, i[d], (int)kd);
+        }
+        if (ok) atomicAdd(&acc[kf], val);
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < g.k_total; t += blockDim.x)
+    u[(long long)plane * g.k_total + t] = acc[t];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+static int pick_splits(long long tiles, int k_chunks) {
+  // enough CTAs for ~3 waves, but keep >= 8 chunks per split
+  long long want = (3ll * kNumSMs + tiles - 1) / tiles;
+  long long cap = std::max(1, k_chunks / 8);
+  return (int)std::max<long long>(1, std::min<long long>(std::min(want, cap), 512));
+}
+
+template <typename Prob>
+static int launch_gemm(const Prob& p, int groups, cudaStream_t stream, const char* name) {
+  dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, BN), groups * p.k_splits);
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return EINCONV_OK;
+  EINCONV_CHECK_ARG(grid.y < 65536 && grid.z < 65536, "%s: problem too large for the generic kernel", name);
+  gather_gemm_kernel<Prob><<<grid, NT, 0, stream>>>(p);
+  EINCONV_CHECK_LAUNCH(name);
+  return EINCONV_OK;
+}
+
+template <typename F>
+static int dispatch_nd(int n_dims, F&& f) {
+  if (n_dims <= 3) return f(std::integral_constant<int, 3>{});
+  return f(std::integral_constant<int, kMaxDims>{});
+}
+
+static bool fits_int(long long v) { return v >= 0 && v < (1ll << 31); }
+
+int ffma_conv_fwd(const void* x, const void* w, const void* bias, void* y, int dtype,
+                  const DevGeom& g, cudaStream_t stream) {
+  const long long M = (long long)g.batch * g.out_total, K = (long long)g.c_in_g * g.k_total;
+  EINCONV_CHECK_ARG(fits_int(M) && fits_int(K), "conv_fwd: index space exceeds 2^31");
+  return dispatch_dtype(dtype, [&](auto* tag) -> int {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    return dispatch_nd(g.n_dims, [&](auto nd) -> int {
+      constexpr int ND = decltype(nd)::value;
+      FwdProb<T, ND> p;
+      fill_base<T, ND>(p, g);
+      p.M = (int)M; p.N = g.c_out_g; p.K = (int)K;
+      p.x = (const T*)x; p.w = (const T*)w; p.bias = (const T*)bias; p.y = (T*)y;
+      return launch_gemm(p, g.groups, stream, "ffma_conv_fwd");
+    });
+  });
+}
+
+int ffma_conv_input_vjp(const void* w, const void* v, void* gx, int dtype, const DevGeom& g,
+                        cudaStream_t stream) {
+  const long long M = (long long)g.batch * g.in_total, K = (long long)g.c_out_g * g.k_total;
+  EINCONV_CHECK_ARG(fits_int(M) && fits_int(K), "conv_input_vjp: index space exceeds 2^31");
+  return dispatch_dtype(dtype, [&](auto* tag) -> int {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    return dispatch_nd(g.n_dims, [&](auto nd) -> int {
+      constexpr int ND = decltype(nd)::value;
+      // one launch per group: the cotangent's channel base moves with the group
+      for (int grp = 0; grp < g.groups; ++grp) {
+        InVjpProb<T, ND> p;
+        fill_base<T, ND>(p, g);
+        p.M = (int)M; p.N = g.c_in_g; p.K = (int)K;
+        p.w = (const T*)w + (long long)grp * g.c_out_g * g.c_in_g * g.k_total;
+        p.v = (const T*)v + (long long)grp * g.c_out_g * g.out_total;
+        p.gx = (T*)gx + (long long)grp * g.c_in_g * g.in_total;
+        int st = launch_gemm(p, 1, stream, "ffma_conv_input_vjp");
+        if (st) return st;
+      }
+      return EINCONV_OK;
+    });
+  });
+}
+
+int64_t ffma_splitk_workspace(int op, const DevGeom& g, int dtype, int* splits_out) {
+  long long M, N, K;
+  if (op == EINCONV_OP_CONV_WEIGHT_VJP) {
+    M = g.c_out_g; N = (long long)g.c_in_g * g.k_total;
+  } else {
+    M = N = (long long)g.c_in_g * g.k_total;
+  }
+  K = (long long)g.batch * g.out_total;
+  const long long tiles = (long long)ceil_div(M, BM) * ceil_div(N, BN) * g.groups;
+  const int splits = pick_splits(std::max(1ll, tiles), ceil_div(std::max(1ll, K), BK));
+  if (splits_out) *splits_out = splits;
+  const int64_t acc = (dtype == EINCONV_F64) ? 8 : 4;
+  int64_t bytes = (int64_t)g.groups * splits * M * N * acc;
+  if (op == EINCONV_OP_KFAC_REDUCE) {
+    // u [B][G*A] + one partial
+    bytes = ((int64_t)g.batch * g.groups * M + (int64_t)g.groups * M * N) * acc;
+  }
+  return bytes;
+}
+
+template <typename T>
+static int launch_reduce(const void* partial, void* out, long long per_group, int splits,
+                         int groups, double scale, cudaStream_t stream) {
+  const long long total = per_group * groups;
+  if (total == 0) return EINCONV_OK;
+  splitk_reduce_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      (const typename Cvt<T>::acc_t*)partial, (T*)out, per_group, splits, groups, scale);
+  EINCONV_CHECK_LAUNCH("splitk_reduce_kernel");
+  return EINCONV_OK;
+}
+
+int ffma_conv_weight_vjp(const void* x, const void* v, void* gw, int dtype, const DevGeom& g,
+                         void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  const long long N = (long long)g.c_in_g * g.k_total, K = (long long)g.batch * g.out_total;
+  EINCONV_CHECK_ARG(fits_int(N) && fits_int(K), "conv_weight_vjp: index space exceeds 2^31");
+  int splits = 1;
+  const int64_t need = ffma_splitk_workspace(EINCONV_OP_CONV_WEIGHT_VJP, g, dtype, &splits);
+  if (workspace_bytes < need || (need > 0 && !workspace)) {
+    set_error("conv_weight_vjp: workspace of %lld bytes required, got %lld", (long long)need,
+              (long long)workspace_bytes);
+    return EINCONV_ERR_WORKSPACE;
+  }
+  return dispatch_dtype(dtype, [&](auto* tag) -> int {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    using acc_t = typename Cvt<T>::acc_t;
+    return dispatch_nd(g.n_dims, [&](auto nd) -> int {
+      constexpr int ND = decltype(nd)::value;
+      WVjpProb<T, ND> p;
+      fill_base<T, ND>(p, g);
+      p.M = g.c_out_g; p.N = (int)N; p.K = (int)K; p.k_splits = splits;
+      p.x = (const T*)x; p.v = (const T*)v; p.partial = (acc_t*)workspace;
+      if (K == 0) {
+        cudaError_t e = cudaMemsetAsync(workspace, 0, need, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "memset");
+      } else {
+        int st = launch_gemm(p, g.groups, stream, "ffma_conv_weight_vjp");
+        if (st) return st;
+      }
+      return launch_reduce<T>(workspace, gw, (long long)p.M * p.N, splits, g.groups, 1.0, stream);
+    });
+  });
+}
+
+int ffma_kfc(const void* x, void* out, int dtype, const DevGeom& g, double scale, void* workspace,
+             int64_t workspace_bytes, cudaStream_t stream) {
+  const long long A = (long long)g.c_in_g * g.k_total, K = (long long)g.batch * g.out_total;
+  EINCONV_CHECK_ARG(fits_int(A) && fits_int(K), "kfc: index space exceeds 2^31");
+  int splits = 1;
+  const int64_t need = ffma_splitk_workspace(EINCONV_OP_KFC, g, dtype, &splits);
+  if (workspace_bytes < need || (need > 0 && !workspace)) {
+    set_error("kfc: workspace of %lld bytes required, got %lld", (long long)need,
+              (long long)workspace_bytes);
+    return EINCONV_ERR_WORKSPACE;
+  }
+  return dispatch_dtype(dtype, [&](auto* tag) -> int {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    using acc_t = typename Cvt<T>::acc_t;
+    return dispatch_nd(g.n_dims, [&](auto nd) -> int {
+      constexpr int ND = decltype(nd)::value;
+      KfcProb<T, ND> p;
+      fill_base<T, ND>(p, g);
+      p.M = p.N = (int)A; p.K = (int)K; p.k_splits = splits;
+      p.x = (const T*)x; p.partial = (acc_t*)workspace;
+      if (K == 0) {
+        cudaError_t e = cudaMemsetAsync(workspace, 0, need, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "memset");
+      } else {
+        int st = launch_gemm(p, g.groups, stream, "ffma_kfc");
+        if (st) return st;
+      }
+      return launch_reduce<T>(workspace, out, A * A, splits, g.groups, scale, stream);
+    });
+  });
+}
+
+int ffma_kfac_reduce(const void* x, void* out, int dtype, const DevGeom& g, double scale,
+                     void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  const long long A = (long long)g.c_in_g * g.k_total;
+  EINCONV_CHECK_ARG(fits_int(A), "kfac_reduce: index space exceeds 2^31");
+  const int64_t need = ffma_splitk_workspace(EINCONV_OP_KFAC_REDUCE, g, dtype, nullptr);
+  if (workspace_bytes < need || (need > 0 && !workspace)) {
+    set_error("kfac_reduce: workspace of %lld bytes required, got %lld", (long long)need,
+              (long long)workspace_bytes);
+    return EINCONV_ERR_WORKSPACE;
+  }
+  return dispatch_dtype(dtype, [&](auto* tag) -> int {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    using acc_t = typename Cvt<T>::acc_t;
+    acc_t* u = (acc_t*)workspace;
+    acc_t* partial = u + (long long)g.batch * g.groups * A;
+    const int planes = g.batch * g.groups * g.c_in_g;
+    if (planes > 0 && g.k_total > 0) {
+      const size_t smem = (size_t)g.k_total * sizeof(acc_t);
+      EINCONV_CHECK_ARG(smem <= 48 * 1024, "kfac_reduce: kernel too large (%d taps)", g.k_total);
+      window_sum_kernel<T><<<planes, 256, smem, stream>>>((const T*)x, u, g, planes);
+      EINCONV_CHECK_LAUNCH("window_sum_kernel");
+    }
+    OuterProb<T, 3> p;
+    fill_base<T, 3>(p, g);
+    p.M = p.N = (int)A; p.K = g.batch; p.k_splits = 1;
+    p.u = u; p.partial = partial;
+    int st = launch_gemm(p, g.groups, stream, "ffma_kfac_outer");
+    if (st) return st;
+    return launch_reduce<T>(partial, out, A * A, 1, g.groups, scale, stream);
+  });
+}
+
+}  // namespace einconv

@@ -1,0 +1,273 @@
+// K7-depthwise: direct stencil kernels for groups == in_channels (c_in_g == 1), 1-d and 2-d.
+//
+// This is what the reference's simplifier reaches by squeezing c_in / c_out out of the network
+// (simplifications/opt.py:148-171; observed equation `ngbc,deb,fhc,gdf->ngeh`):
+// each output channel reads a single input channel, so there is no reduction over channels to feed
+// a tensor core with — the op is an HBM-bound stencil (2.25 flop/B for 3x3).  Forward
+// (expressions/convNd_forward.py:48-55) and input VJP (expressions/convNd_input_vjp.py:53-60).
+//
+// A CTA owns one (b, c) input plane and a tile of output rows.  It stages the zero-padded input
+// window of the tile in shared memory once and produces the tile for all `c_out_g` output channels
+// of that group; taps are unrolled at compile time for the common kernel sizes, weights live in
+// registers.
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace einconv {
+
+struct DwParams {
+  int batch, channels, mult;   // B, C (= groups), c_out_g
+  int in_h, in_w, out_h, out_w;
+  int k_h, k_w, s_h, s_w, d_h, d_w, p_h, p_w;
+  int tile_h, n_tiles;         // rows of the produced tensor per CTA
+  int rows_cap, cols;          // staged window
+  FastDiv w_div;               // / width of the produced tensor
+};
+
+// ---- forward: y[b, c*m + j, oh, ow] = bias + sum_{kh,kw} x[b, c, s*oh + d*kh - p, ..] * w[c*m + j, kh, kw]
+template <typename T, int KH, int KW>
+__global__ void __launch_bounds__(256) dw_fwd_kernel(const T* __restrict__ x,
+                                                     const T* __restrict__ w,
+                                                     const T* __restrict__ bias, T* __restrict__ y,
+                                                     const __grid_constant__ DwParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* win = reinterpret_cast<float*>(smem_raw);  // [rows][cols], zero padded
+  const int k_h = KH > 0 ? KH : p.k_h, k_w = KW > 0 ? KW : p.k_w;
+
+  const int tile = blockIdx.x % p.n_tiles;
+  const int bc = blockIdx.x / p.n_tiles;
+  const int b = bc / p.channels, c = bc - b * p.channels;
+  const int oh0 = tile * p.tile_h;
+  const int th = min(p.tile_h, p.out_h - oh0);
+  const int rows = p.s_h * (th - 1) + p.d_h * (k_h - 1) + 1;
+  const int cols = p.cols;
+
+  const T* src = x + (long long)bc * p.in_h * p.in_w;
+  const int r0 = p.s_h * oh0 - p.p_h;
+  for (int idx = threadIdx.x; idx < rows * cols; idx += blockDim.x) {
+    const int jr = idx / cols, jc = idx - jr * cols;
+    const int r = r0 + jr, cc = jc - p.p_w;
+    float val = 0.f;
+    if (r >= 0 && r < p.in_h && cc >= 0 && cc < p.in_w) val = (float)Cvt<T>::load(src + r * p.in_w + cc);
+    win[idx] = val;
+  }
+  __syncthreads();
+
+  const int chunk = th * p.out_w;
+  for (int j = 0; j < p.mult; ++j) {
+    const int co = c * p.mult + j;
+    const T* wc = w + (long long)co * k_h * k_w;
+    float wreg[(KH > 0 ? KH * KW : 1)];
+    if (KH > 0) {
+#pragma unroll
+      for (int t = 0; t < KH * KW; ++t) wreg[t] = (float)Cvt<T>::load(wc + t);
+    }
+    const float bv = bias ? (float)Cvt<T>::load(bias + co) : 0.f;
+    T* dst = y + ((long long)b * p.channels * p.mult + co) * p.out_h * p.out_w + (long long)oh0 * p.out_w;
+    for (int e = threadIdx.x; e < chunk; e += blockDim.x) {
+      uint32_t ohl, ow;
+      p.w_div.divmod((uint32_t)e, ohl, ow);
+      const float* base = win + (p.s_h * (int)ohl) * cols + p.s_w * (int)ow;
+      float acc = 0.f;
+      if (KH > 0) {
+#pragma unroll
+        for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < KW; ++kw)
+            acc = fmaf(base[p.d_h * kh * cols + p.d_w * kw], wreg[kh * KW + kw], acc);
+      } else {
+        for (int kh = 0; kh < k_h; ++kh)
+          for (int kw = 0; kw < k_w; ++kw)
+            acc = fmaf(base[p.d_h * kh * cols + p.d_w * kw],
+                       (float)Cvt<T>::load(wc + kh * k_w + kw), acc);
+      }
+      Cvt<T>::store(dst + e, (typename Cvt<T>::acc_t)(acc + bv));
+    }
+  }
+}
+
+// ---- input VJP: gx[b, c, ih, iw] = sum_j sum_{kh,kw : s | (i + p - d*k)} v[b, c*m + j, (ih+p-d*kh)/s, ..] * w[c*m + j, kh, kw]
+// The CTA stages the cotangent rows its input-row tile can touch, for one output channel at a time.
+template <typename T, int KH, int KW>
+__global__ void __launch_bounds__(256) dw_input_vjp_kernel(const T* __restrict__ w,
+                                                           const T* __restrict__ v,
+                                                           T* __restrict__ gx,
+                                                           const __grid_constant__ DwParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* win = reinterpret_cast<float*>(smem_raw);  // [rows][out_w + 2*halo], zero padded
+  const int k_h = KH > 0 ? KH : p.k_h, k_w = KW > 0 ? KW : p.k_w;
+
+  const int tile = blockIdx.x % p.n_tiles;
+  const int bc = blockIdx.x / p.n_tiles;
+  const int b = bc / p.channels, c = bc - b * p.channels;
+  const int ih0 = tile * p.tile_h;
+  const int th = min(p.tile_h, p.in_h - ih0);
+  // cotangent rows that can be touched: oh in [floor((ih0 + p - d(K-1)) / s), (ih0 + th - 1 + p) / s]
+  const int lo_num = ih0 + p.p_h - p.d_h * (k_h - 1);
+  const int oh_lo = lo_num >= 0 ? lo_num / p.s_h : -((-lo_num + p.s_h - 1) / p.s_h);
+  const int oh_hi = (ih0 + th - 1 + p.p_h) / p.s_h;
+  const int rows = oh_hi - oh_lo + 1;
+  // cotangent columns: ow in [ow_lo, ow_hi] for the full input width
+  const int wl_num = p.p_w - p.d_w * (k_w - 1);
+  const int ow_lo = wl_num >= 0 ? wl_num / p.s_w : -((-wl_num + p.s_w - 1) / p.s_w);
+  const int cols = p.cols;
+
+  const int chunk = th * p.in_w;
+
+  // accumulate over the group's output channels; partial sums stay in registers across j by
+  // looping e in the outer position would need storage, so loop j outermost with a smem pass each.
+  T* dst = gx + (long long)bc * p.in_h * p.in_w + (long long)ih0 * p.in_w;
+  for (int j = 0; j < p.mult; ++j) {
+    const int co = c * p.mult + j;
+    const T* srcv = v + ((long long)b * p.channels * p.mult + co) * p.out_h * p.out_w;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < rows * cols; idx += blockDim.x) {
+      const int jr = idx / cols, jc = idx - jr * cols;
+      const int oh = oh_lo + jr, ow = ow_lo + jc;
+      float val = 0.f;
+      if (oh >= 0 && oh < p.out_h && ow >= 0 && ow < p.out_w)
+        val = (float)Cvt<T>::load(srcv + oh * p.out_w + ow);
+      win[idx] = val;
+    }
+    __syncthreads();
+    const T* wc = w + (long long)co * k_h * k_w;
+    float wreg[(KH > 0 ? KH * KW : 1)];
+    if (KH > 0) {
+#pragma unroll
+      for (int t = 0; t < KH * KW; ++t) wreg[t] = (float)Cvt<T>::load(wc + t);
+    }
+    for (int e = threadIdx.x; e < chunk; e += blockDim.x) {
+      uint32_t ihl, iw;
+      p.w_div.divmod((uint32_t)e, ihl, iw);
+      const int ih = ih0 + (int)ihl;
+      float acc = 0.f;
+      auto tap = [&](int kh, int kw, float wv) {
+        const int th_ = ih + p.p_h - p.d_h * kh;
+        const int tw_ = (int)iw + p.p_w - p.d_w * kw;
+        // floor division is not needed: negative numerators are rejected
+        const int oh = th_ / p.s_h, ow = tw_ / p.s_w;
+        if (th_ >= 0 && tw_ >= 0 && oh * p.s_h == th_ && ow * p.s_w == tw_)
+          acc = fmaf(win[(oh - oh_lo) * cols + (ow - ow_lo)], wv, acc);
+      };
+      if (KH > 0) {
+#pragma unroll
+        for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < KW; ++kw) tap(kh, kw, wreg[kh * KW + kw]);
+      } else {
+        for (int kh = 0; kh < k_h; ++kh)
+          for (int kw = 0; kw < k_w; ++kw) tap(kh, kw, (float)Cvt<T>::load(wc + kh * k_w + kw));
+      }
+      if (j > 0) acc += (float)Cvt<T>::load(dst + e);  // running sum over the group's channels
+      Cvt<T>::store(dst + e, (typename Cvt<T>::acc_t)acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+bool depthwise_supported(const DevGeom& g, int dtype) {
+  return g.c_in_g == 1 && g.groups > 1 && g.n_dims <= 2 && dtype != EINCONV_F64 && g.out_total > 0 &&
+         g.in_total > 0;
+}
+
+static void fill_dw(DwParams& p, const DevGeom& g) {
+  const int N = g.n_dims;
+  auto get = [&](const int* a, int which, int dflt) {  // which: 0 = H, 1 = W
+    const int d = N - 2 + which;
+    return d >= 0 ? a[d] : dflt;
+  };
+  p.batch = g.batch; p.channels = g.groups; p.mult = g.c_out_g;
+  p.in_h = get(g.in, 0, 1);   p.in_w = get(g.in, 1, 1);
+  p.out_h = get(g.out, 0, 1); p.out_w = get(g.out, 1, 1);
+  p.k_h = get(g.k, 0, 1);     p.k_w = get(g.k, 1, 1);
+  p.s_h = get(g.stride, 0, 1); p.s_w = get(g.stride, 1, 1);
+  p.d_h = get(g.dil, 0, 1);   p.d_w = get(g.dil, 1, 1);
+  p.p_h = get(g.pad, 0, 0);   p.p_w = get(g.pad, 1, 0);
+}
+
+template <typename F>
+static int dispatch_taps(int k_h, int k_w, F&& f) {
+  if (k_h == 3 && k_w == 3) return f(std::integral_constant<int, 3>{}, std::integral_constant<int, 3>{});
+  if (k_h == 5 && k_w == 5) return f(std::integral_constant<int, 5>{}, std::integral_constant<int, 5>{});
+  if (k_h == 1 && k_w == 3) return f(std::integral_constant<int, 1>{}, std::integral_constant<int, 3>{});
+  return f(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+}
+
+int dw_conv_fwd(const void* x, const void* w, const void* bias, void* y, int dtype,
+                const DevGeom& g, cudaStream_t stream) {
+  DwParams p{};
+  fill_dw(p, g);
+  p.cols = p.s_w * (p.out_w - 1) + p.d_w * (p.k_w - 1) + 1;
+  auto rows_for = [&](int th) { return p.s_h * (th - 1) + p.d_h * (p.k_h - 1) + 1; };
+  int th = p.out_h;
+  while (th > 1 && (long long)rows_for(th) * p.cols * 4 > 32 * 1024) th = (th + 1) / 2;
+  EINCONV_CHECK_ARG((long long)rows_for(th) * p.cols * 4 <= 200 * 1024, "depthwise: row too wide");
+  p.tile_h = th; p.n_tiles = ceil_div(p.out_h, th); p.rows_cap = rows_for(th);
+  p.w_div = FastDiv((uint32_t)p.out_w);
+  const size_t smem = (size_t)p.rows_cap * p.cols * 4;
+  const long long grid = (long long)p.batch * p.channels * p.n_tiles;
+  EINCONV_CHECK_ARG(grid < (1ll << 31), "depthwise: grid too large");
+  return dispatch_dtype(dtype, [&](auto* tag) -> int {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    if constexpr (std::is_same_v<T, double>) {
+      set_error("depthwise: fp64 unsupported");
+      return EINCONV_ERR_UNSUPPORTED;
+    } else {
+      return dispatch_taps(p.k_h, p.k_w, [&](auto kh, auto kw) -> int {
+        auto kern = dw_fwd_kernel<T, decltype(kh)::value, decltype(kw)::value>;
+        if (smem > 48 * 1024) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dw_fwd)");
+        }
+        kern<<<(unsigned)grid, 256, smem, stream>>>((const T*)x, (const T*)w, (const T*)bias, (T*)y, p);
+        EINCONV_CHECK_LAUNCH("dw_fwd_kernel");
+        return EINCONV_OK;
+      });
+    }
+  });
+}
+
+int dw_conv_input_vjp(const void* w, const void* v, void* gx, int dtype, const DevGeom& g,
+                      cudaStream_t stream) {
+  DwParams p{};
+  fill_dw(p, g);
+  // staged cotangent window: all columns any input column can touch
+  auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+  const int ow_lo = fdiv(p.p_w - p.d_w * (p.k_w - 1), p.s_w);
+  const int ow_hi = (p.in_w - 1 + p.p_w) / p.s_w;
+  p.cols = ow_hi - ow_lo + 1;
+  auto rows_for = [&](int th) {
+    // worst case over tile origins
+    return (th - 1 + p.d_h * (p.k_h - 1)) / p.s_h + 2;
+  };
+  int th = p.in_h;
+  while (th > 1 && (long long)rows_for(th) * p.cols * 4 > 32 * 1024) th = (th + 1) / 2;
+  EINCONV_CHECK_ARG((long long)rows_for(th) * p.cols * 4 <= 200 * 1024, "depthwise: row too wide");
+  p.tile_h = th; p.n_tiles = ceil_div(p.in_h, th); p.rows_cap = rows_for(th);
+  p.w_div = FastDiv((uint32_t)p.in_w);
+  const size_t smem = (size_t)p.rows_cap * p.cols * 4;
+  const long long grid = (long long)p.batch * p.channels * p.n_tiles;
+  EINCONV_CHECK_ARG(grid < (1ll << 31), "depthwise: grid too large");
+  return dispatch_dtype(dtype, [&](auto* tag) -> int {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    if constexpr (std::is_same_v<T, double>) {
+      set_error("depthwise: fp64 unsupported");
+      return EINCONV_ERR_UNSUPPORTED;
+    } else {
+      return dispatch_taps(p.k_h, p.k_w, [&](auto kh, auto kw) -> int {
+        auto kern = dw_input_vjp_kernel<T, decltype(kh)::value, decltype(kw)::value>;
+        if (smem > 48 * 1024) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dw_input_vjp)");
+        }
+        kern<<<(unsigned)grid, 256, smem, stream>>>((const T*)w, (const T*)v, (T*)gx, p);
+        EINCONV_CHECK_LAUNCH("dw_input_vjp_kernel");
+        return EINCONV_OK;
+      });
+    }
+  });
+}
+
+}  // namespace einconv

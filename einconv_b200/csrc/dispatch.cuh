@@ -1,0 +1,44 @@
+// Internal prototypes shared between api.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace einconv {
+
+// unfold.cu
+int launch_unfold(const void* x, const int64_t* x_strides, void* out, int dtype,
+                  const einconv_geom* geom, cudaStream_t stream);
+int launch_fold(const void* gu, void* gx, int dtype, const einconv_geom* geom, cudaStream_t stream);
+
+// contract_ffma.cu
+int ffma_conv_fwd(const void* x, const void* w, const void* bias, void* y, int dtype,
+                  const DevGeom& g, cudaStream_t stream);
+int ffma_conv_input_vjp(const void* w, const void* v, void* gx, int dtype, const DevGeom& g,
+                        cudaStream_t stream);
+int ffma_conv_weight_vjp(const void* x, const void* v, void* gw, int dtype, const DevGeom& g,
+                         void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+int ffma_kfc(const void* x, void* out, int dtype, const DevGeom& g, double scale, void* workspace,
+             int64_t workspace_bytes, cudaStream_t stream);
+int ffma_kfac_reduce(const void* x, void* out, int dtype, const DevGeom& g, double scale,
+                     void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+int64_t ffma_splitk_workspace(int op, const DevGeom& g, int dtype, int* splits_out);
+
+// depthwise.cu
+bool depthwise_supported(const DevGeom& g, int dtype);
+int dw_conv_fwd(const void* x, const void* w, const void* bias, void* y, int dtype,
+                const DevGeom& g, cudaStream_t stream);
+int dw_conv_input_vjp(const void* w, const void* v, void* gx, int dtype, const DevGeom& g,
+                      cudaStream_t stream);
+
+// tc_gemm.cu (tcgen05 / TMEM tensor-core kernels)
+bool tc_supported(int op, const DevGeom& g, int dtype, int math);
+const char* tc_kernel_name(int op, const DevGeom& g, int dtype, int math);
+int64_t tc_workspace_bytes(int op, const DevGeom& g, int dtype, int math);
+int tc_conv_fwd(const void* x, const void* w, const void* bias, void* y, int dtype,
+                const DevGeom& g, int math, void* workspace, int64_t workspace_bytes,
+                cudaStream_t stream);
+int tc_conv_weight_vjp(const void* x, const void* v, void* gw, int dtype, const DevGeom& g,
+                       int math, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+int tc_kfc(const void* x, void* out, int dtype, const DevGeom& g, double scale, int math,
+           void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace einconv

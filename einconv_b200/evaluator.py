@@ -1,0 +1,468 @@
+"""Native evaluation of einconv's convolution tensor networks on sm_100a.
+
+This module is the host side of the drop-in boundary: it stands where the reference calls
+``torch.einsum(equation, *operands).reshape(shape)`` (``einconv/functionals/conv.py:61``,
+``einconv/functionals/unfold.py:56``, user code per ``README.md:64-73``) and calls the C ABI of
+``libeinconv_b200.so`` instead.  Geometry is resolved exactly as the reference does
+(``einconv/utils.py:97-160``) and handed to the kernels as an ``einconv_geom``; index patterns are
+never built.
+
+Two entry styles:
+
+* direct functions (``conv_forward``, ``conv_input_vjp``, ``conv_weight_vjp``, ``unfold``, ``kfc``,
+  ``kfac_reduce``) used by ``functionals`` / ``modules``;
+* :func:`einsum`, reached through ``torch.einsum`` whenever an operand is a lazy
+  :class:`~einconv_b200.conv_index_pattern.IndexPattern`: expressions returned by
+  ``einconv_b200.expressions.*.einsum_expression`` carry a :class:`Plan` on their equation string,
+  so the familiar ``torch.einsum(equation, *operands).reshape(shape)`` runs the native kernel.
+"""
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import Tensor
+
+from einconv_b200 import _native as nat
+from einconv_b200.utils import _tuple, resolve_geometry
+
+# --------------------------------------------------------------------------------------------
+# math-mode policy
+# --------------------------------------------------------------------------------------------
+_FP32_MATH = "auto"
+
+
+def set_fp32_math(mode: str) -> None:
+    """How float32 contractions are computed.
+
+    ``"fp32"``: CUDA-core FMA, full fp32 accumulation (meets the reference's ``rtol=1e-5``).
+    ``"tf32"``: tcgen05 ``kind::tf32`` tensor cores with fp32 accumulation in TMEM.
+    ``"auto"`` (default): follow ``torch.backends.cuda.matmul.allow_tf32`` — the switch that
+    governs the ``bmm`` calls the reference's ``torch.einsum`` ends in.
+    """
+    global _FP32_MATH
+    if mode not in ("auto", "fp32", "tf32"):
+        raise ValueError(f"Unknown fp32 math mode {mode!r}.")
+    _FP32_MATH = mode
+
+
+def get_fp32_math() -> str:
+    return _FP32_MATH
+
+
+def _math_for(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        mode = _FP32_MATH
+        if mode == "auto":
+            mode = "tf32" if torch.backends.cuda.matmul.allow_tf32 else "fp32"
+        return nat.MATH_TF32 if mode == "tf32" else nat.MATH_FP32
+    return nat.MATH_AUTO
+
+
+def _kernels_for(simplify: bool) -> int:
+    # simplify=True may use specialised kernels, simplify=False always the generic one; results
+    # agree (the reference tests every case both ways, test/utils.py:98).
+    return nat.KERNELS_SPECIALIZED if simplify else nat.KERNELS_GENERIC
+
+
+# --------------------------------------------------------------------------------------------
+# geometry helpers
+# --------------------------------------------------------------------------------------------
+def _check_sizes(out: Sequence[int], what: str) -> None:
+    if any(o < 0 for o in out):
+        raise ValueError(
+            f"{what}: kernel does not fit into the padded input (output sizes {tuple(out)})."
+        )
+
+
+def _geom(batch, groups, c_in_g, c_out_g, input_size, kernel_size, stride, padding, dilation):
+    t_in, t_k, t_s, t_d, p_left, out = resolve_geometry(
+        input_size, kernel_size, stride, padding, dilation
+    )
+    _check_sizes(out, "convolution geometry")
+    g = nat.make_geom(batch, groups, c_in_g, c_out_g, t_in, t_k, t_s, t_d, p_left, out)
+    return g, t_k, out
+
+
+def _workspace(op: int, g, dtype_code: int, math: int, kernels: int, device) -> Tuple[Optional[Tensor], int]:
+    nbytes = nat.lib().einconv_workspace_bytes(op, g, dtype_code, math, kernels)
+    if nbytes < 0:
+        nat.check(-1, "einconv_workspace_bytes")
+    if nbytes == 0:
+        return None, 0
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
+def _same_dtype(*tensors: Tensor) -> torch.dtype:
+    dtype = tensors[0].dtype
+    for t in tensors[1:]:
+        if t is not None and t.dtype != dtype:
+            raise RuntimeError(f"Expected operands of equal dtype. Got {dtype} and {t.dtype}.")
+    return dtype
+
+
+def selected_kernel(op: int, g, dtype: torch.dtype, simplify: bool = True) -> str:
+    """Name of the kernel family the dispatcher picks (for tests and logs)."""
+    name = nat.lib().einconv_selected_kernel(
+        op, g, nat.dtype_code(dtype), _math_for(dtype), _kernels_for(simplify)
+    )
+    return name.decode() if name else ""
+
+
+# --------------------------------------------------------------------------------------------
+# raw (non-differentiable) native calls
+# --------------------------------------------------------------------------------------------
+def unfold(x: Tensor, kernel_size, dilation=1, padding=0, stride=1) -> Tensor:
+    """``[B, C, *in] -> [B, C * prod(k), prod(out)]`` — network of ``convNd_unfold.py:42-53``."""
+    device = nat.require_cuda(x)
+    if x.dim() < 3:
+        raise ValueError(f"unfoldNd expects [batch, channels, *spatial]. Got shape {tuple(x.shape)}.")
+    B, C = x.shape[:2]
+    g, t_k, out = _geom(B, 1, C, 0, x.shape[2:], kernel_size, stride, padding, dilation)
+    k_total = 1
+    for k in t_k:
+        k_total *= k
+    o_total = 1
+    for o in out:
+        o_total *= o
+    result = torch.empty((B, C * k_total, o_total), dtype=x.dtype, device=device)
+    if result.numel() == 0:
+        return result
+    strides = (nat.ctypes.c_int64 * x.dim())(*x.stride())
+    with torch.cuda.device(device):
+        st = nat.lib().einconv_unfold(
+            x.data_ptr(), strides, result.data_ptr(), nat.dtype_code(x.dtype), g, nat.stream_ptr(device)
+        )
+    nat.check(st, "einconv_unfold")
+    return result
+
+
+def fold(gu: Tensor, channels: int, input_size, kernel_size, dilation=1, padding=0, stride=1) -> Tensor:
+    """Adjoint of :func:`unfold`: ``[B, C * prod(k), prod(out)] -> [B, C, *in]``."""
+    device = nat.require_cuda(gu)
+    gu = gu.contiguous()
+    B = gu.shape[0]
+    g, _, _ = _geom(B, 1, channels, 0, input_size, kernel_size, stride, padding, dilation)
+    result = torch.empty((B, channels, *input_size), dtype=gu.dtype, device=device)
+    if result.numel() == 0:
+        return result
+    with torch.cuda.device(device):
+        st = nat.lib().einconv_fold(
+            gu.data_ptr(), result.data_ptr(), nat.dtype_code(gu.dtype), g, nat.stream_ptr(device)
+        )
+    nat.check(st, "einconv_fold")
+    return result
+
+
+def _conv_check(x: Tensor, weight: Tensor, bias: Optional[Tensor], groups: int) -> None:
+    """Argument checks of ``einconv/functionals/conv.py:72-116`` (same errors)."""
+    N = x.dim() - 2
+    in_channels = x.shape[1]
+    out_channels = weight.shape[0]
+    if weight.dim() != N + 2:
+        raise ValueError(f"For Conv(N={N})d, the kernel must be {N+2}d. Got {weight.dim()}d.")
+    if weight.shape[0] % groups != 0:
+        raise ValueError(f"Groups ({groups}) must divide out_channels ({weight.shape[0]}).")
+    if weight.shape[1] * groups != in_channels:
+        raise ValueError(
+            f"Kernel dimension 1 ({weight.shape[1]}) multiplied by groups ({groups})"
+            + f" must equal in_channels ({in_channels})."
+        )
+    if bias is not None and (bias.dim() != 1 or bias.numel() != out_channels):
+        raise ValueError(f"Bias should have shape [{out_channels}]. Got {bias.shape}.")
+
+
+def conv_forward_raw(x, weight, bias, stride, padding, dilation, groups, simplify=True) -> Tensor:
+    device = nat.require_cuda(x, weight, bias)
+    dtype = _same_dtype(x, weight, bias)
+    x, weight = x.contiguous(), weight.contiguous()
+    bias = None if bias is None else bias.contiguous()
+    B, c_out = x.shape[0], weight.shape[0]
+    g, _, out = _geom(
+        B, groups, weight.shape[1], c_out // groups, x.shape[2:], tuple(weight.shape[2:]),
+        stride, padding, dilation,
+    )
+    y = torch.empty((B, c_out, *out), dtype=dtype, device=device)
+    if y.numel() == 0:
+        return y
+    code, math, kern = nat.dtype_code(dtype), _math_for(dtype), _kernels_for(simplify)
+    ws, ws_bytes = _workspace(nat.OP_CONV_FWD, g, code, math, kern, device)
+    with torch.cuda.device(device):
+        st = nat.lib().einconv_conv_fwd(
+            x.data_ptr(), weight.data_ptr(), nat.ptr(bias), y.data_ptr(), code, g, math, kern,
+            nat.ptr(ws), ws_bytes, nat.stream_ptr(device),
+        )
+    nat.check(st, "einconv_conv_fwd")
+    return y
+
+
+def conv_input_vjp_raw(weight, v, input_size, stride, padding, dilation, groups, simplify=True) -> Tensor:
+    device = nat.require_cuda(weight, v)
+    dtype = _same_dtype(weight, v)
+    weight, v = weight.contiguous(), v.contiguous()
+    N = weight.dim() - 2
+    t_input = _tuple(input_size if isinstance(input_size, int) else tuple(input_size), N)
+    B, c_out = v.shape[0], weight.shape[0]
+    c_in_g = weight.shape[1]
+    g, _, out = _geom(
+        B, groups, c_in_g, c_out // groups, t_input, tuple(weight.shape[2:]), stride, padding, dilation
+    )
+    if tuple(v.shape[2:]) != tuple(out) or v.shape[1] != c_out:
+        raise ValueError(
+            f"Cotangent has shape {tuple(v.shape)}, expected {(B, c_out, *out)} for this geometry."
+        )
+    gx = torch.empty((B, groups * c_in_g, *t_input), dtype=dtype, device=device)
+    if gx.numel() == 0:
+        return gx
+    if v.numel() == 0:
+        return gx.zero_()
+    code, math, kern = nat.dtype_code(dtype), _math_for(dtype), _kernels_for(simplify)
+    ws, ws_bytes = _workspace(nat.OP_CONV_INPUT_VJP, g, code, math, kern, device)
+    with torch.cuda.device(device):
+        st = nat.lib().einconv_conv_input_vjp(
+            weight.data_ptr(), v.data_ptr(), gx.data_ptr(), code, g, math, kern,
+            nat.ptr(ws), ws_bytes, nat.stream_ptr(device),
+        )
+    nat.check(st, "einconv_conv_input_vjp")
+    return gx
+
+
+def conv_weight_vjp_raw(x, v, kernel_size, dilation, padding, stride, groups, simplify=True) -> Tensor:
+    device = nat.require_cuda(x, v)
+    dtype = _same_dtype(x, v)
+    x, v = x.contiguous(), v.contiguous()
+    N = x.dim() - 2
+    B, c_in, c_out = x.shape[0], x.shape[1], v.shape[1]
+    g, t_k, out = _geom(
+        B, groups, c_in // groups, c_out // groups, x.shape[2:], kernel_size, stride, padding, dilation
+    )
+    if tuple(v.shape[2:]) != tuple(out) or v.shape[0] != B:
+        raise ValueError(
+            f"Cotangent has shape {tuple(v.shape)}, expected {(B, c_out, *out)} for this geometry."
+        )
+    gw = torch.empty((c_out, c_in // groups, *t_k), dtype=dtype, device=device)
+    if gw.numel() == 0:
+        return gw
+    code, math, kern = nat.dtype_code(dtype), _math_for(dtype), _kernels_for(simplify)
+    ws, ws_bytes = _workspace(nat.OP_CONV_WEIGHT_VJP, g, code, math, kern, device)
+    with torch.cuda.device(device):
+        st = nat.lib().einconv_conv_weight_vjp(
+            x.data_ptr(), v.data_ptr(), gw.data_ptr(), code, g, math, kern,
+            nat.ptr(ws), ws_bytes, nat.stream_ptr(device),
+        )
+    nat.check(st, "einconv_conv_weight_vjp")
+    return gw
+
+
+def _factor(op: int, x, kernel_size, stride, padding, dilation, groups, simplify, scale) -> Tensor:
+    device = nat.require_cuda(x)
+    x = x.contiguous()
+    B, c_in = x.shape[0], x.shape[1]
+    if c_in % groups != 0:
+        raise ValueError(f"Groups ({groups}) must divide in_channels ({c_in}).")
+    g, t_k, out = _geom(B, groups, c_in // groups, 0, x.shape[2:], kernel_size, stride, padding, dilation)
+    k_total = 1
+    for k in t_k:
+        k_total *= k
+    A = c_in // groups * k_total
+    if scale is None:
+        if op == nat.OP_KFC:
+            # Tensor([1 / B]) in x.dtype, convNd_kfc.py:105
+            scale = float(torch.tensor([1.0 / B]).to(x.dtype)) if B > 0 else 0.0
+        else:
+            o_total = 1
+            for o in out:
+                o_total *= o
+            # Tensor([1 / (B * prod(out)^2)]) in x.dtype, convNd_kfac_reduce.py:106-108
+            denom = B * o_total**2
+            scale = float(torch.tensor([1.0 / denom]).to(x.dtype)) if denom > 0 else 0.0
+    result = torch.empty((groups, A, A), dtype=x.dtype, device=device)
+    if result.numel() == 0:
+        return result
+    code, math, kern = nat.dtype_code(x.dtype), _math_for(x.dtype), _kernels_for(simplify)
+    ws, ws_bytes = _workspace(op, g, code, math, kern, device)
+    fn = nat.lib().einconv_kfc if op == nat.OP_KFC else nat.lib().einconv_kfac_reduce
+    with torch.cuda.device(device):
+        st = fn(
+            x.data_ptr(), result.data_ptr(), code, g, float(scale), math, kern,
+            nat.ptr(ws), ws_bytes, nat.stream_ptr(device),
+        )
+    nat.check(st, "einconv_kfc" if op == nat.OP_KFC else "einconv_kfac_reduce")
+    return result
+
+
+def kfc(x, kernel_size, stride=1, padding=0, dilation=1, groups=1, simplify=True, scale=None) -> Tensor:
+    """KFC factor ``[G, A, A]`` (``convNd_kfc.py:75-116``).  ``scale`` defaults to ``1/B``; pass the
+    global ``1/B`` when ``x`` is a batch shard whose factors will be summed across ranks."""
+    return _factor(nat.OP_KFC, x, kernel_size, stride, padding, dilation, groups, simplify, scale)
+
+
+def kfac_reduce(x, kernel_size, stride=1, padding=0, dilation=1, groups=1, simplify=True, scale=None) -> Tensor:
+    """KFAC-reduce factor ``[G, A, A]`` (``convNd_kfac_reduce.py:77-119``)."""
+    return _factor(nat.OP_KFAC_REDUCE, x, kernel_size, stride, padding, dilation, groups, simplify, scale)
+
+
+# --------------------------------------------------------------------------------------------
+# differentiable wrappers (the reference's einsum is differentiable, modules/conv.py:173-182)
+# --------------------------------------------------------------------------------------------
+class _ConvNdFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups, simplify):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        ctx.hyper = (stride, padding, dilation, groups, simplify)
+        return conv_forward_raw(x, weight, bias, stride, padding, dilation, groups, simplify)
+
+    @staticmethod
+    def backward(ctx, v):
+        x, weight = ctx.saved_tensors
+        stride, padding, dilation, groups, simplify = ctx.hyper
+        gx = gw = gb = None
+        v = v.contiguous()
+        if ctx.needs_input_grad[0]:
+            gx = conv_input_vjp_raw(
+                weight, v, tuple(x.shape[2:]), stride, padding, dilation, groups, simplify
+            )
+        if ctx.needs_input_grad[1]:
+            gw = conv_weight_vjp_raw(
+                x, v, tuple(weight.shape[2:]), dilation, padding, stride, groups, simplify
+            )
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = v.sum(dim=[0] + list(range(2, v.dim())))
+        return gx, gw, gb, None, None, None, None, None
+
+
+class _UnfoldNdFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel_size, dilation, padding, stride):
+        ctx.geometry = (x.shape[1], tuple(x.shape[2:]), kernel_size, dilation, padding, stride)
+        return unfold(x, kernel_size, dilation, padding, stride)
+
+    @staticmethod
+    def backward(ctx, gu):
+        channels, input_size, kernel_size, dilation, padding, stride = ctx.geometry
+        return fold(gu, channels, input_size, kernel_size, dilation, padding, stride), None, None, None, None
+
+
+def conv_forward(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, simplify=True) -> Tensor:
+    """Differentiable N-d convolution on the native kernels (``functionals/conv.py:11-69``)."""
+    _conv_check(x, weight, bias, groups)
+    needs_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (x, weight, bias)
+    )
+    if needs_grad:
+        return _ConvNdFunction.apply(x, weight, bias, stride, padding, dilation, groups, simplify)
+    return conv_forward_raw(x, weight, bias, stride, padding, dilation, groups, simplify)
+
+
+def unfold_autograd(x, kernel_size, dilation=1, padding=0, stride=1) -> Tensor:
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _UnfoldNdFunction.apply(x, kernel_size, dilation, padding, stride)
+    return unfold(x, kernel_size, dilation, padding, stride)
+
+
+# --------------------------------------------------------------------------------------------
+# torch.einsum interception
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Plan:
+    """What an expression computes, in terms the native evaluator understands."""
+
+    kind: str                       # forward | input_vjp | weight_vjp | unfold | kfc | kfac_reduce
+    tensors: Dict[str, Tensor]      # the un-rearranged tensors (x, weight, v)
+    hyper: Dict[str, Any]           # stride / padding / dilation / groups / kernel_size / input_size
+    shape: Tuple[int, ...]          # shape the reference reshapes the einsum result to
+    simplify: bool
+    operands: List[Any] = field(default_factory=list)  # exactly the operand objects returned
+
+    def run(self) -> Tensor:
+        t, h = self.tensors, self.hyper
+        if self.kind == "forward":
+            return conv_forward(t["x"], t["weight"], None, h["stride"], h["padding"], h["dilation"],
+                                h["groups"], self.simplify)
+        if self.kind == "input_vjp":
+            return conv_input_vjp_raw(t["weight"], t["v"], h["input_size"], h["stride"], h["padding"],
+                                      h["dilation"], h["groups"], self.simplify)
+        if self.kind == "weight_vjp":
+            return conv_weight_vjp_raw(t["x"], t["v"], h["kernel_size"], h["dilation"], h["padding"],
+                                       h["stride"], h["groups"], self.simplify)
+        if self.kind == "unfold":
+            return unfold_autograd(t["x"], h["kernel_size"], h["dilation"], h["padding"], h["stride"])
+        if self.kind == "kfc":
+            return kfc(t["x"], h["kernel_size"], h["stride"], h["padding"], h["dilation"], h["groups"],
+                       self.simplify)
+        if self.kind == "kfac_reduce":
+            return kfac_reduce(t["x"], h["kernel_size"], h["stride"], h["padding"], h["dilation"],
+                               h["groups"], self.simplify)
+        raise AssertionError(self.kind)
+
+
+class Equation(str):
+    """An einsum equation string that remembers which convolution network it encodes."""
+
+    plan: Optional[Plan] = None
+
+    def __new__(cls, text: str, plan: Optional[Plan] = None):
+        self = super().__new__(cls, text)
+        self.plan = plan
+        return self
+
+
+def _einsum_output_shape(equation: str, operands: Sequence[Any]) -> Tuple[int, ...]:
+    lhs, rhs = equation.replace(" ", "").split("->")
+    dims: Dict[str, int] = {}
+    for letters, op in zip(lhs.split(","), operands):
+        for letter, size in zip(letters, op.shape):
+            dims[letter] = int(size)
+    return tuple(dims[letter] for letter in rhs)
+
+
+def _dense(op):
+    from einconv_b200.conv_index_pattern import IndexPattern
+
+    return op.materialize() if isinstance(op, IndexPattern) else op
+
+
+def einsum(equation, *operands):
+    """``torch.einsum`` for expressions that contain lazy index patterns.
+
+    A planned expression (equation and operand list exactly as returned by one of this package's
+    ``einsum_expression`` functions, all on CUDA) runs the native sm_100a kernel and comes back in
+    the shape ``torch.einsum`` would have produced.  Anything else is a user-composed network: the
+    patterns are written out and torch contracts them — on CUDA tensors only.
+    """
+    if len(operands) == 1 and isinstance(operands[0], (list, tuple)):
+        operands = tuple(operands[0])
+    tensors = [op for op in operands if isinstance(op, Tensor)]
+    nat.require_cuda(*tensors)
+
+    plan = getattr(equation, "plan", None)
+    if (
+        plan is not None
+        and len(plan.operands) == len(operands)
+        and all(a is b for a, b in zip(plan.operands, operands))
+    ):
+        result = plan.run()
+        return result.reshape(_einsum_output_shape(str(equation), operands))
+
+    with torch._C.DisableTorchFunctionSubclass():
+        return torch.einsum(str(equation), *[_dense(op) for op in operands])
+
+
+def evaluate(equation, operands, shape=None) -> Tensor:
+    """``torch.einsum(equation, *operands)`` (optionally ``.reshape(shape)``) on the native kernels.
+
+    Also covers simplified expressions in which no index pattern is left (dense / 1x1 cases),
+    which ``torch.einsum`` alone would hand to cuBLAS without this package noticing.
+    """
+    plan = getattr(equation, "plan", None)
+    if (
+        plan is not None
+        and len(plan.operands) == len(operands)
+        and all(a is b for a, b in zip(plan.operands, operands))
+    ):
+        nat.require_cuda(*[op for op in operands if isinstance(op, Tensor)])
+        result = plan.run()
+        return result.reshape(shape if shape is not None else _einsum_output_shape(str(equation), operands))
+    result = einsum(equation, *operands)
+    return result if shape is None else result.reshape(shape)
