@@ -69,9 +69,12 @@ def _kernels_for(simplify: bool) -> int:
 # geometry helpers
 # --------------------------------------------------------------------------------------------
 def _check_sizes(out: Sequence[int], what: str) -> None:
-    if any(o < 0 for o in out):
-        raise ValueError(
-            f"{what}: kernel does not fit into the padded input (output sizes {tuple(out)})."
+    # The reference fails inside conv1d while building the pattern (conv_index_pattern.py:61):
+    # "Kernel size can't be greater than actual input size".  Same exception type here.
+    if any(o <= 0 for o in out):
+        raise RuntimeError(
+            f"{what}: kernel size can't be greater than the padded input size "
+            f"(output sizes would be {tuple(out)})."
         )
 
 

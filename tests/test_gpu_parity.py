@@ -1,0 +1,403 @@
+"""GPU parity: the sm_100a kernels (through the Python host API -> C ABI) against the oracle.
+
+Bars (stated per test):
+* unfoldNd / fold-free gathers: bit-exact (``torch.equal``) for fp32, fp64, bf16, fp16;
+* fp32 contractions in EINCONV_MATH_FP32 (default): the reference's own tolerances
+  (``test/utils.py:10-16`` rtol 1e-5 / small atol; factors rtol 5e-5, ``test_convNd_kfc.py:59``);
+* fp64: rtol 1e-10;
+* bf16 / fp16 I/O (fp32 accumulate): compared with the fp64 oracle on the SAME rounded inputs,
+  ``|delta| <= 2^-8 |ref| + small`` (bf16) resp. ``2^-11`` (fp16): one output rounding.
+Every case runs with ``simplify`` True and False (specialised vs generic kernel), like the
+reference's ``SIMPLIFIES`` axis (``test/utils.py:98``).
+"""
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import einconv_b200
+from einconv_b200 import _native as nat
+from einconv_b200 import evaluator
+from einconv_b200.expressions import (
+    convNd_forward,
+    convNd_input_vjp,
+    convNd_kfac_reduce,
+    convNd_kfc,
+    convNd_unfold,
+    convNd_weight_vjp,
+)
+from einconv_b200.functionals import convNd, unfoldNd
+from einconv_b200.modules import ConvNd, UnfoldNd
+from oracle import direct
+from tests import cases as C
+from tests.conftest import forward_out_shape, golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SIMPLIFY = [True, False]
+
+
+def close(got, want, rtol, atol, what=""):
+    got = got.detach().double().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = np.abs(got - want)
+    bound = atol + rtol * np.abs(want)
+    if not (err <= bound).all():
+        idx = np.unravel_index(np.argmax(err - bound), err.shape)
+        raise AssertionError(
+            f"{what}: max violation at {idx}: got {got[idx]!r} want {want[idx]!r} "
+            f"(|d|={err[idx]:.3e}, allowed {bound[idx]:.3e}); mismatches {(err > bound).sum()}/{err.size}"
+        )
+
+
+def test_native_library_is_loaded_and_counts_launches():
+    before = nat.launch_count()
+    x = torch.rand(1, 2, 8, 8, device=DEV)
+    unfoldNd(x, 3)
+    assert nat.launch_count() > before
+    assert nat.LIB_PATH.exists()
+
+
+# =============================================================================================
+# unfold: bit-exact
+# =============================================================================================
+@pytest.mark.parametrize("case", C.UNFOLD_CASES, ids=[c["id"] for c in C.UNFOLD_CASES])
+@pytest.mark.parametrize("simplify", SIMPLIFY)
+def test_unfold_bit_exact(case, simplify):
+    x = C.draw_input(case)
+    want = direct.unfold(x.numpy(), case["kernel_size"], **case["kwargs"])
+    got = unfoldNd(x.to(DEV), case["kernel_size"], **case["kwargs"], simplify=simplify)
+    assert got.dtype == x.dtype and tuple(got.shape) == want.shape
+    assert torch.equal(got.cpu(), torch.from_numpy(want))
+    golden("unfold").check(case["id"], got.cpu().numpy(), 0, 0, exact=True)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float64])
+@pytest.mark.parametrize("case", [C.UNFOLD_CASES[5], C.UNFOLD_CASES[11], C.UNFOLD_CASES[18]],
+                         ids=lambda c: c["id"])
+def test_unfold_bit_exact_other_dtypes(case, dtype):
+    x = C.draw_input(case).to(dtype)
+    raw = x.view(torch.int16).numpy() if dtype in (torch.bfloat16, torch.float16) else x.numpy()
+    want = direct.unfold(raw, case["kernel_size"], **case["kwargs"])
+    got = unfoldNd(x.to(DEV), case["kernel_size"], **case["kwargs"]).cpu()
+    got_raw = got.view(torch.int16).numpy() if dtype in (torch.bfloat16, torch.float16) else got.numpy()
+    assert np.array_equal(got_raw, want)
+
+
+UNFOLD_EXTRA = [
+    dict(x=(1, 1, 11), kernel_size=4, kwargs=dict(padding=6)),                      # padding > kernel
+    dict(x=(2, 2, 91), kernel_size=4, kwargs=dict(stride=2, padding=20, dilation=3)),
+    dict(x=(2, 3, 9, 8), kernel_size=4, kwargs=dict(padding="same")),               # asymmetric same
+    dict(x=(3, 2, 7, 7), kernel_size=7, kwargs=dict(padding=3)),
+    dict(x=(2, 3, 224, 224), kernel_size=7, kwargs=dict(stride=2, padding=3)),      # row-tiled staging
+    dict(x=(5, 70, 7, 7), kernel_size=3, kwargs=dict(padding=1)),                   # many tiny planes
+    dict(x=(2, 2, 6, 5, 4, 7), kernel_size=(2, 3, 2, 3), kwargs=dict(padding=1, stride=(1, 2, 1, 2))),  # N = 4
+    dict(x=(1, 2, 3, 4, 5, 4, 6), kernel_size=2, kwargs=dict(dilation=(1, 2, 1, 1, 2))),              # N = 5
+    dict(x=(0, 3, 8, 8), kernel_size=3, kwargs={}),                                  # empty batch
+    dict(x=(2, 3, 4, 4), kernel_size=5, kwargs=dict(padding=0), expect_error=True),  # kernel larger than input
+]
+
+
+@pytest.mark.parametrize("case", UNFOLD_EXTRA, ids=lambda c: "x".join(map(str, c["x"])) + f"-k{c['kernel_size']}")
+def test_unfold_edge_cases(case):
+    torch.manual_seed(1)
+    x = torch.rand(*case["x"])
+    if case.get("expect_error"):
+        with pytest.raises(RuntimeError, match="can't be greater"):
+            unfoldNd(x.to(DEV), case["kernel_size"], **case["kwargs"])
+        return
+    want = direct.unfold(x.numpy(), case["kernel_size"], **case["kwargs"])
+    got = unfoldNd(x.to(DEV), case["kernel_size"], **case["kwargs"])
+    assert tuple(got.shape) == want.shape
+    assert torch.equal(got.cpu(), torch.from_numpy(want))
+
+
+def test_unfold_non_contiguous_input_and_module():
+    torch.manual_seed(0)
+    base = torch.rand(2, 12, 6, 10, device=DEV)
+    x = base.permute(0, 2, 1, 3)[:, :, ::2, 1:9]  # [2, 6, 6, 8], strided view
+    assert not x.is_contiguous()
+    got = UnfoldNd((3, 2), dilation=1, padding=1, stride=2)(x)
+    want = direct.unfold(x.contiguous().cpu().numpy(), (3, 2), padding=1, stride=2)
+    assert torch.equal(got.cpu(), torch.from_numpy(want))
+    assert torch.equal(got, F.unfold(x.contiguous(), (3, 2), padding=1, stride=2))
+
+
+def test_unfold_matches_torch_unfold_4d_and_is_differentiable():
+    torch.manual_seed(0)
+    x = torch.rand(3, 4, 17, 13, device=DEV, requires_grad=True)
+    kw = dict(kernel_size=(3, 2), dilation=2, padding=1, stride=2)
+    u = unfoldNd(x, **kw)
+    ref = F.unfold(x, **kw)
+    assert torch.equal(u, ref)
+    g = torch.rand_like(u)
+    (gx,) = torch.autograd.grad(u, x, g)
+    (gref,) = torch.autograd.grad(ref, x, g)
+    close(gx, gref.cpu().numpy(), 1e-6, 1e-6, "fold")
+    want = direct.fold(g.cpu().numpy(), 4, (17, 13), **kw)
+    close(gx, want, 1e-6, 1e-6, "fold vs oracle")
+
+
+def _slices_unfold(x, k, s, d, p):
+    """Reference-free construction on the GPU: strided slices of the padded input (exact)."""
+    N = x.dim() - 2
+    pad = []
+    for dim in reversed(range(N)):
+        pad += [p[dim], p[dim] + s[dim]]  # generous right padding
+    xp = F.pad(x, pad)
+    out = [1 + (x.shape[2 + i] + 2 * p[i] - (d[i] * (k[i] - 1) + 1)) // s[i] for i in range(N)]
+    cols = []
+    import itertools
+
+    for taps in itertools.product(*[range(kk) for kk in k]):
+        idx = [slice(None), slice(None)]
+        for i in range(N):
+            start = taps[i] * d[i]
+            idx.append(slice(start, start + s[i] * (out[i] - 1) + 1, s[i]))
+        cols.append(xp[tuple(idx)].reshape(x.shape[0], x.shape[1], 1, -1))
+    return torch.cat(cols, dim=2).reshape(x.shape[0], x.shape[1] * len(cols), -1)
+
+
+def test_unfold_baseline_c2_full_size_exact():
+    """BASELINE C2 at full size: N=16 C=32 16x56x56 k=3 stride=2 dilation=2 (bit-exact gather)."""
+    torch.manual_seed(0)
+    x = torch.rand(16, 32, 16, 56, 56).to(DEV)
+    got = unfoldNd(x, 3, dilation=2, padding=0, stride=2)
+    assert tuple(got.shape) == (16, 864, 4056)
+    want = _slices_unfold(x, (3, 3, 3), (2, 2, 2), (2, 2, 2), (0, 0, 0))
+    assert torch.equal(got, want)
+    # oracle on one sample
+    ref = direct.unfold(x[3:4].cpu().numpy(), 3, dilation=2, padding=0, stride=2)
+    assert torch.equal(got[3:4].cpu(), torch.from_numpy(ref))
+
+
+# =============================================================================================
+# forward
+# =============================================================================================
+FWD = C.CONV_CASES + C.SPECIAL_CASES + C.EDGE_CASES
+
+
+@pytest.mark.parametrize("case", FWD, ids=[c["id"] for c in FWD])
+@pytest.mark.parametrize("simplify", SIMPLIFY)
+def test_forward_fp32(case, simplify):
+    """fp32, EINCONV_MATH_FP32: rtol 1e-5 (+ atol 1e-5 for cancellation-free rand inputs)."""
+    x, w, b = C.draw_forward(case)
+    want = direct.conv_forward(x.numpy(), w.numpy(), None if b is None else b.numpy(), **case["kwargs"])
+    got = convNd(x.to(DEV), w.to(DEV), None if b is None else b.to(DEV), **case["kwargs"], simplify=simplify)
+    assert got.dtype == torch.float32
+    close(got, want, 1e-5, 1e-5, case["id"])
+    golden("forward").check(case["id"], got.cpu().numpy(), 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize("case", [C.CONV_CASES[9], C.CONV_CASES[18], C.SPECIAL_CASES[5], C.EDGE_CASES[6]],
+                         ids=lambda c: c["id"])
+def test_forward_fp64(case):
+    x, w, b = C.draw_forward(case)
+    x, w = x.double(), w.double()
+    b = None if b is None else b.double()
+    want = direct.conv_forward(x.numpy(), w.numpy(), None if b is None else b.numpy(), **case["kwargs"])
+    got = convNd(x.to(DEV), w.to(DEV), None if b is None else b.to(DEV), **case["kwargs"])
+    assert got.dtype == torch.float64
+    close(got, want, 1e-10, 1e-12, case["id"])
+
+
+@pytest.mark.parametrize("dtype,ulp", [(torch.bfloat16, 2.0**-8), (torch.float16, 2.0**-11)])
+@pytest.mark.parametrize("case", [C.CONV_CASES[8], C.CONV_CASES[11], C.SPECIAL_CASES[5], C.SPECIAL_CASES[0]],
+                         ids=lambda c: c["id"])
+@pytest.mark.parametrize("simplify", SIMPLIFY)
+def test_forward_16bit(case, dtype, ulp, simplify):
+    """16-bit I/O, fp32 accumulation: one output rounding against the fp64 oracle on the same bits."""
+    x, w, b = C.draw_forward(case)
+    x, w = x.to(dtype), w.to(dtype)
+    b = None if b is None else b.to(dtype)
+    want = direct.conv_forward(x.double().numpy(), w.double().numpy(),
+                               None if b is None else b.double().numpy(), **case["kwargs"])
+    got = convNd(x.to(DEV), w.to(DEV), None if b is None else b.to(DEV), **case["kwargs"], simplify=simplify)
+    assert got.dtype == dtype
+    close(got, want, ulp, 1e-4, case["id"])
+
+
+def test_forward_matches_torch_conv_and_module():
+    """Mirror of test/modules/test_conv.py: nn.ConvNd -> ConvNd.from_nn_Conv, atol 1e-6 rtol 1e-5."""
+    torch.manual_seed(0)
+    for ref in (
+        torch.nn.Conv1d(6, 9, 5, stride=2, padding=1, dilation=2, groups=3),
+        torch.nn.Conv2d(6, 9, (5, 4), padding="same", dilation=(1, 2), groups=3),
+        torch.nn.Conv3d(3, 4, 3, stride=2, padding=1, bias=False),
+    ):
+        ref = ref.to(DEV)
+        N = ref.weight.dim() - 2
+        x = torch.rand(2, ref.in_channels, *([13, 11, 9][:N]), device=DEV)
+        for simplify in SIMPLIFY:
+            mine = ConvNd.from_nn_Conv(ref, simplify=simplify)
+            with torch.backends.cudnn.flags(allow_tf32=False):
+                want = ref(x)
+            close(mine(x), want.detach().cpu().numpy(), 1e-5, 1e-5, f"module N={N}")
+
+
+def test_forward_baseline_c1_shape_and_linearity():
+    """BASELINE C1 (N=32 C=64 56x56 k3 p1 fp32) at full size: against cuDNN fp32 and linearity."""
+    torch.manual_seed(0)
+    x = torch.rand(32, 64, 56, 56, device=DEV)
+    w = torch.rand(64, 64, 3, 3, device=DEV)
+    y = convNd(x, w, padding=1)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        ref = F.conv2d(x.double(), w.double(), padding=1)
+    close(y, ref.cpu().numpy(), 2e-5, 1e-4, "C1 vs fp64 conv")
+    y2 = convNd(2.0 * x, w, padding=1)
+    assert torch.equal(y2, 2.0 * y)  # scaling by a power of two is exact
+    # oracle on a slice of the batch
+    want = direct.conv_forward(x[:1].cpu().numpy(), w.cpu().numpy(), None, padding=1)
+    close(y[:1], want, 1e-5, 1e-4, "C1 slice vs oracle")
+
+
+# =============================================================================================
+# VJPs through the reference's calling convention: torch.einsum(equation, *operands).reshape(shape)
+# =============================================================================================
+VJP = C.VJP_CASES + C.SPECIAL_CASES
+
+
+@pytest.mark.parametrize("case", VJP, ids=[c["id"] for c in VJP])
+@pytest.mark.parametrize("simplify", SIMPLIFY)
+def test_input_vjp_fp32(case, simplify):
+    """Reference tolerance for the input VJP: atol 5e-7 (test_convNd_input_vjp.py:55) plus rtol 1e-5."""
+    w, x, v = C.draw_vjp(case, forward_out_shape(case))
+    want = direct.conv_input_vjp(w.numpy(), v.numpy(), tuple(x.shape[2:]), **case["kwargs"])
+    eq, ops, shape = convNd_input_vjp.einsum_expression(
+        w.to(DEV), v.to(DEV), tuple(x.shape[2:]), **case["kwargs"], simplify=simplify
+    )
+    before = nat.launch_count()
+    got = torch.einsum(eq, *ops).reshape(shape)
+    assert nat.launch_count() > before, "einsum did not reach the native kernels"
+    close(got, want, 1e-5, 5e-6, case["id"])
+    if golden("input_vjp").has(case["id"]):
+        golden("input_vjp").check(case["id"], got.cpu().numpy(), 1e-5, 5e-6)
+
+
+@pytest.mark.parametrize("case", VJP, ids=[c["id"] for c in VJP])
+@pytest.mark.parametrize("simplify", SIMPLIFY)
+def test_weight_vjp_fp32(case, simplify):
+    """fp32 weight VJP: rtol 2e-5 (reductions over up to 10^5 terms, SURVEY.md 7 'precision')."""
+    w, x, v = C.draw_vjp(case, forward_out_shape(case))
+    want = direct.conv_weight_vjp(x.numpy(), v.numpy(), tuple(w.shape[2:]), **case["kwargs"])
+    eq, ops, shape = convNd_weight_vjp.einsum_expression(
+        x.to(DEV), v.to(DEV), tuple(w.shape[2:]), **case["kwargs"], simplify=simplify
+    )
+    before = nat.launch_count()
+    got = torch.einsum(eq, *ops).reshape(shape)
+    assert nat.launch_count() > before
+    assert tuple(got.shape) == tuple(w.shape)
+    close(got, want, 2e-5, 1e-5, case["id"])
+    if golden("weight_vjp").has(case["id"]):
+        golden("weight_vjp").check(case["id"], got.cpu().numpy(), 2e-5, 1e-5)
+
+
+def test_einsum_result_has_the_shape_torch_would_return():
+    x = torch.rand(2, 4, 9, 9, device=DEV)
+    w = torch.rand(6, 2, 3, 3, device=DEV)
+    eq, ops, shape = convNd_forward.einsum_expression(x, w, groups=2, simplify=False)
+    out = torch.einsum(eq, *ops)
+    assert tuple(out.shape) == (2, 2, 3, 7, 7)  # n g c_out o0 o1
+    assert tuple(out.reshape(shape).shape) == (2, 6, 7, 7)
+    # a user-composed network with a pattern still evaluates (written-out pattern, torch on CUDA)
+    pat = einconv_b200.index_pattern(9, 3, device=x.device, dtype=x.dtype)
+    manual = torch.einsum("nchw,koh->nckow", x, pat)
+    assert tuple(manual.shape) == (2, 4, 3, 7, 9)
+
+
+def test_autograd_through_convnd_matches_torch():
+    torch.manual_seed(0)
+    for kw in (dict(padding=1), dict(stride=2, padding=2, dilation=2, groups=2),
+               dict(padding=1, groups=8)):
+        groups = kw.get("groups", 1)
+        x = torch.rand(3, 8, 12, 10, device=DEV, requires_grad=True)
+        w = torch.rand(16, 8 // groups, 3, 3, device=DEV, requires_grad=True)
+        b = torch.rand(16, device=DEV, requires_grad=True)
+        for simplify in SIMPLIFY:
+            y = convNd(x, w, b, **kw, simplify=simplify)
+            g = torch.rand_like(y)
+            gx, gw, gb = torch.autograd.grad(y, (x, w, b), g)
+            with torch.backends.cudnn.flags(allow_tf32=False):
+                yr = F.conv2d(x.double(), w.double(), b.double(), **kw)
+                rx, rw, rb = torch.autograd.grad(yr, (x, w, b), g.double())
+            close(gx, rx.cpu().numpy(), 1e-5, 1e-5, f"gx {kw}")
+            close(gw, rw.cpu().numpy(), 2e-5, 1e-4, f"gw {kw}")
+            close(gb, rb.cpu().numpy(), 1e-5, 1e-4, f"gb {kw}")
+
+
+def test_weight_vjp_baseline_c4_reduced_bf16():
+    """BASELINE C4 geometry (3-d, k3 p1) at reduced size in bf16: fp32 accumulate, bf16 output."""
+    torch.manual_seed(0)
+    x = torch.rand(2, 16, 6, 28, 28).bfloat16()
+    v = torch.rand(2, 16, 6, 28, 28).bfloat16()
+    want = direct.conv_weight_vjp(x.double().numpy(), v.double().numpy(), 3, padding=1)
+    for simplify in SIMPLIFY:
+        eq, ops, shape = convNd_weight_vjp.einsum_expression(x.to(DEV), v.to(DEV), 3, padding=1, simplify=simplify)
+        got = torch.einsum(eq, *ops).reshape(shape)
+        assert got.dtype == torch.bfloat16
+        close(got, want, 2.0**-8, 1e-2, "C4 reduced")
+
+
+# =============================================================================================
+# Kronecker factors
+# =============================================================================================
+def _factor_truth(x, kernel_size, kwargs, kind):
+    """Ground truth of the reference's tests (test_convNd_kfc.py:47-52, test_convNd_kfac_reduce.py:48-53):
+    unfold (already proven bit-exact above), then the outer products in fp64 on the GPU."""
+    groups = kwargs.get("groups", 1)
+    ukw = {k: v for k, v in kwargs.items() if k != "groups"}
+    u = unfoldNd(x.to(DEV), kernel_size, **ukw).double()
+    B = u.shape[0]
+    u = u.reshape(B, groups, u.shape[1] // groups, u.shape[2])
+    if kind == "kfc":
+        return torch.einsum("ngik,ngjk->gij", u, u) / B
+    m = u.mean(-1)
+    return torch.einsum("ngi,ngj->gij", m, m) / B
+
+
+@pytest.mark.parametrize("case", C.FACTOR_CASES, ids=[c["id"] for c in C.FACTOR_CASES])
+@pytest.mark.parametrize("simplify", SIMPLIFY)
+@pytest.mark.parametrize("kind", ["kfc", "kfac_reduce"])
+def test_factors_fp32(case, simplify, kind):
+    """rtol 5e-5 as in the reference (test_convNd_kfc.py:59, test_convNd_kfac_reduce.py:60)."""
+    x = C.draw_input(case)
+    mod = convNd_kfc if kind == "kfc" else convNd_kfac_reduce
+    eq, ops, shape = mod.einsum_expression(x.to(DEV), case["kernel_size"], **case["kwargs"], simplify=simplify)
+    before = nat.launch_count()
+    got = torch.einsum(eq, *ops).reshape(shape)
+    assert nat.launch_count() > before
+    truth = _factor_truth(x, case["kernel_size"], case["kwargs"], kind)
+    close(got, truth.cpu().numpy(), 5e-5, 1e-6 if kind == "kfc" else 1e-8, f"{kind} {case['id']}")
+    if golden(kind).has(case["id"]):
+        golden(kind).check(case["id"], got.cpu().numpy(), 5e-5, 1e-6)
+    if len(case["x"]) <= 4:
+        fn = direct.kfc if kind == "kfc" else direct.kfac_reduce
+        close(got, fn(x.numpy(), case["kernel_size"], **case["kwargs"]), 5e-5, 1e-6, f"{kind} oracle")
+
+
+def test_factors_resnet_layers_reduced_batch():
+    """A few ResNet-50 geometries of BASELINE C5 at batch 4."""
+    layers = [(3, 56, 7, 2, 3), (64, 28, 3, 1, 1), (128, 28, 3, 2, 1), (256, 14, 1, 1, 0), (256, 14, 1, 2, 0)]
+    for n, (c, h, k, s, p) in enumerate(layers):
+        torch.manual_seed(n)
+        x = torch.rand(4, c, h, h)
+        kw = dict(stride=s, padding=p)
+        for kind, fn in (("kfc", evaluator.kfc), ("kfac_reduce", evaluator.kfac_reduce)):
+            got = fn(x.to(DEV), k, **kw)
+            truth = _factor_truth(x, k, kw, kind)
+            close(got, truth.cpu().numpy(), 5e-5, 1e-6 if kind == "kfc" else 1e-9, f"{kind} layer {n}")
+            assert torch.allclose(got, got.transpose(1, 2), rtol=1e-6, atol=1e-7)  # symmetric
+
+
+def test_factor_sharding_identity_on_one_gpu():
+    """Sum of shard factors computed with the global scale == the full-batch factor."""
+    torch.manual_seed(0)
+    x = torch.rand(8, 6, 14, 14, device=DEV)
+    full_k = evaluator.kfc(x, 3, padding=1)
+    full_r = evaluator.kfac_reduce(x, 3, padding=1)
+    parts_k = sum(evaluator.kfc(x[i : i + 2], 3, padding=1, scale=1.0 / 8) for i in range(0, 8, 2))
+    parts_r = sum(evaluator.kfac_reduce(x[i : i + 2], 3, padding=1, scale=1.0 / (8 * 196**2)) for i in range(0, 8, 2))
+    close(parts_k, full_k.cpu().numpy(), 1e-5, 1e-6, "kfc shards")
+    close(parts_r, full_r.cpu().numpy(), 1e-5, 1e-9, "kfac_reduce shards")
