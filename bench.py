@@ -285,14 +285,19 @@ class ClockSampler:
 
 
 def flush_l2(buf):
-    buf.zero_()
+    """Evict the workload's tensors from the 126 MB L2: write 256 MiB, then read 256 MiB so that the
+    cache ends up holding CLEAN lines (dirty flush lines would otherwise be written back inside the
+    timed region and be charged to the kernel under test)."""
+    half = buf.numel() // 2
+    buf[:half].zero_()
+    buf[half:].sum()
 
 
 def time_steps(wl, steps, warmup, device, flush=True):
     """Per-step CUDA-event timing on the current stream; returns (list of ms, launches per step)."""
     from einconv_b200 import _native as nat
 
-    buf = torch.empty(256 << 20, dtype=torch.uint8, device=device) if flush else None
+    buf = torch.zeros(512 << 20, dtype=torch.uint8, device=device).view(torch.int32) if flush else None
     for _ in range(warmup):
         wl.step()
     torch.cuda.synchronize(device)
@@ -486,7 +491,7 @@ def main():
             metric=wl.metric, value=value, unit=wl.unit, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=wl.dtype,
             data="synthetic",
-            config=dict(workload=wl.name, l2="flushed between steps (256 MiB write)",
+            config=dict(workload=wl.name, l2="flushed between steps (256 MiB write + 256 MiB read, outside the timed events)",
                         timing="CUDA events per step on the launch stream, max over ranks",
                         parallelism=f"batch shards x{world}, no collective" if args.workload != "factors"
                         else f"batch 256 split x{world}, NCCL all-reduce of factors"),

@@ -122,8 +122,12 @@ template <> struct Cvt<double> {
 };
 template <> struct Cvt<__nv_bfloat16> {
   using acc_t = float;
+  // NB: read the bits through the builtin __ldg(unsigned short*).  The bf16/half __ldg overloads
+  // are non-volatile inline asm, which the compiler may hoist above the bounds predicate of a
+  // `ok ? load(p) : 0` select and fault on padding addresses.
   static __device__ __forceinline__ float load(const __nv_bfloat16* p) {
-    return __bfloat162float(__ldg(p));
+    const unsigned short u = __ldg(reinterpret_cast<const unsigned short*>(p));
+    return __uint_as_float(static_cast<unsigned int>(u) << 16);
   }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, float v) {
     *p = __float2bfloat16_rn(v);
@@ -131,7 +135,10 @@ template <> struct Cvt<__nv_bfloat16> {
 };
 template <> struct Cvt<__half> {
   using acc_t = float;
-  static __device__ __forceinline__ float load(const __half* p) { return __half2float(__ldg(p)); }
+  static __device__ __forceinline__ float load(const __half* p) {
+    const unsigned short u = __ldg(reinterpret_cast<const unsigned short*>(p));
+    return __half2float(__ushort_as_half(u));
+  }
   static __device__ __forceinline__ void store(__half* p, float v) { *p = __float2half_rn(v); }
 };
 

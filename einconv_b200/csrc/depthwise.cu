@@ -167,6 +167,156 @@ __global__ void __launch_bounds__(256) dw_input_vjp_kernel(const T* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fast path: register-tiled direct stencil, dilation 1, compile-time taps and stride.
+//
+//   out[b, q, oh, ow] = bias[q] + sum_{j<J} sum_{kh,kw} in[b, src(q,j), S*oh + kh - p_h, S*ow + kw - p_w] * w[wsrc(q,j), t(kh,kw)]
+//
+// forward:          q = output channel, J = 1, src = q / mult, wsrc = q, t = kh*KW + kw
+// input VJP (S=1):  q = input channel,  J = mult, src = wsrc = q*mult + j, t flipped, p' = K-1-p
+//                   (the adjoint of a stride-1 correlation is the correlation with the flipped kernel)
+//
+// A thread produces RV vertically adjacent outputs at one column, so consecutive lanes read
+// consecutive addresses (coalesced, L1-resident re-reads) and each loaded row is reused by up to
+// KH outputs from registers.  No shared memory, no barrier; x is read once from HBM and y written
+// once: the kernel is HBM-bound (2.25 flop/B for 3x3).
+// ---------------------------------------------------------------------------------------------
+struct DwFastParams {
+  int planes_out;          // B * (number of produced channels)
+  int chan_out;            // produced channels per sample
+  int mult;                // c_out_g
+  int J;                   // planes summed per output plane
+  int in_h, in_w, out_h, out_w, p_h, p_w;
+  int n_vgroups;           // ceil(out_h / RV)
+  int flip;                // 1: use taps in reversed order (input VJP)
+  int in_chan;             // channels per sample of the read tensor
+  FastDiv ow_div, vg_div, chan_div, mult_div;
+  long long total;         // planes_out * n_vgroups * out_w threads
+};
+
+template <typename T, int KH, int KW, int S, int RV, bool FLIP>
+__global__ void __launch_bounds__(256) dw_direct_kernel(const T* __restrict__ in,
+                                                        const T* __restrict__ w,
+                                                        const T* __restrict__ bias,
+                                                        T* __restrict__ out,
+                                                        const __grid_constant__ DwFastParams p) {
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (unsigned)p.total) return;
+  uint32_t rest, ow, plane, vg, b, q;
+  p.ow_div.divmod(tid, rest, ow);
+  p.vg_div.divmod(rest, plane, vg);
+  p.chan_div.divmod(plane, b, q);
+  const int oh0 = (int)vg * RV;
+  constexpr int ROWS = S * (RV - 1) + KH;
+  const int in_w = p.in_w, in_h = p.in_h;
+  const int r0 = S * oh0 - p.p_h;
+  const int c0 = S * (int)ow - p.p_w;
+  const bool interior = r0 >= 0 && r0 + ROWS <= in_h && c0 >= 0 && c0 + KW <= in_w;
+  const int plane_elems = in_h * in_w;
+  const int off0 = r0 * in_w + c0;  // may be negative; only dereferenced where in bounds
+
+  float acc[RV];
+#pragma unroll
+  for (int r = 0; r < RV; ++r) acc[r] = 0.f;
+
+  const int J = FLIP ? p.mult : 1;
+  for (int j = 0; j < J; ++j) {
+    int src;
+    if (FLIP) {
+      src = (int)q * p.mult + j;
+    } else {
+      src = (int)p.mult_div.quot(q);
+    }
+    const int wsrc = FLIP ? src : (int)q;
+    float wreg[KH * KW];
+#pragma unroll
+    for (int t = 0; t < KH * KW; ++t)
+      wreg[t] = (float)Cvt<T>::load(w + wsrc * (KH * KW) + (FLIP ? KH * KW - 1 - t : t));
+    const T* base = in + ((long long)b * p.in_chan + src) * plane_elems + off0;
+
+    auto accumulate = [&](int rr, const float* val) {
+      // input row rr feeds output (rr - kh) / S for every kh with S | (rr - kh)
+#pragma unroll
+      for (int kh = 0; kh < KH; ++kh) {
+        if ((rr - kh) >= 0 && (rr - kh) % S == 0 && (rr - kh) / S < RV) {
+#pragma unroll
+          for (int kw = 0; kw < KW; ++kw)
+            acc[(rr - kh) / S] = fmaf(val[kw], wreg[kh * KW + kw], acc[(rr - kh) / S]);
+        }
+      }
+    };
+
+    if (interior) {
+#pragma unroll
+      for (int rr = 0; rr < ROWS; ++rr) {
+        float val[KW];
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw) val[kw] = (float)Cvt<T>::load(base + rr * in_w + kw);
+        accumulate(rr, val);
+      }
+    } else {
+      bool col_ok[KW];
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw) col_ok[kw] = (c0 + kw >= 0) && (c0 + kw < in_w);
+#pragma unroll
+      for (int rr = 0; rr < ROWS; ++rr) {
+        const bool row_ok = (r0 + rr >= 0) && (r0 + rr < in_h);
+        float val[KW];
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw) {
+          val[kw] = 0.f;
+          if (row_ok && col_ok[kw]) val[kw] = (float)Cvt<T>::load(base + rr * in_w + kw);
+        }
+        accumulate(rr, val);
+      }
+    }
+  }
+  const float bv = bias ? (float)Cvt<T>::load(bias + q) : 0.f;
+  const int out_w = p.out_w;
+  T* dst = out + (long long)plane * p.out_h * out_w + oh0 * out_w + (int)ow;
+#pragma unroll
+  for (int r = 0; r < RV; ++r)
+    if (oh0 + r < p.out_h) Cvt<T>::store(dst + r * out_w, (typename Cvt<T>::acc_t)(acc[r] + bv));
+}
+
+template <typename T, int KH, int KW, int S>
+static int launch_dw_direct(const void* in, const void* w, const void* bias, void* out,
+                            DwFastParams& p, cudaStream_t stream) {
+  constexpr int RV = 4;
+  p.n_vgroups = ceil_div(p.out_h, RV);
+  p.ow_div = FastDiv((uint32_t)p.out_w);
+  p.vg_div = FastDiv((uint32_t)p.n_vgroups);
+  p.chan_div = FastDiv((uint32_t)p.chan_out);
+  p.mult_div = FastDiv((uint32_t)p.mult);
+  p.total = (long long)p.planes_out * p.n_vgroups * p.out_w;
+  EINCONV_CHECK_ARG(p.total < (1ll << 31) && (long long)p.in_h * p.in_w < (1ll << 30),
+                    "depthwise: tensor too large");
+  const unsigned grid = (unsigned)((p.total + 255) / 256);
+  if (p.flip)
+    dw_direct_kernel<T, KH, KW, S, RV, true><<<grid, 256, 0, stream>>>(
+        (const T*)in, (const T*)w, (const T*)bias, (T*)out, p);
+  else
+    dw_direct_kernel<T, KH, KW, S, RV, false><<<grid, 256, 0, stream>>>(
+        (const T*)in, (const T*)w, (const T*)bias, (T*)out, p);
+  EINCONV_CHECK_LAUNCH("dw_direct_kernel");
+  return EINCONV_OK;
+}
+
+// returns 1 if a fast variant was launched, 0 if none applies, <0 on error
+template <typename T>
+static int try_dw_direct(const void* in, const void* w, const void* bias, void* out,
+                         DwFastParams& p, int k_h, int k_w, int s_h, int s_w, int d_h, int d_w,
+                         cudaStream_t stream) {
+  if (d_h != 1 || d_w != 1 || s_h != s_w) return 0;
+  int st = 1;
+  if (k_h == 3 && k_w == 3 && s_h == 1) st = launch_dw_direct<T, 3, 3, 1>(in, w, bias, out, p, stream);
+  else if (k_h == 3 && k_w == 3 && s_h == 2) st = launch_dw_direct<T, 3, 3, 2>(in, w, bias, out, p, stream);
+  else if (k_h == 5 && k_w == 5 && s_h == 1) st = launch_dw_direct<T, 5, 5, 1>(in, w, bias, out, p, stream);
+  else if (k_h == 1 && k_w == 3 && s_h == 1) st = launch_dw_direct<T, 1, 3, 1>(in, w, bias, out, p, stream);
+  else return 0;
+  return st == EINCONV_OK ? 1 : st;
+}
+
+// ---------------------------------------------------------------------------------------------
 bool depthwise_supported(const DevGeom& g, int dtype) {
   return g.c_in_g == 1 && g.groups > 1 && g.n_dims <= 2 && dtype != EINCONV_F64 && g.out_total > 0 &&
          g.in_total > 0;
@@ -199,6 +349,18 @@ int dw_conv_fwd(const void* x, const void* w, const void* bias, void* y, int dty
                 const DevGeom& g, cudaStream_t stream) {
   DwParams p{};
   fill_dw(p, g);
+  if (dtype != EINCONV_F64) {
+    DwFastParams f{};
+    f.planes_out = p.batch * p.channels * p.mult; f.chan_out = p.channels * p.mult;
+    f.mult = p.mult; f.J = 1; f.flip = 0; f.in_chan = p.channels;
+    f.in_h = p.in_h; f.in_w = p.in_w; f.out_h = p.out_h; f.out_w = p.out_w; f.p_h = p.p_h; f.p_w = p.p_w;
+    int fast = dispatch_dtype(dtype, [&](auto* tag) -> int {
+      using T = std::remove_pointer_t<decltype(tag)>;
+      if constexpr (std::is_same_v<T, double>) return 0;
+      else return try_dw_direct<T>(x, w, bias, y, f, p.k_h, p.k_w, p.s_h, p.s_w, p.d_h, p.d_w, stream);
+    });
+    if (fast != 0) return fast > 0 ? EINCONV_OK : fast;
+  }
   p.cols = p.s_w * (p.out_w - 1) + p.d_w * (p.k_w - 1) + 1;
   auto rows_for = [&](int th) { return p.s_h * (th - 1) + p.d_h * (p.k_h - 1) + 1; };
   int th = p.out_h;
@@ -233,6 +395,21 @@ int dw_conv_input_vjp(const void* w, const void* v, void* gx, int dtype, const D
                       cudaStream_t stream) {
   DwParams p{};
   fill_dw(p, g);
+  // stride 1: the adjoint is the same stencil with flipped taps and padding K-1-p (>= 0 required)
+  if (dtype != EINCONV_F64 && p.s_h == 1 && p.s_w == 1 && p.k_h - 1 - p.p_h >= 0 &&
+      p.k_w - 1 - p.p_w >= 0) {
+    DwFastParams f{};
+    f.planes_out = p.batch * p.channels; f.chan_out = p.channels;
+    f.mult = p.mult; f.J = p.mult; f.flip = 1; f.in_chan = p.channels * p.mult;
+    f.in_h = p.out_h; f.in_w = p.out_w; f.out_h = p.in_h; f.out_w = p.in_w;
+    f.p_h = p.k_h - 1 - p.p_h; f.p_w = p.k_w - 1 - p.p_w;
+    int fast = dispatch_dtype(dtype, [&](auto* tag) -> int {
+      using T = std::remove_pointer_t<decltype(tag)>;
+      if constexpr (std::is_same_v<T, double>) return 0;
+      else return try_dw_direct<T>(v, w, nullptr, gx, f, p.k_h, p.k_w, 1, 1, p.d_h, p.d_w, stream);
+    });
+    if (fast != 0) return fast > 0 ? EINCONV_OK : fast;
+  }
   // staged cotangent window: all columns any input column can touch
   auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
   const int ow_lo = fdiv(p.p_w - p.d_w * (p.k_w - 1), p.s_w);

@@ -20,27 +20,36 @@
 
 namespace einconv {
 
+constexpr int kMaxOuterTaps = 256;  // prod(k) over the outer dims handled by one CTA
+
 struct UnfoldParams {
   DevGeom g;  // n_dims >= 2 (a dummy unit dimension is inserted in front of a 1-d problem)
   long long xs_b, xs_c;       // element strides of x: batch, channel
   long long xs[kMaxDims];     // element strides of the spatial dims
   int channels;               // C = groups * c_in_g
   int n_outer;                // n_dims - 2
-  int vrange[kMaxDims];       // virtual extent of outer dim d
-  int v_total;                // prod(vrange[0..n_outer))
+  int vstep[kMaxDims];        // gcd(stride, dilation) of outer dim d: only every vstep-th virtual
+                              // coordinate can be reached by a tap
+  int vcount[kMaxDims];       // number of visited virtual coordinates of outer dim d
+  int v_total;                // prod(vcount[0..n_outer))
   int k_outer_total;          // prod(k[0..n_outer))
   int k_inner_total;          // k[H] * k[W]
   int tile_h, n_tiles;        // output rows per tile, tiles per plane
   int cb;                     // (b, c) planes per CTA
-  int n_bc_groups;            // ceil(B*C / cb)
   int gh, gw;                 // gcd(stride, dilation) of the two inner dims
   int sh, dh, sw, dw;         // stride/g and dilation/g of the inner dims
   int rows_cap;               // staged rows for a full tile
   int cols;                   // staged columns
-  FastDiv ow_div;             // / O_w
+  int owv;                    // O_w / V: vectors per output row
+  int lpr_shift;              // log2(lanes per output row); rows per warp pass = 32 >> lpr_shift
   FastDiv kw_div;             // / K_w
   FastDiv kinner_div;         // / (K_h * K_w)
-  int n_seg, seg_shift;       // segments each (plane, tap) run is split into (power of two)
+  FastDiv tiles_div;          // / n_tiles
+  FastDiv vtotal_div;         // / v_total
+  FastDiv chan_div;           // / channels
+  FastDiv vc_div[kMaxDims];   // / vcount[d]
+  FastDiv ko_div[kMaxDims];   // / k[d]       (outer dims)
+  FastDiv so_div[kMaxDims];   // / stride[d]  (outer dims)
 };
 
 static __host__ __device__ inline int igcd(int a, int b) {
@@ -52,12 +61,36 @@ static __host__ __device__ inline int igcd(int a, int b) {
   return a;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) unfold_plane_kernel(const T* __restrict__ x,
+template <typename T, int V> struct alignas(sizeof(T) * V) VecOf { T v[V]; };
+
+// streaming (evict-first) vector store: `out` is written once and never re-read by this kernel
+template <typename T, int V>
+__device__ __forceinline__ void store_stream(VecOf<T, V>* dst, const VecOf<T, V>& val) {
+  constexpr int bytes = sizeof(T) * V;
+  if constexpr (bytes == 16) {
+    __stcs(reinterpret_cast<uint4*>(dst), *reinterpret_cast<const uint4*>(&val));
+  } else if constexpr (bytes == 8) {
+    __stcs(reinterpret_cast<uint2*>(dst), *reinterpret_cast<const uint2*>(&val));
+  } else if constexpr (bytes == 4) {
+    __stcs(reinterpret_cast<unsigned int*>(dst), *reinterpret_cast<const unsigned int*>(&val));
+  } else {
+    *dst = val;
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256, 8) unfold_plane_kernel(const T* __restrict__ x,
                                                            T* __restrict__ out,
                                                            const __grid_constant__ UnfoldParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* plane = reinterpret_cast<T*>(smem_raw);
+  using VecT = VecOf<T, V>;
+  // CTA-uniform bookkeeping, computed once by warp 0
+  __shared__ int s_combo_kq[kMaxOuterTaps];     // outer tap combinations that land on this plane
+  __shared__ int s_combo_oflat[kMaxOuterTaps];  // ... and their flattened outer output index
+  __shared__ int s_n_combos;
+  __shared__ int s_plane_real;
+  __shared__ long long s_x_outer_off;
 
   const DevGeom& g = p.g;
   const int H = g.n_dims - 2, W = g.n_dims - 1;
@@ -65,116 +98,203 @@ __global__ void __launch_bounds__(256) unfold_plane_kernel(const T* __restrict__
   const int warp = threadIdx.x >> 5;
   const int n_warps = blockDim.x >> 5;
 
-  // ---- decode CTA coordinates: tile fastest, then virtual outer coordinate, then plane group
-  uint32_t bid = blockIdx.x;
-  const int tile = bid % p.n_tiles;
-  bid /= p.n_tiles;
-  uint32_t vflat = bid % p.v_total;
-  const int bcg = bid / p.v_total;
+  // ---- CTA coordinates: tile fastest, then virtual outer coordinate, then plane group
+  uint32_t rest, tile, vflat, bcg;
+  p.tiles_div.divmod(blockIdx.x, rest, tile);
+  p.vtotal_div.divmod(rest, bcg, vflat);
 
-  int v[kMaxDims];  // real input coordinate of outer dims (may be outside [0, in) = padding)
-  bool plane_real = true;
-  long long x_outer_off = 0;
-  for (int d = p.n_outer - 1; d >= 0; --d) {
-    const int vd = (int)(vflat % p.vrange[d]) - g.pad[d];
-    vflat /= p.vrange[d];
-    v[d] = vd;
-    if (vd < 0 || vd >= g.in[d]) plane_real = false;
-    else x_outer_off += (long long)vd * p.xs[d];
-  }
-
-  // ---- which outer tap combinations land on this plane?  (block-uniform, usually 0..3 of them)
-  // Early exit if none: e.g. odd planes when stride and dilation are both even.
-  int n_valid = 0;
-  for (int kq = 0; kq < p.k_outer_total; ++kq) {
-    int rem = kq;
-    bool ok = true;
+  if (warp == 0) {
+    // virtual outer coordinates of this CTA (input frame; outside [0, in) means padding)
+    int v[kMaxDims];
+    bool plane_real = true;
+    long long x_off = 0;
+    uint32_t rem = vflat;
     for (int d = p.n_outer - 1; d >= 0; --d) {
-      const int kd = rem % g.k[d];
-      rem /= g.k[d];
-      const int t = v[d] + g.pad[d] - g.dil[d] * kd;
-      if (t < 0 || t % g.stride[d] != 0 || t / g.stride[d] >= g.out[d]) ok = false;
+      uint32_t q, r;
+      p.vc_div[d].divmod(rem, q, r);
+      rem = q;
+      const int vd = (int)r * p.vstep[d] - g.pad[d];
+      v[d] = vd;
+      if (vd < 0 || vd >= g.in[d]) plane_real = false;
+      else x_off += (long long)vd * p.xs[d];
     }
-    n_valid += ok;
+    // outer tap combinations kq (lane-strided) that map this plane to a valid output coordinate
+    int count = 0;
+    for (int kq0 = 0; kq0 < p.k_outer_total; kq0 += 32) {
+      const int kq = kq0 + lane;
+      bool ok = kq < p.k_outer_total;
+      int oflat = 0, omul = 1;
+      uint32_t krem = ok ? (uint32_t)kq : 0u;
+      for (int d = p.n_outer - 1; d >= 0; --d) {
+        uint32_t q, kd;
+        p.ko_div[d].divmod(krem, q, kd);
+        krem = q;
+        const int t = v[d] + g.pad[d] - g.dil[d] * (int)kd;
+        uint32_t o = 0, r = 0;
+        if (t >= 0) p.so_div[d].divmod((uint32_t)t, o, r);
+        if (t < 0 || r != 0 || (int)o >= g.out[d]) ok = false;
+        oflat += (int)o * omul;
+        omul *= g.out[d];
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int slot = count + __popc(mask & ((1u << lane) - 1u));
+        s_combo_kq[slot] = kq;
+        s_combo_oflat[slot] = oflat;
+      }
+      count += __popc(mask);
+    }
+    if (lane == 0) {
+      s_n_combos = count;
+      s_plane_real = plane_real ? 1 : 0;
+      s_x_outer_off = x_off;
+    }
   }
-  if (n_valid == 0) return;
+  __syncthreads();
+  const int n_combos = s_n_combos;
+  if (n_combos == 0) return;  // no tap reaches this plane
+  const bool plane_real = s_plane_real != 0;
+  const long long x_outer_off = s_x_outer_off;
 
-  const int oh0 = tile * p.tile_h;
+  const int oh0 = (int)tile * p.tile_h;
   const int th = min(p.tile_h, g.out[H] - oh0);
   const int rows = (p.sh * (th - 1) + p.dh * (g.k[H] - 1)) + 1;  // staged rows (compacted by gh)
   const int cols = p.cols;
   const int plane_elems = p.rows_cap * cols;
-  const int bc0 = bcg * p.cb;
+  const int bc0 = (int)bcg * p.cb;
   const int n_planes = min(p.cb, g.batch * p.channels - bc0);
 
   // ---- stage: plane[pl][jr][jc] = x[b, c, v.., r0 + jr*gh, -p_w + jc*gw] or 0
   {
     const int r0 = g.stride[H] * oh0 - g.pad[H];
-    for (int ri = warp; ri < n_planes * rows; ri += n_warps) {
-      const int pl = ri / rows;
-      const int jr = ri - pl * rows;
-      const int r = r0 + jr * p.gh;
-      const bool row_real = plane_real && r >= 0 && r < g.in[H];
-      const int bc = bc0 + pl;
-      const int b = bc / p.channels;
-      const int c = bc - b * p.channels;
-      const T* src = x + (long long)b * p.xs_b + (long long)c * p.xs_c + x_outer_off +
-                     (long long)r * p.xs[H];
-      T* dst = plane + pl * plane_elems + jr * cols;
-      for (int jc = lane; jc < cols; jc += 32) {
-        const int cc = jc * p.gw - g.pad[W];
-        T val = T(0);
-        if (row_real && cc >= 0 && cc < g.in[W]) val = __ldg(src + (long long)cc * p.xs[W]);
-        dst[jc] = val;
+    const int gh = p.gh, gw = p.gw, pad_w = g.pad[W], in_w = g.in[W], in_h = g.in[H];
+    const long long xs_h = p.xs[H];
+    const int xs_w = (int)p.xs[W];  // |stride| of the innermost dim fits in 32 bits (checked on host)
+    for (int pl = 0; pl < n_planes; ++pl) {
+      uint32_t b, c;
+      p.chan_div.divmod((uint32_t)(bc0 + pl), b, c);
+      const T* src_plane = x + (long long)b * p.xs_b + (long long)c * p.xs_c + x_outer_off;
+      T* dst_plane = plane + pl * plane_elems;
+#pragma unroll 4
+      for (int jr = warp; jr < rows; jr += n_warps) {
+        const int r = r0 + jr * gh;
+        const bool row_real = plane_real && r >= 0 && r < in_h;
+        const T* src = src_plane + (long long)r * xs_h;
+        T* dst = dst_plane + jr * cols;
+        for (int jc = lane; jc < cols; jc += 32) {
+          const int cc = jc * gw - pad_w;
+          T val = T(0);
+          if (row_real && cc >= 0 && cc < in_w) val = __ldg(src + cc * xs_w);
+          dst[jc] = val;
+        }
       }
     }
   }
   __syncthreads();
 
-  // ---- emit: for every valid outer tap combo, every inner tap, the contiguous run of th*O_w outputs
-  const int chunk = th * g.out[W];
-  const int n_wchunks = (chunk + 31) >> 5;
-  const long long out_plane = (long long)g.k_total * g.out_total;  // elements per (b, c)
-  const int inner_out = g.out[H] * g.out[W];
-
-  for (int kq = 0; kq < p.k_outer_total; ++kq) {
-    int rem = kq;
-    bool ok = true;
-    int o_outer_flat = 0, o_mul = 1;
-    for (int d = p.n_outer - 1; d >= 0; --d) {
-      const int kd = rem % g.k[d];
-      rem /= g.k[d];
-      const int t = v[d] + g.pad[d] - g.dil[d] * kd;
-      if (t < 0 || t % g.stride[d] != 0 || t / g.stride[d] >= g.out[d]) ok = false;
-      else {
-        o_outer_flat += (t / g.stride[d]) * o_mul;
-        o_mul *= g.out[d];
-      }
+  // ---- emit.  For a fixed (plane, outer tap combo, inner tap) the tile's outputs are th * O_w
+  // consecutive elements of `out`.  Lanes are arranged as (32 >> lpr_shift) rows x (1 << lpr_shift)
+  // vector columns, so the walk needs no division: consecutive lanes write consecutive vectors of
+  // V elements (V | O_w: a vector never straddles an output row).  Everything the row loop needs
+  // is held in registers; per-tap offsets come from a small shared table.
+  __shared__ int s_tap_tab[256];
+  const int k_inner = p.k_inner_total;
+  int* tap_tab = (k_inner <= 256) ? s_tap_tab : nullptr;
+  if (tap_tab) {
+    for (int t = threadIdx.x; t < k_inner; t += blockDim.x) {
+      uint32_t kh, kw;
+      p.kw_div.divmod((uint32_t)t, kh, kw);
+      tap_tab[t] = p.dh * (int)kh * cols + p.dw * (int)kw;
     }
-    if (!ok) continue;
+    __syncthreads();
+  }
 
-    // out[bc][kq * k_inner + tap][o_outer_flat * inner_out + oh0 * O_w + e]
-    const long long base = (long long)kq * p.k_inner_total * g.out_total +
-                           (long long)o_outer_flat * inner_out + (long long)oh0 * g.out[W];
-    // work item = (plane, tap, segment of 32-wide chunks); a warp walks its segment's chunks
-    const int per_seg = (n_wchunks + p.n_seg - 1) >> p.seg_shift;
-    const int n_items = (n_planes * p.k_inner_total) << p.seg_shift;
-    for (int wi = warp; wi < n_items; wi += n_warps) {
-      const int seg = wi & (p.n_seg - 1);
-      uint32_t pl, tap, kh, kw;
-      p.kinner_div.divmod((uint32_t)(wi >> p.seg_shift), pl, tap);
-      p.kw_div.divmod(tap, kh, kw);
-      const T* src = plane + pl * plane_elems + p.dh * (int)kh * cols + p.dw * (int)kw;
-      T* dst = out + (long long)(bc0 + (int)pl) * out_plane + base + (long long)tap * g.out_total;
-      const int wc_end = min((seg + 1) * per_seg, n_wchunks);
-#pragma unroll 4
-      for (int wc = seg * per_seg; wc < wc_end; ++wc) {
-        const int e = (wc << 5) + lane;
-        if (e < chunk) {
-          uint32_t ohl, ow;
-          p.ow_div.divmod((uint32_t)e, ohl, ow);
-          dst[e] = src[p.sh * (int)ohl * cols + p.sw * (int)ow];
+  const int lpr_shift = p.lpr_shift;
+  const int rpw = 32 >> lpr_shift;
+  const int lr = lane >> lpr_shift;
+  const int lc = lane & ((1 << lpr_shift) - 1);
+  const int owv = p.owv;
+  const int sw = p.sw;
+  const int n_cp = n_combos * n_planes;
+  // split a (plane, tap) run into row segments only if the CTA would otherwise have fewer than two
+  // units per warp, keeping >= 3 warp passes per unit so its set-up stays amortised
+  int seg_shift = 0;
+  {
+    const int passes = (th + rpw - 1) / rpw;
+    while (((n_cp * k_inner) << seg_shift) < 2 * n_warps && (passes >> (seg_shift + 1)) >= 3) ++seg_shift;
+  }
+  const int seg_mask = (1 << seg_shift) - 1;
+  const long long out_plane = (long long)g.k_total * g.out_total;  // elements per (b, c)
+  const long long out_total = g.out_total;
+  const int inner_out = g.out[H] * g.out[W];
+  const int row_pitch = p.sh * cols;
+  const int rows_per_seg = (th + seg_mask) >> seg_shift;
+  const int units_per_cp = k_inner << seg_shift;        // units per (combo, plane)
+  const int n_units = n_cp * units_per_cp;
+  const int src_step = rpw * row_pitch;
+  const int dst_step = rpw * owv;
+  const int lane_src = lr * row_pitch + lc * (sw * V);
+  const int lane_dst = lr * owv + lc;
+  const bool lane_on = lc < owv;
+
+  // warp-uniform walk over units; (cp, u) advance incrementally, no division in the loop
+  int cp = 0, u = warp;
+  int cur_cp = -1;
+  const T* src_cp = plane;
+  T* dst_cp = out;
+  for (int unit = warp; unit < n_units; unit += n_warps, u += n_warps) {
+    while (u >= units_per_cp) {
+      u -= units_per_cp;
+      ++cp;
+    }
+    if (cp != cur_cp) {
+      cur_cp = cp;
+      const int combo = cp / n_planes;
+      const int pl = cp - combo * n_planes;
+      // out[bc][kq * k_inner + tap][o_outer_flat * inner_out + (oh0 + ohl) * O_w + ow]
+      dst_cp = out + (long long)(bc0 + pl) * out_plane +
+               (long long)s_combo_kq[combo] * k_inner * out_total +
+               (long long)s_combo_oflat[combo] * inner_out + (long long)oh0 * g.out[W];
+      src_cp = plane + pl * plane_elems;
+    }
+    const int tap = u >> seg_shift;
+    const int seg = u & seg_mask;
+    const int row_begin = seg * rows_per_seg;
+    const int n_rows = min(rows_per_seg, th - row_begin);
+    int tap_off;
+    if (tap_tab) {
+      tap_off = tap_tab[tap];
+    } else {
+      uint32_t kh, kw;
+      p.kw_div.divmod((uint32_t)tap, kh, kw);
+      tap_off = p.dh * (int)kh * cols + p.dw * (int)kw;
+    }
+    const T* src = src_cp + tap_off + row_begin * row_pitch + lane_src;
+    VecT* dst = reinterpret_cast<VecT*>(dst_cp + (long long)tap * out_total) +
+                (row_begin * owv + lane_dst);
+    if (owv <= 32) {
+      // one pass per row group: the common case
+      if (lane_on) {
+#pragma unroll 2
+        for (int r = lr; r < n_rows; r += rpw) {
+          VecT val;
+#pragma unroll
+          for (int j = 0; j < V; ++j) val.v[j] = src[j * sw];
+          store_stream<T, V>(dst, val);
+          src += src_step;
+          dst += dst_step;
         }
+      }
+    } else {
+      for (int r = 0; r < n_rows; ++r) {  // lpr == 32, rpw == 1
+        for (int o = 0; lc + o < owv; o += 32) {  // src / dst already point at column lc
+          VecT val;
+#pragma unroll
+          for (int j = 0; j < V; ++j) val.v[j] = src[o * (sw * V) + j * sw];
+          store_stream<T, V>(dst + o, val);
+        }
+        src += src_step;
+        dst += dst_step;
       }
     }
   }
@@ -224,11 +344,11 @@ __global__ void __launch_bounds__(256) fold_kernel(const T* __restrict__ gu, T* 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int V>
 static int launch_unfold_t(const void* x, void* out, const UnfoldParams& p, size_t smem,
                            unsigned grid, cudaStream_t stream) {
-  auto kern = unfold_plane_kernel<T>;
-  if (smem > 48 * 1024) {
+  auto kern = unfold_plane_kernel<T, V>;
+  if (smem > 32 * 1024) {  // static tables + dynamic staging may exceed the 48 KB default
     cudaError_t err =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(unfold)");
@@ -291,11 +411,18 @@ int launch_unfold(const void* x, const int64_t* x_strides, void* out, int dtype,
   p.n_outer = N - 2;
   long long v_total = 1, k_outer = 1;
   for (int d = 0; d < p.n_outer; ++d) {
-    p.vrange[d] = g.stride[d] * (g.out[d] - 1) + g.dil[d] * (g.k[d] - 1) + 1;
-    v_total *= p.vrange[d];
+    // virtual coordinate v (input frame shifted by the padding) is touched by a tap only if
+    // gcd(stride, dilation) | v, so only those planes get a CTA
+    const int vrange = g.stride[d] * (g.out[d] - 1) + g.dil[d] * (g.k[d] - 1) + 1;
+    p.vstep[d] = igcd(g.stride[d], g.dil[d]);
+    p.vcount[d] = (vrange - 1) / p.vstep[d] + 1;
+    v_total *= p.vcount[d];
     k_outer *= g.k[d];
   }
-  EINCONV_CHECK_ARG(v_total < (1ll << 30) && k_outer < (1ll << 20), "unfold: geometry too large");
+  EINCONV_CHECK_ARG(v_total < (1ll << 30), "unfold: geometry too large");
+  EINCONV_CHECK_ARG(p.xs[W] > -(1ll << 31) && p.xs[W] < (1ll << 31), "unfold: innermost stride too large");
+  EINCONV_CHECK_ARG(k_outer <= kMaxOuterTaps,
+                    "unfold: more than %d taps over the leading dimensions", kMaxOuterTaps);
   p.v_total = (int)v_total;
   p.k_outer_total = (int)k_outer;
   p.k_inner_total = g.k[H] * g.k[W];
@@ -305,13 +432,35 @@ int launch_unfold(const void* x, const int64_t* x_strides, void* out, int dtype,
   p.sh = g.stride[H] / p.gh; p.dh = g.dil[H] / p.gh;
   p.sw = g.stride[W] / p.gw; p.dw = g.dil[W] / p.gw;
   p.cols = p.sw * (g.out[W] - 1) + p.dw * (g.k[W] - 1) + 1;
-  p.ow_div = FastDiv((uint32_t)g.out[W]);
   p.kw_div = FastDiv((uint32_t)g.k[W]);
+  p.chan_div = FastDiv((uint32_t)C);
+  for (int d = 0; d < p.n_outer; ++d) {
+    p.vc_div[d] = FastDiv((uint32_t)p.vcount[d]);
+    p.ko_div[d] = FastDiv((uint32_t)g.k[d]);
+    p.so_div[d] = FastDiv((uint32_t)g.stride[d]);
+  }
 
-  // tile of output rows: stage at most ~40 KB per plane
+  // vector width of the output stores: V | O_w keeps a vector inside one output row; every run
+  // starts at a multiple of O_w elements from `out`, which must itself be aligned.
+  int V = 1;
+  for (int cand : {4, 2}) {
+    if (g.out[W] % cand == 0 && cand * esz <= 16 && ((uintptr_t)out % (cand * esz)) == 0) {
+      V = cand;
+      break;
+    }
+  }
+  p.owv = g.out[W] / V;
+  p.lpr_shift = 0;
+  while ((1 << p.lpr_shift) < p.owv && p.lpr_shift < 5) ++p.lpr_shift;
+
+  // Work per CTA: ~8-16k output elements per valid outer tap, so that there are many more CTAs
+  // than the 148 x 8 resident slots and the tail stays short.  Row tiles only when one plane is
+  // larger than that (or its staging window exceeds the shared-memory budget).
   const long long budget = 40 * 1024;
   auto rows_for = [&](int th) { return (long long)p.sh * (th - 1) + (long long)p.dh * (g.k[H] - 1) + 1; };
+  const long long per_row_out = (long long)p.k_inner_total * g.out[W];
   int th = g.out[H];
+  if (per_row_out * th > 16384) th = (int)std::max<long long>(1, 12288 / per_row_out);
   while (th > 1 && rows_for(th) * p.cols * esz > budget) th = (th + 1) / 2;
   EINCONV_CHECK_ARG(rows_for(th) * p.cols * esz <= 200 * 1024,
                     "unfold: one row tile does not fit in shared memory");
@@ -319,35 +468,47 @@ int launch_unfold(const void* x, const int64_t* x_strides, void* out, int dtype,
   p.n_tiles = ceil_div(g.out[H], th);
   p.rows_cap = (int)rows_for(th);
 
-  // planes per CTA: aim at >= 16k output elements per CTA, <= 48 KB of staging
-  const long long per_plane_out = (long long)p.k_inner_total * th * g.out[W];
-  const long long per_plane_smem = (long long)p.rows_cap * p.cols * esz;
-  long long cb = (16384 + per_plane_out - 1) / per_plane_out;
-  cb = std::min<long long>(cb, std::max<long long>(1, (48 * 1024) / per_plane_smem));
+  long long per_plane_out = per_row_out * th;
+  long long per_plane_smem = (long long)p.rows_cap * p.cols * esz;
+  long long cb = std::max<long long>(1, 12288 / per_plane_out);
+  cb = std::min<long long>(cb, std::max<long long>(1, (40 * 1024) / per_plane_smem));
   cb = std::max<long long>(1, std::min<long long>(cb, (long long)g.batch * C));
   cb = std::min<long long>(cb, 64);
+  // Prefer more, smaller CTAs (shorter tail) while there are fewer than ~4 waves of the
+  // 148 x 8 resident slots: fewer planes per CTA.
+  const long long want_ctas = 4ll * kNumSMs * 8;
+  auto n_ctas = [&](long long cb_, int th_) {
+    return (long long)ceil_div((long long)g.batch * C, cb_) * p.v_total * ceil_div(g.out[H], th_);
+  };
+  while (cb > 1 && n_ctas(cb, th) < want_ctas) cb = (cb + 1) / 2;
+  p.tile_h = th;
+  p.n_tiles = ceil_div(g.out[H], th);
+  p.rows_cap = (int)rows_for(th);
+  per_plane_out = per_row_out * th;
+  per_plane_smem = (long long)p.rows_cap * p.cols * esz;
   p.cb = (int)cb;
-  p.n_bc_groups = ceil_div((long long)g.batch * C, cb);
+  const int n_bc_groups = ceil_div((long long)g.batch * C, cb);
   p.kinner_div = FastDiv((uint32_t)p.k_inner_total);
-  {
-    // split each (plane, tap) run so that the CTA's 8 warps get >= 4 items each
-    const long long runs = cb * p.k_inner_total;
-    const int wchunks = ceil_div((long long)th * g.out[W], 32);
-    int shift_ = 0;
-    while ((runs << shift_) < 32 && (1 << (shift_ + 1)) <= wchunks) ++shift_;
-    p.seg_shift = shift_;
-    p.n_seg = 1 << shift_;
-  }
-
-  const long long grid = (long long)p.n_bc_groups * p.v_total * p.n_tiles;
+  p.tiles_div = FastDiv((uint32_t)p.n_tiles);
+  p.vtotal_div = FastDiv((uint32_t)p.v_total);
+  const long long grid = (long long)n_bc_groups * p.v_total * p.n_tiles;
   EINCONV_CHECK_ARG(grid > 0 && grid < (1ll << 31), "unfold: grid too large");
   const size_t smem = (size_t)(cb * per_plane_smem);
 
-  switch (esz) {
-    case 2: return launch_unfold_t<uint16_t>(x, out, p, smem, (unsigned)grid, stream);
-    case 4: return launch_unfold_t<uint32_t>(x, out, p, smem, (unsigned)grid, stream);
-    default: return launch_unfold_t<unsigned long long>(x, out, p, smem, (unsigned)grid, stream);
+#define EINCONV_UNFOLD_CASE(TYPE)                                                              \
+  switch (V) {                                                                                 \
+    case 4: if constexpr (sizeof(TYPE) * 4 <= 16)                                              \
+              return launch_unfold_t<TYPE, 4>(x, out, p, smem, (unsigned)grid, stream);        \
+            [[fallthrough]];                                                                   \
+    case 2: return launch_unfold_t<TYPE, 2>(x, out, p, smem, (unsigned)grid, stream);          \
+    default: return launch_unfold_t<TYPE, 1>(x, out, p, smem, (unsigned)grid, stream);         \
   }
+  switch (esz) {
+    case 2: EINCONV_UNFOLD_CASE(uint16_t)
+    case 4: EINCONV_UNFOLD_CASE(uint32_t)
+    default: EINCONV_UNFOLD_CASE(unsigned long long)
+  }
+#undef EINCONV_UNFOLD_CASE
 }
 
 int launch_fold(const void* gu, void* gx, int dtype, const einconv_geom* geom,

@@ -411,6 +411,43 @@ class Equation(str):
         return self
 
 
+class PlannedOperand(Tensor):
+    """Marker type for the first operand of a planned expression that has no index pattern left.
+
+    When the simplifier removes every pattern (dense / 1x1 / down-sampling cases,
+    ``simplifications/opt.py:196-300``) nothing in the operand list would route ``torch.einsum`` to
+    the native evaluator, so the first data operand is tagged with this zero-cost subclass (same
+    storage, same autograd history).  Every other torch function sees a plain tensor.
+    """
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func is torch.einsum or func is torch.functional.einsum:
+            return einsum(*args, **kwargs)
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*args, **kwargs)
+
+
+def tag_for_dispatch(operands: List[Any]) -> List[Any]:
+    """Make sure ``torch.einsum`` over ``operands`` reaches :func:`einsum` (see PlannedOperand)."""
+    from einconv_b200.conv_index_pattern import IndexPattern
+
+    if any(isinstance(op, IndexPattern) for op in operands):
+        return operands
+    for pos, op in enumerate(operands):
+        if isinstance(op, Tensor):
+            operands = list(operands)
+            operands[pos] = op.as_subclass(PlannedOperand)
+            break
+    return operands
+
+
+def plain(operands: Sequence[Any]) -> List[Tensor]:
+    """Ordinary dense tensors for ``operands``: patterns written out, dispatch tags removed."""
+    return [_dense(op) for op in operands]
+
+
 def _einsum_output_shape(equation: str, operands: Sequence[Any]) -> Tuple[int, ...]:
     lhs, rhs = equation.replace(" ", "").split("->")
     dims: Dict[str, int] = {}
@@ -423,7 +460,11 @@ def _einsum_output_shape(equation: str, operands: Sequence[Any]) -> Tuple[int, .
 def _dense(op):
     from einconv_b200.conv_index_pattern import IndexPattern
 
-    return op.materialize() if isinstance(op, IndexPattern) else op
+    if isinstance(op, IndexPattern):
+        return op.materialize()
+    if isinstance(op, PlannedOperand):
+        return op.as_subclass(Tensor)
+    return op
 
 
 def einsum(equation, *operands):

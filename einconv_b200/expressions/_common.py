@@ -5,7 +5,7 @@ from typing import Any, Dict, List, Tuple
 from torch import Tensor
 
 import einconv_b200
-from einconv_b200.evaluator import Equation, Plan
+from einconv_b200.evaluator import Equation, Plan, tag_for_dispatch
 from einconv_b200.expressions.utils import translate_to_torch
 
 
@@ -33,6 +33,7 @@ def finish(
     equation = translate_to_torch("->".join([",".join(lhs), rhs]))
     if simplify:
         equation, operands = einconv_b200.simplify(equation, operands)
+        operands = tag_for_dispatch(operands)
     plan = Plan(kind=kind, tensors=tensors, hyper=hyper, shape=shape, simplify=simplify,
                 operands=list(operands))
     return Equation(equation, plan), operands, shape
