@@ -401,3 +401,111 @@ def test_factor_sharding_identity_on_one_gpu():
     parts_r = sum(evaluator.kfac_reduce(x[i : i + 2], 3, padding=1, scale=1.0 / (8 * 196**2)) for i in range(0, 8, 2))
     close(parts_k, full_k.cpu().numpy(), 1e-5, 1e-6, "kfc shards")
     close(parts_r, full_r.cpu().numpy(), 1e-5, 1e-9, "kfac_reduce shards")
+
+
+# =============================================================================================
+# tensor-core (tcgen05 / TMEM) paths: bf16 / fp16 natively, fp32 via TF32 when opted in
+# =============================================================================================
+TC_CASES = [
+    # (x shape, w shape, kwargs)
+    ((2, 32, 20, 20), (48, 32, 3, 3), dict(padding=1)),
+    ((3, 16, 23, 17), (40, 16, 3, 3), dict(padding=1, stride=2)),
+    ((2, 24, 19, 19), (16, 12, 5, 3), dict(padding=(2, 0), dilation=(1, 2), groups=2)),
+    ((2, 8, 300), (24, 8, 7), dict(padding=3, stride=2)),
+    ((1, 8, 9, 12, 10), (16, 8, 3, 3, 3), dict(padding=1)),
+    ((2, 70, 9, 9), (130, 70, 1, 1), dict()),
+    ((1, 64, 14, 14), (64, 64, 3, 3), dict(padding=1)),
+]
+TC_IDS = ["x".join(map(str, c[0])) + "-w" + "x".join(map(str, c[1])) for c in TC_CASES]
+
+
+def _tc_inputs(case, dtype):
+    xs, ws, kw = case
+    torch.manual_seed(0)
+    x = (torch.rand(*xs) - 0.3).to(dtype)
+    w = (torch.rand(*ws) - 0.5).to(dtype)
+    b = (torch.rand(ws[0]) - 0.5).to(dtype)
+    return x, w, b, kw
+
+
+def _rel_to_max(got, want, tol, what):
+    got = got.detach().double().cpu().numpy()
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = np.abs(got - want).max()
+    ref = np.abs(want).max()
+    assert err <= tol * ref, f"{what}: max|d| = {err:.3e}, max|ref| = {ref:.3e}, ratio {err / ref:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=TC_IDS)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_tc_forward_16bit(case, dtype):
+    """kind::f16 MMA, fp32 accumulate in TMEM, one rounding to the 16-bit output:
+    max|d| <= 2^-7 (bf16) / 2^-10 (fp16) of max|ref| against the fp64 oracle on the same bits."""
+    x, w, b, kw = _tc_inputs(case, dtype)
+    g = nat.make_geom(1, 1, 1, 1, (1,), (1,), (1,), (1,), (0,), (1,))
+    want = direct.conv_forward(x.double().numpy(), w.double().numpy(), b.double().numpy(), **kw)
+    got = convNd(x.to(DEV), w.to(DEV), b.to(DEV), **kw)
+    _rel_to_max(got, want, 2.0**-7 if dtype == torch.bfloat16 else 2.0**-10, "tc fwd")
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=TC_IDS)
+def test_tc_forward_tf32(case):
+    """kind::tf32 (operands rounded to 10-bit mantissa, fp32 accumulate): max|d| <= 1e-3 max|ref|
+    (SURVEY.md 8c).  Opt-in through set_fp32_math / torch.backends.cuda.matmul.allow_tf32."""
+    x, w, b, kw = _tc_inputs(case, torch.float32)
+    want = direct.conv_forward(x.numpy(), w.numpy(), b.numpy(), **kw)
+    evaluator.set_fp32_math("tf32")
+    try:
+        got = convNd(x.to(DEV), w.to(DEV), b.to(DEV), **kw)
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, 1e-3, "tc fwd tf32")
+    exact = convNd(x.to(DEV), w.to(DEV), b.to(DEV), **kw)  # default stays exact fp32
+    close(exact, want, 1e-5, 1e-5, "fp32 default")
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=TC_IDS)
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_tc_weight_vjp(case, mode):
+    xs, ws, kw = case
+    torch.manual_seed(1)
+    dtype = torch.bfloat16 if mode == "bf16" else torch.float32
+    x = (torch.rand(*xs) - 0.3).to(dtype)
+    yshape = forward_out_shape(dict(x=xs, w=ws, kwargs=kw))
+    v = (torch.rand(*yshape) - 0.5).to(dtype)
+    want = direct.conv_weight_vjp(x.double().numpy(), v.double().numpy(), tuple(ws[2:]), **kw)
+    evaluator.set_fp32_math("tf32" if mode == "tf32" else "auto")
+    try:
+        eq, ops, shape = convNd_weight_vjp.einsum_expression(x.to(DEV), v.to(DEV), tuple(ws[2:]), **kw)
+        got = torch.einsum(eq, *ops).reshape(shape)
+    finally:
+        evaluator.set_fp32_math("auto")
+    assert tuple(got.shape) == tuple(ws)
+    _rel_to_max(got, want, 2.0**-7 if mode == "bf16" else 1e-3, f"tc wgrad {mode}")
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=TC_IDS)
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_tc_kfc(case, mode):
+    xs, ws, kw = case
+    torch.manual_seed(2)
+    dtype = torch.bfloat16 if mode == "bf16" else torch.float32
+    x = torch.rand(*xs).to(dtype)
+    want = direct.kfc(x.double().numpy(), tuple(ws[2:]), **kw)
+    evaluator.set_fp32_math("tf32" if mode == "tf32" else "auto")
+    try:
+        got = evaluator.kfc(x.to(DEV), tuple(ws[2:]), **kw)
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, 2.0**-7 if mode == "bf16" else 1e-3, f"tc kfc {mode}")
+
+
+def test_tc_kernels_are_selected():
+    g = nat.make_geom(2, 1, 32, 48, (20, 20), (3, 3), (1, 1), (1, 1), (1, 1), (20, 20))
+    lib = nat.lib()
+    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_fwd_f16"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 0, nat.MATH_TF32, 0) == b"tcgen05_fwd_tf32"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 0, nat.MATH_FP32, 0) == b"ffma_gather_gemm"
+    assert lib.einconv_selected_kernel(nat.OP_KFC, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_kfc_f16"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g, 1, nat.MATH_AUTO, 1) == b"ffma_gather_gemm"
