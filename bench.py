@@ -59,6 +59,7 @@ class Workload:
     unit = ""
     bound = "hbm"
     dtype = "f32"
+    fp32_math = "fp32"  # how fp32 contractions run: "fp32" (CUDA cores, exact) or "tf32" (tcgen05)
 
     def setup(self, device, seed=0):
         raise NotImplementedError
@@ -139,6 +140,9 @@ class ConvFwdC1(Workload):
         self.x = torch.rand(32, 64, 56, 56).to(device)
         self.w = torch.rand(64, 64, 3, 3).to(device)
 
+    dtype = "f32 (tf32 MMA, fp32 accumulate)"
+    fp32_math = "tf32"
+
     def step(self):
         self.out = self.fn(self.x, self.w, padding=1)
 
@@ -200,6 +204,8 @@ class FactorsC5(Workload):
     metric = "KFC+KFAC-reduce factors/s"
     unit = "factors/s"
     bound = "tensor"
+    dtype = "f32 (KFC: tf32 MMA, fp32 accumulate; KFAC-reduce: fp32)"
+    fp32_math = "tf32"
 
     def __init__(self, world=1, rank=0, global_batch=256):
         self.world, self.rank, self.global_batch = world, rank, global_batch
@@ -411,7 +417,10 @@ def main():
         return cls(world, rank) if name == "factors" else cls()
 
     def measure(name, steps, warmup):
+        from einconv_b200 import evaluator
+
         wl = make(name)
+        evaluator.set_fp32_math(wl.fp32_math)
         wl.setup(device, seed=rank)
         if world > 1:
             dist.barrier()

@@ -79,7 +79,7 @@ int make_dev_geom(const einconv_geom* g, DevGeom* out, bool need_c_out) {
 // ---------------------------------------------------------------------------------------------
 // kernel selection
 // ---------------------------------------------------------------------------------------------
-enum class Path { FFMA, DEPTHWISE, TENSOR };
+enum class Path { FFMA, DEPTHWISE, TENSOR, TMA };
 
 static int resolve_math(int dtype, int math) {
   if (math == EINCONV_MATH_AUTO)
@@ -92,8 +92,14 @@ static Path select_path(int op, const DevGeom& g, int dtype, int math, int kerne
   if ((op == EINCONV_OP_CONV_FWD || op == EINCONV_OP_CONV_INPUT_VJP) && depthwise_supported(g, dtype))
     return Path::DEPTHWISE;
   const int m = resolve_math(dtype, math);
-  if ((m == EINCONV_MATH_TF32 || m == EINCONV_MATH_HALF) && tc_supported(op, g, dtype, m))
-    return Path::TENSOR;
+  if (m == EINCONV_MATH_TF32 || m == EINCONV_MATH_HALF) {
+    // reduction networks: TMA-fed tcgen05 kernel when the layout allows it (16-byte aligned rows);
+    // the software-gather tensor-core kernel is kept for the forward pass only (for the reduction
+    // networks it is slower than the CUDA-core kernel)
+    if (op == EINCONV_OP_CONV_WEIGHT_VJP || op == EINCONV_OP_KFC)
+      return tma::tma_supported(op, g, dtype) ? Path::TMA : Path::FFMA;
+    if (tc_supported(op, g, dtype, m)) return Path::TENSOR;
+  }
   return Path::FFMA;
 }
 
@@ -136,6 +142,7 @@ const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype,
   switch (select_path(op, g, dtype, math, kernels)) {
     case Path::DEPTHWISE: return "depthwise_stencil";
     case Path::TENSOR: return tc_kernel_name(op, g, dtype, resolve_math(dtype, math));
+    case Path::TMA: return op == EINCONV_OP_KFC ? "tcgen05_tma_kfc" : "tcgen05_tma_wgrad";
     default: return "ffma_gather_gemm";
   }
 }
@@ -148,6 +155,7 @@ int64_t einconv_workspace_bytes(int op, const einconv_geom* geom, int dtype, int
   const Path path = select_path(op, g, dtype, math, kernels);
   if (path == Path::DEPTHWISE) return 0;
   if (path == Path::TENSOR) return tc_workspace_bytes(op, g, dtype, resolve_math(dtype, math));
+  if (path == Path::TMA) return tma::tma_workspace_bytes(op, g, dtype);
   switch (op) {
     case EINCONV_OP_CONV_WEIGHT_VJP:
     case EINCONV_OP_KFC:
@@ -212,6 +220,8 @@ int einconv_conv_weight_vjp(const void* x, const void* v, void* gw, int dtype,
   if ((long long)g.groups * g.c_out_g * g.c_in_g * g.k_total == 0) return EINCONV_OK;
   cudaStream_t s = (cudaStream_t)stream;
   switch (select_path(EINCONV_OP_CONV_WEIGHT_VJP, g, dtype, math, kernels)) {
+    case Path::TMA:
+      return tma::tma_run(EINCONV_OP_CONV_WEIGHT_VJP, x, v, gw, dtype, g, 1.0, workspace, workspace_bytes, s);
     case Path::TENSOR:
       return tc_conv_weight_vjp(x, v, gw, dtype, g, resolve_math(dtype, math), workspace, workspace_bytes, s);
     default: return ffma_conv_weight_vjp(x, v, gw, dtype, g, workspace, workspace_bytes, s);
@@ -228,6 +238,8 @@ int einconv_kfc(const void* x, void* out, int dtype, const einconv_geom* geom, d
   if ((long long)g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
   cudaStream_t s = (cudaStream_t)stream;
   switch (select_path(EINCONV_OP_KFC, g, dtype, math, kernels)) {
+    case Path::TMA:
+      return tma::tma_run(EINCONV_OP_KFC, x, nullptr, out, dtype, g, scale, workspace, workspace_bytes, s);
     case Path::TENSOR:
       return tc_kfc(x, out, dtype, g, scale, resolve_math(dtype, math), workspace, workspace_bytes, s);
     default: return ffma_kfc(x, out, dtype, g, scale, workspace, workspace_bytes, s);

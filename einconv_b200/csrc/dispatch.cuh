@@ -41,4 +41,13 @@ int tc_conv_weight_vjp(const void* x, const void* v, void* gw, int dtype, const 
 int tc_kfc(const void* x, void* out, int dtype, const DevGeom& g, double scale, int math,
            void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 
+
+// tc_tma.cu (TMA-fed tcgen05 kernels for the reduction networks)
+namespace tma {
+bool tma_supported(int op, const DevGeom& g, int dtype);
+int64_t tma_workspace_bytes(int op, const DevGeom& g, int dtype);
+int tma_run(int op, const void* x, const void* v, void* out, int dtype, const DevGeom& g, double scale,
+            void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+}  // namespace tma
+
 }  // namespace einconv

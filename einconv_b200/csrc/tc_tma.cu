@@ -1,0 +1,845 @@
+// TMA-fed tcgen05 kernels for the two reduction-dominated networks: convNd weight VJP
+// (expressions/convNd_weight_vjp.py:51-58) and the KFC factor (expressions/convNd_kfc.py:75-90).
+//
+//   weight VJP   gW[co, (ci,tap)]        = sum_{b,o} V[b,co,o]        * X[b,ci, s*o + d*tap - p]
+//   KFC          K [(ci,tap),(ci',tap')] = sum_{b,o} X[b,ci, i(o,tap)] * X[b,ci', i(o,tap')]
+//
+// Both reduce over output positions, and in the reference's channels-first layout positions are the
+// contiguous axis — i.e. both operands are already K-major.  A K block is a small patch of output
+// positions (BD x BH x BW = 64 bf16 / 32 fp32 positions = one 128-byte row per channel) of one sample.
+// For tap t the matching input patch is the same box shifted by d*t - p: ONE TMA tiled load per
+// (tap, channel block) brings `CB` channels x 128 B into shared memory with the 128-byte swizzle the
+// tensor core expects; out-of-bounds coordinates are zero-filled by the TMA unit, which *is* the
+// zero padding of the convolution (and of partial patches at the image border).  No index pattern,
+// no unfolded tensor, no per-element address arithmetic on the SMs.
+//
+// GEMM tile: M = 128 rows = (128 / CB) consecutive taps x CB channels of the unfolded input,
+//            N = BN columns = output channels (weight VJP, read from the cotangent) or another
+//                (taps x channels) block (KFC),  K = positions, split across CTAs (split-K).
+// Roles (256 threads): warp 0 lane 0 issues TMA; warp 1 lane 0 issues tcgen05.mma (kind::f16 or
+// kind::tf32, M=128, fp32 accumulators in TMEM); warp 2 owns the TMEM allocation; warps 4-7 drain
+// the accumulator and write fp32 partial tiles, which a small second kernel sums over the splits,
+// scales, un-permutes (rows are produced tap-major) and casts.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <type_traits>
+
+#include "dispatch.cuh"
+
+namespace einconv {
+namespace tma {
+
+constexpr int kStages = 4;
+constexpr int kTileM = 128;
+constexpr int kThreads = 256;
+constexpr int kRowBytes = 128;  // one swizzle-128B row = one channel's K block
+constexpr int kMaxKw = 32;      // widest kernel (innermost dim) the TMA path handles
+constexpr int kMaxMaps = 32;    // tensor maps kept at the head of the workspace
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers (same conventions as tc_gemm.cu)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a protocol bug must not hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 5-d TMA tiled load, completion on an mbarrier (coordinates innermost first)
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// K-major swizzled shared-memory descriptor: rows of `row_bytes`, 8-row groups 8 * row_bytes apart
+// (cute::UMMA::SmemDescriptor: start >> 4 @0, LBO >> 4 @16 (unused, 1), SBO >> 4 @32, version 1 @46,
+//  layout SWIZZLE_128B = 2 @61)
+// `row_bytes` = 128 / 64 / 32 selects SWIZZLE_128B (2) / 64B (4) / 32B (6); an 8-row group is 8 * row_bytes.
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
+  // c_format F32 = 1 @4, a/b_format @7/@10, both K-major, N >> 3 @17, M >> 4 @24
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Params {
+  // reduction blocks: patches of positions, enumerated (b, d-tile, h-tile, w-tile), w fastest
+  int n_wt, n_ht, n_dt;
+  FastDiv wt_div, ht_div, dt_div;
+  int BW, BH, BD;                 // patch extent in output positions
+  int PB, n_pieces;               // bytes of one (d, h) line of the patch per channel; lines per patch
+  int k_blocks, k_splits;
+  // geometry of the three innermost spatial dims (W, H, D order), missing dims are unit
+  int stride[3], dil[3], pad[3], k[3];
+  FastDiv kw_div, kh_div;         // tap index -> (kd, kh, kw)
+  int k_total;
+  // rows: CB channels x (128 / CB) taps per 128-row tile
+  int CB, taps_per_tile, tap_groups;   // tap_groups = ceil(k_total / taps_per_tile)
+  int c_in_g, c_out_g, groups;
+  int c_blocks;                        // ceil(c_in_g / CB)
+  int m_tiles, n_tiles;                // m_tiles = c_blocks * tap_groups
+  int Mp, Np;                          // padded partial extents: m_tiles * 128, n_tiles * BN
+  // innermost-dimension taps: TMA needs 16-byte aligned start coordinates, so tap kw reads from the
+  // pre-shifted copy `kw_map[kw]` of x at the aligned coordinate ow0 * stride + kw_c0[kw]
+  signed char kw_map[kMaxKw];
+  signed char kw_map_b[kMaxKw];        // KFC column operand: same data, W extent clipped to valid outputs
+  int out_h, out_d;                    // output extents of the two outer dims (line validity)
+  int kw_c0[kMaxKw];
+  int v_map, v_c0;                     // tensor map index of the cotangent and its coordinate margin
+  int is_kfc;
+  int debug;                           // bring-up switch (EINCONV_TMA_DEBUG): 1 = no TMA/MMA, 2 = TMA only
+  float* partial;                      // [groups][k_splits][Mp][Np]
+};
+
+template <typename T> struct Elem;
+template <> struct Elem<float> { static constexpr bool TF32 = true; static constexpr int FMT = 2; static constexpr int UMMA_K = 8; };
+template <> struct Elem<__nv_bfloat16> { static constexpr bool TF32 = false; static constexpr int FMT = 1; static constexpr int UMMA_K = 16; };
+template <> struct Elem<__half> { static constexpr bool TF32 = false; static constexpr int FMT = 0; static constexpr int UMMA_K = 16; };
+
+template <int BN>
+struct Smem {
+  static constexpr int a_bytes = kTileM * kRowBytes;  // 16 KB
+  static constexpr int b_bytes = BN * kRowBytes;
+  static constexpr int stage_bytes = a_bytes + b_bytes;
+  static constexpr int total = kStages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+tma_reduce_gemm_kernel(const CUtensorMap* __restrict__ maps, const __grid_constant__ Params p) {
+  // tensor maps live in global memory (head of the caller's workspace): one per shifted copy of the
+  // input, plus the cotangent's
+  using E = Elem<T>;
+  using S = Smem<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  // SWIZZLE_128B tiles must start on 1024-byte boundaries
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                                         ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* accum_bar = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  const int m_tile = blockIdx.x;
+  const int n_tile = blockIdx.y;
+  const int grp = blockIdx.z / p.k_splits;
+  const int split = blockIdx.z - grp * p.k_splits;
+  const int kb_per_split = (p.k_blocks + p.k_splits - 1) / p.k_splits;
+  const int kb_begin = split * kb_per_split;
+  const int kb_end = min(p.k_blocks, kb_begin + kb_per_split);
+  const int n_kb = max(0, kb_end - kb_begin);
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // rows of this CTA's tiles
+  const int a_cblock = m_tile % p.c_blocks, a_tapgroup = m_tile / p.c_blocks;
+  const int b_cblock = n_tile % p.c_blocks, b_tapgroup = n_tile / p.c_blocks;  // KFC only
+
+  if (warp == 0 && lane == 0) {
+    // ================================= TMA producer ==========================================
+    const int b_rows_per_load = p.is_kfc ? p.CB : BN;
+    const int b_loads = p.is_kfc ? BN / p.CB : 1;
+    // taps actually present in the A / B tiles (the last tap group may be partial)
+    const int a_taps = min(p.taps_per_tile, p.k_total - a_tapgroup * p.taps_per_tile);
+    const int b_taps = p.is_kfc ? min(b_loads, p.k_total - b_tapgroup * b_loads) : 1;
+    const uint32_t tx_bytes = (uint32_t)(a_taps * p.CB + b_taps * b_rows_per_load) * kRowBytes;
+    for (int i = 0; i < n_kb; ++i) {
+      const int s = i % kStages;
+      const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      // patch origin in output coordinates
+      uint32_t rest = (uint32_t)(kb_begin + i), wt, ht, dt, b;
+      p.wt_div.divmod(rest, rest, wt);
+      p.ht_div.divmod(rest, rest, ht);
+      p.dt_div.divmod(rest, b, dt);
+      const int ow0 = (int)wt * p.BW, oh0 = (int)ht * p.BH, od0 = (int)dt * p.BD;
+      unsigned char* a_img = smem + s * S::stage_bytes;
+      unsigned char* b_img = a_img + S::a_bytes;
+      if (p.debug == 1) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+        continue;
+      }
+      // lines of the patch beyond the output extent contribute nothing: neither loaded nor multiplied
+      int n_valid = 0;
+      for (int pc = 0; pc < p.n_pieces; ++pc)
+        n_valid += (oh0 + pc % p.BH < p.out_h) && (od0 + pc / p.BH < p.out_d);
+      mbar_expect_tx(&full_bar[s], (tx_bytes / p.n_pieces) * n_valid);
+      // one TMA box per (patch line, tap): CB channels x PB bytes, written as a K-major swizzled
+      // sub-tile [line][row][PB] so that every MMA K step finds its 128 (or BN) rows contiguous
+      for (int pc = 0; pc < p.n_pieces; ++pc) {
+        const int hh = pc % p.BH, dd = pc / p.BH;
+        const int oh = oh0 + hh, od = od0 + dd;
+        if (oh >= p.out_h || od >= p.out_d) continue;
+        unsigned char* a_line = a_img + pc * (kTileM * p.PB);
+        unsigned char* b_line = b_img + pc * (BN * p.PB);
+        for (int t = 0; t < a_taps; ++t) {
+          uint32_t tap = (uint32_t)(a_tapgroup * p.taps_per_tile + t), kd, kh, kw, r2;
+          p.kw_div.divmod(tap, r2, kw);
+          p.kh_div.divmod(r2, kd, kh);
+          tma_load_5d(a_line + t * p.CB * p.PB, maps + p.kw_map[kw], &full_bar[s],
+                      ow0 * p.stride[0] + p.kw_c0[kw],
+                      oh * p.stride[1] + (int)kh * p.dil[1] - p.pad[1],
+                      od * p.stride[2] + (int)kd * p.dil[2] - p.pad[2],
+                      grp * p.c_in_g + a_cblock * p.CB, (int)b);
+        }
+        if (p.is_kfc) {
+          for (int t = 0; t < b_taps; ++t) {
+            uint32_t tap = (uint32_t)(b_tapgroup * b_loads + t), kd, kh, kw, r2;
+            p.kw_div.divmod(tap, r2, kw);
+            p.kh_div.divmod(r2, kd, kh);
+            tma_load_5d(b_line + t * p.CB * p.PB, maps + p.kw_map_b[kw], &full_bar[s],
+                        ow0 * p.stride[0] + p.kw_c0[kw],
+                        oh * p.stride[1] + (int)kh * p.dil[1] - p.pad[1],
+                        od * p.stride[2] + (int)kd * p.dil[2] - p.pad[2],
+                        grp * p.c_in_g + b_cblock * p.CB, (int)b);
+          }
+        } else {
+          tma_load_5d(b_line, maps + p.v_map, &full_bar[s], ow0 + p.v_c0, oh, od,
+                      grp * p.c_out_g + n_tile * BN, (int)b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================= MMA issuer ============================================
+    constexpr uint32_t idesc = make_idesc(E::FMT, kTileM, BN);
+    const int steps_per_line = p.PB / 32;  // 32 bytes of K per instruction (16 bf16 / 8 tf32)
+    uint32_t first = 1u;                   // the first MMA of the tile overwrites the accumulator
+    for (int i = 0; i < n_kb; ++i) {
+      const int s = i % kStages;
+      const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0 && p.debug != 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+        if (i == n_kb - 1)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(accum_bar)) : "memory");
+      } else if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * S::stage_bytes);
+        const uint32_t b_addr = a_addr + S::a_bytes;
+        uint32_t rest = (uint32_t)(kb_begin + i), wt, ht, dt, bb;
+        p.wt_div.divmod(rest, rest, wt);
+        p.ht_div.divmod(rest, rest, ht);
+        p.dt_div.divmod(rest, bb, dt);
+        const int oh0 = (int)ht * p.BH, od0 = (int)dt * p.BD;
+        for (int pc = 0; pc < p.n_pieces; ++pc) {
+          if (oh0 + pc % p.BH >= p.out_h || od0 + pc / p.BH >= p.out_d) continue;
+          for (int j = 0; j < steps_per_line; ++j) {
+            umma<E::TF32>(tmem_base, make_desc_kmajor(a_addr + pc * (kTileM * p.PB) + j * 32, p.PB),
+                          make_desc_kmajor(b_addr + pc * (BN * p.PB) + j * 32, p.PB), idesc, first ? 0u : 1u);
+            first = 0u;
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (i == n_kb - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ================================= epilogue ==============================================
+    const int ew = warp - 4;              // TMEM lane quarter owned by this warp
+    const int row = ew * 32 + lane;       // D row held by this thread
+    if (n_kb > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
+    float* dst = p.partial + (((long long)grp * p.k_splits + split) * p.Mp + (m_tile * kTileM + row)) * p.Np +
+                 n_tile * BN;
+#pragma unroll 1
+    for (int n0 = 0; n0 < BN; n0 += 16) {
+      uint32_t r[16];
+      if (n_kb > 0) {
+        tmem_ld16(lane_base + n0, r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0u;
+      }
+      float4* d4 = reinterpret_cast<float4*>(dst + n0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass: aligned shifted copies.  copy_r[row][j] = x[row][j - A + r] (zero outside [0, W)), rows =
+// (b, c, d, h), j in [0, Wp), A = 16 / sizeof(T) elements, Wp a multiple of A.  A conv tap whose offset
+// along the innermost dimension is t = A*q + r then reads copy_r at the ALIGNED coordinate
+// w + A*(q + 1), which is what the TMA unit requires of its innermost start coordinate.
+// One thread writes one 16-byte unit.
+// ---------------------------------------------------------------------------------------------
+// With a stride s > 1 along the innermost dimension the copy also subsamples (one copy per tap):
+//   copy_t[row][j] = x[row][s * (j - A) + t],  so that  x[s*w + t] = copy_t[w + A].
+template <typename T>
+__global__ void __launch_bounds__(256) shift_copy_kernel(const T* __restrict__ x, T* __restrict__ out,
+                                                         long long rows, int W, int Wp, int r, int s) {
+  constexpr int A = 16 / sizeof(T);
+  const int units = Wp / A;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * units) return;
+  const long long row = idx / units;
+  const int u = (int)(idx - row * units);
+  const T* src = x + row * W;
+  alignas(16) T vals[A];
+#pragma unroll
+  for (int e = 0; e < A; ++e) {
+    const int j = s * (u * A + e - A) + r;
+    vals[e] = (j >= 0 && j < W) ? src[j] : T(0);
+  }
+  *reinterpret_cast<uint4*>(out + row * Wp + (long long)u * A) = *reinterpret_cast<const uint4*>(vals);
+}
+
+// ---------------------------------------------------------------------------------------------
+// second pass: sum the split-K partials, scale, un-permute rows/columns (tiles are tap-major:
+// tile row r of (c-block, tap-group) is tap = group*TPT + r / CB, ci = block*CB + r % CB), cast.
+//   weight VJP: out[grp*Cout_g + co][ci][tap]          (partial columns are co)
+//   KFC:        out[grp][ci*Kt + tap][ci'*Kt + tap']
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) tma_finish_kernel(const float* __restrict__ partial, T* __restrict__ out,
+                                                         const __grid_constant__ Params p, float scale) {
+  const int Kt = p.k_total, A = p.c_in_g * Kt;
+  const long long per_group = p.is_kfc ? (long long)A * A : (long long)p.c_out_g * A;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per_group * p.groups) return;
+  const int grp = (int)(idx / per_group);
+  const long long rem = idx - (long long)grp * per_group;
+  auto tile_row = [&](int a) {  // a = ci*Kt + tap  ->  row index in the padded, tap-major partial
+    const int ci = a / Kt, tap = a - ci * Kt;
+    const int cblock = ci / p.CB, cl = ci - cblock * p.CB;
+    const int tg = tap / p.taps_per_tile, tl = tap - tg * p.taps_per_tile;
+    return (tg * p.c_blocks + cblock) * kTileM + tl * p.CB + cl;
+  };
+  int prow, pcol;
+  if (p.is_kfc) {
+    const int a = (int)(rem / A), a2 = (int)(rem - (long long)a * A);
+    prow = tile_row(a);
+    // KFC column tiles hold (BN / CB) taps each
+    const int ci = a2 / Kt, tap = a2 - ci * Kt;
+    const int cblock = ci / p.CB, cl = ci - cblock * p.CB;
+    const int tpt_n = (p.Np / p.n_tiles) / p.CB;
+    const int tg = tap / tpt_n, tl = tap - tg * tpt_n;
+    pcol = (tg * p.c_blocks + cblock) * (p.Np / p.n_tiles) + tl * p.CB + cl;
+  } else {
+    const int co = (int)(rem / A), a = (int)(rem - (long long)co * A);
+    prow = tile_row(a);
+    pcol = co;
+  }
+  const long long tile = (long long)p.Mp * p.Np;
+  const float* src = partial + (long long)grp * p.k_splits * tile + (long long)prow * p.Np + pcol;
+  float s = 0.f;
+  for (int k = 0; k < p.k_splits; ++k) s += src[(long long)k * tile];
+  Cvt<T>::store(out + idx, s * scale);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(ptr);
+  });
+  return fn;
+}
+
+struct Plan {
+  bool ok = false;
+  int BW, BH, BD, PB, kpos;
+  int CB, taps_per_tile, tap_groups, c_blocks;
+  int bn, m_tiles, n_tiles, k_blocks, k_splits;
+  int n_wt, n_ht, n_dt;
+  long long Mp, Np;
+  // shifted copies of the input (and an aligned copy of the cotangent when its rows are not
+  // 16-byte multiples): residue r -> copy index, -1 = not needed, kDirect = read x itself
+  int A;                       // elements per 16 bytes
+  int n_copies;                // copies of x to write
+  int copy_res[16];            // residue of copy i
+  int res_map[16];             // residue -> tensor map index (or -1)
+  bool x_direct;               // residue 0 served by x itself (rows already 16-byte multiples)
+  bool per_tap;                // innermost stride > 1: one subsampled copy per tap, copy_res = tap offset
+  bool v_copy;                 // cotangent needs an aligned copy
+  int Wp_x, Wp_v;              // padded row pitch (elements) of the copies
+  long long x_rows, v_rows;    // rows (b, c, d, h) of x / v
+  long long copy_x_bytes, copy_v_bytes;
+};
+
+// geometry in (W, H, D) order with unit dims for missing ones
+struct Geo3 {
+  int in[3], out[3], k[3], stride[3], dil[3], pad[3];
+};
+static Geo3 geo3(const DevGeom& g) {
+  Geo3 q;
+  for (int i = 0; i < 3; ++i) {
+    const int d = g.n_dims - 1 - i;
+    if (d >= 0) {
+      q.in[i] = g.in[d]; q.out[i] = g.out[d]; q.k[i] = g.k[d];
+      q.stride[i] = g.stride[d]; q.dil[i] = g.dil[d]; q.pad[i] = g.pad[d];
+    } else {
+      q.in[i] = 1; q.out[i] = 1; q.k[i] = 1; q.stride[i] = 1; q.dil[i] = 1; q.pad[i] = 0;
+    }
+  }
+  return q;
+}
+
+static Plan make_plan(int op, const DevGeom& g, int dtype) {
+  Plan pl;
+  if (g.n_dims > 3) return pl;
+  const int es = (int)elem_size(dtype);
+  if (es != 2 && es != 4) return pl;
+  const Geo3 q = geo3(g);
+  if (q.k[0] > kMaxKw) return pl;
+  const long long x_elems = (long long)g.batch * g.groups * g.c_in_g * g.in_total;
+  if (x_elems >= (1ll << 40)) return pl;
+  pl.kpos = kRowBytes / es;
+  // patch shape: one (d, h) line of the patch is PB = 128 / 64 / 32 bytes per channel (BW = PB / es
+  // positions, the TMA box's inner extent and the swizzle span); 128 / PB lines (BH x BD) make one
+  // 128-byte K block.  Minimise out-of-range positions; prefer long lines on ties.
+  double best = 1e30;
+  for (int pb = 128; pb >= 32; pb /= 2) {
+    const int bw = pb / es, lines = kRowBytes / pb;
+    for (int bh = 1; bh <= lines; bh *= 2) {
+      const int bd = lines / bh;
+      const double cover = (double)ceil_div(q.out[0], bw) * bw * ceil_div(q.out[1], bh) * bh *
+                           ceil_div(q.out[2], bd) * bd;
+      const double waste = cover / ((double)q.out[0] * q.out[1] * q.out[2]);
+      const double score = waste - 1e-4 * pb - 1e-6 * bh;
+      if (score < best) {
+        best = score;
+        pl.BW = bw; pl.BH = bh; pl.BD = bd; pl.PB = pb;
+      }
+    }
+  }
+  if (best > 1e29) return pl;
+  pl.n_wt = ceil_div(q.out[0], pl.BW);
+  pl.n_ht = ceil_div(q.out[1], pl.BH);
+  pl.n_dt = ceil_div(q.out[2], pl.BD);
+  const long long kb = (long long)g.batch * pl.n_wt * pl.n_ht * pl.n_dt;
+  if (kb >= (1ll << 31) || kb == 0) return pl;
+  pl.k_blocks = (int)kb;
+
+  // channel block: largest power of two <= 128 that does not exceed c_in_g rounded up to 8
+  int cb = 128;
+  while (cb > 8 && cb > g.c_in_g) cb /= 2;
+  pl.CB = cb;
+  pl.taps_per_tile = kTileM / cb;
+  pl.tap_groups = ceil_div(g.k_total, pl.taps_per_tile);
+  pl.c_blocks = ceil_div(g.c_in_g, cb);
+  pl.m_tiles = pl.c_blocks * pl.tap_groups;
+  if (op == EINCONV_OP_KFC) {
+    pl.bn = 128;  // same tiling as the rows
+    pl.n_tiles = pl.m_tiles;
+  } else {
+    pl.bn = g.c_out_g > 128 ? 256 : (g.c_out_g > 64 ? 128 : 64);
+    pl.n_tiles = ceil_div(g.c_out_g, pl.bn);
+  }
+  pl.Mp = (long long)pl.m_tiles * kTileM;
+  pl.Np = (long long)pl.n_tiles * pl.bn;
+  const long long tiles = (long long)pl.m_tiles * pl.n_tiles * g.groups;
+  long long want = (2ll * kNumSMs + tiles - 1) / tiles;
+  long long cap = std::max(1, pl.k_blocks / 8);
+  pl.k_splits = (int)std::max<long long>(1, std::min<long long>(std::min(want, cap), 64));
+  if (pl.m_tiles >= 65536 || pl.n_tiles >= 65536 || (long long)g.groups * pl.k_splits >= 65536) return pl;
+
+  // which residues (mod A elements = 16 bytes) do the innermost tap offsets t = kw*dil - pad have?
+  const int A = 16 / es;
+  pl.A = A;
+  for (int r = 0; r < 16; ++r) pl.res_map[r] = -1;
+  pl.per_tap = q.stride[0] > 1;
+  pl.x_direct = !pl.per_tap && (q.in[0] * es) % 16 == 0;
+  pl.n_copies = 0;
+  int n_maps = 0;
+  if (pl.per_tap) {
+    if (2 * q.k[0] + 1 >= kMaxMaps) return pl;
+    for (int kw = 0; kw < q.k[0]; ++kw) pl.copy_res[pl.n_copies++] = kw * q.dil[0] - q.pad[0];
+    n_maps = q.k[0];
+    pl.Wp_x = ((q.out[0] + A - 1) / A) * A + A;
+  } else {
+    for (int kw = 0; kw < q.k[0]; ++kw) {
+      const int t = kw * q.dil[0] - q.pad[0];
+      const int r = ((t % A) + A) % A;
+      if (pl.res_map[r] >= 0) continue;
+      pl.res_map[r] = n_maps++;
+      if (!(r == 0 && pl.x_direct)) pl.copy_res[pl.n_copies++] = r;
+    }
+    pl.Wp_x = ((q.in[0] + A + A - 1) / A) * A;
+  }
+  if (n_maps + q.k[0] + 1 >= kMaxMaps) return pl;
+  pl.x_rows = (long long)g.batch * g.groups * g.c_in_g * q.in[2] * q.in[1];
+  pl.copy_x_bytes = (((long long)pl.x_rows * pl.Wp_x * es + 255) / 256) * 256;
+  pl.v_copy = (op == EINCONV_OP_CONV_WEIGHT_VJP) && (q.out[0] * es) % 16 != 0;
+  pl.Wp_v = ((q.out[0] + A - 1) / A) * A + A;
+  pl.v_rows = (long long)g.batch * g.groups * std::max(1, g.c_out_g) * q.out[2] * q.out[1];
+  pl.copy_v_bytes = pl.v_copy ? (((long long)pl.v_rows * pl.Wp_v * es + 255) / 256) * 256 : 0;
+  pl.ok = encode_fn() != nullptr;
+  return pl;
+}
+
+bool tma_supported(int op, const DevGeom& g, int dtype) {
+  if (op != EINCONV_OP_CONV_WEIGHT_VJP && op != EINCONV_OP_KFC) return false;
+  if (g.batch == 0 || g.out_total == 0 || g.c_in_g == 0) return false;
+  if (op == EINCONV_OP_CONV_WEIGHT_VJP && g.c_out_g == 0) return false;
+  return make_plan(op, g, dtype).ok;
+}
+
+constexpr int64_t kMapBytes = kMaxMaps * 128;  // CUtensorMaps at the head of the workspace
+
+// workspace layout: [tensor maps][shifted copies of x][aligned copy of v][fp32 partial tiles]
+int64_t tma_workspace_bytes(int op, const DevGeom& g, int dtype) {
+  const Plan pl = make_plan(op, g, dtype);
+  return kMapBytes + pl.n_copies * pl.copy_x_bytes + pl.copy_v_bytes +
+         (int64_t)g.groups * pl.k_splits * pl.Mp * pl.Np * 4;
+}
+
+static int encode_map(CUtensorMap* map, int dtype, const void* base, const int extent[5],
+                      const int box[5], const int estride[5], int line_bytes, int pitch_w = 0) {
+  const int es = (int)elem_size(dtype);
+  CUtensorMapDataType dt = dtype == EINCONV_F32    ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+                           : dtype == EINCONV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                   : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t bx[5], st[5];
+  unsigned long long acc = (unsigned long long)es;
+  for (int i = 0; i < 5; ++i) {
+    dims[i] = (cuuint64_t)extent[i];
+    if (i > 0) strides[i - 1] = acc;
+    // the innermost extent may be clipped (zero fill beyond it) while rows keep their pitch
+    acc *= (unsigned long long)((i == 0 && pitch_w > 0) ? pitch_w : extent[i]);
+    bx[i] = (cuuint32_t)box[i];
+    st[i] = (cuuint32_t)estride[i];
+  }
+  CUtensorMapSwizzle swz = line_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                           : line_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (const char* e = getenv("EINCONV_TMA_SWZ")) swz = (CUtensorMapSwizzle)atoi(e);   // bring-up only
+  if (const char* e = getenv("EINCONV_TMA_L2P")) l2p = (CUtensorMapL2promotion)atoi(e);
+  CUresult r = encode_fn()(map, dt, 5, const_cast<void*>(base), dims, strides, bx, st,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return EINCONV_ERR_CUDA;
+  }
+  return EINCONV_OK;
+}
+
+template <typename T, int BN>
+static int launch(const CUtensorMap* maps, const Params& p, const Plan& pl, int groups, cudaStream_t stream) {
+  using S = Smem<BN>;
+  auto kern = tma_reduce_gemm_kernel<T, BN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tma_reduce_gemm)");
+  dim3 grid(pl.m_tiles, pl.n_tiles, groups * pl.k_splits);
+  kern<<<grid, kThreads, S::total, stream>>>(maps, p);
+  EINCONV_CHECK_LAUNCH("tma_reduce_gemm_kernel");
+  return EINCONV_OK;
+}
+
+int tma_run(int op, const void* x, const void* v, void* out, int dtype, const DevGeom& g, double scale,
+            void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  const Plan pl = make_plan(op, g, dtype);
+  EINCONV_CHECK_ARG(pl.ok, "tma path not available for this geometry");
+  const int64_t need = tma_workspace_bytes(op, g, dtype);
+  if (workspace_bytes < need || !workspace) {
+    set_error("workspace of %lld bytes required, got %lld", (long long)need, (long long)workspace_bytes);
+    return EINCONV_ERR_WORKSPACE;
+  }
+  const Geo3 q = geo3(g);
+  const bool kfc = op == EINCONV_OP_KFC;
+
+  EINCONV_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  const int es = (int)elem_size(dtype);
+  const int A = pl.A;
+  char* ws = (char*)workspace;
+  char* copies_x = ws + kMapBytes;
+  char* copy_v = copies_x + pl.n_copies * pl.copy_x_bytes;
+  float* partial = (float*)(copy_v + pl.copy_v_bytes);
+
+  // ---- pre-pass: aligned shifted copies -------------------------------------------------------
+  auto shift_copy = [&](const void* src, void* dst, long long rows, int W, int Wp, int r, int sw) -> int {
+    const long long units = rows * (Wp / A);
+    const unsigned blocks = (unsigned)((units + 255) / 256);
+    if (es == 2)
+      shift_copy_kernel<uint16_t><<<blocks, 256, 0, stream>>>((const uint16_t*)src, (uint16_t*)dst, rows, W, Wp, r, sw);
+    else
+      shift_copy_kernel<uint32_t><<<blocks, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, rows, W, Wp, r, sw);
+    EINCONV_CHECK_LAUNCH("shift_copy_kernel");
+    return EINCONV_OK;
+  };
+  for (int i = 0; i < pl.n_copies; ++i) {
+    int st = shift_copy(x, copies_x + i * pl.copy_x_bytes, pl.x_rows, q.in[0], pl.Wp_x, pl.copy_res[i],
+                        pl.per_tap ? q.stride[0] : 1);
+    if (st) return st;
+  }
+  if (pl.v_copy) {
+    int st = shift_copy(v, copy_v, pl.v_rows, q.out[0], pl.Wp_v, 0, 1);
+    if (st) return st;
+  }
+
+  // ---- tensor maps ------------------------------------------------------------------------------
+  alignas(64) CUtensorMap host_maps[kMaxMaps];
+  memset(host_maps, 0, sizeof(host_maps));
+  int n_maps = 0, copy_i = 0;
+  int res_margin[16];  // coordinate margin of the map serving residue r: A for copies, 0 for x itself
+  if (pl.per_tap) {
+    for (int kw = 0; kw < q.k[0]; ++kw) {
+      const void* base = copies_x + (long long)kw * pl.copy_x_bytes;
+      const int extent[5] = {pl.Wp_x, q.in[1], q.in[2], g.groups * g.c_in_g, g.batch};
+      const int box[5] = {pl.BW, 1, 1, pl.CB, 1};
+      const int est[5] = {1, 1, 1, 1, 1};
+      int st = encode_map(&host_maps[n_maps++], dtype, base, extent, box, est, pl.PB);
+      if (st) return st;
+    }
+  } else {
+    bool seen[16] = {false};
+    for (int kw = 0; kw < q.k[0]; ++kw) {
+      const int t = kw * q.dil[0] - q.pad[0];
+      const int r = ((t % A) + A) % A;
+      if (seen[r]) continue;
+      seen[r] = true;
+      const bool direct = (r == 0 && pl.x_direct);
+      const void* base = direct ? x : (const void*)(copies_x + (copy_i++) * pl.copy_x_bytes);
+      const int Wext = direct ? q.in[0] : pl.Wp_x;
+      res_margin[r] = direct ? 0 : A;
+      const int extent[5] = {Wext, q.in[1], q.in[2], g.groups * g.c_in_g, g.batch};
+      const int box[5] = {pl.BW, 1, 1, pl.CB, 1};
+      const int est[5] = {1, 1, 1, 1, 1};
+      int st = encode_map(&host_maps[n_maps++], dtype, base, extent, box, est, pl.PB);
+      if (st) return st;
+    }
+  }
+  const int v_map = n_maps;
+  if (!kfc) {
+    const void* base = pl.v_copy ? (const void*)copy_v : v;
+    const int Wext = pl.v_copy ? pl.Wp_v : q.out[0];
+    const int extent[5] = {Wext, q.out[1], q.out[2], g.groups * g.c_out_g, g.batch};
+    const int box[5] = {pl.BW, 1, 1, pl.bn, 1};
+    const int est[5] = {1, 1, 1, 1, 1};
+    int st = encode_map(&host_maps[n_maps++], dtype, base, extent, box, est, pl.PB);
+    if (st) return st;
+  }
+
+  Params p{};
+  p.n_wt = pl.n_wt; p.n_ht = pl.n_ht; p.n_dt = pl.n_dt;
+  p.wt_div = FastDiv((uint32_t)pl.n_wt); p.ht_div = FastDiv((uint32_t)pl.n_ht); p.dt_div = FastDiv((uint32_t)pl.n_dt);
+  p.BW = pl.BW; p.BH = pl.BH; p.BD = pl.BD;
+  p.PB = pl.PB; p.n_pieces = kRowBytes / pl.PB;
+  p.k_blocks = pl.k_blocks; p.k_splits = pl.k_splits;
+  for (int i = 0; i < 3; ++i) {
+    p.stride[i] = q.stride[i]; p.dil[i] = q.dil[i]; p.pad[i] = q.pad[i]; p.k[i] = q.k[i];
+  }
+  p.kw_div = FastDiv((uint32_t)q.k[0]); p.kh_div = FastDiv((uint32_t)q.k[1]);
+  p.k_total = g.k_total;
+  p.CB = pl.CB; p.taps_per_tile = pl.taps_per_tile; p.tap_groups = pl.tap_groups;
+  p.c_in_g = g.c_in_g; p.c_out_g = g.c_out_g; p.groups = g.groups;
+  p.c_blocks = pl.c_blocks; p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles;
+  p.Mp = (int)pl.Mp; p.Np = (int)pl.Np;
+  p.is_kfc = kfc ? 1 : 0;
+  {
+    const char* dbg = getenv("EINCONV_TMA_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  for (int kw = 0; kw < q.k[0]; ++kw) {
+    if (pl.per_tap) {
+      // copy_kw[j] = x[s*(j - A) + t_kw]  =>  x[s*w + t_kw] = copy_kw[w + A]
+      p.kw_map[kw] = (signed char)kw;
+      p.kw_c0[kw] = A;
+      continue;
+    }
+    const int t = kw * q.dil[0] - q.pad[0];
+    const int r = ((t % A) + A) % A;
+    const int qq = (t - r) / A;  // floor(t / A)
+    p.kw_map[kw] = (signed char)pl.res_map[r];
+    // copy_r[j] = x[j - A + r]  =>  x[w + t] = copy_r[w + A*qq + A];  direct map (r == 0): x[w + t] = x[w + A*qq]
+    p.kw_c0[kw] = A * qq + res_margin[r];
+  }
+  if (pl.per_tap) p.stride[0] = 1;  // the copies are already subsampled along the innermost dimension
+  p.out_h = q.out[1];
+  p.out_d = q.out[2];
+  for (int kw = 0; kw < q.k[0]; ++kw) p.kw_map_b[kw] = p.kw_map[kw];
+  if (kfc) {
+    // column operand of KFC: positions beyond the output width must read as zero (the row operand
+    // may then hold anything there).  Same memory as the row operand's map for this tap, with the
+    // innermost extent clipped to the last valid output; rows keep their pitch.
+    for (int kw = 0; kw < q.k[0]; ++kw) {
+      const int t = kw * q.dil[0] - q.pad[0];
+      const int r = ((t % A) + A) % A;
+      const bool direct = !pl.per_tap && r == 0 && pl.x_direct;
+      const void* base;
+      if (pl.per_tap) base = copies_x + (long long)kw * pl.copy_x_bytes;
+      else if (direct) base = x;
+      else {
+        int ci = 0;  // index of the copy that serves residue r
+        for (int i = 0; i < pl.n_copies; ++i) if (pl.copy_res[i] == r) ci = i;
+        base = copies_x + (long long)ci * pl.copy_x_bytes;
+      }
+      const int pitch = direct ? q.in[0] : pl.Wp_x;
+      const int clipped = std::max(1, std::min(pitch, q.out[0] + p.kw_c0[kw]));
+      const int extent[5] = {clipped, q.in[1], q.in[2], g.groups * g.c_in_g, g.batch};
+      const int box[5] = {pl.BW, 1, 1, pl.CB, 1};
+      const int est[5] = {1, 1, 1, 1, 1};
+      EINCONV_CHECK_ARG(n_maps < kMaxMaps, "kfc: too many tensor maps");
+      p.kw_map_b[kw] = (signed char)n_maps;
+      int st = encode_map(&host_maps[n_maps++], dtype, base, extent, box, est, pl.PB, pitch);
+      if (st) return st;
+    }
+  }
+  p.v_map = v_map;
+  p.v_c0 = pl.v_copy ? A : 0;
+  p.partial = partial;
+  const CUtensorMap* dev_maps = (const CUtensorMap*)workspace;
+  {
+    // pageable-host source: the runtime stages the 256 bytes before returning, so the stack copy is safe
+    cudaError_t e = cudaMemcpyAsync(workspace, host_maps, sizeof(host_maps), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(tensor maps)");
+  }
+
+  auto run = [&](auto* tag) -> int {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    int st;
+    if (pl.bn == 256) st = launch<T, 256>(dev_maps, p, pl, g.groups, stream);
+    else if (pl.bn == 128) st = launch<T, 128>(dev_maps, p, pl, g.groups, stream);
+    else st = launch<T, 64>(dev_maps, p, pl, g.groups, stream);
+    if (st) return st;
+    const long long A = (long long)g.c_in_g * g.k_total;
+    const long long total = (kfc ? A * A : (long long)g.c_out_g * A) * g.groups;
+    tma_finish_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p.partial, (T*)out, p,
+                                                                              (float)scale);
+    EINCONV_CHECK_LAUNCH("tma_finish_kernel");
+    return EINCONV_OK;
+  };
+  switch (dtype) {
+    case EINCONV_F32: return run((float*)nullptr);
+    case EINCONV_BF16: return run((__nv_bfloat16*)nullptr);
+    case EINCONV_F16: return run((__half*)nullptr);
+    default: set_error("tma path: unsupported dtype %d", dtype); return EINCONV_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace tma
+}  // namespace einconv

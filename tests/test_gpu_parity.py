@@ -507,5 +507,64 @@ def test_tc_kernels_are_selected():
     assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_fwd_f16"
     assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 0, nat.MATH_TF32, 0) == b"tcgen05_fwd_tf32"
     assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 0, nat.MATH_FP32, 0) == b"ffma_gather_gemm"
-    assert lib.einconv_selected_kernel(nat.OP_KFC, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_kfc_f16"
-    assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g, 1, nat.MATH_AUTO, 1) == b"ffma_gather_gemm"
+    # reduction networks: TMA-fed kernel (aligned shifted copies make any row length usable)
+    assert lib.einconv_selected_kernel(nat.OP_KFC, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_kfc"
+    assert lib.einconv_selected_kernel(nat.OP_KFC, g, 0, nat.MATH_TF32, 0) == b"tcgen05_tma_kfc"
+    assert lib.einconv_selected_kernel(nat.OP_KFC, g, 0, nat.MATH_FP32, 0) == b"ffma_gather_gemm"
+    g24 = nat.make_geom(2, 1, 32, 48, (24, 24), (3, 3), (1, 1), (1, 1), (1, 1), (24, 24))
+    assert lib.einconv_selected_kernel(nat.OP_KFC, g24, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_kfc"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_wgrad"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 1, nat.MATH_AUTO, 1) == b"ffma_gather_gemm"
+
+
+# ---- TMA-fed reduction kernels: geometries whose rows are 16-byte aligned ---------------------------
+TMA_CASES = [
+    ((2, 32, 24, 24), (48, 32, 3, 3), dict(padding=1)),
+    ((2, 16, 16, 32), (24, 16, 3, 3), dict(padding=1, stride=2)),
+    ((2, 24, 16, 16), (16, 12, 5, 3), dict(padding=(2, 0), dilation=(1, 2), groups=2)),
+    ((2, 8, 256), (24, 8, 5), dict(padding=2)),
+    ((1, 8, 6, 8, 16), (16, 8, 3, 3, 3), dict(padding=1)),
+    ((2, 3, 32, 32), (16, 3, 7, 7), dict(padding=3, stride=2)),      # C_in = 3 (partial channel block), 49 taps
+    ((2, 72, 8, 8), (200, 72, 1, 1), dict()),                         # BN = 256, c_in not a power of two
+    ((1, 160, 8, 16), (32, 160, 3, 3), dict(padding=1)),              # two channel blocks of 128
+    ((3, 64, 8, 8), (64, 64, 3, 3), dict(padding=1)),
+]
+TMA_IDS = ["x".join(map(str, c[0])) + "-w" + "x".join(map(str, c[1])) for c in TMA_CASES]
+
+
+@pytest.mark.parametrize("case", TMA_CASES, ids=TMA_IDS)
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "tf32"])
+def test_tma_weight_vjp(case, mode):
+    xs, ws, kw = case
+    torch.manual_seed(1)
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "tf32": torch.float32}[mode]
+    x = (torch.rand(*xs) - 0.3).to(dtype)
+    yshape = forward_out_shape(dict(x=xs, w=ws, kwargs=kw))
+    v = (torch.rand(*yshape) - 0.5).to(dtype)
+    want = direct.conv_weight_vjp(x.double().numpy(), v.double().numpy(), tuple(ws[2:]), **kw)
+    evaluator.set_fp32_math("tf32" if mode == "tf32" else "auto")
+    try:
+        got = evaluator.conv_weight_vjp_raw(
+            x.to(DEV), v.to(DEV), tuple(ws[2:]), kw.get("dilation", 1), kw.get("padding", 0),
+            kw.get("stride", 1), kw.get("groups", 1),
+        )
+    finally:
+        evaluator.set_fp32_math("auto")
+    tol = {"bf16": 2.0**-7, "fp16": 2.0**-10, "tf32": 1e-3}[mode]
+    _rel_to_max(got, want, tol, f"tma wgrad {mode}")
+
+
+@pytest.mark.parametrize("case", TMA_CASES, ids=TMA_IDS)
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_tma_kfc(case, mode):
+    xs, ws, kw = case
+    torch.manual_seed(2)
+    dtype = torch.bfloat16 if mode == "bf16" else torch.float32
+    x = torch.rand(*xs).to(dtype)
+    want = direct.kfc(x.double().numpy(), tuple(ws[2:]), **kw)
+    evaluator.set_fp32_math("tf32" if mode == "tf32" else "auto")
+    try:
+        got = evaluator.kfc(x.to(DEV), tuple(ws[2:]), **kw)
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, 2.0**-7 if mode == "bf16" else 1e-3, f"tma kfc {mode}")
