@@ -103,6 +103,30 @@ static Path select_path(int op, const DevGeom& g, int dtype, int math, int kerne
   return Path::FFMA;
 }
 
+// KFAC-reduce on tensor cores: stage 1 (window sums, HBM-bound) writes u as a channels-first 1-d
+// "image" [G*A channels][B positions] in fp32; stage 2 (sum_b u u^T) is then exactly the KFC network
+// of a 1x1 convolution over that image and runs on the TMA-fed tcgen05 kernel (TF32).
+static bool kfac_stage2_geom(const DevGeom& g, DevGeom* g2) {
+  const long long A = (long long)g.c_in_g * g.k_total;
+  if (A >= (1ll << 24) || g.batch < 1) return false;
+  einconv_geom e{};
+  e.n_dims = 1; e.groups = g.groups; e.batch = 1; e.c_in_g = A; e.c_out_g = 0;
+  e.in[0] = g.batch; e.k[0] = 1; e.stride[0] = 1; e.dilation[0] = 1; e.pad_left[0] = 0; e.out[0] = g.batch;
+  return make_dev_geom(&e, g2, false) == EINCONV_OK;
+}
+
+static bool kfac_reduce_tensor(const DevGeom& g, int dtype, int math, int kernels, DevGeom* g2) {
+  if (kernels == EINCONV_KERNELS_GENERIC || dtype == EINCONV_F64) return false;
+  const int m = resolve_math(dtype, math);
+  if (m != EINCONV_MATH_TF32 && m != EINCONV_MATH_HALF) return false;
+  if ((long long)g.c_in_g * g.k_total < 256) return false;  // tiny factors: the CUDA-core GEMM is as fast
+  return kfac_stage2_geom(g, g2) && tma::tma_supported(EINCONV_OP_KFC, *g2, EINCONV_F32);
+}
+
+static int64_t kfac_u_bytes(const DevGeom& g) {
+  return (((int64_t)g.batch * g.groups * g.c_in_g * g.k_total * 4 + 255) / 256) * 256;
+}
+
 static int check_math(int dtype, int math) {
   EINCONV_CHECK_ARG(math >= EINCONV_MATH_AUTO && math <= EINCONV_MATH_HALF, "unknown math mode %d", math);
   EINCONV_CHECK_ARG(elem_size(dtype) > 0, "unknown dtype %d", dtype);
@@ -157,9 +181,14 @@ int64_t einconv_workspace_bytes(int op, const einconv_geom* geom, int dtype, int
   if (path == Path::TENSOR) return tc_workspace_bytes(op, g, dtype, resolve_math(dtype, math));
   if (path == Path::TMA) return tma::tma_workspace_bytes(op, g, dtype);
   switch (op) {
+    case EINCONV_OP_KFAC_REDUCE: {
+      DevGeom g2;
+      if (kfac_reduce_tensor(g, dtype, math, kernels, &g2))
+        return kfac_u_bytes(g) + tma::tma_workspace_bytes(EINCONV_OP_KFC, g2, EINCONV_F32);
+      return ffma_splitk_workspace(op, g, dtype, nullptr);
+    }
     case EINCONV_OP_CONV_WEIGHT_VJP:
-    case EINCONV_OP_KFC:
-    case EINCONV_OP_KFAC_REDUCE: return ffma_splitk_workspace(op, g, dtype, nullptr);
+    case EINCONV_OP_KFC: return ffma_splitk_workspace(op, g, dtype, nullptr);
     default: return 0;
   }
 }
@@ -255,6 +284,22 @@ int einconv_kfac_reduce(const void* x, void* out, int dtype, const einconv_geom*
   if (st) return st;
   if ((st = check_math(dtype, math))) return st;
   if ((long long)g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
+  DevGeom g2;
+  if (kfac_reduce_tensor(g, dtype, math, kernels, &g2)) {
+    const int64_t u_bytes = kfac_u_bytes(g);
+    const int64_t need = u_bytes + tma::tma_workspace_bytes(EINCONV_OP_KFC, g2, EINCONV_F32);
+    if (workspace_bytes < need || !workspace) {
+      set_error("kfac_reduce: workspace of %lld bytes required, got %lld", (long long)need,
+                (long long)workspace_bytes);
+      return EINCONV_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    st = kfac_window_sums(x, workspace, dtype, g, /*transposed=*/1, s);
+    if (st) return st;
+    // the finish kernel of the tensor-core path casts to `dtype`; u itself is fp32
+    return tma::tma_run_typed_out(EINCONV_OP_KFC, workspace, nullptr, out, EINCONV_F32, dtype, g2, scale,
+                                  (char*)workspace + u_bytes, workspace_bytes - u_bytes, s);
+  }
   return ffma_kfac_reduce(x, out, dtype, g, scale, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

@@ -531,7 +531,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) window_sum_kernel(const T* __restrict__ x,
                                                          typename Cvt<T>::acc_t* __restrict__ u,
                                                          const __grid_constant__ DevGeom g,
-                                                         int planes) {
+                                                         int planes, int transposed) {
   using acc_t = typename Cvt<T>::acc_t;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   acc_t* acc = reinterpret_cast<acc_t*>(smem_raw);  // [k_total]
@@ -617,8 +617,121 @@ __global__ void __launch_bounds__(256) window_sum_kernel(const T* __restrict__ x
     }
   }
   __syncthreads();
+  const int chans = g.groups * g.c_in_g;
+  const int b = plane / chans, c = plane - b * chans;
   for (int t = threadIdx.x; t < g.k_total; t += blockDim.x)
-    u[(long long)plane * g.k_total + t] = acc[t];
+    u[transposed ? ((long long)c * g.k_total + t) * g.batch + b : (long long)plane * g.k_total + t] = acc[t];
+}
+
+// ---------------------------------------------------------------------------------------------
+// KFAC-reduce stage 1, fast path: one WARP per (b, c) plane, no barrier, no atomics.
+// Lane l owns columns l, l+32, ... of the innermost dimension.  For every element it adds the value
+// to the accumulators of the outer tap combinations its row belongs to (a warp-uniform bit mask
+// looked up per row); column membership is applied once at the end when the per-lane column sums
+// are reduced across the warp.  One coalesced pass over x: the kernel is HBM-bound.
+//   member_d[i] = bit mask over k_d with  i = s_d*o + dil_d*k_d - p_d  for some valid o
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MAXJ, int MAXKO>
+__global__ void __launch_bounds__(256) window_sum_warp_kernel(const T* __restrict__ x,
+                                                              typename Cvt<T>::acc_t* __restrict__ u,
+                                                              const __grid_constant__ DevGeom g,
+                                                              int planes, int transposed) {
+  using acc_t = typename Cvt<T>::acc_t;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned* member = reinterpret_cast<unsigned*>(smem_raw);  // per dim: in[d] masks, concatenated
+  const int W = g.n_dims - 1;
+  // membership tables (shared by the CTA's warps)
+  int table_off[kMaxDims];
+  {
+    int off = 0;
+    for (int d = 0; d <= W; ++d) {
+      table_off[d] = off;
+      off += g.in[d];
+    }
+    for (int idx = threadIdx.x; idx < off; idx += blockDim.x) {
+      int d = 0;
+      while (d < W && idx >= table_off[d] + g.in[d]) ++d;
+      const int i = idx - table_off[d];
+      unsigned mask = 0;
+      for (int k = 0; k < g.k[d]; ++k)
+        if (tap_member(g, d, i, k)) mask |= 1u << k;
+      member[idx] = mask;
+    }
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int plane = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (plane >= planes) return;
+  const int in_w = g.in[W], k_w = g.k[W];
+  const int n_rows = g.in_total / in_w;
+  const int k_outer = g.k_total / k_w;
+  const T* src = x + (long long)plane * g.in_total;
+
+  acc_t acc[MAXJ][MAXKO];
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j)
+#pragma unroll
+    for (int ko = 0; ko < MAXKO; ++ko) acc[j][ko] = acc_t(0);
+
+  // walk the rows; outer coordinates advance like an odometer
+  int coord[kMaxDims];
+  for (int d = 0; d < W; ++d) coord[d] = 0;
+  for (int row = 0; row < n_rows; ++row) {
+    // outer tap combinations this row belongs to: bit (k_0, .., k_{W-1}) flattened, last fastest
+    unsigned mask = 1u;
+    for (int d = 0; d < W; ++d) {
+      const unsigned md = member[table_off[d] + coord[d]];
+      // mask_new[(ko_prev * K_d) + k] = mask[ko_prev] & md[k]
+      unsigned out = 0;
+      int kprev_total = 1;
+      for (int dd = 0; dd < d; ++dd) kprev_total *= g.k[dd];
+      for (int kp = 0; kp < kprev_total; ++kp)
+        if (mask >> kp & 1u) out |= md << (kp * g.k[d]);
+      mask = out;
+    }
+    if (mask != 0u) {
+      const T* rp = src + (long long)row * in_w;
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int c = lane + 32 * j;
+        if (c < in_w) {
+          const acc_t v = Cvt<T>::load(rp + c);
+#pragma unroll
+          for (int ko = 0; ko < MAXKO; ++ko)
+            if (mask >> ko & 1u) acc[j][ko] += v;
+        }
+      }
+    }
+    for (int d = W - 1; d >= 0; --d) {
+      if (++coord[d] < g.in[d]) break;
+      coord[d] = 0;
+    }
+  }
+
+  // apply column membership and reduce across lanes
+  for (int ko = 0; ko < k_outer; ++ko) {
+    for (int kw = 0; kw < k_w; ++kw) {
+      acc_t s = acc_t(0);
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int c = lane + 32 * j;
+        acc_t a = acc_t(0);
+#pragma unroll
+        for (int q = 0; q < MAXKO; ++q)
+          if (q == ko) a = acc[j][q];
+        if (c < in_w && (member[table_off[W] + c] >> kw & 1u)) s += a;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) {
+        const int t = ko * k_w + kw;
+        const int chans = g.groups * g.c_in_g;
+        const int b = plane / chans, c = plane - b * chans;
+        u[transposed ? ((long long)c * g.k_total + t) * g.batch + b : (long long)plane * g.k_total + t] = s;
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -785,6 +898,43 @@ int ffma_kfc(const void* x, void* out, int dtype, const DevGeom& g, double scale
   });
 }
 
+// stage 1 only: u (acc_t) = window sums.  transposed = 0: [B][G*A]; 1: [G*A][B] (batch contiguous,
+// the channels-first layout the tensor-core KFC kernel consumes as a 1-d "image" of length B)
+int kfac_window_sums(const void* x, void* u_out, int dtype, const DevGeom& g, int transposed,
+                     cudaStream_t stream) {
+  return dispatch_dtype(dtype, [&](auto* tag) -> int {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    using acc_t = typename Cvt<T>::acc_t;
+    acc_t* u = (acc_t*)u_out;
+    const int planes = g.batch * g.groups * g.c_in_g;
+    if (planes == 0 || g.k_total == 0) return EINCONV_OK;
+    const int W = g.n_dims - 1;
+    const int k_outer = g.k_total / g.k[W];
+    long long table = 0;
+    bool masks_fit = true;
+    for (int d = 0; d <= W; ++d) {
+      table += g.in[d];
+      masks_fit = masks_fit && g.k[d] <= 32;
+    }
+    if (g.in[W] <= 32 * 8 && k_outer <= 9 && masks_fit && table * 4 <= 40 * 1024) {
+      const unsigned blocks = (unsigned)((planes + 7) / 8);
+      if (g.in[W] <= 32 * 2)
+        window_sum_warp_kernel<T, 2, 9><<<blocks, 256, table * 4, stream>>>((const T*)x, u, g, planes, transposed);
+      else if (g.in[W] <= 32 * 4)
+        window_sum_warp_kernel<T, 4, 9><<<blocks, 256, table * 4, stream>>>((const T*)x, u, g, planes, transposed);
+      else
+        window_sum_warp_kernel<T, 8, 9><<<blocks, 256, table * 4, stream>>>((const T*)x, u, g, planes, transposed);
+      EINCONV_CHECK_LAUNCH("window_sum_warp_kernel");
+    } else {
+      const size_t smem = (size_t)g.k_total * sizeof(acc_t);
+      EINCONV_CHECK_ARG(smem <= 48 * 1024, "kfac_reduce: kernel too large (%d taps)", g.k_total);
+      window_sum_kernel<T><<<planes, 256, smem, stream>>>((const T*)x, u, g, planes, transposed);
+      EINCONV_CHECK_LAUNCH("window_sum_kernel");
+    }
+    return EINCONV_OK;
+  });
+}
+
 int ffma_kfac_reduce(const void* x, void* out, int dtype, const DevGeom& g, double scale,
                      void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   const long long A = (long long)g.c_in_g * g.k_total;
@@ -800,12 +950,9 @@ int ffma_kfac_reduce(const void* x, void* out, int dtype, const DevGeom& g, doub
     using acc_t = typename Cvt<T>::acc_t;
     acc_t* u = (acc_t*)workspace;
     acc_t* partial = u + (long long)g.batch * g.groups * A;
-    const int planes = g.batch * g.groups * g.c_in_g;
-    if (planes > 0 && g.k_total > 0) {
-      const size_t smem = (size_t)g.k_total * sizeof(acc_t);
-      EINCONV_CHECK_ARG(smem <= 48 * 1024, "kfac_reduce: kernel too large (%d taps)", g.k_total);
-      window_sum_kernel<T><<<planes, 256, smem, stream>>>((const T*)x, u, g, planes);
-      EINCONV_CHECK_LAUNCH("window_sum_kernel");
+    {
+      int st1 = kfac_window_sums(x, u, dtype, g, /*transposed=*/0, stream);
+      if (st1) return st1;
     }
     OuterProb<T, 3> p;
     fill_base<T, 3>(p, g);

@@ -21,6 +21,8 @@ int ffma_kfc(const void* x, void* out, int dtype, const DevGeom& g, double scale
 int ffma_kfac_reduce(const void* x, void* out, int dtype, const DevGeom& g, double scale,
                      void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 int64_t ffma_splitk_workspace(int op, const DevGeom& g, int dtype, int* splits_out);
+int kfac_window_sums(const void* x, void* u_out, int dtype, const DevGeom& g, int transposed,
+                     cudaStream_t stream);
 
 // depthwise.cu
 bool depthwise_supported(const DevGeom& g, int dtype);
@@ -48,6 +50,8 @@ bool tma_supported(int op, const DevGeom& g, int dtype);
 int64_t tma_workspace_bytes(int op, const DevGeom& g, int dtype);
 int tma_run(int op, const void* x, const void* v, void* out, int dtype, const DevGeom& g, double scale,
             void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype, int out_dtype, const DevGeom& g,
+                      double scale, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 }  // namespace tma
 
 }  // namespace einconv

@@ -71,6 +71,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a protocol bug must not hang the GPU
   }
 }
+// for warps that wait for the whole main loop (epilogue): sleep between polls so that they do not
+// take issue slots from the producer / MMA warps of their sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(256);
+    if (clock64() - t0 > 20000000000ll) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -242,67 +251,115 @@ tma_reduce_gemm_kernel(const CUtensorMap* __restrict__ maps, const __grid_consta
   const int a_cblock = m_tile % p.c_blocks, a_tapgroup = m_tile / p.c_blocks;
   const int b_cblock = n_tile % p.c_blocks, b_tapgroup = n_tile / p.c_blocks;  // KFC only
 
-  if (warp == 0 && lane == 0) {
+  // patch walker: reduction block kb -> (b, d-tile, h-tile, w-tile), advanced incrementally
+  struct Walker {
+    int wt, ht, dt, b;
+    __device__ void init(const Params& p, int kb) {
+      uint32_t rest = (uint32_t)kb, a, c, d, e;
+      p.wt_div.divmod(rest, rest, a);
+      p.ht_div.divmod(rest, rest, c);
+      p.dt_div.divmod(rest, e, d);
+      wt = (int)a; ht = (int)c; dt = (int)d; b = (int)e;
+    }
+    __device__ void next(const Params& p) {
+      if (++wt == p.n_wt) { wt = 0; if (++ht == p.n_ht) { ht = 0; if (++dt == p.n_dt) { dt = 0; ++b; } } }
+    }
+  };
+
+  if (warp == 0) {
     // ================================= TMA producer ==========================================
+    // A k block needs n_pieces * (a_taps + b_loads) boxes.  Every lane owns up to kLoadsPerLane of
+    // them and precomputes everything that does not depend on the patch position, so the per-block
+    // work of a lane is a handful of adds and the TMA instruction itself.
+    constexpr int kLoadsPerLane = 4;
     const int b_rows_per_load = p.is_kfc ? p.CB : BN;
     const int b_loads = p.is_kfc ? BN / p.CB : 1;
-    // taps actually present in the A / B tiles (the last tap group may be partial)
     const int a_taps = min(p.taps_per_tile, p.k_total - a_tapgroup * p.taps_per_tile);
     const int b_taps = p.is_kfc ? min(b_loads, p.k_total - b_tapgroup * b_loads) : 1;
-    const uint32_t tx_bytes = (uint32_t)(a_taps * p.CB + b_taps * b_rows_per_load) * kRowBytes;
-    for (int i = 0; i < n_kb; ++i) {
+    const int per_piece = a_taps + b_taps;
+    const int n_loads = p.n_pieces * per_piece;
+    const uint32_t line_tx = (uint32_t)(a_taps * p.CB + b_taps * b_rows_per_load) * p.PB;
+    const int bh_shift = 31 - __clz(p.BH);  // BH is a power of two
+
+    const CUtensorMap* l_map[kLoadsPerLane];
+    int l_dst[kLoadsPerLane], l_cw[kLoadsPerLane], l_ch[kLoadsPerLane], l_cd[kLoadsPerLane];
+    int l_hh[kLoadsPerLane], l_dd[kLoadsPerLane], l_chan[kLoadsPerLane];
+    bool l_on[kLoadsPerLane];
+#pragma unroll
+    for (int q = 0; q < kLoadsPerLane; ++q) {
+      const int li = lane + 32 * q;
+      l_on[q] = li < n_loads;
+      const int pc = l_on[q] ? li / per_piece : 0;
+      const int slot = l_on[q] ? li - pc * per_piece : 0;
+      l_hh[q] = pc & (p.BH - 1);
+      l_dd[q] = pc >> bh_shift;
+      const bool is_a = slot < a_taps;
+      int tap, dst, chan;
+      const CUtensorMap* mp;
+      if (is_a) {
+        tap = a_tapgroup * p.taps_per_tile + slot;
+        dst = pc * (kTileM * p.PB) + slot * p.CB * p.PB;
+        chan = grp * p.c_in_g + a_cblock * p.CB;
+      } else if (p.is_kfc) {
+        tap = b_tapgroup * b_loads + (slot - a_taps);
+        dst = S::a_bytes + pc * (BN * p.PB) + (slot - a_taps) * p.CB * p.PB;
+        chan = grp * p.c_in_g + b_cblock * p.CB;
+      } else {
+        tap = -1;
+        dst = S::a_bytes + pc * (BN * p.PB);
+        chan = grp * p.c_out_g + n_tile * BN;
+      }
+      if (tap >= 0) {
+        uint32_t kd, kh, kw, r2;
+        p.kw_div.divmod((uint32_t)tap, r2, kw);
+        p.kh_div.divmod(r2, kd, kh);
+        mp = maps + (is_a ? p.kw_map[kw] : p.kw_map_b[kw]);
+        l_cw[q] = p.kw_c0[kw];
+        l_ch[q] = (int)kh * p.dil[1] - p.pad[1];
+        l_cd[q] = (int)kd * p.dil[2] - p.pad[2];
+      } else {
+        mp = maps + p.v_map;
+        l_cw[q] = p.v_c0;
+        l_ch[q] = 0;
+        l_cd[q] = 0;
+      }
+      l_map[q] = mp;
+      l_dst[q] = dst;
+      l_chan[q] = chan;
+    }
+    // the cotangent is indexed by output coordinates, the input by stride * output + tap offset
+    const int sw = p.stride[0], sh = p.stride[1], sd = p.stride[2];
+
+    Walker wk;
+    wk.init(p, kb_begin);
+    for (int i = 0; i < n_kb; ++i, wk.next(p)) {
       const int s = i % kStages;
       const uint32_t ph = (uint32_t)(i / kStages) & 1u;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      // patch origin in output coordinates
-      uint32_t rest = (uint32_t)(kb_begin + i), wt, ht, dt, b;
-      p.wt_div.divmod(rest, rest, wt);
-      p.ht_div.divmod(rest, rest, ht);
-      p.dt_div.divmod(rest, b, dt);
-      const int ow0 = (int)wt * p.BW, oh0 = (int)ht * p.BH, od0 = (int)dt * p.BD;
-      unsigned char* a_img = smem + s * S::stage_bytes;
-      unsigned char* b_img = a_img + S::a_bytes;
-      if (p.debug == 1) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
-        continue;
-      }
-      // lines of the patch beyond the output extent contribute nothing: neither loaded nor multiplied
-      int n_valid = 0;
-      for (int pc = 0; pc < p.n_pieces; ++pc)
-        n_valid += (oh0 + pc % p.BH < p.out_h) && (od0 + pc / p.BH < p.out_d);
-      mbar_expect_tx(&full_bar[s], (tx_bytes / p.n_pieces) * n_valid);
-      // one TMA box per (patch line, tap): CB channels x PB bytes, written as a K-major swizzled
-      // sub-tile [line][row][PB] so that every MMA K step finds its 128 (or BN) rows contiguous
-      for (int pc = 0; pc < p.n_pieces; ++pc) {
-        const int hh = pc % p.BH, dd = pc / p.BH;
-        const int oh = oh0 + hh, od = od0 + dd;
-        if (oh >= p.out_h || od >= p.out_d) continue;
-        unsigned char* a_line = a_img + pc * (kTileM * p.PB);
-        unsigned char* b_line = b_img + pc * (BN * p.PB);
-        for (int t = 0; t < a_taps; ++t) {
-          uint32_t tap = (uint32_t)(a_tapgroup * p.taps_per_tile + t), kd, kh, kw, r2;
-          p.kw_div.divmod(tap, r2, kw);
-          p.kh_div.divmod(r2, kd, kh);
-          tma_load_5d(a_line + t * p.CB * p.PB, maps + p.kw_map[kw], &full_bar[s],
-                      ow0 * p.stride[0] + p.kw_c0[kw],
-                      oh * p.stride[1] + (int)kh * p.dil[1] - p.pad[1],
-                      od * p.stride[2] + (int)kd * p.dil[2] - p.pad[2],
-                      grp * p.c_in_g + a_cblock * p.CB, (int)b);
-        }
-        if (p.is_kfc) {
-          for (int t = 0; t < b_taps; ++t) {
-            uint32_t tap = (uint32_t)(b_tapgroup * b_loads + t), kd, kh, kw, r2;
-            p.kw_div.divmod(tap, r2, kw);
-            p.kh_div.divmod(r2, kd, kh);
-            tma_load_5d(b_line + t * p.CB * p.PB, maps + p.kw_map_b[kw], &full_bar[s],
-                        ow0 * p.stride[0] + p.kw_c0[kw],
-                        oh * p.stride[1] + (int)kh * p.dil[1] - p.pad[1],
-                        od * p.stride[2] + (int)kd * p.dil[2] - p.pad[2],
-                        grp * p.c_in_g + b_cblock * p.CB, (int)b);
-          }
+      const int ow0 = wk.wt * p.BW, oh0 = wk.ht * p.BH, od0 = wk.dt * p.BD;
+      if (lane == 0) {
+        if (p.debug == 1) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
         } else {
-          tma_load_5d(b_line, maps + p.v_map, &full_bar[s], ow0 + p.v_c0, oh, od,
-                      grp * p.c_out_g + n_tile * BN, (int)b);
+          // lines of the patch beyond the output extent contribute nothing: not loaded, not multiplied
+          int n_valid = 0;
+          for (int pc = 0; pc < p.n_pieces; ++pc)
+            n_valid += (oh0 + (pc & (p.BH - 1)) < p.out_h) && (od0 + (pc >> bh_shift) < p.out_d);
+          mbar_expect_tx(&full_bar[s], line_tx * n_valid);
+        }
+      }
+      __syncwarp();
+      if (p.debug != 1) {
+        unsigned char* stage = smem + s * S::stage_bytes;
+#pragma unroll
+        for (int q = 0; q < kLoadsPerLane; ++q) {
+          if (!l_on[q]) continue;
+          const int oh = oh0 + l_hh[q], od = od0 + l_dd[q];
+          if (oh >= p.out_h || od >= p.out_d) continue;
+          const bool is_v = l_map[q] == maps + p.v_map && !p.is_kfc;
+          tma_load_5d(stage + l_dst[q], l_map[q], &full_bar[s],
+                      (is_v ? ow0 : ow0 * sw) + l_cw[q], (is_v ? oh : oh * sh) + l_ch[q],
+                      (is_v ? od : od * sd) + l_cd[q], l_chan[q], wk.b);
         }
       }
     }
@@ -310,8 +367,11 @@ tma_reduce_gemm_kernel(const CUtensorMap* __restrict__ maps, const __grid_consta
     // ================================= MMA issuer ============================================
     constexpr uint32_t idesc = make_idesc(E::FMT, kTileM, BN);
     const int steps_per_line = p.PB / 32;  // 32 bytes of K per instruction (16 bf16 / 8 tf32)
+    const int bh_shift = 31 - __clz(p.BH);
     uint32_t first = 1u;                   // the first MMA of the tile overwrites the accumulator
-    for (int i = 0; i < n_kb; ++i) {
+    Walker wk;
+    wk.init(p, kb_begin);
+    for (int i = 0; i < n_kb; ++i, wk.next(p)) {
       const int s = i % kStages;
       const uint32_t ph = (uint32_t)(i / kStages) & 1u;
       mbar_wait(&full_bar[s], ph);
@@ -323,13 +383,9 @@ tma_reduce_gemm_kernel(const CUtensorMap* __restrict__ maps, const __grid_consta
       } else if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + s * S::stage_bytes);
         const uint32_t b_addr = a_addr + S::a_bytes;
-        uint32_t rest = (uint32_t)(kb_begin + i), wt, ht, dt, bb;
-        p.wt_div.divmod(rest, rest, wt);
-        p.ht_div.divmod(rest, rest, ht);
-        p.dt_div.divmod(rest, bb, dt);
-        const int oh0 = (int)ht * p.BH, od0 = (int)dt * p.BD;
+        const int oh0 = wk.ht * p.BH, od0 = wk.dt * p.BD;
         for (int pc = 0; pc < p.n_pieces; ++pc) {
-          if (oh0 + pc % p.BH >= p.out_h || od0 + pc / p.BH >= p.out_d) continue;
+          if (oh0 + (pc & (p.BH - 1)) >= p.out_h || od0 + (pc >> bh_shift) >= p.out_d) continue;
           for (int j = 0; j < steps_per_line; ++j) {
             umma<E::TF32>(tmem_base, make_desc_kmajor(a_addr + pc * (kTileM * p.PB) + j * 32, p.PB),
                           make_desc_kmajor(b_addr + pc * (BN * p.PB) + j * 32, p.PB), idesc, first ? 0u : 1u);
@@ -346,7 +402,7 @@ tma_reduce_gemm_kernel(const CUtensorMap* __restrict__ maps, const __grid_consta
     const int ew = warp - 4;              // TMEM lane quarter owned by this warp
     const int row = ew * 32 + lane;       // D row held by this thread
     if (n_kb > 0) {
-      mbar_wait(accum_bar, 0);
+      mbar_wait_relaxed(accum_bar, 0);
       tc_fence_after();
     }
     const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
@@ -547,6 +603,8 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
   int cb = 128;
   while (cb > 8 && cb > g.c_in_g) cb /= 2;
   pl.CB = cb;
+  // tiny channel blocks mean many 1 KB TMA boxes per k block: the CUDA-core kernel is faster there
+  if (cb < 32) return pl;
   pl.taps_per_tile = kTileM / cb;
   pl.tap_groups = ceil_div(g.k_total, pl.taps_per_tile);
   pl.c_blocks = ceil_div(g.c_in_g, cb);
@@ -558,12 +616,21 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
     pl.bn = g.c_out_g > 128 ? 256 : (g.c_out_g > 64 ? 128 : 64);
     pl.n_tiles = ceil_div(g.c_out_g, pl.bn);
   }
+  {
+    const int b_loads = (op == EINCONV_OP_KFC) ? pl.bn / pl.CB : 1;
+    if ((kRowBytes / pl.PB) * (pl.taps_per_tile + b_loads) > 128) return pl;  // boxes per k block (4 per lane)
+  }
   pl.Mp = (long long)pl.m_tiles * kTileM;
   pl.Np = (long long)pl.n_tiles * pl.bn;
+  // split-K so that the grid is exactly one wave of resident CTAs (a partial second wave would
+  // double the run time): resident = 148 SMs x CTAs that fit in shared memory
   const long long tiles = (long long)pl.m_tiles * pl.n_tiles * g.groups;
-  long long want = (2ll * kNumSMs + tiles - 1) / tiles;
+  const int stage_bytes = (kTileM + pl.bn) * kRowBytes;
+  const int ctas_per_sm = std::max(1, (227 * 1024) / (kStages * stage_bytes + 2048));
+  const long long resident = (long long)kNumSMs * ctas_per_sm;
+  long long want = tiles >= resident ? 1 : resident / tiles;
   long long cap = std::max(1, pl.k_blocks / 8);
-  pl.k_splits = (int)std::max<long long>(1, std::min<long long>(std::min(want, cap), 64));
+  pl.k_splits = (int)std::max<long long>(1, std::min<long long>(std::min(want, cap), 512));
   if (pl.m_tiles >= 65536 || pl.n_tiles >= 65536 || (long long)g.groups * pl.k_splits >= 65536) return pl;
 
   // which residues (mod A elements = 16 bytes) do the innermost tap offsets t = kw*dil - pad have?
@@ -660,8 +727,8 @@ static int launch(const CUtensorMap* maps, const Params& p, const Plan& pl, int 
   return EINCONV_OK;
 }
 
-int tma_run(int op, const void* x, const void* v, void* out, int dtype, const DevGeom& g, double scale,
-            void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype, int out_dtype, const DevGeom& g,
+                      double scale, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   const Plan pl = make_plan(op, g, dtype);
   EINCONV_CHECK_ARG(pl.ok, "tma path not available for this geometry");
   const int64_t need = tma_workspace_bytes(op, g, dtype);
@@ -819,26 +886,39 @@ int tma_run(int op, const void* x, const void* v, void* out, int dtype, const De
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(tensor maps)");
   }
 
-  auto run = [&](auto* tag) -> int {
+  auto run_main = [&](auto* tag) -> int {
     using T = std::remove_pointer_t<decltype(tag)>;
-    int st;
-    if (pl.bn == 256) st = launch<T, 256>(dev_maps, p, pl, g.groups, stream);
-    else if (pl.bn == 128) st = launch<T, 128>(dev_maps, p, pl, g.groups, stream);
-    else st = launch<T, 64>(dev_maps, p, pl, g.groups, stream);
-    if (st) return st;
-    const long long A = (long long)g.c_in_g * g.k_total;
-    const long long total = (kfc ? A * A : (long long)g.c_out_g * A) * g.groups;
-    tma_finish_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p.partial, (T*)out, p,
-                                                                              (float)scale);
+    if (pl.bn == 256) return launch<T, 256>(dev_maps, p, pl, g.groups, stream);
+    if (pl.bn == 128) return launch<T, 128>(dev_maps, p, pl, g.groups, stream);
+    return launch<T, 64>(dev_maps, p, pl, g.groups, stream);
+  };
+  int st;
+  switch (dtype) {
+    case EINCONV_F32: st = run_main((float*)nullptr); break;
+    case EINCONV_BF16: st = run_main((__nv_bfloat16*)nullptr); break;
+    case EINCONV_F16: st = run_main((__half*)nullptr); break;
+    default: set_error("tma path: unsupported dtype %d", dtype); return EINCONV_ERR_UNSUPPORTED;
+  }
+  if (st) return st;
+  const long long Atot = (long long)g.c_in_g * g.k_total;
+  const long long total = (kfc ? Atot * Atot : (long long)g.c_out_g * Atot) * g.groups;
+  auto run_finish = [&](auto* tag) -> int {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    tma_finish_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p.partial, (T*)out, p, (float)scale);
     EINCONV_CHECK_LAUNCH("tma_finish_kernel");
     return EINCONV_OK;
   };
-  switch (dtype) {
-    case EINCONV_F32: return run((float*)nullptr);
-    case EINCONV_BF16: return run((__nv_bfloat16*)nullptr);
-    case EINCONV_F16: return run((__half*)nullptr);
-    default: set_error("tma path: unsupported dtype %d", dtype); return EINCONV_ERR_UNSUPPORTED;
+  switch (out_dtype) {
+    case EINCONV_F32: return run_finish((float*)nullptr);
+    case EINCONV_BF16: return run_finish((__nv_bfloat16*)nullptr);
+    case EINCONV_F16: return run_finish((__half*)nullptr);
+    default: set_error("tma path: unsupported output dtype %d", out_dtype); return EINCONV_ERR_UNSUPPORTED;
   }
+}
+
+int tma_run(int op, const void* x, const void* v, void* out, int dtype, const DevGeom& g, double scale,
+            void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  return tma_run_typed_out(op, x, v, out, dtype, dtype, g, scale, workspace, workspace_bytes, stream);
 }
 
 }  // namespace tma

@@ -568,3 +568,21 @@ def test_tma_kfc(case, mode):
     finally:
         evaluator.set_fp32_math("auto")
     _rel_to_max(got, want, 2.0**-7 if mode == "bf16" else 1e-3, f"tma kfc {mode}")
+
+
+@pytest.mark.parametrize("case", TMA_CASES, ids=TMA_IDS)
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_tensor_core_kfac_reduce(case, mode):
+    """KFAC-reduce with the outer products on tensor cores (TF32 on the fp32 window sums):
+    max|d| <= 1e-3 max|ref| (tf32) / 2^-7 (bf16 output rounding)."""
+    xs, ws, kw = case
+    torch.manual_seed(3)
+    dtype = torch.bfloat16 if mode == "bf16" else torch.float32
+    x = torch.rand(*xs).to(dtype)
+    want = direct.kfac_reduce(x.double().numpy(), tuple(ws[2:]), **kw)
+    evaluator.set_fp32_math("tf32" if mode == "tf32" else "auto")
+    try:
+        got = evaluator.kfac_reduce(x.to(DEV), tuple(ws[2:]), **kw)
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, 2.0**-7 if mode == "bf16" else 1e-3, f"kfac_reduce {mode}")
