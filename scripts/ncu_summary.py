@@ -1,0 +1,64 @@
+"""Summarise an .ncu-rep (raw page) into a short text file for profiles/.
+
+usage: python scripts/ncu_summary.py REPORT.ncu-rep [kernel-substring] > profiles/rNN_<what>.txt
+"""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum",
+    "dram__bytes_read.sum",
+    "dram__bytes_write.sum",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum",
+    "lts__t_sectors_srcunit_tex_op_read.sum",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed.sum",
+    "sm__inst_issued.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subunit_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.sum",
+    "launch__grid_size",
+    "launch__block_size",
+    "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic",
+    "launch__shared_mem_per_block_static",
+    "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem",
+    "launch__waves_per_multiprocessor",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio",
+]
+
+
+def main():
+    rep = sys.argv[1]
+    flt = sys.argv[2] if len(sys.argv) > 2 else ""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    print(f"# ncu --set full --clock-control none summary of {rep} (raw page)")
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        if flt and flt not in name:
+            continue
+        print(f"kernel: {name}")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"  {k:<85s} {r[i]:>16s} {units[i]}")
+        print()
+
+
+if __name__ == "__main__":
+    main()
