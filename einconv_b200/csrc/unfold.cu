@@ -14,6 +14,7 @@
 // x is therefore read once from L2/HBM (plus row halos) while `out` (prod(k) times larger) is
 // written with full-line coalesced stores — the kernel is bound by HBM write bandwidth.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -301,6 +302,166 @@ __global__ void __launch_bounds__(256, 8) unfold_plane_kernel(const T* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Whole-plane variant.  When the zero-padded, gcd-compacted N-d window of one (b, c) plane fits in
+// shared memory, a CTA stages it once and then streams every kernel tap as ONE contiguous run of
+// P = prod(out) elements:  out[bc, t, j] = plane[src(j) + tap_off(t)], where src(j) (the staged
+// offset of output position j for tap 0) is tap-independent and lives in registers for the whole
+// tap loop.  The inner loop is one shared load, one add and one coalesced streaming store per
+// element and has no per-row or per-run set-up, which is what made the tiled kernel above
+// instruction-issue bound on small planes (ncu: 38 M warp instructions for C2).
+// ---------------------------------------------------------------------------------------------
+constexpr int kFlatThreads = 256;
+constexpr int kFlatJpt = 8;        // outputs per thread per chunk
+constexpr int kFlatMaxTaps = 2048;
+
+template <int ND>
+struct FlatParams {
+  long long xs_b, xs_c;
+  int xs[ND];        // element strides of the spatial dims (|.| < 2^31, plane span < 2^31)
+  int channels;
+  int in[ND], pad[ND], gstep[ND];
+  int ext[ND];       // staged extent per dim, compact coordinates: virtual v = jc * gstep - pad
+  int so[ND];        // staged offset per unit of o_d : (stride / g) * pitch
+  int ko[ND];        // staged offset per unit of k_d : (dil / g) * pitch
+  int out[ND], k[ND];
+  int P, K, box;
+  int tap_chunks, taps_per_chunk;
+  FastDiv ext_div[ND], out_div[ND], k_div[ND], chan_div, chunk_div;
+};
+
+template <typename T>
+__device__ __forceinline__ void store_stream1(T* dst, T val) {
+  if constexpr (sizeof(T) == 8) {
+    __stcs(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)val);
+  } else if constexpr (sizeof(T) == 4) {
+    __stcs(reinterpret_cast<unsigned int*>(dst), (unsigned int)val);
+  } else {
+    __stcs(reinterpret_cast<unsigned short*>(dst), (unsigned short)val);
+  }
+}
+
+template <typename T, int ND>
+__global__ void __launch_bounds__(kFlatThreads, 4)
+unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
+                   const __grid_constant__ FlatParams<ND> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* plane = reinterpret_cast<T*>(smem_raw);
+  int* tap_off = reinterpret_cast<int*>(smem_raw + (((size_t)p.box * sizeof(T) + 15) & ~(size_t)15));
+  const int tid = threadIdx.x;
+
+  uint32_t bc, chunk;
+  p.chunk_div.divmod(blockIdx.x, bc, chunk);
+  const int t0 = (int)chunk * p.taps_per_chunk;
+  const int t1 = min(p.K, t0 + p.taps_per_chunk);
+
+  // tap table: staged offset of tap t relative to tap 0
+  for (int t = t0 + tid; t < t1; t += kFlatThreads) {
+    uint32_t rem = (uint32_t)t;
+    int off = 0;
+#pragma unroll
+    for (int d = ND - 1; d >= 0; --d) {
+      uint32_t q, kd;
+      p.k_div[d].divmod(rem, q, kd);
+      rem = q;
+      off += (int)kd * p.ko[d];
+    }
+    tap_off[t - t0] = off;
+  }
+
+  // ---- stage: plane[c_0..c_{ND-1}] = x[b, c, c_d * gstep_d - pad_d] or 0
+  {
+    uint32_t b, c;
+    p.chan_div.divmod(bc, b, c);
+    const T* src = x + (long long)b * p.xs_b + (long long)c * p.xs_c;
+    int cc[ND], est[ND];
+    {
+      uint32_t r0 = (uint32_t)tid, r1 = (uint32_t)kFlatThreads;
+#pragma unroll
+      for (int d = ND - 1; d >= 1; --d) {
+        uint32_t q, r;
+        p.ext_div[d].divmod(r0, q, r);
+        cc[d] = (int)r;
+        r0 = q;
+        p.ext_div[d].divmod(r1, q, r);
+        est[d] = (int)r;
+        r1 = q;
+      }
+      cc[0] = (int)r0;  // >= ext[0] only for e >= box, which the loop excludes
+      est[0] = (int)r1;
+    }
+    constexpr int U = 8;  // independent loads in flight per thread
+    for (int e0 = tid; e0 < p.box; e0 += kFlatThreads * U) {
+      T vals[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        bool ok = e0 + u * kFlatThreads < p.box;
+        int off = 0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+          const int v = cc[d] * p.gstep[d] - p.pad[d];
+          ok = ok && (unsigned)v < (unsigned)p.in[d];
+          off += v * p.xs[d];
+        }
+        vals[u] = T(0);
+        if (ok) vals[u] = __ldg(src + off);
+        int carry = 0;
+#pragma unroll
+        for (int d = ND - 1; d >= 1; --d) {
+          const int nc = cc[d] + est[d] + carry;
+          carry = nc >= p.ext[d] ? 1 : 0;
+          cc[d] = nc - (carry ? p.ext[d] : 0);
+        }
+        cc[0] += est[0] + carry;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (e0 + u * kFlatThreads < p.box) plane[e0 + u * kFlatThreads] = vals[u];
+    }
+  }
+  __syncthreads();
+
+  // ---- emit
+  T* dst_plane = out + ((long long)bc * p.K + t0) * (long long)p.P + tid;
+  constexpr int kChunk = kFlatThreads * kFlatJpt;
+  for (int jb = 0; jb < p.P; jb += kChunk) {
+    int off[kFlatJpt];
+#pragma unroll
+    for (int i = 0; i < kFlatJpt; ++i) {
+      const int j = jb + i * kFlatThreads + tid;
+      uint32_t rem = (uint32_t)(j < p.P ? j : 0);
+      int o = 0;
+#pragma unroll
+      for (int d = ND - 1; d >= 0; --d) {
+        uint32_t q, od;
+        p.out_div[d].divmod(rem, q, od);
+        rem = q;
+        o += (int)od * p.so[d];
+      }
+      off[i] = o;
+    }
+    T* dst = dst_plane + jb;
+    if (jb + kChunk <= p.P) {
+      for (int t = t0; t < t1; ++t, dst += p.P) {
+        const T* s = plane + tap_off[t - t0];
+        T v[kFlatJpt];
+#pragma unroll
+        for (int i = 0; i < kFlatJpt; ++i) v[i] = s[off[i]];
+#pragma unroll
+        for (int i = 0; i < kFlatJpt; ++i) store_stream1<T>(dst + i * kFlatThreads, v[i]);
+      }
+    } else {
+      const int left = p.P - jb - tid;  // this thread's element i is valid iff i * 256 < left
+      for (int t = t0; t < t1; ++t, dst += p.P) {
+        const T* s = plane + tap_off[t - t0];
+#pragma unroll
+        for (int i = 0; i < kFlatJpt; ++i)
+          if (i * kFlatThreads < left) store_stream1<T>(dst + i * kFlatThreads, s[off[i]]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fold: gx[bc, i..] = sum_k gu[bc, k.., o..(i,k)]   (gather form of the adjoint)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -358,6 +519,100 @@ static int launch_unfold_t(const void* x, void* out, const UnfoldParams& p, size
   return EINCONV_OK;
 }
 
+// EINCONV_UNFOLD_TILED=1 forces the tiled kernel (tests exercise both variants on every geometry)
+static bool unfold_force_tiled() {
+  const char* e = getenv("EINCONV_UNFOLD_TILED");
+  return e && e[0] == '1';
+}
+
+// Whole-plane kernel: returns 1 if it took the job, 0 if the geometry does not qualify, < 0 on error.
+template <typename T, int ND>
+static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, const long long* xs,
+                                int C, cudaStream_t stream) {
+  FlatParams<ND> p{};
+  const int N0 = g0.n_dims, lead = ND - N0;
+  p.xs_b = xs[0];
+  p.xs_c = xs[1];
+  p.channels = C;
+  int stride[ND], dil[ND];
+  for (int d = 0; d < ND; ++d) {
+    const bool real = d >= lead;
+    const int s = d - lead;
+    p.in[d] = real ? g0.in[s] : 1;
+    p.k[d] = real ? g0.k[s] : 1;
+    p.out[d] = real ? g0.out[s] : 1;
+    p.pad[d] = real ? g0.pad[s] : 0;
+    stride[d] = real ? g0.stride[s] : 1;
+    dil[d] = real ? g0.dil[s] : 1;
+    const long long xsd = real ? xs[s + 2] : 0;
+    if (xsd <= -(1ll << 31) || xsd >= (1ll << 31)) return 0;
+    p.xs[d] = (int)xsd;
+    p.gstep[d] = igcd(stride[d], dil[d]);
+  }
+  long long box = 1, span = 0;
+  for (int d = ND - 1; d >= 0; --d) {
+    const long long ext = (long long)(stride[d] / p.gstep[d]) * (p.out[d] - 1) +
+                          (long long)(dil[d] / p.gstep[d]) * (p.k[d] - 1) + 1;
+    if (ext * box > (1 << 20)) return 0;
+    p.ext[d] = (int)ext;
+    p.so[d] = (int)((stride[d] / p.gstep[d]) * box);
+    p.ko[d] = (int)((dil[d] / p.gstep[d]) * box);
+    box *= ext;
+    span += (long long)(p.in[d] - 1) * (p.xs[d] < 0 ? -(long long)p.xs[d] : (long long)p.xs[d]);
+  }
+  if (span >= (1ll << 31)) return 0;
+  p.box = (int)box;
+  p.P = g0.out_total;
+  p.K = g0.k_total;
+  const long long n_planes = (long long)g0.batch * C;
+
+  // CTAs per plane: split the taps while there are fewer CTAs than ~4 per SM
+  int chunks = 1;
+  while (n_planes * chunks < 2ll * kNumSMs && chunks * 2 <= p.K) chunks *= 2;
+  if (const char* e = getenv("EINCONV_UNFOLD_CHUNKS")) chunks = std::max(1, std::min(p.K, atoi(e)));
+  p.taps_per_chunk = ceil_div(p.K, chunks);
+  p.tap_chunks = ceil_div(p.K, p.taps_per_chunk);
+  if (p.taps_per_chunk > kFlatMaxTaps) return 0;
+  const size_t smem = (((size_t)p.box * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4;
+  if (smem > 56 * 1024) return 0;  // keep >= 4 CTAs per SM resident
+  const long long grid = n_planes * p.tap_chunks;
+  if (grid >= (1ll << 31)) return 0;
+  // Too little output per staged element: the tiled kernel amortises its staging better.
+  for (int d = 0; d < ND; ++d) {
+    p.ext_div[d] = FastDiv((uint32_t)p.ext[d]);
+    p.out_div[d] = FastDiv((uint32_t)p.out[d]);
+    p.k_div[d] = FastDiv((uint32_t)p.k[d]);
+  }
+  p.chan_div = FastDiv((uint32_t)C);
+  p.chunk_div = FastDiv((uint32_t)p.tap_chunks);
+
+  auto kern = unfold_flat_kernel<T, ND>;
+  if (smem > 32 * 1024) {
+    cudaError_t err =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(unfold_flat)");
+  }
+  kern<<<(unsigned)grid, kFlatThreads, smem, stream>>>((const T*)x, (T*)out, p);
+  {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return cuda_fail(err, "unfold_flat_kernel");
+    count_launch();
+  }
+  return 1;
+}
+
+template <typename T>
+static int launch_unfold_flat(const void* x, void* out, const DevGeom& g0, const long long* xs,
+                              int C, cudaStream_t stream) {
+  switch (g0.n_dims) {
+    case 1: return launch_unfold_flat_t<T, 1>(x, out, g0, xs, C, stream);
+    case 2: return launch_unfold_flat_t<T, 2>(x, out, g0, xs, C, stream);
+    case 3: return launch_unfold_flat_t<T, 3>(x, out, g0, xs, C, stream);
+    case 4: return launch_unfold_flat_t<T, 4>(x, out, g0, xs, C, stream);
+    default: return launch_unfold_flat_t<T, kMaxDims>(x, out, g0, xs, C, stream);
+  }
+}
+
 int launch_unfold(const void* x, const int64_t* x_strides, void* out, int dtype,
                   const einconv_geom* geom, cudaStream_t stream) {
   DevGeom g0;
@@ -385,6 +640,17 @@ int launch_unfold(const void* x, const int64_t* x_strides, void* out, int dtype,
   const long long* xs = x_strides ? (const long long*)x_strides : cs;
   p.xs_b = xs[0];
   p.xs_c = xs[1];
+
+  if ((long long)g0.batch * C * g0.k_total * (long long)g0.out_total == 0) return EINCONV_OK;
+  if (!unfold_force_tiled()) {
+    int took;
+    switch (esz) {
+      case 2: took = launch_unfold_flat<uint16_t>(x, out, g0, xs, C, stream); break;
+      case 4: took = launch_unfold_flat<uint32_t>(x, out, g0, xs, C, stream); break;
+      default: took = launch_unfold_flat<unsigned long long>(x, out, g0, xs, C, stream); break;
+    }
+    if (took != 0) return took < 0 ? took : EINCONV_OK;
+  }
 
   // normalise to >= 2 spatial dims by prepending a unit dimension
   const int shift = (N0 == 1) ? 1 : 0;

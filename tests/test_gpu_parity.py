@@ -63,9 +63,17 @@ def test_native_library_is_loaded_and_counts_launches():
 # =============================================================================================
 # unfold: bit-exact
 # =============================================================================================
+@pytest.fixture(params=["auto", "tiled"])
+def unfold_variant(request, monkeypatch):
+    """Both unfold kernels: "auto" takes the whole-plane kernel whenever the staged window fits in
+    shared memory, "tiled" forces the row-tiled kernel (csrc/unfold.cu reads the variable per call)."""
+    monkeypatch.setenv("EINCONV_UNFOLD_TILED", "1" if request.param == "tiled" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("case", C.UNFOLD_CASES, ids=[c["id"] for c in C.UNFOLD_CASES])
 @pytest.mark.parametrize("simplify", SIMPLIFY)
-def test_unfold_bit_exact(case, simplify):
+def test_unfold_bit_exact(case, simplify, unfold_variant):
     x = C.draw_input(case)
     want = direct.unfold(x.numpy(), case["kernel_size"], **case["kwargs"])
     got = unfoldNd(x.to(DEV), case["kernel_size"], **case["kwargs"], simplify=simplify)
@@ -77,7 +85,7 @@ def test_unfold_bit_exact(case, simplify):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float64])
 @pytest.mark.parametrize("case", [C.UNFOLD_CASES[5], C.UNFOLD_CASES[11], C.UNFOLD_CASES[18]],
                          ids=lambda c: c["id"])
-def test_unfold_bit_exact_other_dtypes(case, dtype):
+def test_unfold_bit_exact_other_dtypes(case, dtype, unfold_variant):
     x = C.draw_input(case).to(dtype)
     raw = x.view(torch.int16).numpy() if dtype in (torch.bfloat16, torch.float16) else x.numpy()
     want = direct.unfold(raw, case["kernel_size"], **case["kwargs"])
@@ -101,7 +109,7 @@ UNFOLD_EXTRA = [
 
 
 @pytest.mark.parametrize("case", UNFOLD_EXTRA, ids=lambda c: "x".join(map(str, c["x"])) + f"-k{c['kernel_size']}")
-def test_unfold_edge_cases(case):
+def test_unfold_edge_cases(case, unfold_variant):
     torch.manual_seed(1)
     x = torch.rand(*case["x"])
     if case.get("expect_error"):
@@ -114,7 +122,7 @@ def test_unfold_edge_cases(case):
     assert torch.equal(got.cpu(), torch.from_numpy(want))
 
 
-def test_unfold_non_contiguous_input_and_module():
+def test_unfold_non_contiguous_input_and_module(unfold_variant):
     torch.manual_seed(0)
     base = torch.rand(2, 12, 6, 10, device=DEV)
     x = base.permute(0, 2, 1, 3)[:, :, ::2, 1:9]  # [2, 6, 6, 8], strided view
@@ -160,7 +168,7 @@ def _slices_unfold(x, k, s, d, p):
     return torch.cat(cols, dim=2).reshape(x.shape[0], x.shape[1] * len(cols), -1)
 
 
-def test_unfold_baseline_c2_full_size_exact():
+def test_unfold_baseline_c2_full_size_exact(unfold_variant):
     """BASELINE C2 at full size: N=16 C=32 16x56x56 k=3 stride=2 dilation=2 (bit-exact gather)."""
     torch.manual_seed(0)
     x = torch.rand(16, 32, 16, 56, 56).to(DEV)
