@@ -310,8 +310,18 @@ __global__ void __launch_bounds__(256, 8) unfold_plane_kernel(const T* __restric
 // element and has no per-row or per-run set-up, which is what made the tiled kernel above
 // instruction-issue bound on small planes (ncu: 38 M warp instructions for C2).
 // ---------------------------------------------------------------------------------------------
-constexpr int kFlatThreads = 256;
-constexpr int kFlatJpt = 8;        // outputs per thread per chunk
+#ifndef EINCONV_FLAT_THREADS
+#define EINCONV_FLAT_THREADS 256
+#endif
+#ifndef EINCONV_FLAT_MINB
+#define EINCONV_FLAT_MINB 4
+#endif
+#ifndef EINCONV_FLAT_JPT
+#define EINCONV_FLAT_JPT 8
+#endif
+constexpr int kFlatThreads = EINCONV_FLAT_THREADS;
+constexpr int kFlatMinBlocks = EINCONV_FLAT_MINB;  // resident CTAs per SM the register budget allows
+constexpr int kFlatJpt = EINCONV_FLAT_JPT;         // outputs per thread per chunk (<= 8)
 constexpr int kFlatMaxTaps = 2048;
 
 template <int ND>
@@ -329,19 +339,47 @@ struct FlatParams {
   FastDiv ext_div[ND], out_div[ND], k_div[ND], chan_div, chunk_div;
 };
 
+#ifndef EINCONV_FLAT_EXP
+#define EINCONV_FLAT_EXP 0  // timing experiments only: 1 = no input loads, 2 = no output stores
+#endif
+#ifndef EINCONV_FLAT_STORE
+#define EINCONV_FLAT_STORE 0
+#endif
 template <typename T>
 __device__ __forceinline__ void store_stream1(T* dst, T val) {
-  if constexpr (sizeof(T) == 8) {
-    __stcs(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)val);
-  } else if constexpr (sizeof(T) == 4) {
-    __stcs(reinterpret_cast<unsigned int*>(dst), (unsigned int)val);
-  } else {
-    __stcs(reinterpret_cast<unsigned short*>(dst), (unsigned short)val);
+  using U = std::conditional_t<sizeof(T) == 8, unsigned long long,
+                               std::conditional_t<sizeof(T) == 4, unsigned int, unsigned short>>;
+#if EINCONV_FLAT_STORE == 0
+  __stcs(reinterpret_cast<U*>(dst), (U)val);
+#elif EINCONV_FLAT_STORE == 1
+  *reinterpret_cast<U*>(dst) = (U)val;
+#elif EINCONV_FLAT_STORE == 2
+  __stcg(reinterpret_cast<U*>(dst), (U)val);
+#else
+  __stwt(reinterpret_cast<U*>(dst), (U)val);
+#endif
+}
+
+// One chunk of NI x 256 consecutive outputs for every tap of the CTA: slots 0..NI-2 are valid for
+// all threads, slot NI-1 only where `last_on` (ragged end of the plane; its offset is 0 otherwise).
+template <typename T, int NI>
+__device__ __forceinline__ void flat_emit(const T* __restrict__ plane, const int* __restrict__ tap_off,
+                                          int n_taps, T* __restrict__ dst, int P,
+                                          const int (&off)[kFlatJpt], bool last_on) {
+#pragma unroll 2
+  for (int t = 0; t < n_taps; ++t, dst += P) {
+    const T* s = plane + tap_off[t];
+    T v[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) v[i] = s[off[i]];
+#pragma unroll
+    for (int i = 0; i < NI - 1; ++i) store_stream1<T>(dst + i * kFlatThreads, v[i]);
+    if (last_on) store_stream1<T>(dst + (NI - 1) * kFlatThreads, v[NI - 1]);
   }
 }
 
 template <typename T, int ND>
-__global__ void __launch_bounds__(kFlatThreads, 4)
+__global__ void __launch_bounds__(kFlatThreads, kFlatMinBlocks)
 unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
                    const __grid_constant__ FlatParams<ND> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -403,7 +441,9 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
           off += v * p.xs[d];
         }
         vals[u] = T(0);
+#if EINCONV_FLAT_EXP != 1
         if (ok) vals[u] = __ldg(src + off);
+#endif
         int carry = 0;
 #pragma unroll
         for (int d = ND - 1; d >= 1; --d) {
@@ -439,24 +479,31 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
       }
       off[i] = o;
     }
+    // slots 0 .. n_i-2 are valid for every thread, slot n_i-1 for threads with tid < P - jb - ...
+    const int left = p.P - jb;
+    const int n_i = min(kFlatJpt, (left + kFlatThreads - 1) / kFlatThreads);
+    const bool last_on = (n_i - 1) * kFlatThreads + tid < left;
     T* dst = dst_plane + jb;
-    if (jb + kChunk <= p.P) {
-      for (int t = t0; t < t1; ++t, dst += p.P) {
-        const T* s = plane + tap_off[t - t0];
-        T v[kFlatJpt];
-#pragma unroll
-        for (int i = 0; i < kFlatJpt; ++i) v[i] = s[off[i]];
-#pragma unroll
-        for (int i = 0; i < kFlatJpt; ++i) store_stream1<T>(dst + i * kFlatThreads, v[i]);
-      }
-    } else {
-      const int left = p.P - jb - tid;  // this thread's element i is valid iff i * 256 < left
-      for (int t = t0; t < t1; ++t, dst += p.P) {
-        const T* s = plane + tap_off[t - t0];
-#pragma unroll
-        for (int i = 0; i < kFlatJpt; ++i)
-          if (i * kFlatThreads < left) store_stream1<T>(dst + i * kFlatThreads, s[off[i]]);
-      }
+#if EINCONV_FLAT_EXP == 2
+    const int n_taps = (off[0] == 0x7fffffff) ? 1 : 0;
+#else
+    const int n_taps = t1 - t0;
+#endif
+    switch (n_i) {
+#define EINCONV_FLAT_CASE(NI)                                                         \
+  case NI:                                                                            \
+    if constexpr (NI <= kFlatJpt)                                                     \
+      flat_emit<T, NI>(plane, tap_off, n_taps, dst, p.P, off, last_on);               \
+    break;
+      EINCONV_FLAT_CASE(8)
+      EINCONV_FLAT_CASE(7)
+      EINCONV_FLAT_CASE(6)
+      EINCONV_FLAT_CASE(5)
+      EINCONV_FLAT_CASE(4)
+      EINCONV_FLAT_CASE(3)
+      EINCONV_FLAT_CASE(2)
+#undef EINCONV_FLAT_CASE
+      default: flat_emit<T, 1>(plane, tap_off, n_taps, dst, p.P, off, last_on); break;
     }
   }
 }
@@ -568,13 +615,13 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
 
   // CTAs per plane: split the taps while there are fewer CTAs than ~4 per SM
   int chunks = 1;
-  while (n_planes * chunks < 2ll * kNumSMs && chunks * 2 <= p.K) chunks *= 2;
+  while (n_planes * chunks < 4ll * kNumSMs && chunks * 2 <= p.K) chunks *= 2;
   if (const char* e = getenv("EINCONV_UNFOLD_CHUNKS")) chunks = std::max(1, std::min(p.K, atoi(e)));
   p.taps_per_chunk = ceil_div(p.K, chunks);
   p.tap_chunks = ceil_div(p.K, p.taps_per_chunk);
   if (p.taps_per_chunk > kFlatMaxTaps) return 0;
   const size_t smem = (((size_t)p.box * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4;
-  if (smem > 56 * 1024) return 0;  // keep >= 4 CTAs per SM resident
+  if (smem > 48 * 1024) return 0;  // keep >= 4 CTAs per SM resident
   const long long grid = n_planes * p.tap_chunks;
   if (grid >= (1ll << 31)) return 0;
   // Too little output per staged element: the tiled kernel amortises its staging better.
