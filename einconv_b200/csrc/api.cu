@@ -79,7 +79,7 @@ int make_dev_geom(const einconv_geom* g, DevGeom* out, bool need_c_out) {
 // ---------------------------------------------------------------------------------------------
 // kernel selection
 // ---------------------------------------------------------------------------------------------
-enum class Path { FFMA, DEPTHWISE, TENSOR, TMA };
+enum class Path { FFMA, DEPTHWISE, TENSOR, TMA, CONV_TMA };
 
 static int resolve_math(int dtype, int math) {
   if (math == EINCONV_MATH_AUTO)
@@ -98,6 +98,9 @@ static Path select_path(int op, const DevGeom& g, int dtype, int math, int kerne
     // networks it is slower than the CUDA-core kernel)
     if (op == EINCONV_OP_CONV_WEIGHT_VJP || op == EINCONV_OP_KFC)
       return tma::tma_supported(op, g, dtype) ? Path::TMA : Path::FFMA;
+    // forward / input VJP: TMA-fed implicit GEMM over a zero-padded channels-last copy (stride 1)
+    if ((op == EINCONV_OP_CONV_FWD || op == EINCONV_OP_CONV_INPUT_VJP) && ctma::supported(op, g, dtype, m))
+      return Path::CONV_TMA;
     if (tc_supported(op, g, dtype, m)) return Path::TENSOR;
   }
   return Path::FFMA;
@@ -167,6 +170,7 @@ const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype,
     case Path::DEPTHWISE: return "depthwise_stencil";
     case Path::TENSOR: return tc_kernel_name(op, g, dtype, resolve_math(dtype, math));
     case Path::TMA: return op == EINCONV_OP_KFC ? "tcgen05_tma_kfc" : "tcgen05_tma_wgrad";
+    case Path::CONV_TMA: return op == EINCONV_OP_CONV_FWD ? "tcgen05_tma_conv_fwd" : "tcgen05_tma_conv_input_vjp";
     default: return "ffma_gather_gemm";
   }
 }
@@ -180,6 +184,7 @@ int64_t einconv_workspace_bytes(int op, const einconv_geom* geom, int dtype, int
   if (path == Path::DEPTHWISE) return 0;
   if (path == Path::TENSOR) return tc_workspace_bytes(op, g, dtype, resolve_math(dtype, math));
   if (path == Path::TMA) return tma::tma_workspace_bytes(op, g, dtype);
+  if (path == Path::CONV_TMA) return ctma::workspace_bytes(op, g, dtype);
   switch (op) {
     case EINCONV_OP_KFAC_REDUCE: {
       DevGeom g2;
@@ -216,6 +221,8 @@ int einconv_conv_fwd(const void* x, const void* w, const void* bias, void* y, in
   cudaStream_t s = (cudaStream_t)stream;
   switch (select_path(EINCONV_OP_CONV_FWD, g, dtype, math, kernels)) {
     case Path::DEPTHWISE: return dw_conv_fwd(x, w, bias, y, dtype, g, s);
+    case Path::CONV_TMA:
+      return ctma::run(EINCONV_OP_CONV_FWD, x, w, bias, y, dtype, g, workspace, workspace_bytes, s);
     case Path::TENSOR:
       return tc_conv_fwd(x, w, bias, y, dtype, g, resolve_math(dtype, math), workspace, workspace_bytes, s);
     default: return ffma_conv_fwd(x, w, bias, y, dtype, g, s);
@@ -234,6 +241,8 @@ int einconv_conv_input_vjp(const void* w, const void* v, void* gx, int dtype,
   cudaStream_t s = (cudaStream_t)stream;
   switch (select_path(EINCONV_OP_CONV_INPUT_VJP, g, dtype, math, kernels)) {
     case Path::DEPTHWISE: return dw_conv_input_vjp(w, v, gx, dtype, g, s);
+    case Path::CONV_TMA:
+      return ctma::run(EINCONV_OP_CONV_INPUT_VJP, v, w, nullptr, gx, dtype, g, workspace, workspace_bytes, s);
     default: return ffma_conv_input_vjp(w, v, gx, dtype, g, s);
   }
 }

@@ -1,0 +1,661 @@
+// TMA-fed tcgen05 implicit GEMM for the convNd forward pass (expressions/convNd_forward.py:48-55)
+// and, with the roles of the channels swapped and the taps flipped, its input VJP
+// (expressions/convNd_input_vjp.py:53-60), for stride 1 and any N, dilation, padding, groups.
+//
+//   dst[b, g*Cd + n, o..] = sum_{c, k..} src[b, g*Cs + c, o.. + dil*k.. - pad..] * W[g][k..][n][c]
+//
+// The index pattern turns into a ONE-dimensional row shift.  A pre-pass writes `src` zero-padded and
+// channels-last, xp[b][p_0]..[p_{N-1}][c] with p_d = i_d + pad_d, i.e. a 2-d matrix [rows, channels].
+// Enumerate output positions by the flattened *padded* coordinate q = sum_d o_d * pitch_d
+// (pitch_d = row pitch of the padded grid): the input row of tap (k_0..k_{N-1}) is simply
+// q + shift(k), shift(k) = sum_d dil_d * k_d * pitch_d.  So the A operand of a tile of 128 consecutive
+// q for one tap is 128 consecutive rows of xp (K-major: channels are contiguous), fetched by 2-d TMA
+// boxes with no alignment constraint on the row coordinate, and all the taps of a group (e.g. the
+// whole 3x3 window) read overlapping row ranges of ONE staged slab: the slab is loaded once and each
+// tap's MMA descriptor just starts `shift` rows further down.  Rows with o_d >= O_d (the wrap-around
+// columns of the padded grid) are computed and dropped by the epilogue.
+//
+// Roles (192 threads, persistent CTAs, one per SM): warp 0 lane 0 issues TMA (A slabs, per-tap weight
+// tiles); warp 1 lane 0 issues tcgen05.mma (kind::tf32 / kind::f16, M = 128, N = BN <= 256, fp32
+// accumulators in TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1);
+// warps 2-5 drain TMEM, add the bias, cast and store channels-first (coalesced along positions).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <type_traits>
+
+#include "dispatch.cuh"
+#include "tc_ptx.cuh"
+
+namespace einconv {
+namespace ctma {
+
+using namespace ptx;
+
+constexpr int kThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kMaxGroups = 128;
+constexpr int kMaxTpg = 64;
+constexpr int kSmemBudget = 220 * 1024;
+
+struct Params {
+  // tiles: index = ((g * n_ntiles) + ntile) * n_mtiles + mtile
+  int n_mtiles, n_ntiles, groups;
+  long long total_tiles;
+  // K loop
+  int n_slices, cb_bytes, cb_elems;
+  int n_groups, tpg;
+  int slab_rows, box_rows, slab_bytes;
+  int bn, btile_bytes;
+  int sa, sb;
+  int cs;           // source channels per group (elements): TMA column of group g starts at g * cs
+  int np;           // padded N rows per (g, tap) in the packed weights
+  int taps;
+  int group_shift[kMaxGroups];  // row shift of the first tap of each group
+  int tap_row[kMaxTpg];         // row offset of tap j of a group inside the slab
+  // epilogue
+  int n_dims;
+  long long rows_total;  // B * Ptot
+  int batch;
+  FastDiv ptot_div;
+  FastDiv pitch_div[kMaxDims];
+  int out[kMaxDims];
+  int cd, cd_total;      // dst channels per group / in total
+  long long out_total;
+  const void* bias;
+  void* dst;
+};
+
+template <typename T> struct Elem;
+template <> struct Elem<float> { static constexpr bool TF32 = true; static constexpr int FMT = 2; };
+template <> struct Elem<__nv_bfloat16> { static constexpr bool TF32 = false; static constexpr int FMT = 1; };
+template <> struct Elem<__half> { static constexpr bool TF32 = false; static constexpr int FMT = 0; };
+
+struct Bars {
+  uint64_t full_a[4], empty_a[4];
+  uint64_t full_b[8], empty_b[8];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* a_ring = smem;
+  unsigned char* b_ring = smem + (size_t)p.sa * p.slab_bytes;
+  Bars* bars = reinterpret_cast<Bars*>(b_ring + (size_t)p.sb * p.btile_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.sa; ++i) { mbar_init(&bars->full_a[i], 1); mbar_init(&bars->empty_a[i], 1); }
+    for (int i = 0; i < p.sb; ++i) { mbar_init(&bars->full_b[i], 1); mbar_init(&bars->empty_b[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
+    fence_barrier_init();
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+  }
+  // TMEM: two accumulators of BN fp32 columns (power of two >= 32)
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)p.bn) tmem_cols <<= 1;
+  if (warp == 1) tmem_alloc(&bars->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int ia = 0, ib = 0;
+      uint32_t pa = 0, pb = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int mtile = (int)(tile % p.n_mtiles);
+        const long long rest = tile / p.n_mtiles;
+        const int ntile = (int)(rest % p.n_ntiles);
+        const int g = (int)(rest / p.n_ntiles);
+        const int q0 = mtile * kTileM;
+        for (int s = 0; s < p.n_slices; ++s) {
+          const int col_a = g * p.cs + s * p.cb_elems;
+          const int col_b = s * p.cb_elems;
+          for (int grp = 0; grp < p.n_groups; ++grp) {
+            mbar_wait(&bars->empty_a[ia], pa ^ 1);
+            mbar_expect_tx(&bars->full_a[ia], (uint32_t)(p.slab_rows * p.cb_bytes));
+            unsigned char* slab = a_ring + (size_t)ia * p.slab_bytes;
+            const int row0 = q0 + p.group_shift[grp];
+            for (int r = 0; r < p.slab_rows; r += p.box_rows)
+              tma_load_2d(slab + (size_t)r * p.cb_bytes, &map_a, &bars->full_a[ia], col_a, row0 + r);
+            if (++ia == p.sa) { ia = 0; pa ^= 1; }
+            for (int j = 0; j < p.tpg; ++j) {
+              const int tap = grp * p.tpg + j;
+              mbar_wait(&bars->empty_b[ib], pb ^ 1);
+              mbar_expect_tx(&bars->full_b[ib], (uint32_t)(p.bn * p.cb_bytes));
+              tma_load_2d(b_ring + (size_t)ib * p.btile_bytes, &map_b, &bars->full_b[ib], col_b,
+                          (g * p.taps + tap) * p.np + ntile * p.bn);
+              if (++ib == p.sb) { ib = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(Elem<T>::FMT, kTileM, p.bn);
+      const int k_steps = p.cb_bytes / 32;
+      int ia = 0, ib = 0;
+      uint32_t pa = 0, pb = 0;
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.bn;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.n_slices; ++s) {
+          for (int grp = 0; grp < p.n_groups; ++grp) {
+            mbar_wait(&bars->full_a[ia], pa);
+            const uint32_t slab = smem_u32(a_ring + (size_t)ia * p.slab_bytes);
+            for (int j = 0; j < p.tpg; ++j) {
+              mbar_wait(&bars->full_b[ib], pb);
+              tc_fence_after();
+              // The tap's 128 rows start tap_row rows into the slab.  The swizzle is a function of
+              // the absolute shared-memory address (measured: base-offset field 0 is right, setting
+              // it to row % 8 is wrong), so the descriptor may start at any row of a slab that TMA
+              // wrote with the same swizzle mode.
+              const uint32_t a_addr = slab + (uint32_t)(p.tap_row[j] * p.cb_bytes);
+              const uint32_t b_addr = smem_u32(b_ring + (size_t)ib * p.btile_bytes);
+              for (int k = 0; k < k_steps; ++k) {
+                umma<Elem<T>::TF32>(d_tmem, make_desc_kmajor(a_addr + k * 32, p.cb_bytes),
+                                    make_desc_kmajor(b_addr + k * 32, p.cb_bytes), idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(&bars->empty_b[ib]);
+              if (++ib == p.sb) { ib = 0; pb ^= 1; }
+            }
+            umma_commit(&bars->empty_a[ia]);
+            if (++ia == p.sa) { ia = 0; pa ^= 1; }
+          }
+        }
+        umma_commit(&bars->tmem_full[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    using acc_t = float;
+    const int quarter = warp & 3;  // TMEM lanes 32 * quarter .. + 31 are visible to this warp
+    T* dst = reinterpret_cast<T*>(p.dst);
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int mtile = (int)(tile % p.n_mtiles);
+      const long long rest = tile / p.n_mtiles;
+      const int ntile = (int)(rest % p.n_ntiles);
+      const int g = (int)(rest / p.n_ntiles);
+      // decode this thread's row
+      const long long row = (long long)mtile * kTileM + quarter * 32 + lane;
+      bool valid = row < p.rows_total;
+      uint32_t b = 0, rem = 0;
+      if (valid) p.ptot_div.divmod((uint32_t)row, b, rem);
+      long long oflat = 0;
+      for (int d = 0; d < p.n_dims; ++d) {
+        uint32_t od, r2;
+        p.pitch_div[d].divmod(rem, od, r2);
+        rem = r2;
+        valid = valid && (int)od < p.out[d];
+        oflat = oflat * p.out[d] + od;
+      }
+      const int n0 = ntile * p.bn;
+      T* dst_row = dst + ((long long)b * p.cd_total + (long long)g * p.cd + n0) * p.out_total + oflat;
+      const T* bias_g = bias ? bias + (long long)g * p.cd + n0 : nullptr;
+
+      mbar_wait_relaxed(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * (uint32_t)p.bn + ((uint32_t)(quarter * 32) << 16);
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16_nowait(taddr + c0, r);
+        tmem_ld_wait();
+        if (c0 + 16 >= p.bn) {
+          // all of this warp's accumulator reads are done: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < p.cd) {
+              acc_t v = __uint_as_float(r[j]);
+              if (bias_g) v += Cvt<T>::load(bias_g + c0 + j);
+              Cvt<T>::store(dst_row + (long long)(c0 + j) * p.out_total, v);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass 1: src [B, Ctot, S..] -> xp [B, P_0.., P_{N-1}, Cp], zero-padded, channels-last
+// ---------------------------------------------------------------------------------------------
+struct PackParams {
+  int n_dims;
+  int ctot, cp;
+  int S[kMaxDims], P[kMaxDims], pad[kMaxDims];
+  long long s_total;  // prod(S)
+  FastDiv outer_div[kMaxDims];  // / P[d] for d < n_dims - 1
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_channels_last_kernel(const T* __restrict__ src, T* __restrict__ xp,
+                                                                 const __grid_constant__ PackParams pp) {
+  __shared__ T tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int W = pp.n_dims - 1;
+  // blockIdx.x enumerates (b, p_0, .., p_{N-2})
+  uint32_t rem = blockIdx.x;
+  bool row_real = true;
+  long long src_off = 0, mul = pp.S[W];
+  for (int d = W - 1; d >= 0; --d) {
+    uint32_t q, r;
+    pp.outer_div[d].divmod(rem, q, r);
+    rem = q;
+    const int i = (int)r - pp.pad[d];
+    if (i < 0 || i >= pp.S[d]) row_real = false;
+    src_off += (long long)i * mul;
+    mul *= pp.S[d];
+  }
+  const long long b = rem;
+  const int c0 = blockIdx.y * 32;
+  const T* src_b = src + b * pp.ctot * pp.s_total + src_off;
+  T* dst_row = xp + (long long)blockIdx.x * pp.P[W] * pp.cp;
+  for (int w0 = 0; w0 < pp.P[W]; w0 += 32) {
+    const int iw = w0 + tx - pp.pad[W];
+    const bool col_real = row_real && iw >= 0 && iw < pp.S[W];
+#pragma unroll
+    for (int cy = ty; cy < 32; cy += 8) {
+      const int c = c0 + cy;
+      T v = T(0);
+      if (col_real && c < pp.ctot) v = src_b[(long long)c * pp.s_total + iw];
+      tile[cy][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int wy = ty; wy < 32; wy += 8) {
+      const int w = w0 + wy, c = c0 + tx;
+      if (w < pp.P[W] && c < pp.cp) dst_row[(long long)w * pp.cp + c] = tile[tx][wy];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass 2: weights -> wp [G][tap][Np][Cgp] (K-major rows of source channels), zero-padded.
+//   forward   : wp[g][t][n][c] = w[g*Cog + n, c, t]                   (n: output channel, c: input channel)
+//   input VJP : wp[g][t][n][c] = w[g*Cog + c, n, T-1-t]              (n: input channel,  c: output channel)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const T* __restrict__ w, T* __restrict__ wp, int groups,
+                                                           int taps, int np, int cgp, int cog, int cg,
+                                                           int transpose, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cgp);
+  long long r = idx / cgp;
+  const int n = (int)(r % np);
+  r /= np;
+  const int t = (int)(r % taps);
+  const int g = (int)(r / taps);
+  T v = T(0);
+  if (!transpose) {
+    if (n < cog && c < cg) v = w[(((long long)g * cog + n) * cg + c) * taps + t];
+  } else {
+    if (n < cg && c < cog) v = w[(((long long)g * cog + c) * cg + n) * taps + (taps - 1 - t)];
+  }
+  wp[idx] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(ptr);
+  });
+  return fn;
+}
+
+static int encode_2d(CUtensorMap* map, int dtype, const void* base, long long rows, long long cols,
+                     int box_cols, int box_rows, int swizzle_bytes) {
+  const int es = (int)elem_size(dtype);
+  CUtensorMapDataType dt = dtype == EINCONV_F32    ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+                           : dtype == EINCONV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                   : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * es};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t est[2] = {1, 1};
+  CUtensorMapSwizzle swz = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+  EncodeFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return EINCONV_ERR_CUDA;
+  }
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (2-d) failed with CUresult %d", (int)r);
+    return EINCONV_ERR_CUDA;
+  }
+  return EINCONV_OK;
+}
+
+// The convolution in "role" form: src channels Cs -> dst channels Cd, stride 1.
+struct Role {
+  int n_dims, batch, groups, cs, cd;
+  int S[kMaxDims], O[kMaxDims], K[kMaxDims], dil[kMaxDims], pad[kMaxDims];
+  int transpose;  // weights packed for the input VJP
+};
+
+static bool make_role(int op, const DevGeom& g, Role* r) {
+  r->n_dims = g.n_dims;
+  r->batch = g.batch;
+  r->groups = g.groups;
+  for (int d = 0; d < g.n_dims; ++d) {
+    if (g.stride[d] != 1) return false;
+    r->K[d] = g.k[d];
+    r->dil[d] = g.dil[d];
+  }
+  if (op == EINCONV_OP_CONV_FWD) {
+    r->cs = g.c_in_g;
+    r->cd = g.c_out_g;
+    r->transpose = 0;
+    for (int d = 0; d < g.n_dims; ++d) {
+      r->S[d] = g.in[d];
+      r->O[d] = g.out[d];
+      r->pad[d] = g.pad[d];
+    }
+    return true;
+  }
+  if (op == EINCONV_OP_CONV_INPUT_VJP) {
+    r->cs = g.c_out_g;
+    r->cd = g.c_in_g;
+    r->transpose = 1;
+    for (int d = 0; d < g.n_dims; ++d) {
+      r->S[d] = g.out[d];
+      r->O[d] = g.in[d];
+      r->pad[d] = g.dil[d] * (g.k[d] - 1) - g.pad[d];
+      if (r->pad[d] < 0) return false;
+    }
+    return true;
+  }
+  return false;
+}
+
+struct CPlan {
+  bool ok = false;
+  int es;
+  int cb_bytes, cb_elems, n_slices, cgp, cp;
+  int bn, n_ntiles, np;
+  int level, n_groups, tpg, taps;
+  int slab_rows, box_rows, slab_bytes, btile_bytes, sa, sb;
+  size_t smem;
+  long long P[kMaxDims], pitch[kMaxDims], ptot, rows_total;
+  int n_mtiles;
+  long long xp_bytes, wp_bytes;
+};
+
+static CPlan make_cplan(const Role& r, int dtype) {
+  CPlan pl;
+  pl.es = (int)elem_size(dtype);
+  if (dtype == EINCONV_F64) return pl;
+  const int es = pl.es, N = r.n_dims;
+  if (r.groups > 1 && ((long long)r.cs * es) % 16 != 0) return pl;  // TMA column start must be 16-byte aligned
+  // channel slice: widest swizzle span among those with the least padding
+  {
+    long long best_cost = -1;
+    for (int cb : {128, 64, 32}) {
+      const long long bytes = (long long)r.cs * es;
+      const long long cost = (bytes + cb - 1) / cb * cb;
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        pl.cb_bytes = cb;
+      }
+    }
+    pl.cb_elems = pl.cb_bytes / es;
+    pl.n_slices = (r.cs + pl.cb_elems - 1) / pl.cb_elems;
+    pl.cgp = pl.n_slices * pl.cb_elems;
+    const int per16 = 16 / es;
+    // row pitch of xp: all groups' channels, padded so that every slice box lies inside the row
+    const long long need = (long long)(r.groups - 1) * r.cs + pl.cgp;
+    pl.cp = (int)((need + per16 - 1) / per16 * per16);
+  }
+  pl.n_ntiles = (r.cd + 255) / 256;
+  pl.bn = ((r.cd + pl.n_ntiles - 1) / pl.n_ntiles + 15) / 16 * 16;
+  pl.np = pl.n_ntiles * pl.bn;
+  pl.btile_bytes = (pl.bn * pl.cb_bytes + 1023) / 1024 * 1024;
+
+  pl.ptot = 1;
+  for (int d = N - 1; d >= 0; --d) {
+    pl.P[d] = std::max<long long>(r.S[d] + r.pad[d], (long long)(r.O[d] - 1) + (long long)r.dil[d] * (r.K[d] - 1) + 1);
+    pl.pitch[d] = pl.ptot;
+    pl.ptot *= pl.P[d];
+    if (pl.ptot >= (1ll << 31)) return pl;
+  }
+  pl.rows_total = pl.ptot * r.batch;
+  long long max_shift = 0;
+  pl.taps = 1;
+  for (int d = 0; d < N; ++d) {
+    max_shift += (long long)r.dil[d] * (r.K[d] - 1) * pl.pitch[d];
+    pl.taps *= r.K[d];
+  }
+  if (pl.rows_total + max_shift + 4096 >= (1ll << 31)) return pl;
+  pl.n_mtiles = (int)((pl.rows_total + kTileM - 1) / kTileM);
+  pl.box_rows = std::min(256, 8192 / pl.cb_bytes);
+
+  // tap grouping: the trailing `level` dims of a group share one slab
+  for (int level = N; level >= 0; --level) {
+    long long tpg = 1, span = 0;
+    for (int d = N - level; d < N; ++d) {
+      tpg *= r.K[d];
+      span += (long long)r.dil[d] * (r.K[d] - 1) * pl.pitch[d];
+    }
+    if (tpg > kMaxTpg || pl.taps / tpg > kMaxGroups) continue;
+    const long long rows = (kTileM + span + pl.box_rows - 1) / pl.box_rows * pl.box_rows;
+    const long long slab = rows * pl.cb_bytes;
+    if (2 * slab + 2 * (long long)pl.btile_bytes > kSmemBudget) continue;
+    pl.level = level;
+    pl.tpg = (int)tpg;
+    pl.n_groups = pl.taps / pl.tpg;
+    pl.slab_rows = (int)rows;
+    pl.slab_bytes = (int)slab;  // multiple of 8 KB
+    pl.sa = (int)std::min<long long>(4, std::max<long long>(2, (kSmemBudget * 6 / 10) / slab));
+    while (pl.sa > 2 && (long long)pl.sa * slab + 2ll * pl.btile_bytes > kSmemBudget) --pl.sa;
+    pl.sb = (int)std::min<long long>(8, (kSmemBudget - (long long)pl.sa * slab) / pl.btile_bytes);
+    pl.ok = pl.sb >= 2;
+    if (pl.ok) break;
+  }
+  if (!pl.ok) return pl;
+  pl.smem = (size_t)pl.sa * pl.slab_bytes + (size_t)pl.sb * pl.btile_bytes + sizeof(Bars) + 64;
+  pl.xp_bytes = ((pl.rows_total * pl.cp * es) + 1023) / 1024 * 1024;
+  pl.wp_bytes = (((long long)r.groups * pl.taps * pl.np * pl.cgp * es) + 1023) / 1024 * 1024;
+  return pl;
+}
+
+bool supported(int op, const DevGeom& g, int dtype, int math) {
+  if (dtype == EINCONV_F64) return false;
+  if (dtype == EINCONV_F32 && math != EINCONV_MATH_TF32) return false;
+  if (getenv("EINCONV_NO_CONV_TMA")) return false;
+  Role r;
+  if (!make_role(op, g, &r)) return false;
+  return make_cplan(r, dtype).ok;
+}
+
+int64_t workspace_bytes(int op, const DevGeom& g, int dtype) {
+  Role r;
+  if (!make_role(op, g, &r)) return 0;
+  const CPlan pl = make_cplan(r, dtype);
+  if (!pl.ok) return 0;
+  return pl.xp_bytes + pl.wp_bytes + 1024;
+}
+
+template <typename T>
+static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w, const void* bias, void* dst,
+                 int dtype, void* workspace, cudaStream_t stream) {
+  // workspace may be arbitrarily aligned: TMA needs 16 bytes for the global address
+  uintptr_t base = ((uintptr_t)workspace + 1023) & ~(uintptr_t)1023;
+  T* xp = reinterpret_cast<T*>(base);
+  T* wp = reinterpret_cast<T*>(base + pl.xp_bytes);
+  const int N = r.n_dims;
+
+  // ---- pack the source
+  {
+    PackParams pp{};
+    pp.n_dims = N;
+    pp.ctot = r.groups * r.cs;
+    pp.cp = pl.cp;
+    pp.s_total = 1;
+    long long outer = r.batch;
+    for (int d = 0; d < N; ++d) {
+      pp.S[d] = r.S[d];
+      pp.P[d] = (int)pl.P[d];
+      pp.pad[d] = r.pad[d];
+      pp.s_total *= r.S[d];
+      if (d < N - 1) {
+        outer *= pl.P[d];
+        pp.outer_div[d] = FastDiv((uint32_t)pl.P[d]);
+      }
+    }
+    EINCONV_CHECK_ARG(outer < (1ll << 31), "conv_tma: too many rows to pack");
+    dim3 grid((unsigned)outer, (unsigned)((pl.cp + 31) / 32));
+    EINCONV_CHECK_ARG(grid.y < 65536, "conv_tma: too many channels");
+    pack_channels_last_kernel<T><<<grid, 256, 0, stream>>>((const T*)src, xp, pp);
+    EINCONV_CHECK_LAUNCH("pack_channels_last_kernel");
+  }
+  // ---- pack the weights
+  {
+    const long long total = (long long)r.groups * pl.taps * pl.np * pl.cgp;
+    const int cog = r.transpose ? r.cs : r.cd;
+    const int cg = r.transpose ? r.cd : r.cs;
+    pack_weights_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        (const T*)w, wp, r.groups, pl.taps, pl.np, pl.cgp, cog, cg, r.transpose, total);
+    EINCONV_CHECK_LAUNCH("pack_weights_kernel");
+  }
+  // ---- tensor maps
+  CUtensorMap map_a, map_b;
+  int st = encode_2d(&map_a, dtype, xp, pl.rows_total, pl.cp, pl.cb_elems, pl.box_rows, pl.cb_bytes);
+  if (st) return st;
+  st = encode_2d(&map_b, dtype, wp, (long long)r.groups * pl.taps * pl.np, pl.cgp, pl.cb_elems, pl.bn, pl.cb_bytes);
+  if (st) return st;
+
+  Params p{};
+  p.n_mtiles = pl.n_mtiles;
+  p.n_ntiles = pl.n_ntiles;
+  p.groups = r.groups;
+  p.total_tiles = (long long)pl.n_mtiles * pl.n_ntiles * r.groups;
+  p.n_slices = pl.n_slices;
+  p.cb_bytes = pl.cb_bytes;
+  p.cb_elems = pl.cb_elems;
+  p.n_groups = pl.n_groups;
+  p.tpg = pl.tpg;
+  p.slab_rows = pl.slab_rows;
+  p.box_rows = pl.box_rows;
+  p.slab_bytes = pl.slab_bytes;
+  p.bn = pl.bn;
+  p.btile_bytes = pl.btile_bytes;
+  p.sa = pl.sa;
+  p.sb = pl.sb;
+  p.cs = r.cs;
+  p.np = pl.np;
+  p.taps = pl.taps;
+  // shifts: tap t = (k_0, .., k_{N-1}) row-major; group = leading N - level coordinates
+  for (int t = 0; t < pl.taps; ++t) {
+    long long shift = 0;
+    int rem = t;
+    for (int d = N - 1; d >= 0; --d) {
+      const int kd = rem % r.K[d];
+      rem /= r.K[d];
+      shift += (long long)r.dil[d] * kd * pl.pitch[d];
+    }
+    if (t % pl.tpg == 0) p.group_shift[t / pl.tpg] = (int)shift;
+    if (t < pl.tpg) p.tap_row[t] = (int)shift;  // group 0: offsets relative to its first tap (shift 0)
+  }
+  p.n_dims = N;
+  p.rows_total = pl.rows_total;
+  p.batch = r.batch;
+  p.ptot_div = FastDiv((uint32_t)pl.ptot);
+  p.out_total = 1;
+  for (int d = 0; d < N; ++d) {
+    p.pitch_div[d] = FastDiv((uint32_t)pl.pitch[d]);
+    p.out[d] = r.O[d];
+    p.out_total *= r.O[d];
+  }
+  p.cd = r.cd;
+  p.cd_total = r.groups * r.cd;
+  p.bias = bias;
+  p.dst = dst;
+
+  auto kern = conv_tma_kernel<T>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tma)");
+  const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, kNumSMs);
+  kern<<<grid, kThreads, pl.smem, stream>>>(map_a, map_b, p);
+  EINCONV_CHECK_LAUNCH("conv_tma_kernel");
+  return EINCONV_OK;
+}
+
+int run(int op, const void* src, const void* w, const void* bias, void* dst, int dtype, const DevGeom& g,
+        void* workspace, int64_t workspace_bytes_given, cudaStream_t stream) {
+  Role r;
+  if (!make_role(op, g, &r)) {
+    set_error("conv_tma: unsupported geometry");
+    return EINCONV_ERR_UNSUPPORTED;
+  }
+  const CPlan pl = make_cplan(r, dtype);
+  if (!pl.ok) {
+    set_error("conv_tma: unsupported geometry");
+    return EINCONV_ERR_UNSUPPORTED;
+  }
+  if (!workspace || workspace_bytes_given < pl.xp_bytes + pl.wp_bytes + 1024) {
+    set_error("conv_tma: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes_given,
+              (long long)(pl.xp_bytes + pl.wp_bytes + 1024));
+    return EINCONV_ERR_WORKSPACE;
+  }
+  if ((long long)r.batch * r.groups * r.cd == 0 || pl.rows_total == 0) return EINCONV_OK;
+  switch (dtype) {
+    case EINCONV_F32: return run_t<float>(r, pl, src, w, bias, dst, dtype, workspace, stream);
+    case EINCONV_BF16: return run_t<__nv_bfloat16>(r, pl, src, w, bias, dst, dtype, workspace, stream);
+    case EINCONV_F16: return run_t<__half>(r, pl, src, w, bias, dst, dtype, workspace, stream);
+    default: set_error("conv_tma: unsupported dtype"); return EINCONV_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace ctma
+}  // namespace einconv

@@ -54,4 +54,12 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
                       double scale, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 }  // namespace tma
 
+// conv_tma.cu (TMA-fed tcgen05 implicit GEMM for forward / input VJP, stride 1)
+namespace ctma {
+bool supported(int op, const DevGeom& g, int dtype, int math);
+int64_t workspace_bytes(int op, const DevGeom& g, int dtype);
+int run(int op, const void* src, const void* w, const void* bias, void* dst, int dtype, const DevGeom& g,
+        void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+}  // namespace ctma
+
 }  // namespace einconv
