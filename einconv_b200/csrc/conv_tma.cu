@@ -43,17 +43,19 @@ struct Params {
   // tiles: index = ((g * n_ntiles) + ntile) * n_mtiles + mtile
   int n_mtiles, n_ntiles, groups;
   long long total_tiles;
-  // K loop
+  // K loop: n_slices channel slices x n_groups tap groups; one pipeline stage per (slice, group)
   int n_slices, cb_bytes, cb_elems;
   int n_groups, tpg;
   int slab_rows, box_rows, slab_bytes;
   int bn, btile_bytes;
-  int sa, sb;
+  int stage_bytes, n_stages;
+  int resident;     // every weight tile of one (group, n-tile) class stays in shared memory
+  int w_bytes;      // bytes of the resident weight region (0 when streaming)
   int cs;           // source channels per group (elements): TMA column of group g starts at g * cs
   int np;           // padded N rows per (g, tap) in the packed weights
   int taps;
   int group_shift[kMaxGroups];  // row shift of the first tap of each group
-  int tap_row[kMaxTpg];         // row offset of tap j of a group inside the slab
+  uint32_t tap_off16[kMaxTpg];  // (row offset of tap j of a group inside the slab) * cb_bytes / 16
   // epilogue
   int n_dims;
   long long rows_total;  // B * Ptot
@@ -72,29 +74,52 @@ template <> struct Elem<float> { static constexpr bool TF32 = true; static const
 template <> struct Elem<__nv_bfloat16> { static constexpr bool TF32 = false; static constexpr int FMT = 1; };
 template <> struct Elem<__half> { static constexpr bool TF32 = false; static constexpr int FMT = 0; };
 
+constexpr int kMaxStages = 6;
+
 struct Bars {
-  uint64_t full_a[4], empty_a[4];
-  uint64_t full_b[8], empty_b[8];
+  uint64_t full[kMaxStages], empty[kMaxStages];
   uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t w_full, w_empty;
   uint32_t tmem_base;
+  float bias[256];  // bias of the current (group, n-tile) class, zero where absent
 };
+
+// All MMAs of one pipeline stage: tpg taps x KS k-steps, issued by the elected thread.  Descriptors
+// differ only in the 14-bit start-address field (units of 16 bytes), which never carries out of its
+// field for shared-memory addresses: constant part + offsets, a few uniform adds per MMA.
+template <bool TF32, int KS>
+__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint64_t a_base, uint64_t b_base, uint32_t btile16,
+                                            const uint32_t* tap_off16, int tpg, uint32_t idesc,
+                                            uint32_t accumulate) {
+  for (int j = 0; j < tpg; ++j) {
+    // The tap's 128 rows start tap_row rows into the slab.  The swizzle is a function of the
+    // absolute shared-memory address (measured: base-offset field 0 is right, setting it to
+    // row % 8 is wrong), so a descriptor may start at any row of a slab TMA wrote with that swizzle.
+    const uint64_t a_desc = a_base + (uint64_t)tap_off16[j];
+    const uint64_t b_desc = b_base + (uint64_t)((uint32_t)j * btile16);
+#pragma unroll
+    for (int k = 0; k < KS; ++k) umma<TF32>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate | j | k);
+  }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* a_ring = smem;
-  unsigned char* b_ring = smem + (size_t)p.sa * p.slab_bytes;
-  Bars* bars = reinterpret_cast<Bars*>(b_ring + (size_t)p.sb * p.btile_bytes);
+  // [resident weights | stages: slab (+ the group's weight tiles when streaming) | barriers]
+  unsigned char* w_region = smem;
+  unsigned char* ring = smem + p.w_bytes;
+  Bars* bars = reinterpret_cast<Bars*>(ring + (size_t)p.n_stages * p.stage_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.sa; ++i) { mbar_init(&bars->full_a[i], 1); mbar_init(&bars->empty_a[i], 1); }
-    for (int i = 0; i < p.sb; ++i) { mbar_init(&bars->full_b[i], 1); mbar_init(&bars->empty_b[i], 1); }
+    for (int i = 0; i < p.n_stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
+    mbar_init(&bars->w_full, 1);
+    mbar_init(&bars->w_empty, 1);
     fence_barrier_init();
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
@@ -107,96 +132,135 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  // contiguous chunk of tiles per CTA (m-tile fastest): neighbouring tiles share halo rows in L2 and,
+  // in resident mode, the weights of their (group, n-tile) class
+  const long long tile_begin = p.total_tiles * blockIdx.x / gridDim.x;
+  const long long tile_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+  const int stages_per_tile = p.n_slices * p.n_groups;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int ia = 0, ib = 0;
-      uint32_t pa = 0, pb = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int mtile = (int)(tile % p.n_mtiles);
-        const long long rest = tile / p.n_mtiles;
-        const int ntile = (int)(rest % p.n_ntiles);
-        const int g = (int)(rest / p.n_ntiles);
-        const int q0 = mtile * kTileM;
-        for (int s = 0; s < p.n_slices; ++s) {
-          const int col_a = g * p.cs + s * p.cb_elems;
-          const int col_b = s * p.cb_elems;
-          for (int grp = 0; grp < p.n_groups; ++grp) {
-            mbar_wait(&bars->empty_a[ia], pa ^ 1);
-            mbar_expect_tx(&bars->full_a[ia], (uint32_t)(p.slab_rows * p.cb_bytes));
-            unsigned char* slab = a_ring + (size_t)ia * p.slab_bytes;
+    // (the whole warp runs the loops and waits; one elected lane issues)
+    int st = 0;
+    uint32_t ph = 0, pw = 0;
+    long long cur_class = -1;
+    const uint32_t stage_tx = (uint32_t)(p.slab_rows * p.cb_bytes) +
+                              (p.resident ? 0u : (uint32_t)(p.tpg * p.bn * p.cb_bytes));
+    for (long long tile = tile_begin; tile < tile_end; ++tile) {
+      const int mtile = (int)(tile % p.n_mtiles);
+      const long long cls = tile / p.n_mtiles;
+      const int ntile = (int)(cls % p.n_ntiles);
+      const int g = (int)(cls / p.n_ntiles);
+      const int q0 = mtile * kTileM;
+      const int wrow0 = g * p.taps * p.np + ntile * p.bn;
+      if (p.resident && cls != cur_class) {
+        // (re)load every weight tile of this class once the MMA warp is done with the old ones
+        cur_class = cls;
+        mbar_wait(&bars->w_empty, pw ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&bars->w_full, (uint32_t)(p.n_slices * p.taps * p.bn * p.cb_bytes));
+          for (int s = 0; s < p.n_slices; ++s)
+            for (int tap = 0; tap < p.taps; ++tap)
+              tma_load_2d(w_region + (size_t)(s * p.taps + tap) * p.btile_bytes, &map_b, &bars->w_full,
+                          s * p.cb_elems, wrow0 + tap * p.np);
+        }
+        __syncwarp();
+        pw ^= 1;
+      }
+      for (int s = 0; s < p.n_slices; ++s) {
+        for (int grp = 0; grp < p.n_groups; ++grp) {
+          mbar_wait(&bars->empty[st], ph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&bars->full[st], stage_tx);
+            unsigned char* stage = ring + (size_t)st * p.stage_bytes;
             const int row0 = q0 + p.group_shift[grp];
+            const int col_a = g * p.cs + s * p.cb_elems;
             for (int r = 0; r < p.slab_rows; r += p.box_rows)
-              tma_load_2d(slab + (size_t)r * p.cb_bytes, &map_a, &bars->full_a[ia], col_a, row0 + r);
-            if (++ia == p.sa) { ia = 0; pa ^= 1; }
-            for (int j = 0; j < p.tpg; ++j) {
-              const int tap = grp * p.tpg + j;
-              mbar_wait(&bars->empty_b[ib], pb ^ 1);
-              mbar_expect_tx(&bars->full_b[ib], (uint32_t)(p.bn * p.cb_bytes));
-              tma_load_2d(b_ring + (size_t)ib * p.btile_bytes, &map_b, &bars->full_b[ib], col_b,
-                          (g * p.taps + tap) * p.np + ntile * p.bn);
-              if (++ib == p.sb) { ib = 0; pb ^= 1; }
+              tma_load_2d(stage + (size_t)r * p.cb_bytes, &map_a, &bars->full[st], col_a, row0 + r);
+            if (!p.resident) {
+              unsigned char* bt = stage + p.slab_bytes;
+              for (int j = 0; j < p.tpg; ++j)
+                tma_load_2d(bt + (size_t)j * p.btile_bytes, &map_b, &bars->full[st], s * p.cb_elems,
+                            wrow0 + (grp * p.tpg + j) * p.np);
             }
           }
+          __syncwarp();
+          if (++st == p.n_stages) { st = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(Elem<T>::FMT, kTileM, p.bn);
-      const int k_steps = p.cb_bytes / 32;
-      int ia = 0, ib = 0;
-      uint32_t pa = 0, pb = 0;
-      uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+    // (the whole warp runs the loops and waits; one elected lane issues tcgen05.mma / commit)
+    const uint32_t idesc = make_idesc(Elem<T>::FMT, kTileM, p.bn);
+    const uint64_t desc_const = make_desc_kmajor(0, p.cb_bytes);
+    const uint32_t ring16 = smem_u32(ring) >> 4, w16 = smem_u32(w_region) >> 4;
+    const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, btile16 = (uint32_t)p.btile_bytes >> 4;
+    const uint32_t slab16 = (uint32_t)p.slab_bytes >> 4;
+    int st = 0;
+    uint32_t ph = 0, pw = 0;
+    uint32_t it = 0;
+    long long cur_class = -1;
+    for (long long tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const long long cls = tile / p.n_mtiles;
+      if (p.resident && cls != cur_class) {
+        cur_class = cls;
+        mbar_wait(&bars->w_full, pw);
+        pw ^= 1;
+      }
+      mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.bn;
+      for (int sg = 0; sg < stages_per_tile; ++sg) {
+        mbar_wait(&bars->full[st], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.bn;
-        uint32_t accumulate = 0;
-        for (int s = 0; s < p.n_slices; ++s) {
-          for (int grp = 0; grp < p.n_groups; ++grp) {
-            mbar_wait(&bars->full_a[ia], pa);
-            const uint32_t slab = smem_u32(a_ring + (size_t)ia * p.slab_bytes);
-            for (int j = 0; j < p.tpg; ++j) {
-              mbar_wait(&bars->full_b[ib], pb);
-              tc_fence_after();
-              // The tap's 128 rows start tap_row rows into the slab.  The swizzle is a function of
-              // the absolute shared-memory address (measured: base-offset field 0 is right, setting
-              // it to row % 8 is wrong), so the descriptor may start at any row of a slab that TMA
-              // wrote with the same swizzle mode.
-              const uint32_t a_addr = slab + (uint32_t)(p.tap_row[j] * p.cb_bytes);
-              const uint32_t b_addr = smem_u32(b_ring + (size_t)ib * p.btile_bytes);
-              for (int k = 0; k < k_steps; ++k) {
-                umma<Elem<T>::TF32>(d_tmem, make_desc_kmajor(a_addr + k * 32, p.cb_bytes),
-                                    make_desc_kmajor(b_addr + k * 32, p.cb_bytes), idesc, accumulate);
-                accumulate = 1;
-              }
-              umma_commit(&bars->empty_b[ib]);
-              if (++ib == p.sb) { ib = 0; pb ^= 1; }
-            }
-            umma_commit(&bars->empty_a[ia]);
-            if (++ia == p.sa) { ia = 0; pa ^= 1; }
+        if (elect_one()) {
+          const uint32_t stage_a16 = ring16 + (uint32_t)st * stage16;
+          const uint64_t a_base = desc_const + (uint64_t)stage_a16;
+          // resident: tile (slice, tap) of the class lives at (slice * taps + tap); sg = slice * n_groups + grp
+          const uint64_t b_base = desc_const + (uint64_t)(p.resident ? w16 + (uint32_t)(sg * p.tpg) * btile16
+                                                                      : stage_a16 + slab16);
+          const uint32_t accumulate = sg != 0;
+          switch (p.cb_bytes) {
+            case 128: issue_stage<Elem<T>::TF32, 4>(d_tmem, a_base, b_base, btile16, p.tap_off16, p.tpg, idesc, accumulate); break;
+            case 64: issue_stage<Elem<T>::TF32, 2>(d_tmem, a_base, b_base, btile16, p.tap_off16, p.tpg, idesc, accumulate); break;
+            default: issue_stage<Elem<T>::TF32, 1>(d_tmem, a_base, b_base, btile16, p.tap_off16, p.tpg, idesc, accumulate); break;
+          }
+          umma_commit(&bars->empty[st]);
+          if (sg + 1 == stages_per_tile) {
+            umma_commit(&bars->tmem_full[acc]);
+            // last tile of this class in my chunk: the resident weights may be replaced once these retire
+            if (p.resident && (tile + 1 == tile_end || (tile + 1) / p.n_mtiles != cls)) umma_commit(&bars->w_empty);
           }
         }
-        umma_commit(&bars->tmem_full[acc]);
+        __syncwarp();
+        if (++st == p.n_stages) { st = 0; ph ^= 1; }
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
-    using acc_t = float;
     const int quarter = warp & 3;  // TMEM lanes 32 * quarter .. + 31 are visible to this warp
+    const int etid = threadIdx.x - 64;
     T* dst = reinterpret_cast<T*>(p.dst);
     const T* bias = reinterpret_cast<const T*>(p.bias);
     uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    long long cur_class = -1;
+    for (long long tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int mtile = (int)(tile % p.n_mtiles);
-      const long long rest = tile / p.n_mtiles;
-      const int ntile = (int)(rest % p.n_ntiles);
-      const int g = (int)(rest / p.n_ntiles);
+      const long long cls = tile / p.n_mtiles;
+      const int ntile = (int)(cls % p.n_ntiles);
+      const int g = (int)(cls / p.n_ntiles);
+      const int n0 = ntile * p.bn;
+      if (cls != cur_class) {
+        // bias of this class into shared memory (the four epilogue warps only: named barrier 1)
+        cur_class = cls;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = etid; c < p.bn; c += 128)
+          bars->bias[c] = (bias && n0 + c < p.cd) ? Cvt<T>::load(bias + (long long)g * p.cd + n0 + c) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       // decode this thread's row
       const long long row = (long long)mtile * kTileM + quarter * 32 + lane;
       bool valid = row < p.rows_total;
@@ -210,9 +274,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         valid = valid && (int)od < p.out[d];
         oflat = oflat * p.out[d] + od;
       }
-      const int n0 = ntile * p.bn;
       T* dst_row = dst + ((long long)b * p.cd_total + (long long)g * p.cd + n0) * p.out_total + oflat;
-      const T* bias_g = bias ? bias + (long long)g * p.cd + n0 : nullptr;
 
       mbar_wait_relaxed(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -228,14 +290,16 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
         }
         if (valid) {
+          T* d0 = dst_row + (long long)c0 * p.out_total;
+          if (n0 + c0 + 16 <= p.cd) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < p.cd) {
-              acc_t v = __uint_as_float(r[j]);
-              if (bias_g) v += Cvt<T>::load(bias_g + c0 + j);
-              Cvt<T>::store(dst_row + (long long)(c0 + j) * p.out_total, v);
-            }
+            for (int j = 0; j < 16; ++j)
+              Cvt<T>::store(d0 + (long long)j * p.out_total, __uint_as_float(r[j]) + bars->bias[c0 + j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c0 + j < p.cd)
+                Cvt<T>::store(d0 + (long long)j * p.out_total, __uint_as_float(r[j]) + bars->bias[c0 + j]);
           }
         }
       }
@@ -425,7 +489,7 @@ struct CPlan {
   int cb_bytes, cb_elems, n_slices, cgp, cp;
   int bn, n_ntiles, np;
   int level, n_groups, tpg, taps;
-  int slab_rows, box_rows, slab_bytes, btile_bytes, sa, sb;
+  int slab_rows, box_rows, slab_bytes, btile_bytes, stage_bytes, n_stages, resident = 0, w_bytes = 0;
   size_t smem;
   long long P[kMaxDims], pitch[kMaxDims], ptot, rows_total;
   int n_mtiles;
@@ -480,8 +544,9 @@ static CPlan make_cplan(const Role& r, int dtype) {
   pl.n_mtiles = (int)((pl.rows_total + kTileM - 1) / kTileM);
   pl.box_rows = std::min(256, 8192 / pl.cb_bytes);
 
-  // tap grouping: the trailing `level` dims of a group share one slab
-  for (int level = N; level >= 0; --level) {
+  // tap grouping: the trailing `level` dims of a group share one slab; one pipeline stage holds the
+  // slab of a (slice, group) and, unless the weights are resident, the group's weight tiles
+  for (int level = N; level >= 0 && !pl.ok; --level) {
     long long tpg = 1, span = 0;
     for (int d = N - level; d < N; ++d) {
       tpg *= r.K[d];
@@ -489,21 +554,32 @@ static CPlan make_cplan(const Role& r, int dtype) {
     }
     if (tpg > kMaxTpg || pl.taps / tpg > kMaxGroups) continue;
     const long long rows = (kTileM + span + pl.box_rows - 1) / pl.box_rows * pl.box_rows;
-    const long long slab = rows * pl.cb_bytes;
-    if (2 * slab + 2 * (long long)pl.btile_bytes > kSmemBudget) continue;
+    const long long slab = rows * pl.cb_bytes;  // multiple of 8 KB
     pl.level = level;
     pl.tpg = (int)tpg;
     pl.n_groups = pl.taps / pl.tpg;
     pl.slab_rows = (int)rows;
-    pl.slab_bytes = (int)slab;  // multiple of 8 KB
-    pl.sa = (int)std::min<long long>(4, std::max<long long>(2, (kSmemBudget * 6 / 10) / slab));
-    while (pl.sa > 2 && (long long)pl.sa * slab + 2ll * pl.btile_bytes > kSmemBudget) --pl.sa;
-    pl.sb = (int)std::min<long long>(8, (kSmemBudget - (long long)pl.sa * slab) / pl.btile_bytes);
-    pl.ok = pl.sb >= 2;
-    if (pl.ok) break;
+    pl.slab_bytes = (int)slab;
+    // weights resident in shared memory if every tile of one (group, n-tile) class fits next to two slabs
+    const long long w_bytes = (long long)pl.taps * pl.n_slices * pl.btile_bytes;
+    if (!getenv("EINCONV_CTMA_STREAM") && w_bytes + 2 * slab <= kSmemBudget) {
+      pl.resident = 1;
+      pl.w_bytes = (int)w_bytes;
+      pl.stage_bytes = (int)slab;
+      pl.n_stages = (int)std::min<long long>(kMaxStages, (kSmemBudget - w_bytes) / slab);
+      pl.ok = true;
+      break;
+    }
+    const long long stage = slab + tpg * pl.btile_bytes;
+    if (2 * stage > kSmemBudget) continue;
+    pl.resident = 0;
+    pl.w_bytes = 0;
+    pl.stage_bytes = (int)stage;
+    pl.n_stages = (int)std::min<long long>(kMaxStages, kSmemBudget / stage);
+    pl.ok = true;
   }
   if (!pl.ok) return pl;
-  pl.smem = (size_t)pl.sa * pl.slab_bytes + (size_t)pl.sb * pl.btile_bytes + sizeof(Bars) + 64;
+  pl.smem = (size_t)pl.w_bytes + (size_t)pl.n_stages * pl.stage_bytes + sizeof(Bars) + 64;
   pl.xp_bytes = ((pl.rows_total * pl.cp * es) + 1023) / 1024 * 1024;
   pl.wp_bytes = (((long long)r.groups * pl.taps * pl.np * pl.cgp * es) + 1023) / 1024 * 1024;
   return pl;
@@ -590,8 +666,10 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
   p.slab_bytes = pl.slab_bytes;
   p.bn = pl.bn;
   p.btile_bytes = pl.btile_bytes;
-  p.sa = pl.sa;
-  p.sb = pl.sb;
+  p.stage_bytes = pl.stage_bytes;
+  p.n_stages = pl.n_stages;
+  p.resident = pl.resident;
+  p.w_bytes = pl.w_bytes;
   p.cs = r.cs;
   p.np = pl.np;
   p.taps = pl.taps;
@@ -605,7 +683,8 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
       shift += (long long)r.dil[d] * kd * pl.pitch[d];
     }
     if (t % pl.tpg == 0) p.group_shift[t / pl.tpg] = (int)shift;
-    if (t < pl.tpg) p.tap_row[t] = (int)shift;  // group 0: offsets relative to its first tap (shift 0)
+    // group 0: offsets relative to its first tap (shift 0)
+    if (t < pl.tpg) p.tap_off16[t] = (uint32_t)((shift * pl.cb_bytes) >> 4);
   }
   p.n_dims = N;
   p.rows_total = pl.rows_total;

@@ -12,6 +12,18 @@ namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// One lane of a converged warp (for single-thread issue of TMA / tcgen05 from warp-uniform code:
+// keeping the surrounding control flow uniform lets the compiler hold descriptors and barrier
+// addresses in uniform registers instead of broadcasting them per instruction).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
