@@ -332,7 +332,42 @@ def to_value(wl, ms, n_units=1):
     return wl.work() / (ms * 1e-3)  # factors/s: the sweep is shared by all ranks
 
 
+# ncu --set full captures of the dominant kernel of each workload (summaries committed under profiles/)
+NCU_PROFILES = {
+    "unfold": "profiles/r01_unfold_c2_ncu_full_v8_flat.txt",
+    "depthwise": "profiles/r01_depthwise_c3_ncu_full_v2.txt",
+    "conv_fwd": "profiles/r01_conv_fwd_c1_ncu_full_v2.txt",
+    "weight_vjp": "profiles/r01_wgrad_c4_ncu_full_v1_before.txt",
+}
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the workload's dominant kernel,
+    read from the committed ncu summary; None if there is no capture."""
+    rel = NCU_PROFILES.get(workload)
+    if not rel or not (ROOT / rel).exists():
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, seen = 0.0, 0
+    for line in (ROOT / rel).read_text().splitlines():
+        parts = line.split()
+        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and seen < 2:
+            total += float(parts[1]) * scale.get(parts[2], 1.0)
+            seen += 1
+    return dict(bytes=total, source=rel) if seen == 2 else None
+
+
 def roofline(wl, ms_kernel, pk):
+    r = _roofline(wl, ms_kernel, pk)
+    key = next((k for k, c in WORKLOADS.items() if isinstance(wl, c)), None)
+    t = ncu_traffic(key)
+    if t:
+        r["traffic"] = t["bytes"]
+        r["traffic_source"] = t["source"] + " (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+    return r
+
+
+def _roofline(wl, ms_kernel, pk):
     if wl.bound == "hbm":
         achieved = wl.work() / (ms_kernel * 1e-3) / 1e9
         return dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"],

@@ -512,9 +512,16 @@ def test_tc_kfc(case, mode):
 def test_tc_kernels_are_selected():
     g = nat.make_geom(2, 1, 32, 48, (20, 20), (3, 3), (1, 1), (1, 1), (1, 1), (20, 20))
     lib = nat.lib()
-    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_fwd_f16"
-    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 0, nat.MATH_TF32, 0) == b"tcgen05_fwd_tf32"
+    # stride 1: TMA-fed implicit GEMM over the padded channels-last copy (forward and input VJP)
+    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_conv_fwd"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 0, nat.MATH_TF32, 0) == b"tcgen05_tma_conv_fwd"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_INPUT_VJP, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_conv_input_vjp"
     assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 0, nat.MATH_FP32, 0) == b"ffma_gather_gemm"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 1, nat.MATH_AUTO, 1) == b"ffma_gather_gemm"
+    # stride 2: software-gather tcgen05 kernel
+    gs = nat.make_geom(2, 1, 32, 48, (20, 20), (3, 3), (2, 2), (1, 1), (1, 1), (10, 10))
+    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, gs, 1, nat.MATH_AUTO, 0) == b"tcgen05_fwd_f16"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, gs, 0, nat.MATH_TF32, 0) == b"tcgen05_fwd_tf32"
     # reduction networks: TMA-fed kernel (aligned shifted copies make any row length usable)
     assert lib.einconv_selected_kernel(nat.OP_KFC, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_kfc"
     assert lib.einconv_selected_kernel(nat.OP_KFC, g, 0, nat.MATH_TF32, 0) == b"tcgen05_tma_kfc"
@@ -523,6 +530,77 @@ def test_tc_kernels_are_selected():
     assert lib.einconv_selected_kernel(nat.OP_KFC, g24, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_kfc"
     assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_wgrad"
     assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 1, nat.MATH_AUTO, 1) == b"ffma_gather_gemm"
+
+
+# ---- TMA-fed implicit GEMM for forward / input VJP (csrc/conv_tma.cu): stride 1, any N --------------
+CTMA_CASES = [
+    ((2, 32, 20, 20), (48, 32, 3, 3), dict(padding=1)),
+    ((2, 3, 30, 31), (20, 3, 7, 7), dict(padding=3)),                        # C_in = 3: 32-byte slices, 49 taps
+    ((2, 24, 19, 19), (16, 12, 5, 3), dict(padding=(2, 0), dilation=(1, 2), groups=2)),
+    ((3, 16, 50), (24, 16, 5), dict(padding=2)),                             # N = 1
+    ((2, 16, 9, 10, 11), (40, 16, 3, 3, 3), dict(padding=2, dilation=2)),    # N = 3, dilated
+    ((1, 8, 5, 6, 7, 6), (16, 8, 2, 3, 2, 3), dict(padding=1)),              # N = 4 (tap groups: level < N)
+    ((2, 300, 7, 7), (520, 300, 3, 3), dict(padding=1)),                     # 3 n-tiles, 5 channel slices, streaming
+    ((2, 16, 9, 8), (16, 16, 4, 4), dict(padding="same")),                   # asymmetric padding
+    ((2, 8, 12, 12), (8, 8, 3, 3), dict(padding=0)),
+    ((1, 64, 56, 56), (64, 64, 3, 3), dict(padding=1)),                      # C1 shape, one sample
+    ((2, 64, 14, 14), (256, 64, 1, 1), dict()),                              # 1x1, BN = 256
+]
+CTMA_IDS = ["x".join(map(str, c[0])) + "-w" + "x".join(map(str, c[1])) for c in CTMA_CASES]
+
+
+@pytest.fixture(params=["auto", "stream"])
+def ctma_weights(request, monkeypatch):
+    """Weights resident in shared memory when they fit ("auto") or always streamed per stage."""
+    if request.param == "stream":
+        monkeypatch.setenv("EINCONV_CTMA_STREAM", "1")
+    else:
+        monkeypatch.delenv("EINCONV_CTMA_STREAM", raising=False)
+    return request.param
+
+
+@pytest.mark.parametrize("case", CTMA_CASES, ids=CTMA_IDS)
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "tf32"])
+def test_conv_tma_forward_and_input_vjp(case, mode, ctma_weights):
+    """Same tolerances as the other tensor-core tests: against the fp64 oracle on the same rounded
+    inputs, max|d| <= 2^-7 (bf16) / 2^-10 (fp16) / 1e-3 (TF32) of max|ref|."""
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "tf32": torch.float32}[mode]
+    tol = {"bf16": 2.0**-7, "fp16": 2.0**-10, "tf32": 1e-3}[mode]
+    x, w, b, kw = _tc_inputs(case, dtype)
+    groups = kw.get("groups", 1)
+    N = x.dim() - 2
+    name = evaluator.selected_kernel  # noqa: F841 (kept for debugging sessions)
+    want = direct.conv_forward(x.double().numpy(), w.double().numpy(), b.double().numpy(), **kw)
+    torch.manual_seed(1)
+    v = (torch.rand(*want.shape) - 0.5).to(dtype)
+    want_gx = direct.conv_input_vjp(
+        w.double().numpy(), v.double().numpy(), tuple(x.shape[2:]), **kw
+    )
+    evaluator.set_fp32_math("tf32" if mode == "tf32" else "auto")
+    try:
+        got = convNd(x.to(DEV), w.to(DEV), b.to(DEV), **kw)
+        gx = evaluator.conv_input_vjp_raw(
+            w.to(DEV), v.to(DEV), tuple(x.shape[2:]), kw.get("stride", 1), kw.get("padding", 0),
+            kw.get("dilation", 1), groups,
+        )
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, tol, f"conv_tma fwd {mode}")
+    _rel_to_max(gx, want_gx, tol, f"conv_tma input vjp {mode}")
+
+
+def test_conv_tma_is_used_by_autograd_and_matches_torch():
+    torch.manual_seed(0)
+    x = torch.randn(4, 32, 18, 18, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    w = (torch.randn(48, 32, 3, 3, device=DEV) / 17).to(torch.bfloat16).requires_grad_(True)
+    y = convNd(x, w, None, padding=1)
+    ref = F.conv2d(x.float(), w.float(), None, padding=1)
+    _rel_to_max(y, ref.detach().cpu().numpy(), 2.0**-7, "fwd vs torch")
+    g = torch.randn_like(y)
+    gx, gw = torch.autograd.grad(y, (x, w), g)
+    rx, rw = torch.autograd.grad(ref, (x, w), g.float())
+    _rel_to_max(gx, rx.detach().double().cpu().numpy(), 2.0**-7, "gx vs torch")
+    _rel_to_max(gw, rw.detach().double().cpu().numpy(), 2.0**-6, "gw vs torch")
 
 
 # ---- TMA-fed reduction kernels: geometries whose rows are 16-byte aligned ---------------------------
