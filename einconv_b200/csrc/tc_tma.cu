@@ -186,6 +186,7 @@ struct Params {
   int kw_c0[kMaxKw];
   int v_map, v_c0;                     // tensor map index of the cotangent and its coordinate margin
   int is_kfc;
+  int tri;                             // KFC: only tiles on or above the diagonal are computed (K is symmetric)
   int debug;                           // bring-up switch (EINCONV_TMA_DEBUG): 1 = no TMA/MMA, 2 = TMA only
   float* partial;                      // [groups][k_splits][Mp][Np]
 };
@@ -224,8 +225,18 @@ tma_reduce_gemm_kernel(const CUtensorMap* __restrict__ maps, const __grid_consta
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
-  const int m_tile = blockIdx.x;
-  const int n_tile = blockIdx.y;
+  int m_tile = blockIdx.x;
+  int n_tile = blockIdx.y;
+  if (p.tri) {
+    // blockIdx.x enumerates the tiles (i, j >= i) of the symmetric factor row by row
+    int rest = blockIdx.x, i = 0;
+    while (rest >= p.m_tiles - i) {
+      rest -= p.m_tiles - i;
+      ++i;
+    }
+    m_tile = i;
+    n_tile = i + rest;
+  }
   const int grp = blockIdx.z / p.k_splits;
   const int split = blockIdx.z - grp * p.k_splits;
   const int kb_per_split = (p.k_blocks + p.k_splits - 1) / p.k_splits;
@@ -486,6 +497,21 @@ __global__ void __launch_bounds__(256) tma_finish_kernel(const float* __restrict
   if (p.is_kfc) {
     const int a = (int)(rem / A), a2 = (int)(rem - (long long)a * A);
     prow = tile_row(a);
+    if (p.tri) {
+      // columns are tiled exactly like the rows; tiles below the diagonal are read from their mirror
+      int r = prow, c = tile_row(a2);
+      if (r / kTileM > c / kTileM) {
+        const int t = r;
+        r = c;
+        c = t;
+      }
+      const long long tile = (long long)p.Mp * p.Np;
+      const float* src = partial + (long long)grp * p.k_splits * tile + (long long)r * p.Np + c;
+      float s = 0.f;
+      for (int k = 0; k < p.k_splits; ++k) s += src[(long long)k * tile];
+      Cvt<T>::store(out + idx, s * scale);
+      return;
+    }
     // KFC column tiles hold (BN / CB) taps each
     const int ci = a2 / Kt, tap = a2 - ci * Kt;
     const int cblock = ci / p.CB, cl = ci - cblock * p.CB;
@@ -529,6 +555,7 @@ struct Plan {
   int BW, BH, BD, PB, kpos;
   int CB, taps_per_tile, tap_groups, c_blocks;
   int bn, m_tiles, n_tiles, k_blocks, k_splits;
+  bool tri = false;  // KFC: compute only the tiles on or above the diagonal
   int n_wt, n_ht, n_dt;
   long long Mp, Np;
   // shifted copies of the input (and an aligned copy of the cotangent when its rows are not
@@ -624,7 +651,9 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
   pl.Np = (long long)pl.n_tiles * pl.bn;
   // split-K so that the grid is exactly one wave of resident CTAs (a partial second wave would
   // double the run time): resident = 148 SMs x CTAs that fit in shared memory
-  const long long tiles = (long long)pl.m_tiles * pl.n_tiles * g.groups;
+  pl.tri = (op == EINCONV_OP_KFC) && !getenv("EINCONV_KFC_FULL");
+  const long long tiles =
+      (pl.tri ? (long long)pl.m_tiles * (pl.m_tiles + 1) / 2 : (long long)pl.m_tiles * pl.n_tiles) * g.groups;
   const int stage_bytes = (kTileM + pl.bn) * kRowBytes;
   const int ctas_per_sm = std::max(1, (227 * 1024) / (kStages * stage_bytes + 2048));
   const long long resident = (long long)kNumSMs * ctas_per_sm;
@@ -722,6 +751,7 @@ static int launch(const CUtensorMap* maps, const Params& p, const Plan& pl, int 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tma_reduce_gemm)");
   dim3 grid(pl.m_tiles, pl.n_tiles, groups * pl.k_splits);
+  if (pl.tri) grid = dim3(pl.m_tiles * (pl.m_tiles + 1) / 2, 1, groups * pl.k_splits);
   kern<<<grid, kThreads, S::total, stream>>>(maps, p);
   EINCONV_CHECK_LAUNCH("tma_reduce_gemm_kernel");
   return EINCONV_OK;
@@ -827,6 +857,7 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   p.c_blocks = pl.c_blocks; p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles;
   p.Mp = (int)pl.Mp; p.Np = (int)pl.Np;
   p.is_kfc = kfc ? 1 : 0;
+  p.tri = pl.tri ? 1 : 0;
   {
     const char* dbg = getenv("EINCONV_TMA_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
