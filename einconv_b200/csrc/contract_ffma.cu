@@ -677,36 +677,58 @@ __global__ void __launch_bounds__(256) window_sum_warp_kernel(const T* __restric
   // walk the rows; outer coordinates advance like an odometer
   int coord[kMaxDims];
   for (int d = 0; d < W; ++d) coord[d] = 0;
-  for (int row = 0; row < n_rows; ++row) {
-    // outer tap combinations this row belongs to: bit (k_0, .., k_{W-1}) flattened, last fastest
-    unsigned mask = 1u;
+  // R rows per iteration so that R * MAXJ independent loads are in flight per lane (one row at a
+  // time left the warp latency-bound at ~0.9 TB/s)
+  constexpr int R = 4;
+  int kprev[kMaxDims];
+  {
+    int t = 1;
     for (int d = 0; d < W; ++d) {
-      const unsigned md = member[table_off[d] + coord[d]];
-      // mask_new[(ko_prev * K_d) + k] = mask[ko_prev] & md[k]
-      unsigned out = 0;
-      int kprev_total = 1;
-      for (int dd = 0; dd < d; ++dd) kprev_total *= g.k[dd];
-      for (int kp = 0; kp < kprev_total; ++kp)
-        if (mask >> kp & 1u) out |= md << (kp * g.k[d]);
-      mask = out;
+      kprev[d] = t;
+      t *= g.k[d];
     }
-    if (mask != 0u) {
-      const T* rp = src + (long long)row * in_w;
+  }
+  for (int row0 = 0; row0 < n_rows; row0 += R) {
+    unsigned masks[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      // outer tap combinations this row belongs to: bit (k_0, .., k_{W-1}) flattened, last fastest
+      unsigned mask = 0u;
+      if (row0 + r < n_rows) {
+        mask = 1u;
+        for (int d = 0; d < W; ++d) {
+          const unsigned md = member[table_off[d] + coord[d]];
+          // mask_new[(ko_prev * K_d) + k] = mask[ko_prev] & md[k]
+          unsigned out = 0;
+          for (int kp = 0; kp < kprev[d]; ++kp)
+            if (mask >> kp & 1u) out |= md << (kp * g.k[d]);
+          mask = out;
+        }
+        for (int d = W - 1; d >= 0; --d) {
+          if (++coord[d] < g.in[d]) break;
+          coord[d] = 0;
+        }
+      }
+      masks[r] = mask;
+    }
+    acc_t v[R][MAXJ];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const T* rp = src + (long long)(row0 + r) * in_w;
 #pragma unroll
       for (int j = 0; j < MAXJ; ++j) {
         const int c = lane + 32 * j;
-        if (c < in_w) {
-          const acc_t v = Cvt<T>::load(rp + c);
-#pragma unroll
-          for (int ko = 0; ko < MAXKO; ++ko)
-            if (mask >> ko & 1u) acc[j][ko] += v;
-        }
+        v[r][j] = acc_t(0);
+        if (masks[r] != 0u && c < in_w) v[r][j] = Cvt<T>::load(rp + c);
       }
     }
-    for (int d = W - 1; d >= 0; --d) {
-      if (++coord[d] < g.in[d]) break;
-      coord[d] = 0;
-    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j)
+#pragma unroll
+        for (int ko = 0; ko < MAXKO; ++ko)
+          if (masks[r] >> ko & 1u) acc[j][ko] += v[r][j];
   }
 
   // apply column membership and reduce across lanes
