@@ -15,6 +15,7 @@
 //   KFAC-red.   u[b,(ci,k)] = sum_o X~[(b,o),(ci,k)] ;  C = sum_b u u^T              expressions/convNd_kfac_reduce.py:77-92
 // where X~ is the (virtual) unfolded input and V~ the (virtual) scattered cotangent.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -757,6 +758,87 @@ __global__ void __launch_bounds__(256) window_sum_warp_kernel(const T* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Window sums, flat variant for planes that fit a shared table (in_total <= 12288) and <= 32 taps:
+// a per-CTA table holds, for every input position of a plane, the bit mask of the taps whose window
+// contains it; a warp then streams a whole plane as a flat array (consecutive lanes = consecutive
+// elements, 4 x 32 loads in flight), accumulates one register per tap and reduces with shuffles.
+// Persistent CTAs amortise the table over many planes.  No atomics: the result is deterministic.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int KT>
+__global__ void __launch_bounds__(256) window_sum_flat_kernel(const T* __restrict__ x,
+                                                              typename Cvt<T>::acc_t* __restrict__ u,
+                                                              const __grid_constant__ DevGeom g,
+                                                              int planes, int transposed) {
+  using acc_t = typename Cvt<T>::acc_t;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned* table = reinterpret_cast<unsigned*>(smem_raw);
+  const int n = g.in_total;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    int i[kMaxDims];
+    uint32_t rem = (uint32_t)idx;
+    for (int d = g.n_dims - 1; d >= 0; --d) {
+      uint32_t q, r;
+      g.in_div[d].divmod(rem, q, r);
+      i[d] = (int)r;
+      rem = q;
+    }
+    unsigned mask = 0;
+    for (int t = 0; t < g.k_total; ++t) {
+      uint32_t krem = (uint32_t)t;
+      bool ok = true;
+      for (int d = g.n_dims - 1; d >= 0; --d) {
+        uint32_t q, kd;
+        g.k_div[d].divmod(krem, q, kd);
+        krem = q;
+        ok = ok && tap_member(g, d, i[d], (int)kd);
+      }
+      if (ok) mask |= 1u << t;
+    }
+    table[idx] = mask;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int chans = g.groups * g.c_in_g;
+  constexpr int U = 4;
+  for (int plane = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); plane < planes;
+       plane += gridDim.x * warps_per_cta) {
+    const T* src = x + (long long)plane * n;
+    acc_t acc[KT];
+#pragma unroll
+    for (int t = 0; t < KT; ++t) acc[t] = acc_t(0);
+    for (int base = 0; base < n; base += 32 * U) {
+      acc_t v[U];
+      unsigned m[U];
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        const int idx = base + q * 32 + lane;
+        m[q] = idx < n ? table[idx] : 0u;
+        v[q] = acc_t(0);
+        if (m[q] != 0u) v[q] = Cvt<T>::load(src + idx);
+      }
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+#pragma unroll
+        for (int t = 0; t < KT; ++t)
+          if (m[q] >> t & 1u) acc[t] += v[q];
+    }
+    const int b = plane / chans, c = plane - b * chans;
+#pragma unroll
+    for (int t = 0; t < KT; ++t) {
+      if (t < g.k_total) {
+        acc_t s = acc[t];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0)
+          u[transposed ? ((long long)c * g.k_total + t) * g.batch + b : (long long)plane * g.k_total + t] = s;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
 static int pick_splits(long long tiles, int k_chunks) {
@@ -937,6 +1019,24 @@ int kfac_window_sums(const void* x, void* u_out, int dtype, const DevGeom& g, in
     for (int d = 0; d <= W; ++d) {
       table += g.in[d];
       masks_fit = masks_fit && g.k[d] <= 32;
+    }
+    if (g.in_total <= 12288 && g.k_total <= 32 && !getenv("EINCONV_WINDOW_SUM_ROWS")) {
+      const size_t smem = (size_t)g.in_total * 4;
+      const unsigned blocks = (unsigned)std::min<long long>((planes + 7) / 8, 4ll * kNumSMs);
+      auto launch_flat = [&](auto kt) -> int {
+        constexpr int KT = decltype(kt)::value;
+        auto kern = window_sum_flat_kernel<T, KT>;
+        if (smem > 40 * 1024) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(window_sum_flat)");
+        }
+        kern<<<blocks, 256, smem, stream>>>((const T*)x, u, g, planes, transposed);
+        EINCONV_CHECK_LAUNCH("window_sum_flat_kernel");
+        return EINCONV_OK;
+      };
+      if (g.k_total == 1) return launch_flat(std::integral_constant<int, 1>{});
+      if (g.k_total <= 9) return launch_flat(std::integral_constant<int, 9>{});
+      return launch_flat(std::integral_constant<int, 32>{});
     }
     if (g.in[W] <= 32 * 8 && k_outer <= 9 && masks_fit && table * 4 <= 40 * 1024) {
       const unsigned blocks = (unsigned)((planes + 7) / 8);
