@@ -657,9 +657,29 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
   const int stage_bytes = (kTileM + pl.bn) * kRowBytes;
   const int ctas_per_sm = std::max(1, (227 * 1024) / (kStages * stage_bytes + 2048));
   const long long resident = (long long)kNumSMs * ctas_per_sm;
-  long long want = tiles >= resident ? 1 : resident / tiles;
-  long long cap = std::max(1, pl.k_blocks / 8);
-  pl.k_splits = (int)std::max<long long>(1, std::min<long long>(std::min(want, cap), 512));
+  // Split K so that the CTAs fill whole waves of the resident slots: with `s` splits the main kernel
+  // takes ceil(tiles * s / resident) rounds of 1/s of the reduction each, and the finish kernel reads
+  // s partial copies.  Pick the s with the least estimated time (300 TFLOP/s per round of full
+  // occupancy, 4 TB/s for the partials).
+  {
+    const long long cap = std::max<long long>(1, std::min<long long>(pl.k_blocks / 8, 512));
+    const double k_total_pos = (double)pl.k_blocks * (kRowBytes / es);
+    const double t_main = 2.0 * kTileM * pl.bn * k_total_pos * (double)tiles / 300e12;  // all tiles, one pass
+    const double t_partial = (double)g.groups * pl.Mp * pl.Np * 4.0 / 4e12;          // per split copy
+    double best_t = 1e30;
+    int best_s = 1;
+    for (long long s = 1; s <= cap; ++s) {
+      const long long ctas = tiles * s;
+      const long long rounds = (ctas + resident - 1) / resident;
+      // a round processes `resident` CTA-slots of 1/s of the K range each
+      const double t = t_main * ((double)rounds * resident / (double)ctas) + t_partial * (double)s + 2e-6 * rounds;
+      if (t < best_t) {
+        best_t = t;
+        best_s = (int)s;
+      }
+    }
+    pl.k_splits = best_s;
+  }
   if (pl.m_tiles >= 65536 || pl.n_tiles >= 65536 || (long long)g.groups * pl.k_splits >= 65536) return pl;
 
   // which residues (mod A elements = 16 bytes) do the innermost tap offsets t = kw*dil - pad have?
