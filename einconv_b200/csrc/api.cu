@@ -79,7 +79,7 @@ int make_dev_geom(const einconv_geom* g, DevGeom* out, bool need_c_out) {
 // ---------------------------------------------------------------------------------------------
 // kernel selection
 // ---------------------------------------------------------------------------------------------
-enum class Path { FFMA, DEPTHWISE, TENSOR, TMA, CONV_TMA };
+enum class Path { FFMA, DEPTHWISE, TENSOR, TMA, CONV_TMA, WGRAD_SLAB };
 
 static int resolve_math(int dtype, int math) {
   if (math == EINCONV_MATH_AUTO)
@@ -96,6 +96,7 @@ static Path select_path(int op, const DevGeom& g, int dtype, int math, int kerne
     // reduction networks: TMA-fed tcgen05 kernel when the layout allows it (16-byte aligned rows);
     // the software-gather tensor-core kernel is kept for the forward pass only (for the reduction
     // networks it is slower than the CUDA-core kernel)
+    if (op == EINCONV_OP_CONV_WEIGHT_VJP && wslab::supported(g, dtype)) return Path::WGRAD_SLAB;
     if (op == EINCONV_OP_CONV_WEIGHT_VJP || op == EINCONV_OP_KFC)
       return tma::tma_supported(op, g, dtype) ? Path::TMA : Path::FFMA;
     // forward / input VJP: TMA-fed implicit GEMM over a zero-padded channels-last copy (stride 1)
@@ -198,6 +199,7 @@ const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype,
     case Path::TENSOR: return tc_kernel_name(op, g, dtype, resolve_math(dtype, math));
     case Path::TMA: return op == EINCONV_OP_KFC ? "tcgen05_tma_kfc" : "tcgen05_tma_wgrad";
     case Path::CONV_TMA: return op == EINCONV_OP_CONV_FWD ? "tcgen05_tma_conv_fwd" : "tcgen05_tma_conv_input_vjp";
+    case Path::WGRAD_SLAB: return "tcgen05_slab_wgrad";
     default: return "ffma_gather_gemm";
   }
 }
@@ -217,6 +219,7 @@ int64_t einconv_workspace_bytes(int op, const einconv_geom* geom, int dtype, int
   if (path == Path::TENSOR) return tc_workspace_bytes(op, g, dtype, resolve_math(dtype, math));
   if (path == Path::TMA) return tma::tma_workspace_bytes(op, g, dtype);
   if (path == Path::CONV_TMA) return ctma::workspace_bytes(op, g, dtype);
+  if (path == Path::WGRAD_SLAB) return wslab::workspace_bytes(g, dtype);
   switch (op) {
     case EINCONV_OP_KFAC_REDUCE: {
       DevGeom g2;
@@ -290,6 +293,7 @@ int einconv_conv_weight_vjp(const void* x, const void* v, void* gw, int dtype,
   if ((long long)g.groups * g.c_out_g * g.c_in_g * g.k_total == 0) return EINCONV_OK;
   cudaStream_t s = (cudaStream_t)stream;
   switch (select_path(EINCONV_OP_CONV_WEIGHT_VJP, g, dtype, math, kernels)) {
+    case Path::WGRAD_SLAB: return wslab::run(x, v, gw, dtype, g, workspace, workspace_bytes, s);
     case Path::TMA:
       return tma::tma_run(EINCONV_OP_CONV_WEIGHT_VJP, x, v, gw, dtype, g, 1.0, workspace, workspace_bytes, s);
     case Path::TENSOR:

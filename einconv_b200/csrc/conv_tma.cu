@@ -368,6 +368,43 @@ __global__ void __launch_bounds__(256) pack_channels_last_kernel(const T* __rest
   }
 }
 
+// src [B, ctot, S..] -> xp [B, P_0.., P_{N-1}, cp]: zero-padded by pad[d] in front, channels-last
+int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int batch, int ctot, int cp,
+                       const int* S, const long long* P, const int* pad, cudaStream_t stream) {
+  const int N = n_dims;
+  PackParams pp{};
+  pp.n_dims = N;
+  pp.ctot = ctot;
+  pp.cp = cp;
+  pp.s_total = 1;
+  long long outer = batch;
+  for (int d = 0; d < N; ++d) {
+    pp.S[d] = S[d];
+    pp.P[d] = (int)P[d];
+    pp.pad[d] = pad[d];
+    pp.s_total *= S[d];
+    if (d < N - 1) {
+      outer *= P[d];
+      pp.outer_div[d] = FastDiv((uint32_t)P[d]);
+    }
+  }
+  EINCONV_CHECK_ARG(outer < (1ll << 31), "pack_channels_last: too many rows");
+  if (outer == 0 || cp == 0) return EINCONV_OK;
+  dim3 grid((unsigned)outer, (unsigned)((cp + 31) / 32));
+  EINCONV_CHECK_ARG(grid.y < 65536, "pack_channels_last: too many channels");
+  switch (elem_size(dtype)) {
+    case 4:
+      pack_channels_last_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)xp, pp);
+      break;
+    case 2:
+      pack_channels_last_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)src, (uint16_t*)xp, pp);
+      break;
+    default: set_error("pack_channels_last: unsupported dtype"); return EINCONV_ERR_UNSUPPORTED;
+  }
+  EINCONV_CHECK_LAUNCH("pack_channels_last_kernel");
+  return EINCONV_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // pre-pass 2: weights -> wp [G][tap][Np][Cgp] (K-major rows of source channels), zero-padded.
 //   forward   : wp[g][t][n][c] = w[g*Cog + n, c, t]                   (n: output channel, c: input channel)
@@ -414,7 +451,7 @@ static EncodeFn encode_fn() {
   return fn;
 }
 
-static int encode_2d(CUtensorMap* map, int dtype, const void* base, long long rows, long long cols,
+int encode_2d(CUtensorMap* map, int dtype, const void* base, long long rows, long long cols,
                      int box_cols, int box_rows, int swizzle_bytes) {
   const int es = (int)elem_size(dtype);
   CUtensorMapDataType dt = dtype == EINCONV_F32    ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
@@ -613,27 +650,8 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
 
   // ---- pack the source
   {
-    PackParams pp{};
-    pp.n_dims = N;
-    pp.ctot = r.groups * r.cs;
-    pp.cp = pl.cp;
-    pp.s_total = 1;
-    long long outer = r.batch;
-    for (int d = 0; d < N; ++d) {
-      pp.S[d] = r.S[d];
-      pp.P[d] = (int)pl.P[d];
-      pp.pad[d] = r.pad[d];
-      pp.s_total *= r.S[d];
-      if (d < N - 1) {
-        outer *= pl.P[d];
-        pp.outer_div[d] = FastDiv((uint32_t)pl.P[d]);
-      }
-    }
-    EINCONV_CHECK_ARG(outer < (1ll << 31), "conv_tma: too many rows to pack");
-    dim3 grid((unsigned)outer, (unsigned)((pl.cp + 31) / 32));
-    EINCONV_CHECK_ARG(grid.y < 65536, "conv_tma: too many channels");
-    pack_channels_last_kernel<T><<<grid, 256, 0, stream>>>((const T*)src, xp, pp);
-    EINCONV_CHECK_LAUNCH("pack_channels_last_kernel");
+    int st0 = pack_channels_last(src, xp, dtype, N, r.batch, r.groups * r.cs, pl.cp, r.S, pl.P, r.pad, stream);
+    if (st0) return st0;
   }
   // ---- pack the weights
   {

@@ -1,5 +1,7 @@
 // Internal prototypes shared between api.cu and the kernel translation units.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace einconv {
@@ -60,6 +62,19 @@ bool supported(int op, const DevGeom& g, int dtype, int math);
 int64_t workspace_bytes(int op, const DevGeom& g, int dtype);
 int run(int op, const void* src, const void* w, const void* bias, void* dst, int dtype, const DevGeom& g,
         void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+// shared with wgrad_slab.cu
+int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int batch, int ctot, int cp,
+                       const int* S, const long long* P, const int* pad, cudaStream_t stream);
+int encode_2d(CUtensorMap* map, int dtype, const void* base, long long rows, long long cols, int box_cols,
+              int box_rows, int swizzle_bytes);
 }  // namespace ctma
+
+// wgrad_slab.cu (weight VJP from channels-last padded copies, MN-major tcgen05, stride 1, 16-bit)
+namespace wslab {
+bool supported(const DevGeom& g, int dtype);
+int64_t workspace_bytes(const DevGeom& g, int dtype);
+int run(const void* x, const void* v, void* gw, int dtype, const DevGeom& g, void* workspace,
+        int64_t workspace_bytes, cudaStream_t stream);
+}  // namespace wslab
 
 }  // namespace einconv

@@ -528,7 +528,11 @@ def test_tc_kernels_are_selected():
     assert lib.einconv_selected_kernel(nat.OP_KFC, g, 0, nat.MATH_FP32, 0) == b"ffma_gather_gemm"
     g24 = nat.make_geom(2, 1, 32, 48, (24, 24), (3, 3), (1, 1), (1, 1), (1, 1), (24, 24))
     assert lib.einconv_selected_kernel(nat.OP_KFC, g24, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_kfc"
-    assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_wgrad"
+    # 16-bit, stride 1: slab kernel on channels-last padded copies; fp32 (TF32) and stride > 1: per-tap TMA tiles
+    assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 1, nat.MATH_AUTO, 0) == b"tcgen05_slab_wgrad"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 0, nat.MATH_TF32, 0) == b"tcgen05_tma_wgrad"
+    g24s = nat.make_geom(2, 1, 32, 48, (24, 24), (3, 3), (2, 2), (1, 1), (1, 1), (12, 12))
+    assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24s, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_wgrad"
     assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 1, nat.MATH_AUTO, 1) == b"ffma_gather_gemm"
 
 
@@ -587,6 +591,26 @@ def test_conv_tma_forward_and_input_vjp(case, mode, ctma_weights):
         evaluator.set_fp32_math("auto")
     _rel_to_max(got, want, tol, f"conv_tma fwd {mode}")
     _rel_to_max(gx, want_gx, tol, f"conv_tma input vjp {mode}")
+
+
+@pytest.mark.parametrize("case", CTMA_CASES, ids=CTMA_IDS)
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_slab_weight_vjp(case, mode):
+    """csrc/wgrad_slab.cu (MN-major operands from the channels-last padded copies, tap pairs sharing one
+    slab): max|d| <= 2^-7 (bf16) / 2^-10 (fp16) of max|ref| against the fp64 oracle on the same bits."""
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[mode]
+    x, w, b, kw = _tc_inputs(case, dtype)
+    N = x.dim() - 2
+    groups = kw.get("groups", 1)
+    y = direct.conv_forward(x.double().numpy(), w.double().numpy(), None, **kw)
+    torch.manual_seed(2)
+    v = (torch.rand(*y.shape) - 0.5).to(dtype)
+    want = direct.conv_weight_vjp(x.double().numpy(), v.double().numpy(), tuple(w.shape[2:]), **kw)
+    got = evaluator.conv_weight_vjp_raw(
+        x.to(DEV), v.to(DEV), tuple(w.shape[2:]), kw.get("dilation", 1), kw.get("padding", 0),
+        kw.get("stride", 1), groups,
+    )
+    _rel_to_max(got, want, 2.0**-7 if mode == "bf16" else 2.0**-10, f"slab wgrad {mode}")
 
 
 def test_conv_tma_is_used_by_autograd_and_matches_torch():
