@@ -322,49 +322,83 @@ struct PackParams {
   int ctot, cp;
   int S[kMaxDims], P[kMaxDims], pad[kMaxDims];
   long long s_total;  // prod(S)
+  long long outer_rows;  // B * prod(P[0..N-2])
+  int rows_per_cta;
   FastDiv outer_div[kMaxDims];  // / P[d] for d < n_dims - 1
 };
 
+// T = uint16_t / uint32_t (bit copy).  A CTA transposes tiles of 64 channels x 128 bytes of positions
+// through shared memory: every warp-level global access is one full 128-byte line on both sides and
+// 8 (x2 for 16-bit) independent loads per thread are in flight before the first shared store.
 template <typename T>
 __global__ void __launch_bounds__(256) pack_channels_last_kernel(const T* __restrict__ src, T* __restrict__ xp,
                                                                  const __grid_constant__ PackParams pp) {
-  __shared__ T tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  constexpr int EPW = 4 / sizeof(T);  // elements per 32-bit word
+  constexpr int TW = 32 * EPW;        // positions per tile
+  constexpr int TC = 64;              // channels per tile
+  __shared__ T tile[TC][TW + EPW];    // pitch of 33 words: conflict-free transposed reads
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = pp.n_dims - 1;
-  // blockIdx.x enumerates (b, p_0, .., p_{N-2})
-  uint32_t rem = blockIdx.x;
-  bool row_real = true;
-  long long src_off = 0, mul = pp.S[W];
-  for (int d = W - 1; d >= 0; --d) {
-    uint32_t q, r;
-    pp.outer_div[d].divmod(rem, q, r);
-    rem = q;
-    const int i = (int)r - pp.pad[d];
-    if (i < 0 || i >= pp.S[d]) row_real = false;
-    src_off += (long long)i * mul;
-    mul *= pp.S[d];
-  }
-  const long long b = rem;
-  const int c0 = blockIdx.y * 32;
-  const T* src_b = src + b * pp.ctot * pp.s_total + src_off;
-  T* dst_row = xp + (long long)blockIdx.x * pp.P[W] * pp.cp;
-  for (int w0 = 0; w0 < pp.P[W]; w0 += 32) {
-    const int iw = w0 + tx - pp.pad[W];
-    const bool col_real = row_real && iw >= 0 && iw < pp.S[W];
-#pragma unroll
-    for (int cy = ty; cy < 32; cy += 8) {
-      const int c = c0 + cy;
-      T v = T(0);
-      if (col_real && c < pp.ctot) v = src_b[(long long)c * pp.s_total + iw];
-      tile[cy][tx] = v;
+  const int c0 = blockIdx.y * TC;
+  // blockIdx.x enumerates groups of `rows_per_cta` consecutive outer rows (b, p_0, .., p_{N-2})
+  for (int rr = 0; rr < pp.rows_per_cta; ++rr) {
+    const long long orow = (long long)blockIdx.x * pp.rows_per_cta + rr;
+    if (orow >= pp.outer_rows) break;
+    uint32_t rem = (uint32_t)orow;
+    bool row_real = true;
+    long long src_off = 0, mul = pp.S[W];
+    for (int d = W - 1; d >= 0; --d) {
+      uint32_t q, r;
+      pp.outer_div[d].divmod(rem, q, r);
+      rem = q;
+      const int i = (int)r - pp.pad[d];
+      if (i < 0 || i >= pp.S[d]) row_real = false;
+      src_off += (long long)i * mul;
+      mul *= pp.S[d];
     }
-    __syncthreads();
+    const long long b = rem;
+    const T* src_b = src + b * pp.ctot * pp.s_total + src_off;
+    T* dst_row = xp + orow * pp.P[W] * pp.cp;
+    for (int w0 = 0; w0 < pp.P[W]; w0 += TW) {
+      T vals[8][EPW];
 #pragma unroll
-    for (int wy = ty; wy < 32; wy += 8) {
-      const int w = w0 + wy, c = c0 + tx;
-      if (w < pp.P[W] && c < pp.cp) dst_row[(long long)w * pp.cp + c] = tile[tx][wy];
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + warp + 8 * i;
+#pragma unroll
+        for (int e = 0; e < EPW; ++e) {
+          const int iw = w0 + lane + 32 * e - pp.pad[W];
+          vals[i][e] = T(0);
+          if (row_real && c < pp.ctot && iw >= 0 && iw < pp.S[W])
+            vals[i][e] = __ldg(src_b + (long long)c * pp.s_total + iw);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int e = 0; e < EPW; ++e) tile[warp + 8 * i][lane + 32 * e] = vals[i][e];
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < TW / 8; ++j) {
+        const int wl = warp + 8 * j, w = w0 + wl;
+        if (w < pp.P[W]) {
+          T* d = dst_row + (long long)w * pp.cp;
+          if constexpr (EPW == 1) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int c = c0 + lane + 32 * h;
+              if (c < pp.cp) d[c] = tile[lane + 32 * h][wl];
+            }
+          } else {
+            const int c = c0 + 2 * lane;  // cp is a multiple of 8: both channels of the pair exist or neither
+            if (c < pp.cp) {
+              const uint32_t lo = tile[2 * lane][wl], hi = tile[2 * lane + 1][wl];
+              *reinterpret_cast<uint32_t*>(d + c) = lo | (hi << 16);
+            }
+          }
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -390,16 +424,20 @@ int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int bat
   }
   EINCONV_CHECK_ARG(outer < (1ll << 31), "pack_channels_last: too many rows");
   if (outer == 0 || cp == 0) return EINCONV_OK;
-  dim3 grid((unsigned)outer, (unsigned)((cp + 31) / 32));
+  const int es = (int)elem_size(dtype);
+  EINCONV_CHECK_ARG(es == 2 || es == 4, "pack_channels_last: unsupported dtype");
+  pp.outer_rows = outer;
+  pp.rows_per_cta = getenv("EINCONV_PACK_RG") ? atoi(getenv("EINCONV_PACK_RG")) : 1;
+  if (pp.rows_per_cta < 1) pp.rows_per_cta = 1;
+  dim3 grid((unsigned)((outer + pp.rows_per_cta - 1) / pp.rows_per_cta), (unsigned)((cp + 63) / 64));
   EINCONV_CHECK_ARG(grid.y < 65536, "pack_channels_last: too many channels");
-  switch (elem_size(dtype)) {
+  switch (es) {
     case 4:
       pack_channels_last_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)xp, pp);
       break;
-    case 2:
+    default:
       pack_channels_last_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)src, (uint16_t*)xp, pp);
       break;
-    default: set_error("pack_channels_last: unsupported dtype"); return EINCONV_ERR_UNSUPPORTED;
   }
   EINCONV_CHECK_LAUNCH("pack_channels_last_kernel");
   return EINCONV_OK;

@@ -361,6 +361,8 @@ static int run_t(const Plan& pl, const void* x, const void* v, void* gw, int dty
   int zero_pad[kMaxDims] = {0};
   // xp: X on the padded grid; rows beyond B * Ptot are never written and are excluded from the tensor
   // map (TMA zero-fills them).  vp: V on the same grid, zero where o_d >= O_d.
+  // (running the two transposes concurrently on a forked stream was measured and gains nothing: they
+  // are limited by DRAM efficiency, not by latency)
   int st = ctma::pack_channels_last(x, xp, dtype, N, g.batch, g.groups * g.c_in_g, pl.cxp, g.in, pl.P, g.pad, stream);
   if (st) return st;
   st = ctma::pack_channels_last(v, vp, dtype, N, g.batch, g.groups * g.c_out_g, pl.cvp, g.out, pl.P, zero_pad, stream);
