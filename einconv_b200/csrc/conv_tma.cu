@@ -75,11 +75,12 @@ template <> struct Elem<__nv_bfloat16> { static constexpr bool TF32 = false; sta
 template <> struct Elem<__half> { static constexpr bool TF32 = false; static constexpr int FMT = 0; };
 
 constexpr int kMaxStages = 6;
+constexpr int kMaxWBars = 32;  // resident weights arrive stage by stage: the first MMAs need not wait for all
 
 struct Bars {
   uint64_t full[kMaxStages], empty[kMaxStages];
   uint64_t tmem_full[2], tmem_empty[2];
-  uint64_t w_full, w_empty;
+  uint64_t w_full[kMaxWBars], w_empty;
   uint32_t tmem_base;
   float bias[256];  // bias of the current (group, n-tile) class, zero where absent
 };
@@ -118,7 +119,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.n_stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
-    mbar_init(&bars->w_full, 1);
+    for (int i = 0; i < kMaxWBars; ++i) mbar_init(&bars->w_full[i], 1);
     mbar_init(&bars->w_empty, 1);
     fence_barrier_init();
     prefetch_tensormap(&map_a);
@@ -137,6 +138,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const long long tile_begin = p.total_tiles * blockIdx.x / gridDim.x;
   const long long tile_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
   const int stages_per_tile = p.n_slices * p.n_groups;
+  const int n_wbars = stages_per_tile <= kMaxWBars ? stages_per_tile : 1;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -153,22 +155,31 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int g = (int)(cls / p.n_ntiles);
       const int q0 = mtile * kTileM;
       const int wrow0 = g * p.taps * p.np + ntile * p.bn;
+      bool load_w = false;
       if (p.resident && cls != cur_class) {
-        // (re)load every weight tile of this class once the MMA warp is done with the old ones
+        // (re)load every weight tile of this class once the MMA warp is done with the old ones; the
+        // tiles of stage sg are requested right before that stage's slab and signal w_full[sg]
         cur_class = cls;
+        load_w = true;
         mbar_wait(&bars->w_empty, pw ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(&bars->w_full, (uint32_t)(p.n_slices * p.taps * p.bn * p.cb_bytes));
-          for (int s = 0; s < p.n_slices; ++s)
-            for (int tap = 0; tap < p.taps; ++tap)
-              tma_load_2d(w_region + (size_t)(s * p.taps + tap) * p.btile_bytes, &map_b, &bars->w_full,
-                          s * p.cb_elems, wrow0 + tap * p.np);
-        }
-        __syncwarp();
         pw ^= 1;
       }
+      int sg = 0;
       for (int s = 0; s < p.n_slices; ++s) {
-        for (int grp = 0; grp < p.n_groups; ++grp) {
+        for (int grp = 0; grp < p.n_groups; ++grp, ++sg) {
+          if (load_w && elect_one()) {
+            uint64_t* wb = &bars->w_full[n_wbars > 1 ? sg : 0];
+            if (n_wbars > 1)
+              mbar_expect_tx(wb, (uint32_t)(p.tpg * p.bn * p.cb_bytes));
+            else if (sg == 0)
+              mbar_expect_tx(wb, (uint32_t)(p.n_slices * p.taps * p.bn * p.cb_bytes));
+            for (int j = 0; j < p.tpg; ++j) {
+              const int tap = grp * p.tpg + j;
+              tma_load_2d(w_region + (size_t)(s * p.taps + tap) * p.btile_bytes, &map_b, wb, s * p.cb_elems,
+                          wrow0 + tap * p.np);
+            }
+          }
+          __syncwarp();
           mbar_wait(&bars->empty[st], ph ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&bars->full[st], stage_tx);
@@ -204,15 +215,13 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (long long tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const long long cls = tile / p.n_mtiles;
-      if (p.resident && cls != cur_class) {
-        cur_class = cls;
-        mbar_wait(&bars->w_full, pw);
-        pw ^= 1;
-      }
+      const bool new_w = p.resident && cls != cur_class;
+      cur_class = cls;
       mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.bn;
       for (int sg = 0; sg < stages_per_tile; ++sg) {
+        if (new_w && (n_wbars > 1 || sg == 0)) mbar_wait(&bars->w_full[n_wbars > 1 ? sg : 0], pw);
         mbar_wait(&bars->full[st], ph);
         tc_fence_after();
         if (elect_one()) {
@@ -237,6 +246,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         __syncwarp();
         if (++st == p.n_stages) { st = 0; ph ^= 1; }
       }
+      if (new_w) pw ^= 1;
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
@@ -587,6 +597,10 @@ static CPlan make_cplan(const Role& r, int dtype) {
         best_cost = cost;
         pl.cb_bytes = cb;
       }
+    }
+    if (const char* e = getenv("EINCONV_CTMA_CB")) {  // tuning experiments
+      const int cb = atoi(e);
+      if ((cb == 128 || cb == 64 || cb == 32) && cb <= best_cost) pl.cb_bytes = cb;
     }
     pl.cb_elems = pl.cb_bytes / es;
     pl.n_slices = (r.cs + pl.cb_elems - 1) / pl.cb_elems;
