@@ -334,8 +334,43 @@ struct PackParams {
   long long s_total;  // prod(S)
   long long outer_rows;  // B * prod(P[0..N-2])
   int rows_per_cta;
+  // optional second job fused into the same launch: pack the weights (see pack_weights below)
+  const void* w_src;
+  void* w_dst;
+  int w_groups, w_taps, w_np, w_cgp, w_cog, w_cg, w_transpose;
+  long long w_total;
+  unsigned w_ctas, x_ctas;
   FastDiv outer_div[kMaxDims];  // / P[d] for d < n_dims - 1
 };
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass 2: weights -> wp [G][tap][Np][Cgp] (K-major rows of source channels), zero-padded.
+//   forward   : wp[g][t][n][c] = w[g*Cog + n, c, t]                   (n: output channel, c: input channel)
+//   input VJP : wp[g][t][n][c] = w[g*Cog + c, n, T-1-t]              (n: input channel,  c: output channel)
+// Runs as extra CTAs of the source-packing launch (one launch less on a ~50 us critical path).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void pack_weights_block(const PackParams& pp, unsigned block) {
+  const T* __restrict__ w = reinterpret_cast<const T*>(pp.w_src);
+  T* __restrict__ wp = reinterpret_cast<T*>(pp.w_dst);
+  const int taps = pp.w_taps, np = pp.w_np, cgp = pp.w_cgp, cog = pp.w_cog, cg = pp.w_cg;
+  for (long long idx = (long long)block * 1024 + threadIdx.x; idx < min(pp.w_total, ((long long)block + 1) * 1024);
+       idx += 256) {
+    const int c = (int)(idx % cgp);
+    long long r = idx / cgp;
+    const int n = (int)(r % np);
+    r /= np;
+    const int t = (int)(r % taps);
+    const int g = (int)(r / taps);
+    T v = T(0);
+    if (!pp.w_transpose) {
+      if (n < cog && c < cg) v = w[(((long long)g * cog + n) * cg + c) * taps + t];
+    } else {
+      if (n < cg && c < cog) v = w[(((long long)g * cog + c) * cg + n) * taps + (taps - 1 - t)];
+    }
+    wp[idx] = v;
+  }
+}
 
 // T = uint16_t / uint32_t (bit copy).  A CTA transposes tiles of 64 channels x 128 bytes of positions
 // through shared memory: every warp-level global access is one full 128-byte line on both sides and
@@ -348,6 +383,10 @@ __global__ void __launch_bounds__(256) pack_channels_last_kernel(const T* __rest
   constexpr int TC = 64;              // channels per tile
   __shared__ T tile[TC][TW + EPW];    // pitch of 33 words: conflict-free transposed reads
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x >= pp.x_ctas) {  // fused weight job
+    if (blockIdx.y == 0) pack_weights_block<T>(pp, blockIdx.x - pp.x_ctas);
+    return;
+  }
   const int W = pp.n_dims - 1;
   const int c0 = blockIdx.y * TC;
   // blockIdx.x enumerates groups of `rows_per_cta` consecutive outer rows (b, p_0, .., p_{N-2})
@@ -414,7 +453,8 @@ __global__ void __launch_bounds__(256) pack_channels_last_kernel(const T* __rest
 
 // src [B, ctot, S..] -> xp [B, P_0.., P_{N-1}, cp]: zero-padded by pad[d] in front, channels-last
 int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int batch, int ctot, int cp,
-                       const int* S, const long long* P, const int* pad, cudaStream_t stream) {
+                       const int* S, const long long* P, const int* pad, cudaStream_t stream,
+                       const WeightJob* wj) {
   const int N = n_dims;
   PackParams pp{};
   pp.n_dims = N;
@@ -433,13 +473,23 @@ int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int bat
     }
   }
   EINCONV_CHECK_ARG(outer < (1ll << 31), "pack_channels_last: too many rows");
-  if (outer == 0 || cp == 0) return EINCONV_OK;
+  if ((outer == 0 || cp == 0) && !(wj && wj->total > 0)) return EINCONV_OK;
   const int es = (int)elem_size(dtype);
   EINCONV_CHECK_ARG(es == 2 || es == 4, "pack_channels_last: unsupported dtype");
   pp.outer_rows = outer;
   pp.rows_per_cta = getenv("EINCONV_PACK_RG") ? atoi(getenv("EINCONV_PACK_RG")) : 1;
   if (pp.rows_per_cta < 1) pp.rows_per_cta = 1;
   dim3 grid((unsigned)((outer + pp.rows_per_cta - 1) / pp.rows_per_cta), (unsigned)((cp + 63) / 64));
+  pp.x_ctas = grid.x;
+  if (wj && wj->total > 0) {
+    pp.w_src = wj->src; pp.w_dst = wj->dst;
+    pp.w_groups = wj->groups; pp.w_taps = wj->taps; pp.w_np = wj->np; pp.w_cgp = wj->cgp;
+    pp.w_cog = wj->cog; pp.w_cg = wj->cg; pp.w_transpose = wj->transpose;
+    pp.w_total = wj->total;
+    pp.w_ctas = (unsigned)((wj->total + 1023) / 1024);
+    EINCONV_CHECK_ARG((long long)grid.x + pp.w_ctas < (1ll << 31), "pack_channels_last: grid too large");
+    grid.x += pp.w_ctas;
+  }
   EINCONV_CHECK_ARG(grid.y < 65536, "pack_channels_last: too many channels");
   switch (es) {
     case 4:
@@ -451,32 +501,6 @@ int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int bat
   }
   EINCONV_CHECK_LAUNCH("pack_channels_last_kernel");
   return EINCONV_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// pre-pass 2: weights -> wp [G][tap][Np][Cgp] (K-major rows of source channels), zero-padded.
-//   forward   : wp[g][t][n][c] = w[g*Cog + n, c, t]                   (n: output channel, c: input channel)
-//   input VJP : wp[g][t][n][c] = w[g*Cog + c, n, T-1-t]              (n: input channel,  c: output channel)
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) pack_weights_kernel(const T* __restrict__ w, T* __restrict__ wp, int groups,
-                                                           int taps, int np, int cgp, int cog, int cg,
-                                                           int transpose, long long total) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c = (int)(idx % cgp);
-  long long r = idx / cgp;
-  const int n = (int)(r % np);
-  r /= np;
-  const int t = (int)(r % taps);
-  const int g = (int)(r / taps);
-  T v = T(0);
-  if (!transpose) {
-    if (n < cog && c < cg) v = w[(((long long)g * cog + n) * cg + c) * taps + t];
-  } else {
-    if (n < cg && c < cog) v = w[(((long long)g * cog + c) * cg + n) * taps + (taps - 1 - t)];
-  }
-  wp[idx] = v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -700,19 +724,17 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
   T* wp = reinterpret_cast<T*>(base + pl.xp_bytes);
   const int N = r.n_dims;
 
-  // ---- pack the source
+  // ---- pack the source and (same launch) the weights
   {
-    int st0 = pack_channels_last(src, xp, dtype, N, r.batch, r.groups * r.cs, pl.cp, r.S, pl.P, r.pad, stream);
+    WeightJob wj{};
+    wj.src = w; wj.dst = wp;
+    wj.groups = r.groups; wj.taps = pl.taps; wj.np = pl.np; wj.cgp = pl.cgp;
+    wj.cog = r.transpose ? r.cs : r.cd;
+    wj.cg = r.transpose ? r.cd : r.cs;
+    wj.transpose = r.transpose;
+    wj.total = (long long)r.groups * pl.taps * pl.np * pl.cgp;
+    int st0 = pack_channels_last(src, xp, dtype, N, r.batch, r.groups * r.cs, pl.cp, r.S, pl.P, r.pad, stream, &wj);
     if (st0) return st0;
-  }
-  // ---- pack the weights
-  {
-    const long long total = (long long)r.groups * pl.taps * pl.np * pl.cgp;
-    const int cog = r.transpose ? r.cs : r.cd;
-    const int cg = r.transpose ? r.cd : r.cs;
-    pack_weights_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-        (const T*)w, wp, r.groups, pl.taps, pl.np, pl.cgp, cog, cg, r.transpose, total);
-    EINCONV_CHECK_LAUNCH("pack_weights_kernel");
   }
   // ---- tensor maps
   CUtensorMap map_a, map_b;
@@ -775,6 +797,7 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tma)");
   const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, kNumSMs);
+  // (programmatic dependent launch was measured here: no gain, the GEMM's CTAs need the whole SM)
   kern<<<grid, kThreads, pl.smem, stream>>>(map_a, map_b, p);
   EINCONV_CHECK_LAUNCH("conv_tma_kernel");
   return EINCONV_OK;

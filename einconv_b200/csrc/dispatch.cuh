@@ -63,8 +63,15 @@ int64_t workspace_bytes(int op, const DevGeom& g, int dtype);
 int run(int op, const void* src, const void* w, const void* bias, void* dst, int dtype, const DevGeom& g,
         void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 // shared with wgrad_slab.cu
+struct WeightJob {  // optional weight packing fused into the same launch (conv_tma.cu)
+  const void* src;
+  void* dst;
+  int groups, taps, np, cgp, cog, cg, transpose;
+  long long total;
+};
 int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int batch, int ctot, int cp,
-                       const int* S, const long long* P, const int* pad, cudaStream_t stream);
+                       const int* S, const long long* P, const int* pad, cudaStream_t stream,
+                       const WeightJob* wj = nullptr);
 int encode_2d(CUtensorMap* map, int dtype, const void* base, long long rows, long long cols, int box_cols,
               int box_rows, int swizzle_bytes);
 }  // namespace ctma
