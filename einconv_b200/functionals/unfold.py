@@ -30,3 +30,63 @@ def unfoldNd(
     return evaluator.unfold_autograd(
         x, kernel_size, dilation=dilation, padding=padding, stride=stride
     )
+
+
+_HOST_STREAMS = {}
+
+
+def unfoldNd_host(
+    x_host: Tensor,
+    kernel_size: Union[int, Tuple[int, ...]],
+    dilation: Union[int, Tuple[int, ...]] = 1,
+    padding: Union[int, Tuple[int, ...], str] = 0,
+    stride: Union[int, Tuple[int, ...]] = 1,
+    out: Tensor = None,
+    device=None,
+    chunk: int = 0,
+) -> Tensor:
+    """``unfoldNd`` for HOST tensors: host -> GPU -> host, pipelined over the batch.
+
+    The unfolded tensor is ``prod(kernel_size)`` times larger than the input, so a host round trip is
+    bound by the device-to-host copy.  The batch is cut into chunks that alternate between two CUDA
+    streams: the upload and the gather of chunk ``i + 1`` overlap the download of chunk ``i`` (PCIe
+    is full duplex and the GPU has separate copy engines per direction).  ``x_host`` and ``out``
+    should be pinned (``Tensor.pin_memory()``) or the copies fall back to staged, synchronous ones.
+    Returns ``out`` (allocated pinned if not given) after all work has completed.
+    """
+    import torch
+
+    if x_host.is_cuda:
+        raise ValueError("unfoldNd_host expects a host tensor; use unfoldNd for CUDA tensors")
+    if not torch.cuda.is_available():
+        raise RuntimeError("einconv_b200 has no CPU fallback: unfoldNd_host needs a CUDA device")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    B = x_host.shape[0]
+    kw = dict(kernel_size=kernel_size, dilation=dilation, padding=padding, stride=stride)
+    if chunk <= 0:
+        chunk = max(1, B // 8)
+    # the two side streams are kept per device: the caching allocator pools memory per stream, so fresh
+    # streams on every call would mean fresh cudaMallocs on every call
+    streams = _HOST_STREAMS.get(dev)
+    if streams is None:
+        streams = _HOST_STREAMS[dev] = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(dev))
+    for i, b0 in enumerate(range(0, B, chunk)):
+        s = streams[i % 2]
+        s.wait_event(ready)
+        with torch.cuda.stream(s):
+            xd = x_host[b0 : b0 + chunk].to(dev, non_blocking=True)
+            od = evaluator.unfold(xd, **kw)
+            if out is None:
+                shape = (B,) + tuple(od.shape[1:])
+                out = torch.empty(shape, dtype=od.dtype).pin_memory()
+            out[b0 : b0 + chunk].copy_(od, non_blocking=True)
+            xd.record_stream(s)
+            od.record_stream(s)
+    for s in streams:
+        s.synchronize()
+    if B == 0 and out is None:
+        od = evaluator.unfold(x_host.to(dev), **kw)
+        out = od.cpu()
+    return out

@@ -148,6 +148,24 @@ def test_unfold_matches_torch_unfold_4d_and_is_differentiable():
     close(gx, want, 1e-6, 1e-6, "fold vs oracle")
 
 
+def test_unfold_host_api_is_bit_exact_and_pipelined():
+    """unfoldNd_host: host -> GPU -> host in batch chunks on two streams; same bits as the oracle."""
+    from einconv_b200.functionals import unfoldNd_host
+
+    torch.manual_seed(0)
+    x = torch.rand(7, 3, 9, 10, 6).pin_memory()
+    kw = dict(kernel_size=(3, 2, 3), dilation=(1, 2, 1), padding=(1, 0, 2), stride=(2, 1, 1))
+    want = direct.unfold(x.numpy(), kw["kernel_size"], dilation=kw["dilation"], padding=kw["padding"], stride=kw["stride"])
+    for chunk in (0, 1, 3, 100):
+        got = unfoldNd_host(x, chunk=chunk, **kw)
+        assert got.is_pinned() and not got.is_cuda
+        assert torch.equal(got, torch.from_numpy(want))
+    out = torch.empty_like(got).pin_memory()
+    assert unfoldNd_host(x, out=out, **kw) is out and torch.equal(out, got)
+    with pytest.raises(ValueError):
+        unfoldNd_host(x.to(DEV), **kw)
+
+
 def _slices_unfold(x, k, s, d, p):
     """Reference-free construction on the GPU: strided slices of the padded input (exact)."""
     N = x.dim() - 2
@@ -534,6 +552,49 @@ def test_tc_kernels_are_selected():
     g24s = nat.make_geom(2, 1, 32, 48, (24, 24), (3, 3), (2, 2), (1, 1), (1, 1), (12, 12))
     assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24s, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_wgrad"
     assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 1, nat.MATH_AUTO, 1) == b"ffma_gather_gemm"
+
+
+# ---- depthwise stencils (csrc/depthwise.cu): warp-per-strip kernel and the per-column kernel --------
+DW_CASES = [
+    ((2, 256, 28, 28), 3, dict(padding=1)),          # C3 shape (one strip, two row blocks)
+    ((2, 8, 40, 75), 3, dict(padding=1)),            # three column strips, ragged last strip
+    ((3, 6, 19, 33), 5, dict(padding=2)),            # 5x5
+    ((2, 4, 17, 30), 7, dict(padding=3)),            # 7x7
+    ((2, 5, 1, 50), (1, 3), dict(padding=(0, 1))),   # 1x3
+    ((2, 6, 20, 20), 3, dict(padding=0)),            # no padding: output smaller than input
+    ((2, 6, 9, 9), 3, dict(padding=2)),              # padding = K - 1
+    ((2, 6, 21, 22), 3, dict(padding=1, stride=2)),  # stride 2: per-column kernel
+]
+
+
+@pytest.mark.parametrize("case", DW_CASES, ids=lambda c: "x".join(map(str, c[0])) + f"-k{c[1]}")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("variant", ["warp", "column"])
+def test_depthwise_kernels(case, dtype, variant, monkeypatch):
+    """fp32: CUDA-core FMA in a fixed order, rtol 1e-5 like the reference's tests; bf16: 2^-7 max|ref|."""
+    if variant == "column":
+        monkeypatch.setenv("EINCONV_DW_DIRECT", "1")
+    xs, k, kw = case
+    C = xs[1]
+    ks = (k, k) if isinstance(k, int) else k
+    torch.manual_seed(0)
+    x = (torch.rand(*xs) - 0.3).to(dtype)
+    w = (torch.rand(C, 1, *ks) - 0.5).to(dtype)
+    b = (torch.rand(C) - 0.5).to(dtype)
+    want = direct.conv_forward(x.double().numpy(), w.double().numpy(), b.double().numpy(), groups=C, **kw)
+    got = convNd(x.to(DEV), w.to(DEV), b.to(DEV), groups=C, **kw)
+    torch.manual_seed(1)
+    v = (torch.rand(*want.shape) - 0.5).to(dtype)
+    want_gx = direct.conv_input_vjp(w.double().numpy(), v.double().numpy(), tuple(xs[2:]), groups=C, **kw)
+    gx = evaluator.conv_input_vjp_raw(
+        w.to(DEV), v.to(DEV), tuple(xs[2:]), kw.get("stride", 1), kw.get("padding", 0), 1, C
+    )
+    if dtype == torch.float32:
+        close(got, want, 1e-5, 1e-6, "depthwise fwd")
+        close(gx, want_gx, 1e-5, 1e-6, "depthwise input vjp")
+    else:
+        _rel_to_max(got, want, 2.0**-7, "depthwise fwd bf16")
+        _rel_to_max(gx, want_gx, 2.0**-7, "depthwise input vjp bf16")
 
 
 # ---- TMA-fed implicit GEMM for forward / input VJP (csrc/conv_tma.cu): stride 1, any N --------------
