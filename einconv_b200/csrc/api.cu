@@ -7,6 +7,8 @@
 #include <cstring>
 
 #include "common.cuh"
+#include <cstdlib>
+
 #include "dispatch.cuh"
 
 namespace einconv {
@@ -149,6 +151,27 @@ static bool kfc_via_unfold(const DevGeom& g, int dtype, int math, int kernels, D
   return true;
 }
 
+// KFC of fp32 tensors in TF32 mode runs on scaled fp16 operand copies (same 10-bit mantissa, see
+// convert.cu) whenever a tensor-core path exists for the fp16 problem.  EINCONV_KFC_TF32=1 keeps
+// kind::tf32 on the fp32 data.
+static bool kfc_half_route(const DevGeom& g, int dtype, int math, int kernels, int64_t* x16_bytes) {
+  if (dtype != EINCONV_F32 || kernels == EINCONV_KERNELS_GENERIC) return false;
+  if (resolve_math(dtype, math) != EINCONV_MATH_TF32) return false;
+  if (getenv("EINCONV_KFC_TF32")) return false;
+  // measured on the ResNet-50 layer table (scripts/time_factors.py): the copy pays off for kernels with
+  // several taps (the operand is re-read per tap) up to A = 2304; 1x1 layers and the A = 4608 layers are
+  // faster on kind::tf32 without the extra pass
+  if (g.k_total == 1 || (long long)g.c_in_g * g.k_total > 2304) return false;
+  DevGeom g1;
+  int64_t ub;
+  if (!tma::tma_supported(EINCONV_OP_KFC, g, EINCONV_F16) &&
+      !kfc_via_unfold(g, EINCONV_F16, EINCONV_MATH_HALF, kernels, &g1, &ub))
+    return false;
+  const long long n = (long long)g.batch * g.groups * g.c_in_g * g.in_total;
+  *x16_bytes = 256 + ((n * 2 + 255) / 256) * 256;  // [header: absmax, 1/s^2][fp16 copy]
+  return true;
+}
+
 static int64_t kfac_u_bytes(const DevGeom& g) {
   return (((int64_t)g.batch * g.groups * g.c_in_g * g.k_total * 4 + 255) / 256) * 256;
 }
@@ -191,7 +214,10 @@ const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype,
   }
   if (op == EINCONV_OP_KFC) {
     DevGeom g1;
-    int64_t ub;
+    int64_t ub, hb;
+    if (kfc_half_route(g, dtype, math, kernels, &hb))
+      return kfc_via_unfold(g, EINCONV_F16, EINCONV_MATH_HALF, kernels, &g1, &ub) ? "f16scaled+unfold+tcgen05_tma_kfc"
+                                                                                   : "f16scaled+tcgen05_tma_kfc";
     if (kfc_via_unfold(g, dtype, math, kernels, &g1, &ub)) return "unfold+tcgen05_tma_kfc";
   }
   switch (select_path(op, g, dtype, math, kernels)) {
@@ -211,7 +237,12 @@ int64_t einconv_workspace_bytes(int op, const einconv_geom* geom, int dtype, int
   if (op == EINCONV_OP_UNFOLD || op == EINCONV_OP_FOLD) return 0;
   if (op == EINCONV_OP_KFC) {
     DevGeom g1;
-    int64_t ub;
+    int64_t ub, hb;
+    if (kfc_half_route(g, dtype, math, kernels, &hb)) {
+      if (kfc_via_unfold(g, EINCONV_F16, EINCONV_MATH_HALF, kernels, &g1, &ub))
+        return hb + ub + tma::tma_workspace_bytes(op, g1, EINCONV_F16);
+      return hb + tma::tma_workspace_bytes(op, g, EINCONV_F16);
+    }
     if (kfc_via_unfold(g, dtype, math, kernels, &g1, &ub)) return ub + tma::tma_workspace_bytes(op, g1, dtype);
   }
   const Path path = select_path(op, g, dtype, math, kernels);
@@ -311,6 +342,33 @@ int einconv_kfc(const void* x, void* out, int dtype, const einconv_geom* geom, d
   if ((st = check_math(dtype, math))) return st;
   if ((long long)g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    int64_t hb;
+    if (kfc_half_route(g, dtype, math, kernels, &hb)) {
+      DevGeom g1;
+      int64_t ub = 0;
+      const bool via_unfold = kfc_via_unfold(g, EINCONV_F16, EINCONV_MATH_HALF, kernels, &g1, &ub);
+      const int64_t need = hb + ub + tma::tma_workspace_bytes(EINCONV_OP_KFC, via_unfold ? g1 : g, EINCONV_F16);
+      if (workspace_bytes < need || !workspace) {
+        set_error("kfc: workspace of %lld bytes required, got %lld", (long long)need, (long long)workspace_bytes);
+        return EINCONV_ERR_WORKSPACE;
+      }
+      char* ws = (char*)workspace;
+      __half* x16 = (__half*)(ws + 256);
+      const float* inv_s2 = (const float*)ws + 1;
+      const long long n = (long long)g.batch * g.groups * g.c_in_g * g.in_total;
+      st = scaled_half_copy((const float*)x, x16, n, ws, s);
+      if (st) return st;
+      if (via_unfold) {
+        st = launch_unfold(x16, nullptr, ws + hb, EINCONV_F16, geom, s);
+        if (st) return st;
+        return tma::tma_run_typed_out(EINCONV_OP_KFC, ws + hb, nullptr, out, EINCONV_F16, EINCONV_F32, g1, scale,
+                                      ws + hb + ub, workspace_bytes - hb - ub, s, inv_s2);
+      }
+      return tma::tma_run_typed_out(EINCONV_OP_KFC, x16, nullptr, out, EINCONV_F16, EINCONV_F32, g, scale, ws + hb,
+                                    workspace_bytes - hb, s, inv_s2);
+    }
+  }
   {
     DevGeom g1;
     int64_t ub;

@@ -46,6 +46,9 @@ int tc_kfc(const void* x, void* out, int dtype, const DevGeom& g, double scale, 
            void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 
 
+// convert.cu
+int scaled_half_copy(const float* x, __half* y, long long n, void* header, cudaStream_t stream);
+
 // tc_tma.cu (TMA-fed tcgen05 kernels for the reduction networks)
 namespace tma {
 bool tma_supported(int op, const DevGeom& g, int dtype);
@@ -53,7 +56,8 @@ int64_t tma_workspace_bytes(int op, const DevGeom& g, int dtype);
 int tma_run(int op, const void* x, const void* v, void* out, int dtype, const DevGeom& g, double scale,
             void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype, int out_dtype, const DevGeom& g,
-                      double scale, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+                      double scale, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
+                      const float* scale_dev = nullptr);
 }  // namespace tma
 
 // conv_tma.cu (TMA-fed tcgen05 implicit GEMM for forward / input VJP, stride 1)

@@ -189,6 +189,7 @@ struct Params {
   int tri;                             // KFC: only tiles on or above the diagonal are computed (K is symmetric)
   int debug;                           // bring-up switch (EINCONV_TMA_DEBUG): 1 = no TMA/MMA, 2 = TMA only
   float* partial;                      // [groups][k_splits][Mp][Np]
+  const float* scale_dev;              // optional extra factor read on the device by the finish kernel
 };
 
 template <typename T> struct Elem;
@@ -480,7 +481,8 @@ __global__ void __launch_bounds__(256) shift_copy_kernel(const T* __restrict__ x
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) tma_finish_kernel(const float* __restrict__ partial, T* __restrict__ out,
-                                                         const __grid_constant__ Params p, float scale) {
+                                                         const __grid_constant__ Params p, float scale_host) {
+  const float scale = p.scale_dev ? scale_host * __ldg(p.scale_dev) : scale_host;
   const int Kt = p.k_total, A = p.c_in_g * Kt;
   const long long per_group = p.is_kfc ? (long long)A * A : (long long)p.c_out_g * A;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -778,7 +780,8 @@ static int launch(const CUtensorMap* maps, const Params& p, const Plan& pl, int 
 }
 
 int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype, int out_dtype, const DevGeom& g,
-                      double scale, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+                      double scale, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
+                      const float* scale_dev) {
   const Plan pl = make_plan(op, g, dtype);
   EINCONV_CHECK_ARG(pl.ok, "tma path not available for this geometry");
   const int64_t need = tma_workspace_bytes(op, g, dtype);
@@ -878,6 +881,7 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   p.Mp = (int)pl.Mp; p.Np = (int)pl.Np;
   p.is_kfc = kfc ? 1 : 0;
   p.tri = pl.tri ? 1 : 0;
+  p.scale_dev = scale_dev;
   {
     const char* dbg = getenv("EINCONV_TMA_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;

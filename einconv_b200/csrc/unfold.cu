@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256, 8) unfold_plane_kernel(const T* __restric
 #endif
 constexpr int kFlatThreads = EINCONV_FLAT_THREADS;
 constexpr int kFlatMinBlocks = EINCONV_FLAT_MINB;  // resident CTAs per SM the register budget allows
-constexpr int kFlatJpt = EINCONV_FLAT_JPT;         // outputs per thread per chunk (<= 8)
+constexpr int kFlatJpt = EINCONV_FLAT_JPT;         // outputs per thread per chunk (<= 16)
 constexpr int kFlatMaxTaps = 2048;
 
 template <int ND>
@@ -427,7 +427,10 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
       cc[0] = (int)r0;  // >= ext[0] only for e >= box, which the loop excludes
       est[0] = (int)r1;
     }
-    constexpr int U = 8;  // independent loads in flight per thread
+#ifndef EINCONV_FLAT_U
+#define EINCONV_FLAT_U 8
+#endif
+    constexpr int U = EINCONV_FLAT_U;  // independent loads in flight per thread
     for (int e0 = tid; e0 < p.box; e0 += kFlatThreads * U) {
       T vals[U];
 #pragma unroll
@@ -495,6 +498,14 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
     if constexpr (NI <= kFlatJpt)                                                     \
       flat_emit<T, NI>(plane, tap_off, n_taps, dst, p.P, off, last_on);               \
     break;
+      EINCONV_FLAT_CASE(16)
+      EINCONV_FLAT_CASE(15)
+      EINCONV_FLAT_CASE(14)
+      EINCONV_FLAT_CASE(13)
+      EINCONV_FLAT_CASE(12)
+      EINCONV_FLAT_CASE(11)
+      EINCONV_FLAT_CASE(10)
+      EINCONV_FLAT_CASE(9)
       EINCONV_FLAT_CASE(8)
       EINCONV_FLAT_CASE(7)
       EINCONV_FLAT_CASE(6)

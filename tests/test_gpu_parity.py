@@ -527,6 +527,29 @@ def test_tc_kfc(case, mode):
     _rel_to_max(got, want, 2.0**-7 if mode == "bf16" else 1e-3, f"tc kfc {mode}")
 
 
+@pytest.mark.parametrize("magnitude", [1.0, 3.0e4, 2.0e-7])
+def test_kfc_scaled_fp16_operands_match_tf32_accuracy(magnitude, monkeypatch):
+    """fp32 KFC in TF32 mode runs on fp16 copies scaled by a power of two (csrc/convert.cu): same
+    tolerance as kind::tf32 (1e-3 max|ref|) for any magnitude of the data, and not worse than the
+    kind::tf32 route (EINCONV_KFC_TF32=1) by more than a rounding."""
+    torch.manual_seed(0)
+    x = ((torch.rand(3, 32, 18, 18) - 0.3) * magnitude)
+    want = direct.kfc(x.double().numpy(), (3, 3), padding=1)
+    evaluator.set_fp32_math("tf32")
+    try:
+        got16 = evaluator.kfc(x.to(DEV), (3, 3), padding=1)
+        monkeypatch.setenv("EINCONV_KFC_TF32", "1")
+        got32 = evaluator.kfc(x.to(DEV), (3, 3), padding=1)
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got16, want, 1e-3, "kfc scaled fp16")
+    _rel_to_max(got32, want, 1e-3, "kfc tf32")
+    ref = np.abs(want).max()
+    e16 = np.abs(got16.double().cpu().numpy() - want).max() / ref
+    e32 = np.abs(got32.double().cpu().numpy() - want).max() / ref
+    assert e16 <= 2.0 * e32 + 1e-6, (e16, e32)
+
+
 def test_tc_kernels_are_selected():
     g = nat.make_geom(2, 1, 32, 48, (20, 20), (3, 3), (1, 1), (1, 1), (1, 1), (20, 20))
     lib = nat.lib()
@@ -542,7 +565,10 @@ def test_tc_kernels_are_selected():
     assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, gs, 0, nat.MATH_TF32, 0) == b"tcgen05_fwd_tf32"
     # reduction networks: TMA-fed kernel (aligned shifted copies make any row length usable)
     assert lib.einconv_selected_kernel(nat.OP_KFC, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_kfc"
-    assert lib.einconv_selected_kernel(nat.OP_KFC, g, 0, nat.MATH_TF32, 0) == b"tcgen05_tma_kfc"
+    # fp32 in TF32 mode: scaled fp16 operand copies (same 10-bit mantissa) for kernels with several taps
+    assert lib.einconv_selected_kernel(nat.OP_KFC, g, 0, nat.MATH_TF32, 0) == b"f16scaled+tcgen05_tma_kfc"
+    g11 = nat.make_geom(2, 1, 64, 48, (20, 20), (1, 1), (1, 1), (1, 1), (0, 0), (20, 20))
+    assert lib.einconv_selected_kernel(nat.OP_KFC, g11, 0, nat.MATH_TF32, 0) == b"tcgen05_tma_kfc"
     assert lib.einconv_selected_kernel(nat.OP_KFC, g, 0, nat.MATH_FP32, 0) == b"ffma_gather_gemm"
     g24 = nat.make_geom(2, 1, 32, 48, (24, 24), (3, 3), (1, 1), (1, 1), (1, 1), (24, 24))
     assert lib.einconv_selected_kernel(nat.OP_KFC, g24, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_kfc"
