@@ -20,6 +20,7 @@
 // accumulators in TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1);
 // warps 2-5 drain TMEM, add the bias, cast and store channels-first (coalesced along positions).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -67,6 +68,7 @@ struct Params {
   long long out_total;
   const void* bias;
   void* dst;
+  long long* trace;  // bring-up only (EINCONV_CTMA_TRACE): clock64() stamps of CTA 0, 16 per tile
 };
 
 template <typename T> struct Elem;
@@ -102,6 +104,11 @@ __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint64_t a_base, ui
     for (int k = 0; k < KS; ++k) umma<TF32>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate | j | k);
   }
 }
+
+#define CTMA_TRACE(slot)                                                                     \
+  do {                                                                                       \
+    if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(tile - tile_begin) * 16 + (slot)] = clock64(); \
+  } while (0)
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -164,33 +171,42 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         mbar_wait(&bars->w_empty, pw ^ 1);
         pw ^= 1;
       }
+      CTMA_TRACE(0);
       int sg = 0;
       for (int s = 0; s < p.n_slices; ++s) {
         for (int grp = 0; grp < p.n_groups; ++grp, ++sg) {
-          if (load_w && elect_one()) {
+          // One cp.async.bulk.tensor per LANE: a single issuing thread sustains only ~one 8 KB box per
+          // 550 cycles (28 GB/s per SM, scripts/tma_bw.cu), while several issuing threads scale linearly.
+          if (load_w) {
             uint64_t* wb = &bars->w_full[n_wbars > 1 ? sg : 0];
-            if (n_wbars > 1)
-              mbar_expect_tx(wb, (uint32_t)(p.tpg * p.bn * p.cb_bytes));
-            else if (sg == 0)
-              mbar_expect_tx(wb, (uint32_t)(p.n_slices * p.taps * p.bn * p.cb_bytes));
-            for (int j = 0; j < p.tpg; ++j) {
+            if (lane == 0) {
+              if (n_wbars > 1)
+                mbar_expect_tx(wb, (uint32_t)(p.tpg * p.bn * p.cb_bytes));
+              else if (sg == 0)
+                mbar_expect_tx(wb, (uint32_t)(p.n_slices * p.taps * p.bn * p.cb_bytes));
+            }
+            __syncwarp();
+            for (int j = lane; j < p.tpg; j += 32) {
               const int tap = grp * p.tpg + j;
               tma_load_2d(w_region + (size_t)(s * p.taps + tap) * p.btile_bytes, &map_b, wb, s * p.cb_elems,
                           wrow0 + tap * p.np);
             }
           }
-          __syncwarp();
           mbar_wait(&bars->empty[st], ph ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&bars->full[st], stage_tx);
+          if (sg < 2) CTMA_TRACE(1 + sg);
+          {
+            if (lane == 0) mbar_expect_tx(&bars->full[st], stage_tx);
+            __syncwarp();
             unsigned char* stage = ring + (size_t)st * p.stage_bytes;
             const int row0 = q0 + p.group_shift[grp];
             const int col_a = g * p.cs + s * p.cb_elems;
-            for (int r = 0; r < p.slab_rows; r += p.box_rows)
-              tma_load_2d(stage + (size_t)r * p.cb_bytes, &map_a, &bars->full[st], col_a, row0 + r);
+            const int n_boxes = p.slab_rows / p.box_rows;
+            for (int bx = lane; bx < n_boxes; bx += 32)
+              tma_load_2d(stage + (size_t)bx * p.box_rows * p.cb_bytes, &map_a, &bars->full[st], col_a,
+                          row0 + bx * p.box_rows);
             if (!p.resident) {
               unsigned char* bt = stage + p.slab_bytes;
-              for (int j = 0; j < p.tpg; ++j)
+              for (int j = lane; j < p.tpg; j += 32)
                 tma_load_2d(bt + (size_t)j * p.btile_bytes, &map_b, &bars->full[st], s * p.cb_elems,
                             wrow0 + (grp * p.tpg + j) * p.np);
             }
@@ -217,13 +233,16 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const long long cls = tile / p.n_mtiles;
       const bool new_w = p.resident && cls != cur_class;
       cur_class = cls;
+      CTMA_TRACE(4);
       mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
+      CTMA_TRACE(5);
       const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.bn;
       for (int sg = 0; sg < stages_per_tile; ++sg) {
         if (new_w && (n_wbars > 1 || sg == 0)) mbar_wait(&bars->w_full[n_wbars > 1 ? sg : 0], pw);
         mbar_wait(&bars->full[st], ph);
         tc_fence_after();
+        if (sg < 2) CTMA_TRACE(6 + 2 * sg);
         if (elect_one()) {
           const uint32_t stage_a16 = ring16 + (uint32_t)st * stage16;
           const uint64_t a_base = desc_const + (uint64_t)stage_a16;
@@ -244,6 +263,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
         }
         __syncwarp();
+        if (sg < 2) CTMA_TRACE(7 + 2 * sg);
         if (++st == p.n_stages) { st = 0; ph ^= 1; }
       }
       if (new_w) pw ^= 1;
@@ -286,8 +306,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       T* dst_row = dst + ((long long)b * p.cd_total + (long long)g * p.cd + n0) * p.out_total + oflat;
 
+      if (warp == 2) CTMA_TRACE(10);
       mbar_wait_relaxed(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (warp == 2) CTMA_TRACE(11);
       const uint32_t taddr = tmem_base + acc * (uint32_t)p.bn + ((uint32_t)(quarter * 32) << 16);
       for (int c0 = 0; c0 < p.bn; c0 += 16) {
         uint32_t r[16];
@@ -298,6 +320,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+          if (warp == 2) CTMA_TRACE(12);
         }
         if (valid) {
           T* d0 = dst_row + (long long)c0 * p.out_total;
@@ -313,6 +336,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
         }
       }
+      if (warp == 2) CTMA_TRACE(13);
     }
   }
 
@@ -806,8 +830,32 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tma)");
   const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, kNumSMs);
   // (programmatic dependent launch was measured here: no gain, the GEMM's CTAs need the whole SM)
+  long long* trace = nullptr;
+  const int trace_tiles = 16;
+  if (getenv("EINCONV_CTMA_TRACE")) {
+    cudaMalloc(&trace, trace_tiles * 16 * sizeof(long long));
+    cudaMemset(trace, 0, trace_tiles * 16 * sizeof(long long));
+    p.trace = trace;
+  }
   kern<<<grid, kThreads, pl.smem, stream>>>(map_a, map_b, p);
   EINCONV_CHECK_LAUNCH("conv_tma_kernel");
+  if (trace) {  // bring-up only: synchronises and prints the pipeline timeline of CTA 0
+    long long h[trace_tiles * 16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(trace);
+    long long t0 = 0;
+    for (int i = 0; i < trace_tiles * 16; ++i)
+      if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
+    fprintf(stderr, "conv_tma trace (cycles since first stamp; P=producer M=mma E=epilogue warp 2)\n");
+    fprintf(stderr, "tile  P:start  P:st0   P:st1 | M:start M:tmem  M:full0 M:iss0  M:full1 M:iss1 | E:start E:full  E:ldone E:done\n");
+    for (int t = 0; t < trace_tiles; ++t) {
+      if (!h[t * 16]) continue;
+      fprintf(stderr, "%4d ", t);
+      for (int k : {0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13}) fprintf(stderr, "%7lld ", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   return EINCONV_OK;
 }
 

@@ -7,32 +7,39 @@
 #include <cstdint>
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 template <int RANK>
-__global__ void __launch_bounds__(128, 1) bw(const CUtensorMap* map, int iters, int n_rows_tiles, int depth, int n_w_tiles) {
+__global__ void __launch_bounds__(128, 1) bw(const CUtensorMap* map, int iters, int n_rows_tiles, int depth, int n_w_tiles, int producers) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar[8];
+  __shared__ __align__(8) uint64_t bar[32];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 8; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[s])) : "memory");
+    for (int s = 0; s < 32; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[s])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  // producers > 0: one issuing thread in each of `producers` warps; producers < 0: -producers lanes of warp 0
+  const bool lanes_mode = producers < 0;
+  if (lanes_mode) producers = -producers;
+  if (lanes_mode ? (int)threadIdx.x < producers : ((threadIdx.x & 31) == 0 && (int)(threadIdx.x >> 5) < producers)) {
+    const int pw = lanes_mode ? threadIdx.x : threadIdx.x >> 5;
+    iters /= producers;
+    unsigned char* smem_p = smem + pw * depth * 8192;
+    uint64_t* bar_p = bar + pw * 8;
     for (int i = 0; i < iters + depth; ++i) {
       if (i >= depth) {  // wait for load i - depth
         int s = (i - depth) % depth; uint32_t ph = ((i - depth) / depth) & 1, ok = 0;
-        while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0,1,0,p;\n}\n" : "=r"(ok) : "r"(smem_u32(&bar[s])), "r"(ph) : "memory");
+        while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0,1,0,p;\n}\n" : "=r"(ok) : "r"(smem_u32(&bar_p[s])), "r"(ph) : "memory");
       }
       if (i < iters) {
         int s = i % depth;
-        unsigned tile = (blockIdx.x * 7919u + i * 104729u);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[s])), "r"(8192) : "memory");
+        unsigned tile = ((blockIdx.x * 4 + pw) * 7919u + i * 104729u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_p[s])), "r"(8192) : "memory");
         if constexpr (RANK == 2) {
           int row = (tile % n_rows_tiles) * 64, col = ((tile / n_rows_tiles) % n_w_tiles) * 64;
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                       ::"r"(smem_u32(smem + s * 8192)), "l"((uint64_t)map), "r"(smem_u32(&bar[s])), "r"(col), "r"(row) : "memory");
+                       ::"r"(smem_u32(smem_p + s * 8192)), "l"((uint64_t)map), "r"(smem_u32(&bar_p[s])), "r"(col), "r"(row) : "memory");
         } else {
           int h = tile % n_rows_tiles, col = ((tile / n_rows_tiles) % n_w_tiles) * 64;
           asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                       ::"r"(smem_u32(smem + s * 8192)), "l"((uint64_t)map), "r"(smem_u32(&bar[s])), "r"(col), "r"(h), "r"(0), "r"(0), "r"(0) : "memory");
+                       ::"r"(smem_u32(smem_p + s * 8192)), "l"((uint64_t)map), "r"(smem_u32(&bar_p[s])), "r"(col), "r"(h), "r"(0), "r"(0), "r"(0) : "memory");
         }
       }
     }
@@ -43,7 +50,7 @@ int main(int argc, char** argv) {
   int variant = argc > 1 ? atoi(argv[1]) : 0, depth = argc > 2 ? atoi(argv[2]) : 4, ctas = argc > 3 ? atoi(argv[3]) : 148;
   void* fptr; cudaDriverEntryPointQueryResult q; cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fptr, cudaEnableDefault, &q);
   EncodeFn enc = (EncodeFn)fptr;
-  size_t bytes = 512ull << 20; uint16_t* d; cudaMalloc(&d, bytes); cudaMemset(d, 1, bytes);
+  size_t bytes = (size_t)(argc > 4 ? atoi(argv[4]) : 512) << 20; /* <= 64 MB stays L2-resident */ uint16_t* d; cudaMalloc(&d, bytes); cudaMemset(d, 1, bytes);
   alignas(64) CUtensorMap map; CUresult r; int n_rows_tiles, n_w_tiles = 1;
   if (variant == 0) {        // 2-d, rows of 128 B contiguous (pitch 128 B): box = contiguous 8 KB
     cuuint64_t dims[2] = {64, bytes / 128}; cuuint64_t st[1] = {128}; cuuint32_t box[2] = {64, 64}, es[2] = {1, 1};
@@ -62,15 +69,17 @@ int main(int argc, char** argv) {
   }
   CUtensorMap* gmap; cudaMalloc(&gmap, 128); cudaMemcpy(gmap, &map, 128, cudaMemcpyHostToDevice);
   int iters = 4000;
-  cudaFuncSetAttribute(bw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
-  cudaFuncSetAttribute(bw<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+  int producers = argc > 5 ? atoi(argv[5]) : 1;
+  const int smem_bytes = abs(producers) * depth * 8192;
+  cudaFuncSetAttribute(bw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  cudaFuncSetAttribute(bw<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int rep = 0; rep < 2; ++rep) {
     cudaEventRecord(e0);
-    if (variant < 2) bw<2><<<ctas, 128, 8 * 8192>>>(gmap, iters, n_rows_tiles, depth, n_w_tiles); else bw<5><<<ctas, 128, 8 * 8192>>>(gmap, iters, n_rows_tiles, depth, n_w_tiles);
+    if (variant < 2) bw<2><<<ctas, 128, smem_bytes>>>(gmap, iters, n_rows_tiles, depth, n_w_tiles, producers); else bw<5><<<ctas, 128, smem_bytes>>>(gmap, iters, n_rows_tiles, depth, n_w_tiles, producers);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
   }
   float ms; cudaEventElapsedTime(&ms, e0, e1);
-  printf("variant %d depth %d ctas %d encode %d err %s: %.3f ms, %.1f GB/s total, %.1f cycles/box/SM @1.9GHz\n", variant, depth, ctas, (int)r, cudaGetErrorString(cudaGetLastError()), ms, (double)ctas * iters * 8192 / ms / 1e6, ms * 1e-3 * 1.9e9 / iters);
+  printf("producers %d MB %d variant %d depth %d ctas %d encode %d err %s: %.3f ms, %.1f GB/s total, %.1f cycles/box/SM @1.9GHz\n", producers, (int)(bytes >> 20), variant, depth, ctas, (int)r, cudaGetErrorString(cudaGetLastError()), ms, (double)ctas * iters * 8192 / ms / 1e6, ms * 1e-3 * 1.9e9 / iters);
   return 0;
 }
