@@ -125,18 +125,26 @@ wgrad_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int col_v = g * p.cog + cotile * p.bn;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&bars->empty[st], ph ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&bars->full[st], stage_tx);
+      {
+        // one box per lane: a single issuing thread sustains only ~one 8 KB box per 550 cycles
+        if (lane == 0) mbar_expect_tx(&bars->full[st], stage_tx);
+        __syncwarp();
         unsigned char* stage = ring + (size_t)st * p.stage_bytes;
         const int r0 = kb * p.kb_rows;
         const int xrow0 = r0 + p.group_shift[tg];
-        for (int r = 0; r < p.slab_rows; r += kBoxRows)
-          tma_load_2d(stage + (size_t)r * kRowBytes, &map_x, &bars->full[st], col_x, xrow0 + r);
+        const int x_boxes = p.slab_rows / kBoxRows, v_boxes_per_block = p.kb_rows / kBoxRows;
+        const int n_boxes = x_boxes + p.n_vblocks * v_boxes_per_block;
         unsigned char* vt = stage + p.slab_bytes;
-        for (int nb = 0; nb < p.n_vblocks; ++nb)
-          for (int r = 0; r < p.kb_rows; r += kBoxRows)
+        for (int bx = lane; bx < n_boxes; bx += 32) {
+          if (bx < x_boxes) {
+            tma_load_2d(stage + (size_t)bx * kBoxRows * kRowBytes, &map_x, &bars->full[st], col_x,
+                        xrow0 + bx * kBoxRows);
+          } else {
+            const int v = bx - x_boxes, nb = v / v_boxes_per_block, r = (v - nb * v_boxes_per_block) * kBoxRows;
             tma_load_2d(vt + (size_t)(nb * p.kb_rows + r) * kRowBytes, &map_v, &bars->full[st], col_v + nb * kCB,
                         r0 + r);
+          }
+        }
       }
       __syncwarp();
       if (++st == p.n_stages) { st = 0; ph ^= 1; }
