@@ -22,6 +22,7 @@ MATH_AUTO, MATH_FP32, MATH_TF32, MATH_HALF = 0, 1, 2, 3
 KERNELS_SPECIALIZED, KERNELS_GENERIC = 0, 1
 # einconv_op
 OP_UNFOLD, OP_CONV_FWD, OP_CONV_INPUT_VJP, OP_CONV_WEIGHT_VJP, OP_KFC, OP_KFAC_REDUCE, OP_FOLD = range(7)
+OP_UNFOLD_TRANSPOSE, OP_KFAC_REDUCE_TRANSPOSE = 7, 8
 
 
 class Geom(ctypes.Structure):
@@ -94,6 +95,11 @@ SIGNATURES = {
     ),
     "einconv_kfc": (_INT, [_VOIDP, _VOIDP, _INT, _GEOMP, _DBL, _INT, _INT, _VOIDP, _I64, _VOIDP]),
     "einconv_kfac_reduce": (
+        _INT,
+        [_VOIDP, _VOIDP, _INT, _GEOMP, _DBL, _INT, _INT, _VOIDP, _I64, _VOIDP],
+    ),
+    "einconv_unfold_transpose": (_INT, [_VOIDP, _VOIDP, _INT, _GEOMP, _VOIDP]),
+    "einconv_kfac_reduce_transpose": (
         _INT,
         [_VOIDP, _VOIDP, _INT, _GEOMP, _DBL, _INT, _INT, _VOIDP, _I64, _VOIDP],
     ),

@@ -205,11 +205,14 @@ int64_t einconv_launch_count(void) { return g_launches.load(std::memory_order_re
 const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype, int math,
                                     int kernels) {
   DevGeom g;
-  if (make_dev_geom(geom, &g, op != EINCONV_OP_UNFOLD && op != EINCONV_OP_FOLD)) return nullptr;
+  const bool no_cout = op == EINCONV_OP_UNFOLD || op == EINCONV_OP_FOLD || op == EINCONV_OP_UNFOLD_TRANSPOSE ||
+                       op == EINCONV_OP_KFAC_REDUCE_TRANSPOSE;
+  if (make_dev_geom(geom, &g, !no_cout)) return nullptr;
   if (check_math(dtype, math)) return nullptr;
   switch (op) {
     case EINCONV_OP_UNFOLD: return "unfold_plane";
     case EINCONV_OP_FOLD: return "fold_gather";
+    case EINCONV_OP_UNFOLD_TRANSPOSE: return "unfold_transpose_gather";
     default: break;
   }
   if (op == EINCONV_OP_KFC) {
@@ -232,9 +235,16 @@ const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype,
 
 int64_t einconv_workspace_bytes(int op, const einconv_geom* geom, int dtype, int math, int kernels) {
   DevGeom g;
-  if (make_dev_geom(geom, &g, op != EINCONV_OP_UNFOLD && op != EINCONV_OP_FOLD)) return -1;
+  const bool no_cout = op == EINCONV_OP_UNFOLD || op == EINCONV_OP_FOLD || op == EINCONV_OP_UNFOLD_TRANSPOSE ||
+                       op == EINCONV_OP_KFAC_REDUCE_TRANSPOSE;
+  if (make_dev_geom(geom, &g, !no_cout)) return -1;
   if (check_math(dtype, math)) return -1;
-  if (op == EINCONV_OP_UNFOLD || op == EINCONV_OP_FOLD) return 0;
+  if (op == EINCONV_OP_UNFOLD || op == EINCONV_OP_FOLD || op == EINCONV_OP_UNFOLD_TRANSPOSE) return 0;
+  if (op == EINCONV_OP_KFAC_REDUCE_TRANSPOSE) {
+    // same two stages as KFAC-reduce, on the transpose-convolution view of the geometry
+    op = EINCONV_OP_KFAC_REDUCE;
+    g = swap_io(g);
+  }
   if (op == EINCONV_OP_KFC) {
     DevGeom g1;
     int64_t ub, hb;
@@ -393,15 +403,10 @@ int einconv_kfc(const void* x, void* out, int dtype, const einconv_geom* geom, d
   }
 }
 
-int einconv_kfac_reduce(const void* x, void* out, int dtype, const einconv_geom* geom, double scale,
-                        int math, int kernels, void* workspace, int64_t workspace_bytes,
-                        void* stream) {
-  EINCONV_CHECK_ARG(x && out, "kfac_reduce: NULL tensor pointer");
-  DevGeom g;
-  int st = make_dev_geom(geom, &g, false);
-  if (st) return st;
-  if ((st = check_math(dtype, math))) return st;
+static int kfac_reduce_impl(const void* x, void* out, int dtype, const DevGeom& g, double scale, int math,
+                            int kernels, void* workspace, int64_t workspace_bytes, void* stream) {
   if ((long long)g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
+  int st;
   DevGeom g2;
   if (kfac_reduce_tensor(g, dtype, math, kernels, &g2)) {
     const int64_t u_bytes = kfac_u_bytes(g);
@@ -419,6 +424,34 @@ int einconv_kfac_reduce(const void* x, void* out, int dtype, const einconv_geom*
                                   (char*)workspace + u_bytes, workspace_bytes - u_bytes, s);
   }
   return ffma_kfac_reduce(x, out, dtype, g, scale, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int einconv_kfac_reduce(const void* x, void* out, int dtype, const einconv_geom* geom, double scale,
+                        int math, int kernels, void* workspace, int64_t workspace_bytes,
+                        void* stream) {
+  EINCONV_CHECK_ARG(x && out, "kfac_reduce: NULL tensor pointer");
+  DevGeom g;
+  int st = make_dev_geom(geom, &g, false);
+  if (st) return st;
+  if ((st = check_math(dtype, math))) return st;
+  return kfac_reduce_impl(x, out, dtype, g, scale, math, kernels, workspace, workspace_bytes, stream);
+}
+
+int einconv_unfold_transpose(const void* x, void* out, int dtype, const einconv_geom* g, void* stream) {
+  EINCONV_CHECK_ARG(x && out, "unfold_transpose: NULL tensor pointer");
+  return launch_unfold_transpose(x, out, dtype, g, (cudaStream_t)stream);
+}
+
+int einconv_kfac_reduce_transpose(const void* x, void* out, int dtype, const einconv_geom* geom, double scale,
+                                  int math, int kernels, void* workspace, int64_t workspace_bytes,
+                                  void* stream) {
+  EINCONV_CHECK_ARG(x && out, "kfac_reduce_transpose: NULL tensor pointer");
+  DevGeom g;
+  int st = make_dev_geom(geom, &g, false);
+  if (st) return st;
+  if ((st = check_math(dtype, math))) return st;
+  // x lives on the convolution's OUTPUT grid: swap the roles and use the transpose membership rule
+  return kfac_reduce_impl(x, out, dtype, swap_io(g), scale, math, kernels, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

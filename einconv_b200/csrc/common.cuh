@@ -91,7 +91,26 @@ struct DevGeom {
   FastDiv out_div[kMaxDims];
   FastDiv k_div[kMaxDims];
   FastDiv in_div[kMaxDims];
+  // 0: `in` are the convolution's inputs (window sums ask "is input i under tap k of some output").
+  // 1: transpose-convolution view (swap_io): `in` are the positions o of the tensor being summed and
+  //    a position belongs to tap k iff the convolution input index s*o + dil*k - pad lies in [0, out).
+  int member_mode;
 };
+
+// Geometry of the associated convolution seen from the transpose convolution: in <-> out.
+inline DevGeom swap_io(const DevGeom& g) {
+  DevGeom t = g;
+  for (int d = 0; d < kMaxDims; ++d) {
+    t.in[d] = g.out[d];
+    t.out[d] = g.in[d];
+    t.in_div[d] = g.out_div[d];
+    t.out_div[d] = g.in_div[d];
+  }
+  t.in_total = g.out_total;
+  t.out_total = g.in_total;
+  t.member_mode = 1;
+  return t;
+}
 
 // Validates and converts the ABI struct.  Returns 0 or a negative status (message set).
 int make_dev_geom(const einconv_geom* g, DevGeom* out, bool need_c_out);

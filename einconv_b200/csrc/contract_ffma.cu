@@ -521,6 +521,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(
 constexpr int KW_MAX = 8;
 
 __device__ __forceinline__ bool tap_member(const DevGeom& g, int d, int i, int k) {
+  if (g.member_mode) {  // transpose convolution (conv_transposeNd_kfac_reduce.py): i is an output position
+    const int t = g.stride[d] * i + g.dil[d] * k - g.pad[d];
+    return t >= 0 && t < g.out[d];
+  }
   const int t = i + g.pad[d] - g.dil[d] * k;
   if (t < 0) return false;
   const int s = g.stride[d];

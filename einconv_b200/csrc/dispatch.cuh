@@ -10,6 +10,7 @@ namespace einconv {
 int launch_unfold(const void* x, const int64_t* x_strides, void* out, int dtype,
                   const einconv_geom* geom, cudaStream_t stream);
 int launch_fold(const void* gu, void* gx, int dtype, const einconv_geom* geom, cudaStream_t stream);
+int launch_unfold_transpose(const void* x, void* out, int dtype, const einconv_geom* geom, cudaStream_t stream);
 
 // contract_ffma.cu
 int ffma_conv_fwd(const void* x, const void* w, const void* bias, void* y, int dtype,

@@ -852,4 +852,78 @@ int launch_fold(const void* gu, void* gx, int dtype, const einconv_geom* geom,
   });
 }
 
+// ---------------------------------------------------------------------------------------------
+// unfoldNd_transpose (expressions/conv_transposeNd_unfold.py:81-91):
+//   out[bc, k.., i..] = x[bc, o..] if i_d = s_d o_d + dil_d k_d - p_d for every d, else 0.
+// One thread per (bc, i) walks all taps: consecutive threads hold consecutive i, so for every tap the
+// warp writes one contiguous run of `out` and (for stride 1) reads one contiguous run of x.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) unfold_transpose_kernel(const T* __restrict__ x, T* __restrict__ out,
+                                                               const __grid_constant__ DevGeom g, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long bc = idx / g.in_total;
+  uint32_t rem = (uint32_t)(idx - bc * g.in_total);
+  const uint32_t iflat = rem;
+  int ipos[kMaxDims];
+  for (int d = g.n_dims - 1; d >= 0; --d) {
+    uint32_t q, r;
+    g.in_div[d].divmod(rem, q, r);
+    ipos[d] = (int)r + g.pad[d];
+    rem = q;
+  }
+  const T* src = x + bc * g.out_total;
+  T* dst = out + bc * (long long)g.k_total * g.in_total + iflat;
+  int kpos[kMaxDims];
+  for (int d = 0; d < g.n_dims; ++d) kpos[d] = 0;
+  for (int kf = 0; kf < g.k_total; ++kf) {
+    bool ok = true;
+    int oflat = 0;
+    for (int d = 0; d < g.n_dims; ++d) {
+      const int t = ipos[d] - g.dil[d] * kpos[d];
+      int o = t;
+      if (g.stride[d] != 1) {
+        o = t / g.stride[d];
+        ok = ok && o * g.stride[d] == t;
+      }
+      ok = ok && t >= 0 && o < g.out[d];
+      oflat = oflat * g.out[d] + o;
+    }
+    T v = T(0);
+    if (ok) v = __ldg(src + oflat);
+    store_stream1<T>(dst + (long long)kf * g.in_total, v);
+    for (int d = g.n_dims - 1; d >= 0; --d) {
+      if (++kpos[d] < g.k[d]) break;
+      kpos[d] = 0;
+    }
+  }
+}
+
+int launch_unfold_transpose(const void* x, void* out, int dtype, const einconv_geom* geom, cudaStream_t stream) {
+  DevGeom g;
+  int st = make_dev_geom(geom, &g, /*need_c_out=*/false);
+  if (st) return st;
+  const int64_t esz = elem_size(dtype);
+  EINCONV_CHECK_ARG(esz > 0, "unfold_transpose: unknown dtype %d", dtype);
+  const long long total = (long long)g.batch * g.groups * g.c_in_g * g.in_total;
+  if (total == 0 || g.k_total == 0) return EINCONV_OK;
+  const long long blocks = (total + 255) / 256;
+  EINCONV_CHECK_ARG(blocks < (1ll << 31), "unfold_transpose: tensor too large");
+  switch (esz) {
+    case 2:
+      unfold_transpose_kernel<uint16_t><<<(unsigned)blocks, 256, 0, stream>>>((const uint16_t*)x, (uint16_t*)out, g, total);
+      break;
+    case 4:
+      unfold_transpose_kernel<uint32_t><<<(unsigned)blocks, 256, 0, stream>>>((const uint32_t*)x, (uint32_t*)out, g, total);
+      break;
+    default:
+      unfold_transpose_kernel<unsigned long long><<<(unsigned)blocks, 256, 0, stream>>>(
+          (const unsigned long long*)x, (unsigned long long*)out, g, total);
+      break;
+  }
+  EINCONV_CHECK_LAUNCH("unfold_transpose_kernel");
+  return EINCONV_OK;
+}
+
 }  // namespace einconv

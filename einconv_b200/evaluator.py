@@ -24,7 +24,7 @@ import torch
 from torch import Tensor
 
 from einconv_b200 import _native as nat
-from einconv_b200.utils import _tuple, resolve_geometry
+from einconv_b200.utils import _tuple, get_conv_input_size, resolve_geometry
 
 # --------------------------------------------------------------------------------------------
 # math-mode policy
@@ -306,6 +306,81 @@ def kfac_reduce(x, kernel_size, stride=1, padding=0, dilation=1, groups=1, simpl
 
 
 # --------------------------------------------------------------------------------------------
+# transpose convolutions.  Hyper-parameters are those of the ASSOCIATED
+# convolution; ``x`` has that convolution's OUTPUT sizes.
+# --------------------------------------------------------------------------------------------
+def _transpose_geom(x, groups, kernel_size, stride, padding, output_padding, dilation):
+    """Geometry of the associated convolution for a transpose-convolution input ``x``
+    (``conv_transposeNd_unfold.py:93-112``): its input sizes follow from ``x``'s spatial sizes."""
+    N = x.dim() - 2
+    t_k, t_s, t_p = _tuple(kernel_size, N), _tuple(stride, N), _tuple(padding, N)
+    t_d, t_op = _tuple(dilation, N), _tuple(output_padding, N)
+    in_sizes = tuple(
+        get_conv_input_size(o, k, s, p, op, d)
+        for o, k, s, p, op, d in zip(x.shape[2:], t_k, t_s, t_p, t_op, t_d)
+    )
+    c = x.shape[1]
+    if c % groups != 0:
+        raise ValueError(f"Groups ({groups}) must divide the number of channels ({c}).")
+    g, _, out = _geom(x.shape[0], groups, c // groups, 0, in_sizes, t_k, t_s, t_p, t_d)
+    assert tuple(out) == tuple(x.shape[2:])
+    return g, t_k, in_sizes
+
+
+def unfold_transpose(x: Tensor, kernel_size, stride=1, padding=0, output_padding=0, dilation=1) -> Tensor:
+    """``[B, C, *out] -> [B, C * prod(k), prod(in)]`` — network of ``conv_transposeNd_unfold.py:81-91``
+    (bit-exact gather ``out[b, c, k, i] = x[b, c, o]`` where ``i = s o + d k - p``)."""
+    device = nat.require_cuda(x)
+    x = x.contiguous()
+    g, t_k, in_sizes = _transpose_geom(x, 1, kernel_size, stride, padding, output_padding, dilation)
+    k_total = i_total = 1
+    for k in t_k:
+        k_total *= k
+    for i in in_sizes:
+        i_total *= i
+    result = torch.empty((x.shape[0], x.shape[1] * k_total, i_total), dtype=x.dtype, device=device)
+    if result.numel() == 0:
+        return result
+    with torch.cuda.device(device):
+        st = nat.lib().einconv_unfold_transpose(
+            x.data_ptr(), result.data_ptr(), nat.dtype_code(x.dtype), g, nat.stream_ptr(device)
+        )
+    nat.check(st, "einconv_unfold_transpose")
+    return result
+
+
+def kfac_reduce_transpose(x, kernel_size, stride=1, padding=0, output_padding=0, dilation=1, groups=1,
+                          simplify=True, scale=None) -> Tensor:
+    """Input-based KFAC-reduce factor ``[G, A, A]`` of a transpose convolution
+    (``conv_transposeNd_kfac_reduce.py:95-160``); ``scale`` defaults to ``1 / (B * prod(in)^2)``."""
+    device = nat.require_cuda(x)
+    x = x.contiguous()
+    g, t_k, in_sizes = _transpose_geom(x, groups, kernel_size, stride, padding, output_padding, dilation)
+    k_total = i_total = 1
+    for k in t_k:
+        k_total *= k
+    for i in in_sizes:
+        i_total *= i
+    B = x.shape[0]
+    A = x.shape[1] // groups * k_total
+    if scale is None:
+        denom = B * i_total**2
+        scale = float(torch.tensor([1.0 / denom]).to(x.dtype)) if denom > 0 else 0.0
+    result = torch.empty((groups, A, A), dtype=x.dtype, device=device)
+    if result.numel() == 0:
+        return result
+    code, math, kern = nat.dtype_code(x.dtype), _math_for(x.dtype), _kernels_for(simplify)
+    ws, ws_bytes = _workspace(nat.OP_KFAC_REDUCE_TRANSPOSE, g, code, math, kern, device)
+    with torch.cuda.device(device):
+        st = nat.lib().einconv_kfac_reduce_transpose(
+            x.data_ptr(), result.data_ptr(), code, g, float(scale), math, kern,
+            nat.ptr(ws), ws_bytes, nat.stream_ptr(device),
+        )
+    nat.check(st, "einconv_kfac_reduce_transpose")
+    return result
+
+
+# --------------------------------------------------------------------------------------------
 # differentiable wrappers (the reference's einsum is differentiable, modules/conv.py:173-182)
 # --------------------------------------------------------------------------------------------
 class _ConvNdFunction(torch.autograd.Function):
@@ -397,6 +472,12 @@ class Plan:
         if self.kind == "kfac_reduce":
             return kfac_reduce(t["x"], h["kernel_size"], h["stride"], h["padding"], h["dilation"],
                                h["groups"], self.simplify)
+        if self.kind == "unfold_transpose":
+            return unfold_transpose(t["x"], h["kernel_size"], h["stride"], h["padding"],
+                                    h["output_padding"], h["dilation"])
+        if self.kind == "kfac_reduce_transpose":
+            return kfac_reduce_transpose(t["x"], h["kernel_size"], h["stride"], h["padding"],
+                                         h["output_padding"], h["dilation"], h["groups"], self.simplify)
         raise AssertionError(self.kind)
 
 

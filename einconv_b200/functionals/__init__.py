@@ -1,6 +1,7 @@
-"""Functional interface: ``convNd`` and ``unfoldNd`` (plus ``unfoldNd_host`` for host buffers)."""
+"""Functional interface: ``convNd``, ``unfoldNd``, ``unfoldNd_transpose`` (plus ``unfoldNd_host``)."""
 
 from einconv_b200.functionals.conv import convNd
 from einconv_b200.functionals.unfold import unfoldNd, unfoldNd_host
+from einconv_b200.functionals.unfold_transpose import unfoldNd_transpose
 
-__all__ = ["convNd", "unfoldNd", "unfoldNd_host"]
+__all__ = ["convNd", "unfoldNd", "unfoldNd_transpose", "unfoldNd_host"]

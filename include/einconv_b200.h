@@ -99,7 +99,9 @@ typedef enum {
   EINCONV_OP_CONV_WEIGHT_VJP = 3,
   EINCONV_OP_KFC = 4,
   EINCONV_OP_KFAC_REDUCE = 5,
-  EINCONV_OP_FOLD = 6
+  EINCONV_OP_FOLD = 6,
+  EINCONV_OP_UNFOLD_TRANSPOSE = 7,
+  EINCONV_OP_KFAC_REDUCE_TRANSPOSE = 8
 } einconv_op;
 
 int einconv_abi_version(void);
@@ -155,6 +157,28 @@ int einconv_kfc(const void* x, void* out, int dtype, const einconv_geom* g, doub
 int einconv_kfac_reduce(const void* x, void* out, int dtype, const einconv_geom* g, double scale,
                         int math, int kernels, void* workspace, int64_t workspace_bytes,
                         void* stream);
+
+/* ---- transpose convolutions.  The geometry always describes the ASSOCIATED
+ * convolution: `in` = its input sizes (the transpose convolution's output), `out` = its output sizes
+ * (the spatial sizes of the tensor x passed here), with out = 1 + floor((in + 2p - d(k-1) - 1) / s);
+ * output_padding is already folded into `in` (einconv/utils.py:163-205). ---- */
+
+/* Input unfolding of a transpose convolution.  Replaces torch.einsum at
+ * einconv/functionals/unfold_transpose.py:70 for the network of
+ * expressions/conv_transposeNd_unfold.py:81-91:
+ *   out[b, c, k.., i..] = x[b, c, o..]  if  i_d = s_d o_d + d_d k_d - p_d  for every d,  else 0.
+ * x: contiguous [B, C, out..], C = g->groups * g->c_in_g; out: contiguous [B, C*prod(k), prod(in)].
+ * Bit-exact copy. */
+int einconv_unfold_transpose(const void* x, void* out, int dtype, const einconv_geom* g, void* stream);
+
+/* Input-based KFAC-reduce factor of a transpose convolution (network of
+ * expressions/conv_transposeNd_kfac_reduce.py:95-110), A = C_g * prod(k):
+ *   out[g, a, a'] = scale * sum_b u[b,g,a] u[b,g,a'],
+ *   u[b,g,(c,k..)] = sum_{o.. : 0 <= s o + d k - p < in} x[b, g*C_g + c, o..];
+ * reference scale = 1 / (B * prod(in)^2).  x: [B, G*C_g, out..] with C_g = g->c_in_g. */
+int einconv_kfac_reduce_transpose(const void* x, void* out, int dtype, const einconv_geom* g, double scale,
+                                  int math, int kernels, void* workspace, int64_t workspace_bytes,
+                                  void* stream);
 
 /* Name of the kernel family the dispatcher would pick (static string; for tests, logs and the
  * launch counter in bench.py).  Returns NULL on invalid arguments. */

@@ -187,3 +187,52 @@ def kfac_reduce(x, kernel_size, stride=1, padding=0, dilation=1, groups=1, scale
         ot = int(np.prod(_out_sizes(g)))
         scale = 1.0 / (xs[0] * ot**2)
     return _factor(lib().oracle_kfac_reduce, x, kernel_size, stride, padding, dilation, groups, scale)
+
+
+# ---- transpose convolutions ---------------------------------------------
+def conv_input_size(out_size, kernel_size, stride, padding, output_padding, dilation) -> int:
+    """Input size of the associated convolution (``einconv/utils.py:163-205``), with its check."""
+    i = (out_size - 1) * stride - 2 * padding + dilation * (kernel_size - 1) + 1 + output_padding
+    if out_size != output_size(i, kernel_size, stride, padding, dilation):
+        raise ValueError(f"Output size {out_size} does not match re-computed output size.")
+    return i
+
+
+def _transpose_geometry(x_shape, groups, kernel_size, stride, padding, output_padding, dilation) -> Geom:
+    n = len(x_shape) - 2
+    ks, ss, ds = _tup(kernel_size, n), _tup(stride, n), _tup(dilation, n)
+    ps, ops = _tup(padding, n), _tup(output_padding, n)
+    in_sizes = [conv_input_size(x_shape[2 + d], ks[d], ss[d], ps[d], ops[d], ds[d]) for d in range(n)]
+    g = geometry(x_shape[0], groups, x_shape[1] // groups, 0, in_sizes, ks, ss, ps, ds)
+    assert _out_sizes(g) == list(x_shape[2:]), (_out_sizes(g), x_shape)
+    return g
+
+
+def unfold_transpose(x: np.ndarray, kernel_size, stride=1, padding=0, output_padding=0, dilation=1) -> np.ndarray:
+    """Bit-exact input unfolding of a transpose convolution: ``x`` [B, C, *out] -> [B, C*Kt, It]
+    (``conv_transposeNd_unfold.py:81-91``)."""
+    x = np.ascontiguousarray(x)
+    g = _transpose_geometry(x.shape, 1, kernel_size, stride, padding, output_padding, dilation)
+    n = g.n_dims
+    kt = int(np.prod([g.k[d] for d in range(n)]))
+    it = int(np.prod([g.in_[d] for d in range(n)]))
+    out = np.empty((x.shape[0], x.shape[1] * kt, it), dtype=x.dtype)
+    lib().oracle_unfold_transpose(_p(x), _p(out), ctypes.c_int(x.dtype.itemsize), ctypes.byref(g))
+    return out
+
+
+def kfac_reduce_transpose(x, kernel_size, stride=1, padding=0, output_padding=0, dilation=1, groups=1,
+                          scale=None) -> np.ndarray:
+    """Input-based KFAC-reduce factor of a transpose convolution, scale defaults to
+    1 / (B * prod(in)^2) (``conv_transposeNd_kfac_reduce.py:143-145``)."""
+    x = _f64(x)
+    g = _transpose_geometry(x.shape, groups, kernel_size, stride, padding, output_padding, dilation)
+    n = g.n_dims
+    kt = int(np.prod([g.k[d] for d in range(n)]))
+    it = int(np.prod([g.in_[d] for d in range(n)]))
+    A = x.shape[1] // groups * kt
+    if scale is None:
+        scale = 1.0 / (x.shape[0] * it**2)
+    out = np.empty((groups, A, A), dtype=np.float64)
+    lib().oracle_kfac_reduce_transpose(_p(x), _p(out), ctypes.byref(g), ctypes.c_double(scale))
+    return out

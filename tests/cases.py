@@ -190,6 +190,51 @@ FACTOR_CASES = _mk(
 )
 
 # -------------------------------------------------------------------------------------------
+# transpose convolutions.  x has the associated convolution's OUTPUT sizes.
+# test/functionals/transpose_unfold_cases.py:7-72 and
+# test/expressions/conv_transposeNd_kfac_reduce_cases.py:7-125, plus a few larger / N = 4 cases
+# -------------------------------------------------------------------------------------------
+TRANSPOSE_UNFOLD_CASES = _mk(
+    "tunf",
+    [
+        dict(x=(2, 3, 50), kernel_size=1),
+        dict(x=(5, 2, 9), kernel_size=3, kwargs=dict(stride=2, padding=1, output_padding=1, dilation=2)),
+        dict(x=(2, 3, 10, 10), kernel_size=1),
+        dict(x=(5, 2, 9, 7), kernel_size=(3, 2),
+             kwargs=dict(stride=(2, 1), padding=(1, 0), output_padding=(1, 0), dilation=(2, 2))),
+        dict(x=(2, 3, 10, 10, 10), kernel_size=1),
+        dict(x=(5, 2, 9, 7, 6), kernel_size=(3, 2, 4),
+             kwargs=dict(stride=(2, 1, 3), padding=(1, 0, 2), output_padding=(1, 0, 2), dilation=(2, 2, 1))),
+        # additions
+        dict(x=(3, 4, 17, 13), kernel_size=3, kwargs=dict(padding=1)),
+        dict(x=(2, 3, 12, 11), kernel_size=(4, 3), kwargs=dict(stride=2, padding=1)),
+        dict(x=(1, 2, 4, 5, 3, 4), kernel_size=(2, 3, 2, 2), kwargs=dict(stride=(1, 2, 1, 2), padding=(0, 1, 0, 0))),
+    ],
+)
+
+TRANSPOSE_FACTOR_CASES = _mk(
+    "tfac",
+    [
+        dict(x=(2, 3, 8), kernel_size=5),
+        dict(x=(2, 3, 8), kernel_size=5, kwargs=dict(stride=2)),
+        dict(x=(2, 4, 8), kernel_size=5, kwargs=dict(stride=3, groups=2)),
+        dict(x=(2, 3, 8), kernel_size=5, kwargs=dict(padding=2)),
+        dict(x=(2, 3, 8), kernel_size=5, kwargs=dict(output_padding=1, stride=2)),
+        dict(x=(2, 3, 8), kernel_size=5, kwargs=dict(dilation=2)),
+        dict(x=(2, 3, 8), kernel_size=(3,), kwargs=dict(padding=(1,), stride=(2,), dilation=(1,), output_padding=(1,))),
+        dict(x=(2, 3, 8, 7), kernel_size=5),
+        dict(x=(2, 3, 8, 7), kernel_size=(5, 3),
+             kwargs=dict(padding=(1, 2), stride=(2, 3), dilation=(2, 1), output_padding=(1, 2))),
+        dict(x=(2, 3, 8, 7, 6), kernel_size=5),
+        dict(x=(2, 3, 8, 7, 6), kernel_size=(5, 3, 2),
+             kwargs=dict(padding=(0, 1, 2), stride=(3, 2, 1), dilation=(1, 2, 3), output_padding=(2, 0, 0))),
+        # additions
+        dict(x=(4, 12, 14, 14), kernel_size=3, kwargs=dict(padding=1, groups=3)),
+        dict(x=(3, 40, 9, 9), kernel_size=3, kwargs=dict(stride=2, padding=1, output_padding=1)),
+    ],
+)
+
+# -------------------------------------------------------------------------------------------
 # index pattern — test/conv_index_pattern_cases.py:5-24
 # -------------------------------------------------------------------------------------------
 INDEX_PATTERN_CASES = [

@@ -200,6 +200,68 @@ def test_unfold_baseline_c2_full_size_exact(unfold_variant):
 
 
 # =============================================================================================
+# transpose convolutions: unfold (bit-exact) and KFAC-reduce factor
+# =============================================================================================
+@pytest.mark.parametrize("case", C.TRANSPOSE_UNFOLD_CASES, ids=[c["id"] for c in C.TRANSPOSE_UNFOLD_CASES])
+@pytest.mark.parametrize("simplify", SIMPLIFY)
+def test_unfold_transpose_bit_exact(case, simplify):
+    from einconv_b200.functionals import unfoldNd_transpose
+
+    x = C.draw_input(case)
+    want = direct.unfold_transpose(x.numpy(), case["kernel_size"], **case["kwargs"])
+    got = unfoldNd_transpose(x.to(DEV), case["kernel_size"], **case["kwargs"], simplify=simplify)
+    assert got.dtype == x.dtype and tuple(got.shape) == want.shape
+    assert torch.equal(got.cpu(), torch.from_numpy(want))
+    golden("unfold_transpose").check(case["id"], got.cpu().numpy(), 0, 0, exact=True)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float64])
+def test_unfold_transpose_other_dtypes_and_einsum_hook(dtype):
+    from einconv_b200.expressions import conv_transposeNd_unfold
+
+    case = C.TRANSPOSE_UNFOLD_CASES[5]
+    x = C.draw_input(case).to(dtype)
+    raw = x.view(torch.int16).numpy() if dtype == torch.bfloat16 else x.numpy()
+    want = direct.unfold_transpose(raw, case["kernel_size"], **case["kwargs"])
+    eq, ops, shape = conv_transposeNd_unfold.einsum_expression(x.to(DEV), case["kernel_size"], **case["kwargs"])
+    got = torch.einsum(eq, *ops).reshape(shape).cpu()
+    got_raw = got.view(torch.int16).numpy() if dtype == torch.bfloat16 else got.numpy()
+    assert np.array_equal(got_raw, want)
+
+
+@pytest.mark.parametrize("case", C.TRANSPOSE_FACTOR_CASES, ids=[c["id"] for c in C.TRANSPOSE_FACTOR_CASES])
+@pytest.mark.parametrize("simplify", SIMPLIFY)
+def test_kfac_reduce_transpose_fp32(case, simplify):
+    """Through the reference's calling convention: einsum_expression + torch.einsum(...).reshape(shape);
+    the reference's tolerance for factors (rtol 5e-5)."""
+    from einconv_b200.expressions import conv_transposeNd_kfac_reduce
+
+    x = C.draw_input(case)
+    want = direct.kfac_reduce_transpose(x.numpy(), case["kernel_size"], **case["kwargs"])
+    eq, ops, shape = conv_transposeNd_kfac_reduce.einsum_expression(
+        x.to(DEV), case["kernel_size"], **case["kwargs"], simplify=simplify
+    )
+    got = torch.einsum(eq, *ops).reshape(shape)
+    assert tuple(got.shape) == want.shape
+    close(got, want, 5e-5, 1e-7, "kfac_reduce_transpose")
+    golden("kfac_reduce_transpose").check(case["id"], got.cpu().numpy(), 5e-5, 1e-7)
+
+
+def test_kfac_reduce_transpose_tensor_core_stage2():
+    """A >= 256: window sums + TF32 Gram on the TMA kernel (1e-3 max|ref|)."""
+    torch.manual_seed(0)
+    x = torch.rand(40, 64, 9, 9)
+    kw = dict(stride=2, padding=1, output_padding=1)
+    want = direct.kfac_reduce_transpose(x.numpy(), 3, **kw)
+    evaluator.set_fp32_math("tf32")
+    try:
+        got = evaluator.kfac_reduce_transpose(x.to(DEV), 3, **kw)
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, 1e-3, "kfac_reduce_transpose tf32")
+
+
+# =============================================================================================
 # forward
 # =============================================================================================
 FWD = C.CONV_CASES + C.SPECIAL_CASES + C.EDGE_CASES

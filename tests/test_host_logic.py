@@ -14,6 +14,8 @@ from torch import nn
 import einconv_b200
 from einconv_b200 import index_pattern, index_pattern_logical
 from einconv_b200.expressions import (
+    conv_transposeNd_kfac_reduce,
+    conv_transposeNd_unfold,
     convNd_forward,
     convNd_input_vjp,
     convNd_kfac_reduce,
@@ -235,7 +237,9 @@ def _expr(op, case):
             return convNd_input_vjp.einsum_expression(w, v, tuple(x.shape[2:]), **kw)
         return convNd_weight_vjp.einsum_expression(x, v, tuple(w.shape[2:]), **kw)
     x = C.draw_input(case)
-    mod = {"unfold": convNd_unfold, "kfc": convNd_kfc, "kfac_reduce": convNd_kfac_reduce}[op]
+    mod = {"unfold": convNd_unfold, "kfc": convNd_kfc, "kfac_reduce": convNd_kfac_reduce,
+           "unfold_transpose": conv_transposeNd_unfold,
+           "kfac_reduce_transpose": conv_transposeNd_kfac_reduce}[op]
     return mod.einsum_expression(x, case["kernel_size"], **kw)
 
 
@@ -244,6 +248,8 @@ EQ_CASES = (
     + [(op, c) for op in ("input_vjp", "weight_vjp") for c in C.VJP_CASES + C.SPECIAL_CASES]
     + [("unfold", c) for c in C.UNFOLD_CASES]
     + [(op, c) for op in ("kfc", "kfac_reduce") for c in C.FACTOR_CASES]
+    + [("unfold_transpose", c) for c in C.TRANSPOSE_UNFOLD_CASES]
+    + [("kfac_reduce_transpose", c) for c in C.TRANSPOSE_FACTOR_CASES]
 )
 
 
@@ -264,7 +270,9 @@ NUM_CASES = [("forward", c) for c in C.SPECIAL_CASES] + [("unfold", C.UNFOLD_CAS
                                                          ("kfc", C.FACTOR_CASES[8]),
                                                          ("kfac_reduce", C.FACTOR_CASES[11]),
                                                          ("weight_vjp", C.VJP_CASES[9]),
-                                                         ("input_vjp", C.VJP_CASES[11])]
+                                                         ("input_vjp", C.VJP_CASES[11]),
+                                                         ("unfold_transpose", C.TRANSPOSE_UNFOLD_CASES[5]),
+                                                         ("kfac_reduce_transpose", C.TRANSPOSE_FACTOR_CASES[8])]
 
 
 @pytest.mark.parametrize("op,case", NUM_CASES, ids=[f"{op}:{c['id']}" for op, c in NUM_CASES])
@@ -277,7 +285,7 @@ def test_simplified_expression_is_a_valid_einsum(op, case):
         _, _, b = C.draw_forward(case)
         out = out + b.reshape(1, -1, *([1] * (out.dim() - 2)))
     rtol = 5e-5 if "kf" in op else 2e-5
-    golden(op).check(case["id"], out.numpy(), rtol, 1e-5, exact=(op == "unfold"))
+    golden(op).check(case["id"], out.numpy(), rtol, 1e-5, exact=(op in ("unfold", "unfold_transpose")))
 
 
 # ---- no CPU fallback ------------------------------------------------------------------------------
