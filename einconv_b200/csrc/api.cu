@@ -62,6 +62,7 @@ int make_dev_geom(const einconv_geom* g, DevGeom* out, bool need_c_out) {
     d.out_div[i] = FastDiv((uint32_t)g->out[i]);
     d.k_div[i] = FastDiv((uint32_t)g->k[i]);
     d.in_div[i] = FastDiv((uint32_t)g->in[i]);
+    d.stride_div[i] = FastDiv((uint32_t)g->stride[i]);
     in_total *= g->in[i];
     out_total *= g->out[i];
     k_total *= g->k[i];

@@ -91,6 +91,7 @@ struct DevGeom {
   FastDiv out_div[kMaxDims];
   FastDiv k_div[kMaxDims];
   FastDiv in_div[kMaxDims];
+  FastDiv stride_div[kMaxDims];
   // 0: `in` are the convolution's inputs (window sums ask "is input i under tap k of some output").
   // 1: transpose-convolution view (swap_io): `in` are the positions o of the tensor being summed and
   //    a position belongs to tap k iff the convolution input index s*o + dil*k - pad lies in [0, out).

@@ -861,6 +861,20 @@ int launch_fold(const void* gu, void* gx, int dtype, const einconv_geom* geom,
 template <typename T>
 __global__ void __launch_bounds__(256) unfold_transpose_kernel(const T* __restrict__ x, T* __restrict__ out,
                                                                const __grid_constant__ DevGeom g, long long total) {
+  // per-CTA table: dil_d * k_d of every tap (kMaxDims bytes... ints per tap), so that the tap loop has
+  // no odometer and can be unrolled with its loads issued ahead of the stores
+  extern __shared__ int s_tap[];  // [k_total][n_dims]
+  for (int e = threadIdx.x; e < g.k_total * g.n_dims; e += blockDim.x) {
+    const int kf = e / g.n_dims, d = e - kf * g.n_dims;
+    uint32_t rem = (uint32_t)kf, kd = 0;
+    for (int dd = g.n_dims - 1; dd >= d; --dd) {
+      uint32_t q;
+      g.k_div[dd].divmod(rem, q, kd);
+      rem = q;
+    }
+    s_tap[e] = g.dil[d] * (int)kd;
+  }
+  __syncthreads();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const long long bc = idx / g.in_total;
@@ -875,28 +889,39 @@ __global__ void __launch_bounds__(256) unfold_transpose_kernel(const T* __restri
   }
   const T* src = x + bc * g.out_total;
   T* dst = out + bc * (long long)g.k_total * g.in_total + iflat;
-  int kpos[kMaxDims];
-  for (int d = 0; d < g.n_dims; ++d) kpos[d] = 0;
-  for (int kf = 0; kf < g.k_total; ++kf) {
-    bool ok = true;
+  auto source = [&](int kf, bool& ok) {
+    ok = true;
     int oflat = 0;
+    const int* tap = s_tap + kf * g.n_dims;
     for (int d = 0; d < g.n_dims; ++d) {
-      const int t = ipos[d] - g.dil[d] * kpos[d];
-      int o = t;
-      if (g.stride[d] != 1) {
-        o = t / g.stride[d];
-        ok = ok && o * g.stride[d] == t;
-      }
-      ok = ok && t >= 0 && o < g.out[d];
-      oflat = oflat * g.out[d] + o;
+      const int t = ipos[d] - tap[d];
+      uint32_t o, r;
+      g.stride_div[d].divmod((uint32_t)max(t, 0), o, r);  // multiply-high: no integer division in the loop
+      ok = ok && t >= 0 && r == 0 && (int)o < g.out[d];
+      oflat = oflat * g.out[d] + (int)o;
     }
+    return oflat;
+  };
+  constexpr int U = 4;
+  int kf = 0;
+  for (; kf + U <= g.k_total; kf += U) {
+    T v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      bool ok;
+      const int oflat = source(kf + u, ok);
+      v[u] = T(0);
+      if (ok) v[u] = __ldg(src + oflat);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) store_stream1<T>(dst + (long long)(kf + u) * g.in_total, v[u]);
+  }
+  for (; kf < g.k_total; ++kf) {
+    bool ok;
+    const int oflat = source(kf, ok);
     T v = T(0);
     if (ok) v = __ldg(src + oflat);
     store_stream1<T>(dst + (long long)kf * g.in_total, v);
-    for (int d = g.n_dims - 1; d >= 0; --d) {
-      if (++kpos[d] < g.k[d]) break;
-      kpos[d] = 0;
-    }
   }
 }
 
@@ -910,15 +935,17 @@ int launch_unfold_transpose(const void* x, void* out, int dtype, const einconv_g
   if (total == 0 || g.k_total == 0) return EINCONV_OK;
   const long long blocks = (total + 255) / 256;
   EINCONV_CHECK_ARG(blocks < (1ll << 31), "unfold_transpose: tensor too large");
+  const size_t smem = (size_t)g.k_total * g.n_dims * sizeof(int);
+  EINCONV_CHECK_ARG(smem <= 40 * 1024, "unfold_transpose: more than %d taps", (int)(40 * 1024 / 4 / g.n_dims));
   switch (esz) {
     case 2:
-      unfold_transpose_kernel<uint16_t><<<(unsigned)blocks, 256, 0, stream>>>((const uint16_t*)x, (uint16_t*)out, g, total);
+      unfold_transpose_kernel<uint16_t><<<(unsigned)blocks, 256, smem, stream>>>((const uint16_t*)x, (uint16_t*)out, g, total);
       break;
     case 4:
-      unfold_transpose_kernel<uint32_t><<<(unsigned)blocks, 256, 0, stream>>>((const uint32_t*)x, (uint32_t*)out, g, total);
+      unfold_transpose_kernel<uint32_t><<<(unsigned)blocks, 256, smem, stream>>>((const uint32_t*)x, (uint32_t*)out, g, total);
       break;
     default:
-      unfold_transpose_kernel<unsigned long long><<<(unsigned)blocks, 256, 0, stream>>>(
+      unfold_transpose_kernel<unsigned long long><<<(unsigned)blocks, 256, smem, stream>>>(
           (const unsigned long long*)x, (unsigned long long*)out, g, total);
       break;
   }
