@@ -339,25 +339,12 @@ struct FlatParams {
   FastDiv ext_div[ND], out_div[ND], k_div[ND], chan_div, chunk_div;
 };
 
-#ifndef EINCONV_FLAT_EXP
-#define EINCONV_FLAT_EXP 0  // timing experiments only: 1 = no input loads, 2 = no output stores
-#endif
-#ifndef EINCONV_FLAT_STORE
-#define EINCONV_FLAT_STORE 0
-#endif
+// streaming (evict-first) store; st.global / .cg / .wt were measured and make no difference here
 template <typename T>
 __device__ __forceinline__ void store_stream1(T* dst, T val) {
   using U = std::conditional_t<sizeof(T) == 8, unsigned long long,
                                std::conditional_t<sizeof(T) == 4, unsigned int, unsigned short>>;
-#if EINCONV_FLAT_STORE == 0
   __stcs(reinterpret_cast<U*>(dst), (U)val);
-#elif EINCONV_FLAT_STORE == 1
-  *reinterpret_cast<U*>(dst) = (U)val;
-#elif EINCONV_FLAT_STORE == 2
-  __stcg(reinterpret_cast<U*>(dst), (U)val);
-#else
-  __stwt(reinterpret_cast<U*>(dst), (U)val);
-#endif
 }
 
 // One chunk of NI x 256 consecutive outputs for every tap of the CTA: slots 0..NI-2 are valid for
@@ -444,9 +431,7 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
           off += v * p.xs[d];
         }
         vals[u] = T(0);
-#if EINCONV_FLAT_EXP != 1
         if (ok) vals[u] = __ldg(src + off);
-#endif
         int carry = 0;
 #pragma unroll
         for (int d = ND - 1; d >= 1; --d) {
@@ -487,11 +472,7 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
     const int n_i = min(kFlatJpt, (left + kFlatThreads - 1) / kFlatThreads);
     const bool last_on = (n_i - 1) * kFlatThreads + tid < left;
     T* dst = dst_plane + jb;
-#if EINCONV_FLAT_EXP == 2
-    const int n_taps = (off[0] == 0x7fffffff) ? 1 : 0;
-#else
     const int n_taps = t1 - t0;
-#endif
     switch (n_i) {
 #define EINCONV_FLAT_CASE(NI)                                                         \
   case NI:                                                                            \
@@ -925,6 +906,161 @@ __global__ void __launch_bounds__(256) unfold_transpose_kernel(const T* __restri
   }
 }
 
+// Table-driven variant: per CTA, tab_d[k_d][i_d] = (o_d * prod(O_e, e > d)) or a large negative
+// sentinel (one small table per dimension, sum_d K_d * I_d entries), the (b, c) plane of x staged in
+// shared memory when it fits.  Per output element the tap loop is then ND table look-ups, one add, one
+// sign test, one plane read and one coalesced streaming store, instead of ND divisions.
+constexpr int kTransposeSentinel = -(1 << 28);
+
+template <typename T, int ND>
+__global__ void __launch_bounds__(256) unfold_transpose_tab_kernel(const T* __restrict__ x, T* __restrict__ out,
+                                                                   const __grid_constant__ DevGeom g, int lead,
+                                                                   int tab_total, int plane_in_smem) {
+  // geometry dims lead .. lead + n_dims - 1 of this kernel's ND-vector are real, leading ones are unit
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* tab = reinterpret_cast<int*>(smem_raw);           // per-dim tables, concatenated
+  int* tapk = tab + tab_total;                            // [k_total][ND]: k_d * I_d (row offset into tab_d)
+  T* plane = reinterpret_cast<T*>(smem_raw + ((((size_t)tab_total + (size_t)g.k_total * ND) * 4 + 15) & ~(size_t)15));
+  const int n = g.n_dims;
+  int I[ND], K[ND], base[ND];
+  {
+    int acc = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const bool real = d >= lead;
+      I[d] = real ? g.in[d - lead] : 1;
+      K[d] = real ? g.k[d - lead] : 1;
+      base[d] = acc;
+      acc += I[d] * K[d];
+    }
+  }
+  // tables
+  for (int e = threadIdx.x; e < tab_total; e += blockDim.x) {
+    int d = 0;
+#pragma unroll
+    for (int dd = 1; dd < ND; ++dd)
+      if (e >= base[dd]) d = dd;
+    const int r = e - base[d];
+    const int k = r / I[d], i = r - k * I[d];
+    int val = 0;
+    if (d >= lead) {
+      const int gd = d - lead;
+      const int t = i + g.pad[gd] - g.dil[gd] * k;
+      const int o = t >= 0 ? t / g.stride[gd] : -1;
+      if (t < 0 || o * g.stride[gd] != t || o >= g.out[gd]) {
+        val = kTransposeSentinel;
+      } else {
+        int mul = 1;
+        for (int e2 = gd + 1; e2 < n; ++e2) mul *= g.out[e2];
+        val = o * mul;
+      }
+    }
+    tab[e] = val;
+  }
+  for (int e = threadIdx.x; e < g.k_total * ND; e += blockDim.x) {
+    const int kf = e / ND, d = e - kf * ND;
+    int kd = 0;
+    if (d >= lead) {
+      uint32_t rem = (uint32_t)kf, r = 0;
+      for (int dd = n - 1; dd >= d - lead; --dd) {
+        uint32_t q;
+        g.k_div[dd].divmod(rem, q, r);
+        rem = q;
+      }
+      kd = (int)r;
+    }
+    tapk[e] = kd * I[d];
+  }
+  const long long bc = blockIdx.y;
+  const T* src = x + bc * g.out_total;
+  if (plane_in_smem)
+    for (int e = threadIdx.x; e < g.out_total; e += blockDim.x) plane[e] = __ldg(src + e);
+  __syncthreads();
+
+  // a CTA walks several chunks of 256 positions so that its tables and staged plane are amortised
+  for (int iflat = blockIdx.x * blockDim.x + threadIdx.x; iflat < g.in_total; iflat += gridDim.x * blockDim.x) {
+    const int* tp[ND];
+    {
+      uint32_t rem = (uint32_t)iflat;
+#pragma unroll
+      for (int d = ND - 1; d >= 0; --d) {
+        uint32_t q = 0, r = 0;
+        if (d >= lead) {
+          g.in_div[d - lead].divmod(rem, q, r);
+          rem = q;
+        }
+        tp[d] = tab + base[d] + (int)r;
+      }
+    }
+    T* dst = out + bc * (long long)g.k_total * g.in_total + iflat;
+    constexpr int U = 4;
+    int kf = 0;
+    for (; kf + U <= g.k_total; kf += U) {
+      T v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int* tk = tapk + (kf + u) * ND;
+        int off = 0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) off += tp[d][tk[d]];
+        v[u] = T(0);
+        if (off >= 0) v[u] = plane_in_smem ? plane[off] : __ldg(src + off);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) store_stream1<T>(dst + (long long)(kf + u) * g.in_total, v[u]);
+    }
+    for (; kf < g.k_total; ++kf) {
+      const int* tk = tapk + kf * ND;
+      int off = 0;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) off += tp[d][tk[d]];
+      T v = T(0);
+      if (off >= 0) v = plane_in_smem ? plane[off] : __ldg(src + off);
+      store_stream1<T>(dst + (long long)kf * g.in_total, v);
+    }
+  }
+}
+
+template <typename T, int ND>
+static int launch_unfold_transpose_tab(const void* x, void* out, const DevGeom& g, cudaStream_t stream) {
+  const int lead = ND - g.n_dims;
+  long long tab_total = 0;
+  for (int d = 0; d < g.n_dims; ++d) tab_total += (long long)g.in[d] * g.k[d];
+  tab_total += lead;  // unit dims: one entry each
+  const long long planes = (long long)g.batch * g.groups * g.c_in_g;
+  if (planes >= 65536 || g.out_total >= (1 << 27)) return 0;
+  size_t smem = (size_t)(tab_total + (long long)g.k_total * ND) * 4;
+  if (smem > 40 * 1024) return 0;
+  smem = (smem + 15) & ~(size_t)15;
+  int plane_in_smem = 0;
+  if ((size_t)g.out_total * sizeof(T) + smem <= 44 * 1024) {
+    plane_in_smem = 1;
+    smem += (size_t)g.out_total * sizeof(T);
+  }
+  const long long chunks = (g.in_total + 255) / 256;
+  const long long per_plane = std::max<long long>(1, std::min<long long>(chunks, (16ll * kNumSMs + planes - 1) / planes));
+  dim3 grid((unsigned)per_plane, (unsigned)planes);
+  unfold_transpose_tab_kernel<T, ND><<<grid, 256, smem, stream>>>((const T*)x, (T*)out, g, lead, (int)tab_total,
+                                                                  plane_in_smem);
+  {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return cuda_fail(err, "unfold_transpose_tab_kernel");
+    count_launch();
+  }
+  return 1;
+}
+
+template <typename T>
+static int launch_unfold_transpose_tab_nd(const void* x, void* out, const DevGeom& g, cudaStream_t stream) {
+  if (getenv("EINCONV_UNFOLD_TRANSPOSE_SIMPLE")) return 0;
+  switch (g.n_dims) {
+    case 1: return launch_unfold_transpose_tab<T, 1>(x, out, g, stream);
+    case 2: return launch_unfold_transpose_tab<T, 2>(x, out, g, stream);
+    case 3: return launch_unfold_transpose_tab<T, 3>(x, out, g, stream);
+    default: return 0;  // N > 3: the per-element kernel
+  }
+}
+
 int launch_unfold_transpose(const void* x, void* out, int dtype, const einconv_geom* geom, cudaStream_t stream) {
   DevGeom g;
   int st = make_dev_geom(geom, &g, /*need_c_out=*/false);
@@ -933,6 +1069,15 @@ int launch_unfold_transpose(const void* x, void* out, int dtype, const einconv_g
   EINCONV_CHECK_ARG(esz > 0, "unfold_transpose: unknown dtype %d", dtype);
   const long long total = (long long)g.batch * g.groups * g.c_in_g * g.in_total;
   if (total == 0 || g.k_total == 0) return EINCONV_OK;
+  {
+    int took;
+    switch (esz) {
+      case 2: took = launch_unfold_transpose_tab_nd<uint16_t>(x, out, g, stream); break;
+      case 4: took = launch_unfold_transpose_tab_nd<uint32_t>(x, out, g, stream); break;
+      default: took = launch_unfold_transpose_tab_nd<unsigned long long>(x, out, g, stream); break;
+    }
+    if (took != 0) return took < 0 ? took : EINCONV_OK;
+  }
   const long long blocks = (total + 255) / 256;
   EINCONV_CHECK_ARG(blocks < (1ll << 31), "unfold_transpose: tensor too large");
   const size_t smem = (size_t)g.k_total * g.n_dims * sizeof(int);
