@@ -161,6 +161,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
 }
 
 // ---------------------------------------------------------------------------------------------
+struct MapArray {
+  CUtensorMap m[kMaxMaps];
+};
+
 struct Params {
   // reduction blocks: patches of positions, enumerated (b, d-tile, h-tile, w-tile), w fastest
   int n_wt, n_ht, n_dt;
@@ -207,7 +211,10 @@ struct Smem {
 
 template <typename T, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-tma_reduce_gemm_kernel(const CUtensorMap* __restrict__ maps, const __grid_constant__ Params p) {
+tma_reduce_gemm_kernel(const __grid_constant__ MapArray map_array, const __grid_constant__ Params p) {
+  // tensor maps travel as kernel parameters (4 KB; CUDA >= 12.1 allows 32 KB): no per-call upload and
+  // nothing host-side is read when a captured graph replays
+  const CUtensorMap* maps = map_array.m;
   // tensor maps live in global memory (head of the caller's workspace): one per shifted copy of the
   // input, plus the cotangent's
   using E = Elem<T>;
@@ -767,7 +774,7 @@ static int encode_map(CUtensorMap* map, int dtype, const void* base, const int e
 }
 
 template <typename T, int BN>
-static int launch(const CUtensorMap* maps, const Params& p, const Plan& pl, int groups, cudaStream_t stream) {
+static int launch(const MapArray& maps, const Params& p, const Plan& pl, int groups, cudaStream_t stream) {
   using S = Smem<BN>;
   auto kern = tma_reduce_gemm_kernel<T, BN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
@@ -822,8 +829,9 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   }
 
   // ---- tensor maps ------------------------------------------------------------------------------
-  alignas(64) CUtensorMap host_maps[kMaxMaps];
-  memset(host_maps, 0, sizeof(host_maps));
+  alignas(64) MapArray map_array;
+  memset(&map_array, 0, sizeof(map_array));
+  CUtensorMap* host_maps = map_array.m;
   int n_maps = 0, copy_i = 0;
   int res_margin[16];  // coordinate margin of the map serving residue r: A for copies, 0 for x itself
   if (pl.per_tap) {
@@ -934,18 +942,11 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   p.v_map = v_map;
   p.v_c0 = pl.v_copy ? A : 0;
   p.partial = partial;
-  const CUtensorMap* dev_maps = (const CUtensorMap*)workspace;
-  {
-    // pageable-host source: the runtime stages the 256 bytes before returning, so the stack copy is safe
-    cudaError_t e = cudaMemcpyAsync(workspace, host_maps, sizeof(host_maps), cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(tensor maps)");
-  }
-
   auto run_main = [&](auto* tag) -> int {
     using T = std::remove_pointer_t<decltype(tag)>;
-    if (pl.bn == 256) return launch<T, 256>(dev_maps, p, pl, g.groups, stream);
-    if (pl.bn == 128) return launch<T, 128>(dev_maps, p, pl, g.groups, stream);
-    return launch<T, 64>(dev_maps, p, pl, g.groups, stream);
+    if (pl.bn == 256) return launch<T, 256>(map_array, p, pl, g.groups, stream);
+    if (pl.bn == 128) return launch<T, 128>(map_array, p, pl, g.groups, stream);
+    return launch<T, 64>(map_array, p, pl, g.groups, stream);
   };
   int st;
   switch (dtype) {

@@ -215,7 +215,9 @@ def test_cuda_graph_capture_and_replay():
         y = convNd(xin.to(torch.bfloat16), w, None, padding=1)
         d = convNd(xin, wd, None, padding=1, groups=32)
         gw = evaluator.conv_weight_vjp_raw(xin.to(torch.bfloat16), v, (3, 3), 1, 1, 1, 1)
-        return u, y, d, gw
+        k = evaluator.kfc(xin.to(torch.bfloat16), 3, padding=1)          # per-tap TMA kernel (32 tensor maps)
+        r = evaluator.kfac_reduce(xin, 3, padding=1)
+        return u, y, d, gw, k, r
 
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
