@@ -336,7 +336,9 @@ struct FlatParams {
   int out[ND], k[ND];
   int P, K, box;
   int tap_chunks, taps_per_chunk;
-  FastDiv ext_div[ND], out_div[ND], k_div[ND], chan_div, chunk_div;
+  int planes_per_cta;
+  long long n_planes;
+  FastDiv ext_div[ND], out_div[ND], k_div[ND], chan_div, chunk_div, p_div;
 };
 
 // streaming (evict-first) store; st.global / .cg / .wt were measured and make no difference here
@@ -365,19 +367,39 @@ __device__ __forceinline__ void flat_emit(const T* __restrict__ plane, const int
   }
 }
 
+// Several small planes per CTA: a slot is (plane, position); its destination is no longer a fixed
+// stride from the thread's first slot, so it is kept per slot like the source offset.
+template <typename T, int NI>
+__device__ __forceinline__ void flat_emit_multi(const T* __restrict__ plane, const int* __restrict__ tap_off,
+                                                int n_taps, T* __restrict__ dst, int P,
+                                                const int (&soff)[kFlatJpt], const int (&doff)[kFlatJpt],
+                                                bool last_on) {
+#pragma unroll 2
+  for (int t = 0; t < n_taps; ++t, dst += P) {
+    const T* s = plane + tap_off[t];
+    T v[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) v[i] = s[soff[i]];
+#pragma unroll
+    for (int i = 0; i < NI - 1; ++i) store_stream1<T>(dst + doff[i], v[i]);
+    if (last_on) store_stream1<T>(dst + doff[NI - 1], v[NI - 1]);
+  }
+}
+
 template <typename T, int ND>
 __global__ void __launch_bounds__(kFlatThreads, kFlatMinBlocks)
 unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
                    const __grid_constant__ FlatParams<ND> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* plane = reinterpret_cast<T*>(smem_raw);
-  int* tap_off = reinterpret_cast<int*>(smem_raw + (((size_t)p.box * sizeof(T) + 15) & ~(size_t)15));
+  int* tap_off = reinterpret_cast<int*>(smem_raw + (((size_t)p.box * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15));
   const int tid = threadIdx.x;
 
-  uint32_t bc, chunk;
-  p.chunk_div.divmod(blockIdx.x, bc, chunk);
+  uint32_t bcg, chunk;
+  p.chunk_div.divmod(blockIdx.x, bcg, chunk);
   const int t0 = (int)chunk * p.taps_per_chunk;
   const int t1 = min(p.K, t0 + p.taps_per_chunk);
+  const int n_taps = t1 - t0;
 
   // tap table: staged offset of tap t relative to tap 0
   for (int t = t0 + tid; t < t1; t += kFlatThreads) {
@@ -393,27 +415,90 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
     tap_off[t - t0] = off;
   }
 
-  // ---- stage: plane[c_0..c_{ND-1}] = x[b, c, c_d * gstep_d - pad_d] or 0
-  {
-    uint32_t b, c;
-    p.chan_div.divmod(bc, b, c);
-    const T* src = x + (long long)b * p.xs_b + (long long)c * p.xs_c;
-    int cc[ND], est[ND];
-    {
-      uint32_t r0 = (uint32_t)tid, r1 = (uint32_t)kFlatThreads;
+  constexpr int kChunk = kFlatThreads * kFlatJpt;
+  // staged offsets of this thread's output slots for the chunk starting at jb (only the used slots)
+  auto slot_offsets = [&](int jb, int (&off)[kFlatJpt], int& n_i, bool& last_on) {
+    const int left = p.P - jb;
+    n_i = min(kFlatJpt, (left + kFlatThreads - 1) / kFlatThreads);
+    last_on = (n_i - 1) * kFlatThreads + tid < left;
 #pragma unroll
-      for (int d = ND - 1; d >= 1; --d) {
-        uint32_t q, r;
-        p.ext_div[d].divmod(r0, q, r);
-        cc[d] = (int)r;
-        r0 = q;
-        p.ext_div[d].divmod(r1, q, r);
-        est[d] = (int)r;
-        r1 = q;
+    for (int i = 0; i < kFlatJpt; ++i) {
+      off[i] = 0;
+      if (i < n_i) {
+        const int j = jb + i * kFlatThreads + tid;
+        uint32_t rem = (uint32_t)(j < p.P ? j : 0);
+        int o = 0;
+#pragma unroll
+        for (int d = ND - 1; d >= 0; --d) {
+          uint32_t q, od;
+          p.out_div[d].divmod(rem, q, od);
+          rem = q;
+          o += (int)od * p.so[d];
+        }
+        off[i] = o;
       }
-      cc[0] = (int)r0;  // >= ext[0] only for e >= box, which the loop excludes
-      est[0] = (int)r1;
     }
+  };
+  // slots 0 .. n_i-2 are valid for every thread, slot n_i-1 only where last_on
+  auto emit_chunk = [&](T* dst, int n_i, const int (&off)[kFlatJpt], bool last_on) {
+    switch (n_i) {
+#define EINCONV_FLAT_CASE(NI)                                                         \
+  case NI:                                                                            \
+    if constexpr (NI <= kFlatJpt)                                                     \
+      flat_emit<T, NI>(plane, tap_off, n_taps, dst, p.P, off, last_on);               \
+    break;
+      EINCONV_FLAT_CASE(16)
+      EINCONV_FLAT_CASE(15)
+      EINCONV_FLAT_CASE(14)
+      EINCONV_FLAT_CASE(13)
+      EINCONV_FLAT_CASE(12)
+      EINCONV_FLAT_CASE(11)
+      EINCONV_FLAT_CASE(10)
+      EINCONV_FLAT_CASE(9)
+      EINCONV_FLAT_CASE(8)
+      EINCONV_FLAT_CASE(7)
+      EINCONV_FLAT_CASE(6)
+      EINCONV_FLAT_CASE(5)
+      EINCONV_FLAT_CASE(4)
+      EINCONV_FLAT_CASE(3)
+      EINCONV_FLAT_CASE(2)
+#undef EINCONV_FLAT_CASE
+      default: flat_emit<T, 1>(plane, tap_off, n_taps, dst, p.P, off, last_on); break;
+    }
+  };
+
+  // small planes (one chunk): the slot offsets are the same for every plane of this CTA
+  const bool single = p.P <= kChunk;
+  int off0[kFlatJpt], n_i0 = 0;
+  bool last_on0 = false;
+  if (single && p.planes_per_cta == 1) slot_offsets(0, off0, n_i0, last_on0);
+
+  // staging walk: coordinates of element `tid` and of a stride of kFlatThreads elements
+  int cc0[ND], est[ND];
+  {
+    uint32_t r0 = (uint32_t)tid, r1 = (uint32_t)kFlatThreads;
+#pragma unroll
+    for (int d = ND - 1; d >= 1; --d) {
+      uint32_t q, r;
+      p.ext_div[d].divmod(r0, q, r);
+      cc0[d] = (int)r;
+      r0 = q;
+      p.ext_div[d].divmod(r1, q, r);
+      est[d] = (int)r;
+      r1 = q;
+    }
+    cc0[0] = (int)r0;  // >= ext[0] only for e >= box, which the loop excludes
+    est[0] = (int)r1;
+  }
+
+  // stage one plane: plane_dst[c_0..c_{ND-1}] = x[b, c, c_d * gstep_d - pad_d] or 0
+  auto stage_plane = [&](long long bc, T* plane_dst) {
+    uint32_t b, c;
+    p.chan_div.divmod((uint32_t)bc, b, c);
+    const T* src = x + (long long)b * p.xs_b + (long long)c * p.xs_c;
+    int cc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) cc[d] = cc0[d];
 #ifndef EINCONV_FLAT_U
 #define EINCONV_FLAT_U 8
 #endif
@@ -443,41 +528,50 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (e0 + u * kFlatThreads < p.box) plane[e0 + u * kFlatThreads] = vals[u];
+        if (e0 + u * kFlatThreads < p.box) plane_dst[e0 + u * kFlatThreads] = vals[u];
     }
-  }
-  __syncthreads();
+  };
 
-  // ---- emit
-  T* dst_plane = out + ((long long)bc * p.K + t0) * (long long)p.P + tid;
-  constexpr int kChunk = kFlatThreads * kFlatJpt;
-  for (int jb = 0; jb < p.P; jb += kChunk) {
-    int off[kFlatJpt];
+  if (p.planes_per_cta > 1) {
+    // ---- several tiny planes per CTA (e.g. 14x14): all of them are staged at once and their outputs
+    // emitted as one pool of (plane, position) slots, so that a CTA pays one load latency and one
+    // barrier for tens of kilobytes of output instead of one per 7 KB plane
+    const long long bc0 = (long long)bcg * p.planes_per_cta;
+    const int n_pl = (int)min((long long)p.planes_per_cta, p.n_planes - bc0);
+    for (int pl = 0; pl < n_pl; ++pl) stage_plane(bc0 + pl, plane + pl * p.box);
+    __syncthreads();
+    const int total = n_pl * p.P;  // <= kFlatThreads * kFlatJpt by construction on the host
+    const int n_i = (total + kFlatThreads - 1) / kFlatThreads;
+    const bool last_on = (n_i - 1) * kFlatThreads + tid < total;
+    int soff[kFlatJpt], doff[kFlatJpt];
+    const int plane_out = p.K * p.P;
 #pragma unroll
     for (int i = 0; i < kFlatJpt; ++i) {
-      const int j = jb + i * kFlatThreads + tid;
-      uint32_t rem = (uint32_t)(j < p.P ? j : 0);
-      int o = 0;
+      soff[i] = 0;
+      doff[i] = 0;
+      const int sl = i * kFlatThreads + tid;
+      if (i < n_i && sl < total) {
+        uint32_t pl, jj;
+        p.p_div.divmod((uint32_t)sl, pl, jj);
+        uint32_t rem = jj;
+        int o = 0;
 #pragma unroll
-      for (int d = ND - 1; d >= 0; --d) {
-        uint32_t q, od;
-        p.out_div[d].divmod(rem, q, od);
-        rem = q;
-        o += (int)od * p.so[d];
+        for (int d = ND - 1; d >= 0; --d) {
+          uint32_t q, od;
+          p.out_div[d].divmod(rem, q, od);
+          rem = q;
+          o += (int)od * p.so[d];
+        }
+        soff[i] = (int)pl * p.box + o;
+        doff[i] = (int)pl * plane_out + (int)jj;
       }
-      off[i] = o;
     }
-    // slots 0 .. n_i-2 are valid for every thread, slot n_i-1 for threads with tid < P - jb - ...
-    const int left = p.P - jb;
-    const int n_i = min(kFlatJpt, (left + kFlatThreads - 1) / kFlatThreads);
-    const bool last_on = (n_i - 1) * kFlatThreads + tid < left;
-    T* dst = dst_plane + jb;
-    const int n_taps = t1 - t0;
+    T* dst = out + (bc0 * p.K + t0) * (long long)p.P;
     switch (n_i) {
-#define EINCONV_FLAT_CASE(NI)                                                         \
-  case NI:                                                                            \
-    if constexpr (NI <= kFlatJpt)                                                     \
-      flat_emit<T, NI>(plane, tap_off, n_taps, dst, p.P, off, last_on);               \
+#define EINCONV_FLAT_CASE(NI)                                                              \
+  case NI:                                                                                 \
+    if constexpr (NI <= kFlatJpt)                                                          \
+      flat_emit_multi<T, NI>(plane, tap_off, n_taps, dst, p.P, soff, doff, last_on);       \
     break;
       EINCONV_FLAT_CASE(16)
       EINCONV_FLAT_CASE(15)
@@ -495,7 +589,24 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
       EINCONV_FLAT_CASE(3)
       EINCONV_FLAT_CASE(2)
 #undef EINCONV_FLAT_CASE
-      default: flat_emit<T, 1>(plane, tap_off, n_taps, dst, p.P, off, last_on); break;
+      default: flat_emit_multi<T, 1>(plane, tap_off, n_taps, dst, p.P, soff, doff, last_on); break;
+    }
+    return;
+  }
+
+  // ---- one plane per CTA
+  const long long bc = bcg;
+  stage_plane(bc, plane);
+  __syncthreads();
+  T* dst_plane = out + (bc * p.K + t0) * (long long)p.P + tid;
+  if (single) {
+    emit_chunk(dst_plane, n_i0, off0, last_on0);
+  } else {
+    for (int jb = 0; jb < p.P; jb += kChunk) {
+      int off[kFlatJpt], n_i;
+      bool last_on;
+      slot_offsets(jb, off, n_i, last_on);
+      emit_chunk(dst_plane + jb, n_i, off, last_on);
     }
   }
 }
@@ -612,9 +723,24 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
   p.taps_per_chunk = ceil_div(p.K, chunks);
   p.tap_chunks = ceil_div(p.K, p.taps_per_chunk);
   if (p.taps_per_chunk > kFlatMaxTaps) return 0;
-  const size_t smem = (((size_t)p.box * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4;
+  size_t smem = (((size_t)p.box * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4;
   if (smem > 48 * 1024) return 0;  // keep >= 4 CTAs per SM resident
-  const long long grid = n_planes * p.tap_chunks;
+  // planes per CTA: small planes only; all their (plane, position) slots must fit the thread's slot
+  // registers and their staged windows the shared-memory budget; aim at >= 64 KB of output per CTA
+  // while keeping at least ~8 CTAs per SM in the grid
+  p.n_planes = n_planes;
+  p.planes_per_cta = 1;
+  p.p_div = FastDiv((uint32_t)std::max(1, p.P));
+  if (p.P > 0 && p.P * 2 <= kFlatThreads * kFlatJpt && !getenv("EINCONV_UNFOLD_ONE_PLANE")) {
+    const long long per_plane_bytes = (long long)p.taps_per_chunk * p.P * (long long)sizeof(T);
+    long long pc = std::max<long long>(1, std::min<long long>(32, (64 * 1024 + per_plane_bytes - 1) / per_plane_bytes));
+    pc = std::min<long long>(pc, (kFlatThreads * kFlatJpt) / p.P);
+    pc = std::min<long long>(pc, (long long)(40 * 1024) / std::max<long long>(1, (long long)p.box * (long long)sizeof(T)));
+    while (pc > 1 && ((n_planes + pc - 1) / pc) * p.tap_chunks < 8ll * kNumSMs) pc /= 2;
+    p.planes_per_cta = (int)std::max<long long>(1, pc);
+  }
+  smem = (((size_t)p.box * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4;
+  const long long grid = ((n_planes + p.planes_per_cta - 1) / p.planes_per_cta) * p.tap_chunks;
   if (grid >= (1ll << 31)) return 0;
   // Too little output per staged element: the tiled kernel amortises its staging better.
   for (int d = 0; d < ND; ++d) {
