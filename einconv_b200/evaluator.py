@@ -257,7 +257,7 @@ def conv_weight_vjp_raw(x, v, kernel_size, dilation, padding, stride, groups, si
     return gw
 
 
-def _factor(op: int, x, kernel_size, stride, padding, dilation, groups, simplify, scale) -> Tensor:
+def _factor(op: int, x, kernel_size, stride, padding, dilation, groups, simplify, scale, dest=None) -> Tensor:
     device = nat.require_cuda(x)
     x = x.contiguous()
     B, c_in = x.shape[0], x.shape[1]
@@ -279,7 +279,14 @@ def _factor(op: int, x, kernel_size, stride, padding, dilation, groups, simplify
             # Tensor([1 / (B * prod(out)^2)]) in x.dtype, convNd_kfac_reduce.py:106-108
             denom = B * o_total**2
             scale = float(torch.tensor([1.0 / denom]).to(x.dtype)) if denom > 0 else 0.0
-    result = torch.empty((groups, A, A), dtype=x.dtype, device=device)
+    if dest is None:
+        result = torch.empty((groups, A, A), dtype=x.dtype, device=device)
+    else:
+        # caller-owned output (e.g. a slice of a flat all-reduce bucket, einconv_b200/distributed.py)
+        if tuple(dest.shape) != (groups, A, A) or dest.dtype != x.dtype or not dest.is_contiguous() \
+                or dest.device != x.device:
+            raise ValueError(f"out must be a contiguous {x.dtype} tensor of shape {(groups, A, A)} on {x.device}.")
+        result = dest
     if result.numel() == 0:
         return result
     code, math, kern = nat.dtype_code(x.dtype), _math_for(x.dtype), _kernels_for(simplify)
@@ -294,15 +301,17 @@ def _factor(op: int, x, kernel_size, stride, padding, dilation, groups, simplify
     return result
 
 
-def kfc(x, kernel_size, stride=1, padding=0, dilation=1, groups=1, simplify=True, scale=None) -> Tensor:
+def kfc(x, kernel_size, stride=1, padding=0, dilation=1, groups=1, simplify=True, scale=None, out=None) -> Tensor:
     """KFC factor ``[G, A, A]`` (``convNd_kfc.py:75-116``).  ``scale`` defaults to ``1/B``; pass the
-    global ``1/B`` when ``x`` is a batch shard whose factors will be summed across ranks."""
-    return _factor(nat.OP_KFC, x, kernel_size, stride, padding, dilation, groups, simplify, scale)
+    global ``1/B`` when ``x`` is a batch shard whose factors will be summed across ranks.  ``out``
+    (optional) receives the result in place."""
+    return _factor(nat.OP_KFC, x, kernel_size, stride, padding, dilation, groups, simplify, scale, out)
 
 
-def kfac_reduce(x, kernel_size, stride=1, padding=0, dilation=1, groups=1, simplify=True, scale=None) -> Tensor:
+def kfac_reduce(x, kernel_size, stride=1, padding=0, dilation=1, groups=1, simplify=True, scale=None,
+                out=None) -> Tensor:
     """KFAC-reduce factor ``[G, A, A]`` (``convNd_kfac_reduce.py:77-119``)."""
-    return _factor(nat.OP_KFAC_REDUCE, x, kernel_size, stride, padding, dilation, groups, simplify, scale)
+    return _factor(nat.OP_KFAC_REDUCE, x, kernel_size, stride, padding, dilation, groups, simplify, scale, out)
 
 
 # --------------------------------------------------------------------------------------------

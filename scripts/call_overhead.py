@@ -1,0 +1,22 @@
+"""Host-side cost of one call through the public API (tiny tensors: the GPU work is negligible)."""
+import sys, time
+import torch
+sys.path.insert(0, ".")
+from einconv_b200.functionals import convNd, unfoldNd
+from einconv_b200 import evaluator
+
+x = torch.rand(2, 8, 12, 12, device="cuda")
+w = torch.rand(8, 8, 3, 3, device="cuda")
+xb, wb = x.bfloat16(), w.bfloat16()
+def bench(name, fn, n=2000):
+    for _ in range(50): fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n): fn()
+    torch.cuda.synchronize()
+    print(f"{name:34s} {(time.perf_counter()-t0)/n*1e6:7.1f} us per call")
+bench("unfoldNd", lambda: unfoldNd(x, 3, padding=1))
+bench("convNd fp32 (FFMA)", lambda: convNd(x, w, padding=1))
+bench("convNd bf16 (conv_tma)", lambda: convNd(xb, wb, padding=1))
+bench("kfc fp32", lambda: evaluator.kfc(x, 3, padding=1))
+bench("torch conv2d (reference point)", lambda: torch.nn.functional.conv2d(x, w, padding=1))

@@ -522,6 +522,27 @@ def test_factors_resnet_layers_reduced_batch():
             assert torch.allclose(got, got.transpose(1, 2), rtol=1e-6, atol=1e-7)  # symmetric
 
 
+def test_factor_sweep_graphs_match_eager_and_track_input_updates():
+    """FactorSweep (in-place bucket outputs, one CUDA graph per bucket) reproduces sharded_factors bit
+    for bit, and a replay sees new contents of the (static) input tensors."""
+    from einconv_b200 import distributed as D
+
+    torch.manual_seed(0)
+    xs = [torch.rand(4, 16, 12, 12, device=DEV), torch.rand(4, 32, 6, 6, device=DEV), torch.rand(4, 3, 20, 20, device=DEV)]
+    specs = [D.LayerSpec(3, padding=1), D.LayerSpec(1), D.LayerSpec(5, stride=2, padding=2)]
+    sweep = D.FactorSweep(xs, specs, global_batch=4, bucket_bytes=1 << 16)
+    assert sweep._graphs is not None and len(sweep.buckets) >= 2 and sweep.launches_per_run > 0
+    for trial in range(2):
+        if trial:
+            for x in xs:
+                x.copy_(torch.rand_like(x))
+        got = sweep.run()
+        want = D.sharded_factors(xs, specs, global_batch=4)
+        for kind in ("kfc", "kfac_reduce"):
+            for a, b in zip(got[kind], want[kind]):
+                assert torch.equal(a, b)
+
+
 def test_factor_sharding_identity_on_one_gpu():
     """Sum of shard factors computed with the global scale == the full-batch factor."""
     torch.manual_seed(0)
