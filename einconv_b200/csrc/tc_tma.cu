@@ -194,6 +194,9 @@ struct Params {
   int debug;                           // bring-up switch (EINCONV_TMA_DEBUG): 1 = no TMA/MMA, 2 = TMA only
   float* partial;                      // [groups][k_splits][Mp][Np]
   const float* scale_dev;              // optional extra factor read on the device by the finish kernel
+  float* direct_out;                   // KFC, one split, 1x1 kernel, fp32 output: the epilogue writes the factor itself
+  float direct_scale;
+  int direct_a;                        // A = c_in_g (rows / columns of the factor)
 };
 
 template <typename T> struct Elem;
@@ -425,6 +428,35 @@ tma_reduce_gemm_kernel(const __grid_constant__ MapArray map_array, const __grid_
       tc_fence_after();
     }
     const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
+    if (p.direct_out) {
+      // One split and no tap permutation (1x1 kernel: partial row = channel): scale and store the tile
+      // and its mirror straight into the factor.  Saves the partial round trip and the finish launch,
+      // which are batch-independent costs and dominate at small per-rank batches.
+      const float scale = p.scale_dev ? p.direct_scale * __ldg(p.scale_dev) : p.direct_scale;
+      const int A = p.direct_a;
+      const int gr = m_tile * kTileM + row;
+      float* og = p.direct_out + (long long)grp * A * A;
+#pragma unroll 1
+      for (int n0 = 0; n0 < BN; n0 += 16) {
+        uint32_t r[16];
+        if (n_kb > 0) {
+          tmem_ld16(lane_base + n0, r);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        const int gc0 = n_tile * BN + n0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int gc = gc0 + j;
+          const float v = __uint_as_float(r[j]) * scale;
+          if (gr < A && gc < A) {
+            og[(long long)gr * A + gc] = v;
+            if (m_tile != n_tile) og[(long long)gc * A + gr] = v;  // lanes = consecutive rows: coalesced
+          }
+        }
+      }
+    } else {
     float* dst = p.partial + (((long long)grp * p.k_splits + split) * p.Mp + (m_tile * kTileM + row)) * p.Np +
                  n_tile * BN;
 #pragma unroll 1
@@ -441,6 +473,7 @@ tma_reduce_gemm_kernel(const __grid_constant__ MapArray map_array, const __grid_
       for (int j = 0; j < 4; ++j)
         d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    }
     }
   }
 
@@ -942,6 +975,15 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   p.v_map = v_map;
   p.v_c0 = pl.v_copy ? A : 0;
   p.partial = partial;
+  // fused finish: KFC with one split, a 1x1 kernel whose partial rows are the channels in order
+  // (one channel block, or full 128-channel blocks), upper-triangular tiling and fp32 output
+  const bool direct = kfc && pl.tri && pl.k_splits == 1 && g.k_total == 1 && out_dtype == EINCONV_F32 &&
+                      (pl.CB == kTileM || pl.c_blocks == 1) && !getenv("EINCONV_KFC_NO_DIRECT");
+  if (direct) {
+    p.direct_out = (float*)out;
+    p.direct_scale = (float)scale;
+    p.direct_a = g.c_in_g;
+  }
   auto run_main = [&](auto* tag) -> int {
     using T = std::remove_pointer_t<decltype(tag)>;
     if (pl.bn == 256) return launch<T, 256>(map_array, p, pl, g.groups, stream);
@@ -956,6 +998,7 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
     default: set_error("tma path: unsupported dtype %d", dtype); return EINCONV_ERR_UNSUPPORTED;
   }
   if (st) return st;
+  if (direct) return EINCONV_OK;
   const long long Atot = (long long)g.c_in_g * g.k_total;
   const long long total = (kfc ? Atot * Atot : (long long)g.c_out_g * Atot) * g.groups;
   auto run_finish = [&](auto* tag) -> int {
