@@ -194,9 +194,9 @@ struct Params {
   int debug;                           // bring-up switch (EINCONV_TMA_DEBUG): 1 = no TMA/MMA, 2 = TMA only
   float* partial;                      // [groups][k_splits][Mp][Np]
   const float* scale_dev;              // optional extra factor read on the device by the finish kernel
-  float* direct_out;                   // KFC, one split, 1x1 kernel, fp32 output: the epilogue writes the factor itself
+  float* direct_out;                   // KFC, one split, fp32 output: the epilogue writes the (un-permuted) factor itself
   float direct_scale;
-  int direct_a;                        // A = c_in_g (rows / columns of the factor)
+  int direct_a;                        // A = c_in_g * k_total (rows / columns of the factor)
 };
 
 template <typename T> struct Elem;
@@ -429,12 +429,20 @@ tma_reduce_gemm_kernel(const __grid_constant__ MapArray map_array, const __grid_
     }
     const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
     if (p.direct_out) {
-      // One split and no tap permutation (1x1 kernel: partial row = channel): scale and store the tile
-      // and its mirror straight into the factor.  Saves the partial round trip and the finish launch,
-      // which are batch-independent costs and dominate at small per-rank batches.
+      // One split: scale, un-permute (tile rows are tap-major) and store the tile and its mirror
+      // straight into the factor.  Saves the partial round trip and the finish launch, which are
+      // batch-independent costs and dominate at small per-rank batches.
       const float scale = p.scale_dev ? p.direct_scale * __ldg(p.scale_dev) : p.direct_scale;
-      const int A = p.direct_a;
-      const int gr = m_tile * kTileM + row;
+      const int A = p.direct_a;  // c_in_g * k_total
+      const int Kt = p.k_total;
+      // tile row -> (tap, channel) -> factor index a = ci * Kt + tap   (CB is a power of two)
+      const int cb_shift = 31 - __clz(p.CB);
+      const int m_tg = m_tile / p.c_blocks, m_cb = m_tile - m_tg * p.c_blocks;
+      const int n_tg = n_tile / p.c_blocks, n_cb = n_tile - n_tg * p.c_blocks;
+      const int r_tap = m_tg * p.taps_per_tile + (row >> cb_shift);
+      const int r_ci = m_cb * p.CB + (row & (p.CB - 1));
+      const bool r_ok = r_tap < Kt && r_ci < p.c_in_g;
+      const long long a = (long long)r_ci * Kt + r_tap;
       float* og = p.direct_out + (long long)grp * A * A;
 #pragma unroll 1
       for (int n0 = 0; n0 < BN; n0 += 16) {
@@ -445,14 +453,19 @@ tma_reduce_gemm_kernel(const __grid_constant__ MapArray map_array, const __grid_
 #pragma unroll
           for (int j = 0; j < 16; ++j) r[j] = 0u;
         }
-        const int gc0 = n_tile * BN + n0;
+        // 16 consecutive columns share their tap (CB >= 32 is a multiple of 16)
+        const int c_tap = n_tg * p.taps_per_tile + (n0 >> cb_shift);
+        const int c_ci0 = n_cb * p.CB + (n0 & (p.CB - 1));
+        if (r_ok && c_tap < Kt) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int gc = gc0 + j;
-          const float v = __uint_as_float(r[j]) * scale;
-          if (gr < A && gc < A) {
-            og[(long long)gr * A + gc] = v;
-            if (m_tile != n_tile) og[(long long)gc * A + gr] = v;  // lanes = consecutive rows: coalesced
+          for (int j = 0; j < 16; ++j) {
+            const int c_ci = c_ci0 + j;
+            if (c_ci < p.c_in_g) {
+              const long long a2 = (long long)c_ci * Kt + c_tap;
+              const float v = __uint_as_float(r[j]) * scale;
+              og[a * A + a2] = v;
+              if (m_tile != n_tile) og[a2 * A + a] = v;
+            }
           }
         }
       }
@@ -714,7 +727,10 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
       const long long ctas = tiles * s;
       const long long rounds = (ctas + resident - 1) / resident;
       // a round processes `resident` CTA-slots of 1/s of the K range each
-      const double t = t_main * ((double)rounds * resident / (double)ctas) + t_partial * (double)s + 2e-6 * rounds;
+      // one split writes the factor from the epilogue (KFC); more splits pay the partial copies, the
+      // finish kernel's output pass and its launch
+      const double t_fin = (op == EINCONV_OP_KFC && s == 1) ? 0.0 : t_partial * (double)(s + 1) + 4e-6;
+      const double t = t_main * ((double)rounds * resident / (double)ctas) + t_fin + 2e-6 * rounds;
       if (t < best_t) {
         best_t = t;
         best_s = (int)s;
@@ -977,12 +993,12 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   p.partial = partial;
   // fused finish: KFC with one split, a 1x1 kernel whose partial rows are the channels in order
   // (one channel block, or full 128-channel blocks), upper-triangular tiling and fp32 output
-  const bool direct = kfc && pl.tri && pl.k_splits == 1 && g.k_total == 1 && out_dtype == EINCONV_F32 &&
-                      (pl.CB == kTileM || pl.c_blocks == 1) && !getenv("EINCONV_KFC_NO_DIRECT");
+  const bool direct = kfc && pl.tri && pl.k_splits == 1 && out_dtype == EINCONV_F32 &&
+                      !getenv("EINCONV_KFC_NO_DIRECT");
   if (direct) {
     p.direct_out = (float*)out;
     p.direct_scale = (float)scale;
-    p.direct_a = g.c_in_g;
+    p.direct_a = g.c_in_g * g.k_total;
   }
   auto run_main = [&](auto* tag) -> int {
     using T = std::remove_pointer_t<decltype(tag)>;
