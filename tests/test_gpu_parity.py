@@ -63,11 +63,18 @@ def test_native_library_is_loaded_and_counts_launches():
 # =============================================================================================
 # unfold: bit-exact
 # =============================================================================================
-@pytest.fixture(params=["auto", "tiled"])
+@pytest.fixture(params=["auto", "plane", "tiled"])
 def unfold_variant(request, monkeypatch):
-    """Both unfold kernels: "auto" takes the whole-plane kernel whenever the staged window fits in
-    shared memory, "tiled" forces the row-tiled kernel (csrc/unfold.cu reads the variable per call)."""
+    """All unfold kernels: "auto" prefers the persistent double-buffered whole-plane kernel (4/8-byte
+    types, enough work), "plane" the one-CTA-per-plane(s) kernel, "tiled" the row-tiled kernel
+    (csrc/unfold.cu reads the variables per call)."""
     monkeypatch.setenv("EINCONV_UNFOLD_TILED", "1" if request.param == "tiled" else "0")
+    monkeypatch.delenv("EINCONV_UNFOLD_NO_PERSISTENT", raising=False)
+    monkeypatch.delenv("EINCONV_UNFOLD_PERSISTENT", raising=False)
+    if request.param == "plane":
+        monkeypatch.setenv("EINCONV_UNFOLD_NO_PERSISTENT", "1")
+    elif request.param == "auto":
+        monkeypatch.setenv("EINCONV_UNFOLD_PERSISTENT", "1")  # also where the heuristic would not pick it
     return request.param
 
 
