@@ -107,6 +107,26 @@ class UnfoldC2(Workload):
     def naive_bytes(self):
         return 16 * 32 * 27 * 4056 * 4 + 16 * 32 * 16 * 56 * 56 * 4
 
+    def kernel_ms(self, device, reps=8):
+        """Average duration of the dominant kernel's launches: `reps` calls back to back inside ONE
+        CUDA-event pair, each on its own input and output buffers (8 x 103 MB in, 8 x 224 MB out, far
+        more than the 126 MB L2), so that every launch finds its input cold without a flush kernel
+        between the launches and without the host-side launch gap that a per-step event pair includes."""
+        xs = [self.x.clone() for _ in range(reps)]
+        outs = [self.fn(x, **self.kw) for x in xs]  # allocations + warm-up
+        torch.cuda.synchronize(device)
+        best = None
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(reps):
+                outs[i] = self.fn(xs[i], **self.kw)
+            b.record()
+            b.synchronize()
+            t = a.elapsed_time(b) / reps
+            best = t if best is None else min(best, t)
+        return best
+
     def e2e(self, device, out_host):
         # public host-buffer API: batch chunks alternate between two streams so that uploads and the
         # gather overlap the (dominant) download of the previous chunk
@@ -485,9 +505,21 @@ def main():
     wl, ms, launches, clocks, times = measure(args.workload, args.steps, args.warmup)
     n_units = world if args.workload != "factors" else 1
     value = to_value(wl, ms, n_units)
-    roof = roofline(wl, statistics.mean(times), pk)
+    # roofline of the dominant kernel: its average launch duration (CUDA events around back-to-back
+    # launches on rotating cold buffers) where the workload provides that measurement, else the per-step time
+    step_ms = statistics.mean(times)
+    kern_ms = wl.kernel_ms(device) if hasattr(wl, "kernel_ms") else None
+    if kern_ms is not None and world > 1:
+        t = torch.tensor([kern_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kern_ms = float(t)
+    roof = roofline(wl, kern_ms if kern_ms is not None else step_ms, pk)
+    roof["kernel_ms"] = kern_ms
+    roof["timing"] = ("8 launches back to back in one CUDA-event pair, rotating input/output buffers (2.6 GB >> L2), "
+                      "best of 3" if kern_ms is not None else "per-step CUDA events (includes the launch gap)")
+    roof["frac_per_step"] = wl.work() / (step_ms * 1e-3) / 1e9 / pk["hbm"] if wl.bound == "hbm" else None
     if hasattr(wl, "naive_bytes"):
-        roof["achieved_naive_bytes"] = wl.naive_bytes() / (statistics.mean(times) * 1e-3) / 1e9
+        roof["achieved_naive_bytes"] = wl.naive_bytes() / ((kern_ms or step_ms) * 1e-3) / 1e9
 
     # ---- end to end through the public API with host buffers --------------------------------
     e2e = None
