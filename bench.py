@@ -41,6 +41,9 @@ RESNET50_LAYERS = [
 ]
 
 
+PEAK_TF32_MEASURED = 734.7  # TFLOP/s
+
+
 def peaks():
     path = ROOT / "MEASURED_PEAKS.json"
     if path.exists():
@@ -406,9 +409,14 @@ def _roofline(wl, ms_kernel, pk):
                     traffic=None, peak_source=pk["source"])
     flops = wl.flops() if hasattr(wl, "flops") else wl.work()
     achieved = flops / (ms_kernel * 1e-3) / 1e12
-    return dict(bound="tensor", achieved=achieved, peak=pk["bf16"], unit="TFLOP/s", frac=achieved / pk["bf16"],
-                traffic=None, peak_source=pk["source"],
-                note="peak = measured dense bf16 cuBLAS; fp32 runs on CUDA cores / tf32 at half that rate")
+    r = dict(bound="tensor", achieved=achieved, peak=pk["bf16"], unit="TFLOP/s", frac=achieved / pk["bf16"],
+             traffic=None, peak_source=pk["source"],
+             note="peak = measured dense bf16 cuBLAS; fp32 runs on CUDA cores / tf32 at half that rate")
+    if wl.fp32_math == "tf32":
+        # dense TF32 cuBLAS on this pool's B200 (scripts/measure_tf32_peak.py, 4096^3, best of 5 x 10)
+        r["peak_tf32"] = PEAK_TF32_MEASURED
+        r["frac_tf32"] = achieved / PEAK_TF32_MEASURED
+    return r
 
 
 def run_reference(args):
