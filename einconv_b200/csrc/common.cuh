@@ -177,4 +177,15 @@ inline int dispatch_dtype(int dtype, F&& f) {
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Power-of-two operand scale for the scaled-fp16 copies of fp32 tensors (convert.cu): max|x| * s lies in
+// [2^13, 2^14), far below the fp16 maximum; 1 for empty / all-zero / non-finite tensors.
+__device__ __forceinline__ float operand_scale(unsigned absmax_bits) {
+  const float m = __uint_as_float(absmax_bits);
+  if (!(m > 0.f) || !isfinite(m)) return 1.f;
+  int e;
+  frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
+  const int k = max(-60, min(60, 14 - e));
+  return ldexpf(1.f, k);
+}
+
 }  // namespace einconv

@@ -483,6 +483,92 @@ __global__ void __launch_bounds__(256) pack_channels_last_kernel(const T* __rest
   }
 }
 
+// fp32 source -> scaled fp16 destination, same padded channels-last layout (tile: 64 channels x 32 positions)
+__global__ void __launch_bounds__(256) pack_convert_kernel(const float* __restrict__ src, __half* __restrict__ xp,
+                                                           const __grid_constant__ PackParams pp,
+                                                           const unsigned* __restrict__ absmax_bits) {
+  constexpr int TW = 32, TC = 64, NW = TC / 2;
+  __shared__ uint32_t tile[TW][NW + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float scale = operand_scale(__ldg(absmax_bits));
+  const int W = pp.n_dims - 1;
+  const int c0 = blockIdx.y * TC;
+  const long long orow = blockIdx.x;
+  uint32_t rem = (uint32_t)orow;
+  bool row_real = true;
+  long long src_off = 0, mul = pp.S[W];
+  for (int d = W - 1; d >= 0; --d) {
+    uint32_t q, r;
+    pp.outer_div[d].divmod(rem, q, r);
+    rem = q;
+    const int i = (int)r - pp.pad[d];
+    if (i < 0 || i >= pp.S[d]) row_real = false;
+    src_off += (long long)i * mul;
+    mul *= pp.S[d];
+  }
+  const long long b = rem;
+  const float* rowp[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + 8 * warp + i;
+    rowp[i] = (row_real && c < pp.ctot) ? src + (b * pp.ctot + c) * pp.s_total + src_off : nullptr;
+  }
+  uint32_t* dst_row = reinterpret_cast<uint32_t*>(xp + orow * pp.P[W] * pp.cp + c0);
+  const int cp_words = pp.cp / 2;
+  for (int w0 = 0; w0 < pp.P[W]; w0 += TW) {
+    float vals[8];
+    const int iw = w0 + lane - pp.pad[W];
+    const bool ok = iw >= 0 && iw < pp.S[W];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      vals[i] = 0.f;
+      if (ok && rowp[i]) vals[i] = __ldg(rowp[i] + iw);
+    }
+#pragma unroll
+    for (int ip = 0; ip < 4; ++ip) {
+      const __half2 h = __floats2half2_rn(vals[2 * ip] * scale, vals[2 * ip + 1] * scale);
+      tile[lane][4 * warp + ip] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < TW / 8; ++j) {
+      const int wl = warp + 8 * j, w = w0 + wl;
+      if (w < pp.P[W] && c0 + lane * 2 < pp.cp) dst_row[(long long)w * cp_words + lane] = tile[wl][lane];
+    }
+    __syncthreads();
+  }
+}
+
+int pack_channels_last_f32_to_f16(const float* src, void* xp, int n_dims, int batch, int ctot, int cp, const int* S,
+                                  const long long* P, const int* pad, const unsigned* absmax_bits,
+                                  cudaStream_t stream) {
+  const int N = n_dims;
+  PackParams pp{};
+  pp.n_dims = N;
+  pp.ctot = ctot;
+  pp.cp = cp;
+  pp.s_total = 1;
+  long long outer = batch;
+  for (int d = 0; d < N; ++d) {
+    pp.S[d] = S[d];
+    pp.P[d] = (int)P[d];
+    pp.pad[d] = pad[d];
+    pp.s_total *= S[d];
+    if (d < N - 1) {
+      outer *= P[d];
+      pp.outer_div[d] = FastDiv((uint32_t)P[d]);
+    }
+  }
+  EINCONV_CHECK_ARG(outer < (1ll << 31), "pack_channels_last: too many rows");
+  EINCONV_CHECK_ARG(cp % 8 == 0, "pack_channels_last: channel pitch must be a multiple of 16 bytes");
+  if (outer == 0 || cp == 0) return EINCONV_OK;
+  dim3 grid((unsigned)outer, (unsigned)((cp + 63) / 64));
+  EINCONV_CHECK_ARG(grid.y < 65536, "pack_channels_last: too many channels");
+  pack_convert_kernel<<<grid, 256, 0, stream>>>(src, (__half*)xp, pp, absmax_bits);
+  EINCONV_CHECK_LAUNCH("pack_convert_kernel");
+  return EINCONV_OK;
+}
+
 // src [B, ctot, S..] -> xp [B, P_0.., P_{N-1}, cp]: zero-padded by pad[d] in front, channels-last
 int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int batch, int ctot, int cp,
                        const int* S, const long long* P, const int* pad, cudaStream_t stream,

@@ -33,15 +33,6 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
   if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
 }
 
-__device__ __forceinline__ float operand_scale(unsigned absmax_bits) {
-  const float m = __uint_as_float(absmax_bits);
-  if (!(m > 0.f) || !isfinite(m)) return 1.f;
-  int e;
-  frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
-  const int k = max(-60, min(60, 14 - e));
-  return ldexpf(1.f, k);
-}
-
 __global__ void __launch_bounds__(256) scale_to_half_kernel(const float* __restrict__ x, __half* __restrict__ y,
                                                             long long n, const unsigned* __restrict__ absmax_bits,
                                                             float* __restrict__ inv_s2) {
@@ -61,6 +52,16 @@ __global__ void __launch_bounds__(256) scale_to_half_kernel(const float* __restr
   for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2half_rn(__ldg(x + i) * s);
+}
+
+// max |x| of an fp32 tensor as float bits, atomically maxed into *out_bits (caller zeroes it first)
+int launch_absmax(const float* x, long long n, unsigned* out_bits, cudaStream_t stream) {
+  if (n == 0) return EINCONV_OK;
+  EINCONV_CHECK_ARG(((uintptr_t)x % 16) == 0, "absmax: misaligned tensor");
+  const unsigned blocks = (unsigned)std::min<long long>((n / 4 + 255) / 256 + 1, 8ll * kNumSMs);
+  absmax_kernel<<<blocks, 256, 0, stream>>>(x, n, out_bits);
+  EINCONV_CHECK_LAUNCH("absmax_kernel");
+  return EINCONV_OK;
 }
 
 // header: [0] absmax bits, [1] 1 / s^2 (float); x must be 16-byte aligned (torch allocations are)

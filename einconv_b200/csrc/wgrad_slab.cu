@@ -223,13 +223,16 @@ wgrad_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   }
 }
 
+// absmax != nullptr: the operands were scaled fp16 copies of fp32 tensors; un-scale by 1 / (s_x * s_v)
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ partial, T* __restrict__ gw,
-                                                           long long n, int splits) {
+                                                           long long n, int splits,
+                                                           const unsigned* __restrict__ absmax) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   float s = 0.f;
   for (int k = 0; k < splits; ++k) s += partial[(long long)k * n + idx];
+  if (absmax) s *= 1.f / (operand_scale(__ldg(absmax)) * operand_scale(__ldg(absmax + 1)));
   Cvt<T>::store(gw + idx, s);
 }
 
@@ -250,8 +253,10 @@ struct Plan {
 
 static Plan make_plan(const DevGeom& g, int dtype) {
   Plan pl;
-  if (dtype != EINCONV_BF16 && dtype != EINCONV_F16) return pl;
+  // fp32 tensors (TF32 mode) run on power-of-two-scaled fp16 operand copies: same 10-bit mantissa
+  if (dtype != EINCONV_BF16 && dtype != EINCONV_F16 && dtype != EINCONV_F32) return pl;
   if (getenv("EINCONV_NO_WGRAD_SLAB")) return pl;
+  if (dtype == EINCONV_F32 && getenv("EINCONV_WGRAD_TF32")) return pl;
   const int N = g.n_dims;
   pl.n_dims = N;
   for (int d = 0; d < N; ++d)
@@ -355,31 +360,51 @@ bool supported(const DevGeom& g, int dtype) { return make_plan(g, dtype).ok; }
 int64_t workspace_bytes(const DevGeom& g, int dtype) {
   const Plan pl = make_plan(g, dtype);
   if (!pl.ok) return 0;
-  return pl.xp_bytes + pl.vp_bytes + pl.partial_bytes + 1024;
+  return pl.xp_bytes + pl.vp_bytes + pl.partial_bytes + 2048;
 }
 
+// T: operand type of the kernel (bf16 / fp16); fp32 inputs are converted to scaled fp16 while packing
 template <typename T>
 static int run_t(const Plan& pl, const void* x, const void* v, void* gw, int dtype, const DevGeom& g,
                  void* workspace, cudaStream_t stream) {
   uintptr_t base = ((uintptr_t)workspace + 1023) & ~(uintptr_t)1023;
+  unsigned* absmax = reinterpret_cast<unsigned*>(base);  // [0] max|x|, [1] max|v| (fp32 inputs only)
+  base += 1024;
   T* xp = reinterpret_cast<T*>(base);
   T* vp = reinterpret_cast<T*>(base + pl.xp_bytes);
   float* partial = reinterpret_cast<float*>(base + pl.xp_bytes + pl.vp_bytes);
   const int N = g.n_dims;
+  const int op_dtype = dtype == EINCONV_F32 ? EINCONV_F16 : dtype;
   int zero_pad[kMaxDims] = {0};
   // xp: X on the padded grid; rows beyond B * Ptot are never written and are excluded from the tensor
   // map (TMA zero-fills them).  vp: V on the same grid, zero where o_d >= O_d.
   // (running the two transposes concurrently on a forked stream was measured and gains nothing: they
   // are limited by DRAM efficiency, not by latency)
-  int st = ctma::pack_channels_last(x, xp, dtype, N, g.batch, g.groups * g.c_in_g, pl.cxp, g.in, pl.P, g.pad, stream);
-  if (st) return st;
-  st = ctma::pack_channels_last(v, vp, dtype, N, g.batch, g.groups * g.c_out_g, pl.cvp, g.out, pl.P, zero_pad, stream);
-  if (st) return st;
+  int st;
+  if (dtype == EINCONV_F32) {
+    cudaError_t e = cudaMemsetAsync(absmax, 0, 8, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(absmax)");
+    st = launch_absmax((const float*)x, (long long)g.batch * g.groups * g.c_in_g * g.in_total, absmax, stream);
+    if (st) return st;
+    st = launch_absmax((const float*)v, (long long)g.batch * g.groups * g.c_out_g * g.out_total, absmax + 1, stream);
+    if (st) return st;
+    st = ctma::pack_channels_last_f32_to_f16((const float*)x, xp, N, g.batch, g.groups * g.c_in_g, pl.cxp, g.in, pl.P,
+                                             g.pad, absmax, stream);
+    if (st) return st;
+    st = ctma::pack_channels_last_f32_to_f16((const float*)v, vp, N, g.batch, g.groups * g.c_out_g, pl.cvp, g.out,
+                                             pl.P, zero_pad, absmax + 1, stream);
+    if (st) return st;
+  } else {
+    st = ctma::pack_channels_last(x, xp, dtype, N, g.batch, g.groups * g.c_in_g, pl.cxp, g.in, pl.P, g.pad, stream);
+    if (st) return st;
+    st = ctma::pack_channels_last(v, vp, dtype, N, g.batch, g.groups * g.c_out_g, pl.cvp, g.out, pl.P, zero_pad, stream);
+    if (st) return st;
+  }
 
   CUtensorMap map_x, map_v;
-  st = ctma::encode_2d(&map_x, dtype, xp, pl.rows_total, pl.cxp, kCB, kBoxRows, 128);
+  st = ctma::encode_2d(&map_x, op_dtype, xp, pl.rows_total, pl.cxp, kCB, kBoxRows, 128);
   if (st) return st;
-  st = ctma::encode_2d(&map_v, dtype, vp, pl.rows_total, pl.cvp, kCB, kBoxRows, 128);
+  st = ctma::encode_2d(&map_v, op_dtype, vp, pl.rows_total, pl.cvp, kCB, kBoxRows, 128);
   if (st) return st;
 
   Params p{};
@@ -430,8 +455,11 @@ static int run_t(const Plan& pl, const void* x, const void* v, void* gw, int dty
   const long long grid = (long long)g.groups * pl.n_cblocks * pl.n_tgroups * pl.n_cotiles * pl.k_splits;
   kern<<<(unsigned)grid, kThreads, pl.smem, stream>>>(map_x, map_v, p);
   EINCONV_CHECK_LAUNCH("wgrad_slab_kernel");
-  wgrad_finish_kernel<T><<<(unsigned)((pl.gw_elems + 255) / 256), 256, 0, stream>>>(partial, (T*)gw, pl.gw_elems,
-                                                                                     pl.k_splits);
+  const unsigned fin_blocks = (unsigned)((pl.gw_elems + 255) / 256);
+  if (dtype == EINCONV_F32)
+    wgrad_finish_kernel<float><<<fin_blocks, 256, 0, stream>>>(partial, (float*)gw, pl.gw_elems, pl.k_splits, absmax);
+  else
+    wgrad_finish_kernel<T><<<fin_blocks, 256, 0, stream>>>(partial, (T*)gw, pl.gw_elems, pl.k_splits, nullptr);
   EINCONV_CHECK_LAUNCH("wgrad_finish_kernel");
   return EINCONV_OK;
 }
@@ -443,12 +471,12 @@ int run(const void* x, const void* v, void* gw, int dtype, const DevGeom& g, voi
     set_error("wgrad_slab: unsupported geometry");
     return EINCONV_ERR_UNSUPPORTED;
   }
-  if (!workspace || workspace_bytes_given < pl.xp_bytes + pl.vp_bytes + pl.partial_bytes + 1024) {
+  if (!workspace || workspace_bytes_given < pl.xp_bytes + pl.vp_bytes + pl.partial_bytes + 2048) {
     set_error("wgrad_slab: workspace too small");
     return EINCONV_ERR_WORKSPACE;
   }
   if (dtype == EINCONV_BF16) return run_t<__nv_bfloat16>(pl, x, v, gw, dtype, g, workspace, stream);
-  return run_t<__half>(pl, x, v, gw, dtype, g, workspace, stream);
+  return run_t<__half>(pl, x, v, gw, dtype, g, workspace, stream);  // fp16 and (scaled) fp32
 }
 
 }  // namespace wslab

@@ -52,10 +52,11 @@ typedef enum {
 /* How the multiply-accumulate of a contraction is carried out.
  *  AUTO   : FP32 (f32/f64 I/O) or native 16-bit tensor cores (bf16/f16 I/O)
  *  FP32   : CUDA-core FMA in fp32 (fp64 for f64 I/O); meets the reference's rtol 1e-5
- *  TF32   : tcgen05 kind::tf32 on f32 I/O, fp32 accumulate in TMEM.  The KFC factor may instead
- *           run kind::f16 on operand copies scaled by a power of two and rounded to fp16 — the same
- *           10 explicit mantissa bits as TF32, round-to-nearest instead of truncation — whenever that
- *           is faster (half the operand bytes, twice the MMA rate); the stated 1e-3 tolerance holds.
+ *  TF32   : tcgen05 kind::tf32 on f32 I/O, fp32 accumulate in TMEM.  The KFC factor and the weight
+ *           VJP may instead run kind::f16 on operand copies scaled by a power of two and rounded to
+ *           fp16 — the same 10 explicit mantissa bits as TF32, round-to-nearest instead of truncation —
+ *           whenever that is faster (half the operand bytes, twice the MMA rate); the stated 1e-3
+ *           tolerance holds.
  *  HALF   : tcgen05 kind::f16 on bf16/f16 I/O, fp32 accumulate in TMEM
  */
 typedef enum {

@@ -705,9 +705,9 @@ def test_tc_kernels_are_selected():
     assert lib.einconv_selected_kernel(nat.OP_KFC, g, 0, nat.MATH_FP32, 0) == b"ffma_gather_gemm"
     g24 = nat.make_geom(2, 1, 32, 48, (24, 24), (3, 3), (1, 1), (1, 1), (1, 1), (24, 24))
     assert lib.einconv_selected_kernel(nat.OP_KFC, g24, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_kfc"
-    # 16-bit, stride 1: slab kernel on channels-last padded copies; fp32 (TF32) and stride > 1: per-tap TMA tiles
+    # stride 1: slab kernel on channels-last padded copies (fp32 in TF32 mode as scaled fp16); stride > 1: per-tap TMA tiles
     assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 1, nat.MATH_AUTO, 0) == b"tcgen05_slab_wgrad"
-    assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 0, nat.MATH_TF32, 0) == b"tcgen05_tma_wgrad"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 0, nat.MATH_TF32, 0) == b"tcgen05_slab_wgrad"
     g24s = nat.make_geom(2, 1, 32, 48, (24, 24), (3, 3), (2, 2), (1, 1), (1, 1), (12, 12))
     assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24s, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_wgrad"
     assert lib.einconv_selected_kernel(nat.OP_CONV_WEIGHT_VJP, g24, 1, nat.MATH_AUTO, 1) == b"ffma_gather_gemm"
@@ -814,11 +814,12 @@ def test_conv_tma_forward_and_input_vjp(case, mode, ctma_weights):
 
 
 @pytest.mark.parametrize("case", CTMA_CASES, ids=CTMA_IDS)
-@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "tf32"])
 def test_slab_weight_vjp(case, mode):
     """csrc/wgrad_slab.cu (MN-major operands from the channels-last padded copies, tap pairs sharing one
-    slab): max|d| <= 2^-7 (bf16) / 2^-10 (fp16) of max|ref| against the fp64 oracle on the same bits."""
-    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[mode]
+    slab): max|d| <= 2^-7 (bf16) / 2^-10 (fp16) of max|ref| against the fp64 oracle on the same bits;
+    fp32 tensors in TF32 mode run on scaled fp16 operand copies with the TF32 tolerance 1e-3."""
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "tf32": torch.float32}[mode]
     x, w, b, kw = _tc_inputs(case, dtype)
     N = x.dim() - 2
     groups = kw.get("groups", 1)
@@ -826,11 +827,15 @@ def test_slab_weight_vjp(case, mode):
     torch.manual_seed(2)
     v = (torch.rand(*y.shape) - 0.5).to(dtype)
     want = direct.conv_weight_vjp(x.double().numpy(), v.double().numpy(), tuple(w.shape[2:]), **kw)
-    got = evaluator.conv_weight_vjp_raw(
-        x.to(DEV), v.to(DEV), tuple(w.shape[2:]), kw.get("dilation", 1), kw.get("padding", 0),
-        kw.get("stride", 1), groups,
-    )
-    _rel_to_max(got, want, 2.0**-7 if mode == "bf16" else 2.0**-10, f"slab wgrad {mode}")
+    evaluator.set_fp32_math("tf32" if mode == "tf32" else "auto")
+    try:
+        got = evaluator.conv_weight_vjp_raw(
+            x.to(DEV), v.to(DEV), tuple(w.shape[2:]), kw.get("dilation", 1), kw.get("padding", 0),
+            kw.get("stride", 1), groups,
+        )
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, {"bf16": 2.0**-7, "fp16": 2.0**-10, "tf32": 1e-3}[mode], f"slab wgrad {mode}")
 
 
 def test_conv_tma_is_used_by_autograd_and_matches_torch():
