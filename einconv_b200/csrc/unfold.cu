@@ -337,6 +337,7 @@ struct FlatParams {
   int P, K, box;
   int tap_chunks, taps_per_chunk;
   int planes_per_cta;
+  int pair;  // 16-bit elements, even P, one plane per CTA: two outputs per 32-bit store
   long long n_planes;
   FastDiv ext_div[ND], out_div[ND], k_div[ND], chan_div, chunk_div, p_div;
 };
@@ -383,6 +384,26 @@ __device__ __forceinline__ void flat_emit_multi(const T* __restrict__ plane, con
 #pragma unroll
     for (int i = 0; i < NI - 1; ++i) store_stream1<T>(dst + doff[i], v[i]);
     if (last_on) store_stream1<T>(dst + doff[NI - 1], v[NI - 1]);
+  }
+}
+
+// 16-bit elements, even P: a slot is a PAIR of consecutive outputs, written with one 32-bit store
+// (128 bytes per warp instruction instead of 64); the two sources are independent shared loads.
+template <int NI>
+__device__ __forceinline__ void flat_emit_pair(const uint16_t* __restrict__ plane, const int* __restrict__ tap_off,
+                                               int n_taps, uint16_t* __restrict__ dst, int P,
+                                               const int (&offa)[kFlatJpt], const int (&offb)[kFlatJpt],
+                                               bool last_on) {
+#pragma unroll 2
+  for (int t = 0; t < n_taps; ++t, dst += P) {
+    const uint16_t* s = plane + tap_off[t];
+    uint32_t v[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) v[i] = (uint32_t)s[offa[i]] | ((uint32_t)s[offb[i]] << 16);
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+    for (int i = 0; i < NI - 1; ++i) __stcs(d32 + i * kFlatThreads, v[i]);
+    if (last_on) __stcs(d32 + (NI - 1) * kFlatThreads, v[NI - 1]);
   }
 }
 
@@ -598,6 +619,60 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
   const long long bc = bcg;
   stage_plane(bc, plane);
   __syncthreads();
+  if constexpr (sizeof(T) == 2) {
+    if (p.pair) {
+      // pairs of consecutive outputs per slot (P even, rows 4-byte aligned)
+      const int P2 = p.P >> 1;
+      uint16_t* dst_pairs = reinterpret_cast<uint16_t*>(out) + (bc * p.K + t0) * (long long)p.P + 2 * tid;
+      for (int jb = 0; jb < P2; jb += kChunk) {
+        const int left = P2 - jb;
+        const int n_i = min(kFlatJpt, (left + kFlatThreads - 1) / kFlatThreads);
+        const bool last_on = (n_i - 1) * kFlatThreads + tid < left;
+        int offa[kFlatJpt], offb[kFlatJpt];
+#pragma unroll
+        for (int i = 0; i < kFlatJpt; ++i) {
+          offa[i] = 0;
+          offb[i] = 0;
+          if (i < n_i) {
+            const int s2 = jb + i * kFlatThreads + tid;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int j = 2 * s2 + h;
+              uint32_t rem = (uint32_t)(j < p.P ? j : 0);
+              int o = 0;
+#pragma unroll
+              for (int d = ND - 1; d >= 0; --d) {
+                uint32_t q, od;
+                p.out_div[d].divmod(rem, q, od);
+                rem = q;
+                o += (int)od * p.so[d];
+              }
+              if (h == 0) offa[i] = o; else offb[i] = o;
+            }
+          }
+        }
+        const uint16_t* pl16 = reinterpret_cast<const uint16_t*>(plane);
+        uint16_t* d = dst_pairs + 2 * jb;
+        switch (n_i) {
+#define EINCONV_FLAT_CASE(NI)                                                          \
+  case NI:                                                                             \
+    if constexpr (NI <= kFlatJpt)                                                      \
+      flat_emit_pair<NI>(pl16, tap_off, n_taps, d, p.P, offa, offb, last_on);          \
+    break;
+          EINCONV_FLAT_CASE(8)
+          EINCONV_FLAT_CASE(7)
+          EINCONV_FLAT_CASE(6)
+          EINCONV_FLAT_CASE(5)
+          EINCONV_FLAT_CASE(4)
+          EINCONV_FLAT_CASE(3)
+          EINCONV_FLAT_CASE(2)
+#undef EINCONV_FLAT_CASE
+          default: flat_emit_pair<1>(pl16, tap_off, n_taps, d, p.P, offa, offb, last_on); break;
+        }
+      }
+      return;
+    }
+  }
   T* dst_plane = out + (bc * p.K + t0) * (long long)p.P + tid;
   if (single) {
     emit_chunk(dst_plane, n_i0, off0, last_on0);
@@ -942,6 +1017,10 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     while (pc > 1 && ((n_planes + pc - 1) / pc) * p.tap_chunks < 8ll * kNumSMs) pc /= 2;
     p.planes_per_cta = (int)std::max<long long>(1, pc);
   }
+  p.pair = (sizeof(T) == 2 && p.planes_per_cta == 1 && p.P % 2 == 0 && ((uintptr_t)out % 4) == 0 &&
+            kFlatJpt <= 8 && !getenv("EINCONV_UNFOLD_NO_PAIRS"))
+               ? 1
+               : 0;
   smem = (((size_t)p.box * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4;
   const long long grid = ((n_planes + p.planes_per_cta - 1) / p.planes_per_cta) * p.tap_chunks;
   if (grid >= (1ll << 31)) return 0;
