@@ -338,6 +338,10 @@ struct FlatParams {
   int tap_chunks, taps_per_chunk;
   int planes_per_cta;
   int pair;  // 16-bit elements, even P, one plane per CTA: two outputs per 32-bit store
+  // planes too large for shared memory are cut along the outermost dimension: a CTA stages the window of
+  // `tile0` output coordinates of dim 0 (all of the other dims) and emits P_loc = rows * rest outputs per tap
+  int n_tiles0, tile0, rest, tile_shift;
+  FastDiv tile_div;
   long long n_planes;
   FastDiv ext_div[ND], out_div[ND], k_div[ND], chan_div, chunk_div, p_div;
 };
@@ -416,8 +420,18 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
   int* tap_off = reinterpret_cast<int*>(smem_raw + (((size_t)p.box * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15));
   const int tid = threadIdx.x;
 
-  uint32_t bcg, chunk;
+  uint32_t bcg, chunk, tile = 0;
   p.chunk_div.divmod(blockIdx.x, bcg, chunk);
+  if (p.n_tiles0 > 1) {
+    uint32_t q;
+    p.tile_div.divmod(bcg, q, tile);
+    bcg = q;
+  }
+  // this CTA's share of the plane: P_loc outputs per tap, starting at dst_tile_off
+  const int rows0 = min(p.tile0, p.out[0] - (int)tile * p.tile0);
+  const int P_loc = rows0 * p.rest;
+  const int dst_tile_off = (int)tile * p.tile0 * p.rest;
+  const int cc_shift0 = (int)tile * p.tile_shift;
   const int t0 = (int)chunk * p.taps_per_chunk;
   const int t1 = min(p.K, t0 + p.taps_per_chunk);
   const int n_taps = t1 - t0;
@@ -439,7 +453,7 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
   constexpr int kChunk = kFlatThreads * kFlatJpt;
   // staged offsets of this thread's output slots for the chunk starting at jb (only the used slots)
   auto slot_offsets = [&](int jb, int (&off)[kFlatJpt], int& n_i, bool& last_on) {
-    const int left = p.P - jb;
+    const int left = P_loc - jb;
     n_i = min(kFlatJpt, (left + kFlatThreads - 1) / kFlatThreads);
     last_on = (n_i - 1) * kFlatThreads + tid < left;
 #pragma unroll
@@ -447,7 +461,7 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
       off[i] = 0;
       if (i < n_i) {
         const int j = jb + i * kFlatThreads + tid;
-        uint32_t rem = (uint32_t)(j < p.P ? j : 0);
+        uint32_t rem = (uint32_t)(j < P_loc ? j : 0);
         int o = 0;
 #pragma unroll
         for (int d = ND - 1; d >= 0; --d) {
@@ -489,7 +503,7 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
   };
 
   // small planes (one chunk): the slot offsets are the same for every plane of this CTA
-  const bool single = p.P <= kChunk;
+  const bool single = P_loc <= kChunk;
   int off0[kFlatJpt], n_i0 = 0;
   bool last_on0 = false;
   if (single && p.planes_per_cta == 1) slot_offsets(0, off0, n_i0, last_on0);
@@ -532,7 +546,7 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
         int off = 0;
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
-          const int v = cc[d] * p.gstep[d] - p.pad[d];
+          const int v = (cc[d] + (d == 0 ? cc_shift0 : 0)) * p.gstep[d] - p.pad[d];
           ok = ok && (unsigned)v < (unsigned)p.in[d];
           off += v * p.xs[d];
         }
@@ -622,8 +636,9 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
   if constexpr (sizeof(T) == 2) {
     if (p.pair) {
       // pairs of consecutive outputs per slot (P even, rows 4-byte aligned)
-      const int P2 = p.P >> 1;
-      uint16_t* dst_pairs = reinterpret_cast<uint16_t*>(out) + (bc * p.K + t0) * (long long)p.P + 2 * tid;
+      const int P2 = P_loc >> 1;
+      uint16_t* dst_pairs =
+          reinterpret_cast<uint16_t*>(out) + (bc * p.K + t0) * (long long)p.P + dst_tile_off + 2 * tid;
       for (int jb = 0; jb < P2; jb += kChunk) {
         const int left = P2 - jb;
         const int n_i = min(kFlatJpt, (left + kFlatThreads - 1) / kFlatThreads);
@@ -638,7 +653,7 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int j = 2 * s2 + h;
-              uint32_t rem = (uint32_t)(j < p.P ? j : 0);
+              uint32_t rem = (uint32_t)(j < P_loc ? j : 0);
               int o = 0;
 #pragma unroll
               for (int d = ND - 1; d >= 0; --d) {
@@ -673,11 +688,11 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
       return;
     }
   }
-  T* dst_plane = out + (bc * p.K + t0) * (long long)p.P + tid;
+  T* dst_plane = out + (bc * p.K + t0) * (long long)p.P + dst_tile_off + tid;
   if (single) {
     emit_chunk(dst_plane, n_i0, off0, last_on0);
   } else {
-    for (int jb = 0; jb < p.P; jb += kChunk) {
+    for (int jb = 0; jb < P_loc; jb += kChunk) {
       int off[kFlatJpt], n_i;
       bool last_on;
       slot_offsets(jb, off, n_i, last_on);
@@ -943,9 +958,27 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     p.gstep[d] = igcd(stride[d], dil[d]);
   }
   long long box = 1, span = 0;
+  p.n_tiles0 = 1;
+  p.tile0 = std::max(1, p.out[0]);
+  p.rest = 1;
+  for (int d = 1; d < ND; ++d) p.rest *= std::max(1, p.out[d]);
   for (int d = ND - 1; d >= 0; --d) {
-    const long long ext = (long long)(stride[d] / p.gstep[d]) * (p.out[d] - 1) +
-                          (long long)(dil[d] / p.gstep[d]) * (p.k[d] - 1) + 1;
+    long long ext = (long long)(stride[d] / p.gstep[d]) * (p.out[d] - 1) +
+                    (long long)(dil[d] / p.gstep[d]) * (p.k[d] - 1) + 1;
+    if (d == 0 && !getenv("EINCONV_UNFOLD_NO_TILE0")) {
+      // cut along the outermost dimension so that the staged window fits ~40 KB
+      const long long budget = (40 * 1024) / (long long)sizeof(T);
+      const long long sg = stride[0] / p.gstep[0], halo = (long long)(dil[0] / p.gstep[0]) * (p.k[0] - 1) + 1;
+      if (ext * box > budget) {
+        const long long rows = (budget / std::max<long long>(1, box) - halo) / sg + 1;  // ext(tile0) <= budget / box
+        if (rows < 1) return 0;
+        p.tile0 = (int)std::min<long long>(rows, p.out[0]);
+        p.n_tiles0 = ceil_div(p.out[0], p.tile0);
+        p.tile0 = ceil_div(p.out[0], p.n_tiles0);  // even split
+        ext = sg * (p.tile0 - 1) + halo;
+      }
+      p.tile_shift = (int)(sg * p.tile0);
+    }
     if (ext * box > (1 << 20)) return 0;
     p.ext[d] = (int)ext;
     p.so[d] = (int)((stride[d] / p.gstep[d]) * box);
@@ -954,6 +987,8 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     span += (long long)(p.in[d] - 1) * (p.xs[d] < 0 ? -(long long)p.xs[d] : (long long)p.xs[d]);
   }
   if (span >= (1ll << 31)) return 0;
+  if ((long long)p.tile0 * p.rest >= (1ll << 30)) return 0;
+  p.tile_div = FastDiv((uint32_t)p.n_tiles0);
   p.box = (int)box;
   p.P = g0.out_total;
   p.K = g0.k_total;
@@ -978,7 +1013,8 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     // measured: wins for small planes (14x14: 33 -> 27 us for 58 MB), loses ~5% on C2-sized planes, where
     // one CTA per plane already amortises its set-up (EINCONV_UNFOLD_PERSISTENT=1 forces it)
     const bool small_plane = (long long)p.K * p.P * (long long)sizeof(T) <= 64 * 1024;
-    if (!getenv("EINCONV_UNFOLD_NO_PERSISTENT") && (small_plane || getenv("EINCONV_UNFOLD_PERSISTENT")) && aligned &&
+    if (p.n_tiles0 == 1 && !getenv("EINCONV_UNFOLD_NO_PERSISTENT") &&
+        (small_plane || getenv("EINCONV_UNFOLD_PERSISTENT")) && aligned &&
         p.P > 0 && p.P <= kFlatThreads * kPersJpt &&
         smem_p <= 56 * 1024 && items >= 8ll * grid_p && p.K <= kFlatMaxTaps && n_planes < (1ll << 31)) {
       auto kern = unfold_flat_persistent_kernel<T, ND>;
@@ -996,7 +1032,7 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
 
   // CTAs per plane: split the taps while there are fewer CTAs than ~4 per SM
   int chunks = 1;
-  while (n_planes * chunks < 4ll * kNumSMs && chunks * 2 <= p.K) chunks *= 2;
+  while (n_planes * p.n_tiles0 * chunks < 4ll * kNumSMs && chunks * 2 <= p.K) chunks *= 2;
   if (const char* e = getenv("EINCONV_UNFOLD_CHUNKS")) chunks = std::max(1, std::min(p.K, atoi(e)));
   p.taps_per_chunk = ceil_div(p.K, chunks);
   p.tap_chunks = ceil_div(p.K, p.taps_per_chunk);
@@ -1009,7 +1045,7 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
   p.n_planes = n_planes;
   p.planes_per_cta = 1;
   p.p_div = FastDiv((uint32_t)std::max(1, p.P));
-  if (p.P > 0 && p.P * 2 <= kFlatThreads * kFlatJpt && !getenv("EINCONV_UNFOLD_ONE_PLANE")) {
+  if (p.n_tiles0 == 1 && p.P > 0 && p.P * 2 <= kFlatThreads * kFlatJpt && !getenv("EINCONV_UNFOLD_ONE_PLANE")) {
     const long long per_plane_bytes = (long long)p.taps_per_chunk * p.P * (long long)sizeof(T);
     long long pc = std::max<long long>(1, std::min<long long>(32, (64 * 1024 + per_plane_bytes - 1) / per_plane_bytes));
     pc = std::min<long long>(pc, (kFlatThreads * kFlatJpt) / p.P);
@@ -1017,12 +1053,13 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     while (pc > 1 && ((n_planes + pc - 1) / pc) * p.tap_chunks < 8ll * kNumSMs) pc /= 2;
     p.planes_per_cta = (int)std::max<long long>(1, pc);
   }
-  p.pair = (sizeof(T) == 2 && p.planes_per_cta == 1 && p.P % 2 == 0 && ((uintptr_t)out % 4) == 0 &&
+  p.pair = (sizeof(T) == 2 && p.planes_per_cta == 1 && p.P % 2 == 0 && (p.n_tiles0 == 1 || p.rest % 2 == 0) &&
+            ((uintptr_t)out % 4) == 0 &&
             kFlatJpt <= 8 && !getenv("EINCONV_UNFOLD_NO_PAIRS"))
                ? 1
                : 0;
   smem = (((size_t)p.box * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4;
-  const long long grid = ((n_planes + p.planes_per_cta - 1) / p.planes_per_cta) * p.tap_chunks;
+  const long long grid = ((n_planes + p.planes_per_cta - 1) / p.planes_per_cta) * p.n_tiles0 * p.tap_chunks;
   if (grid >= (1ll << 31)) return 0;
   // Too little output per staged element: the tiled kernel amortises its staging better.
   for (int d = 0; d < ND; ++d) {
