@@ -77,6 +77,30 @@ class Workload:
     def host_inputs(self):
         return []
 
+    graph = None
+    graph_launches = 0
+
+    def capture(self, body):
+        """Capture `body` (public API calls on fixed buffers) in a CUDA graph: a step of a few ~10 us
+        kernels is otherwise bound by the host's launch path, not by the kernels."""
+        from einconv_b200 import _native as nat
+
+        if os.environ.get("EINCONV_BENCH_NO_GRAPHS"):
+            return
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            body()
+            n0 = nat.launch_count()
+            body()
+            self.graph_launches = nat.launch_count() - n0
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = g
+
     def e2e_step(self, dev_inputs):
         raise NotImplementedError
 
@@ -152,7 +176,7 @@ class UnfoldC2(Workload):
 
 
 class ConvFwdC1(Workload):
-    name = "C1 convNd 2d fwd N=32 C=64->64 56x56 k3 s1 p1 fp32"
+    name = "C1 convNd 2d fwd N=32 C=64->64 56x56 k3 s1 p1 fp32 (step = one CUDA-graph replay of the call)"
     metric = "convNd fwd TFLOP/s"
     unit = "TFLOP/s"
     bound = "tensor"
@@ -164,19 +188,26 @@ class ConvFwdC1(Workload):
         self.fn = convNd
         self.x = torch.rand(32, 64, 56, 56).to(device)
         self.w = torch.rand(64, 64, 3, 3).to(device)
+        self.capture(self._calls)
 
     dtype = "f32 (tf32 MMA, fp32 accumulate)"
     fp32_math = "tf32"
 
-    def step(self):
+    def _calls(self):
         self.out = self.fn(self.x, self.w, padding=1)
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._calls()
 
     def work(self):
         return 2 * 32 * 64 * 64 * 9 * 56 * 56
 
 
 class DepthwiseC3(Workload):
-    name = "C3 depthwise 2d fwd + input VJP N=32 C=256 28x28 k3 p1 fp32"
+    name = "C3 depthwise 2d fwd + input VJP N=32 C=256 28x28 k3 p1 fp32 (step = one CUDA-graph replay of the two calls)"
     metric = "depthwise fwd+input-VJP HBM GB/s"
     unit = "GB/s"
     bound = "hbm"
@@ -191,9 +222,17 @@ class DepthwiseC3(Workload):
         self.w = torch.rand(256, 1, 3, 3).to(device)
         self.v = torch.rand(32, 256, 28, 28).to(device)
 
-    def step(self):
+        self.capture(self._calls)
+
+    def _calls(self):
         self.y = self.fwd(self.x, self.w, padding=1, groups=256)
         self.gx = self.vjp(self.w, self.v, (28, 28), 1, 1, 1, 256)
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._calls()
 
     def work(self):
         one = 2 * 32 * 256 * 28 * 28 * 4 + 256 * 9 * 4
@@ -352,6 +391,8 @@ def time_steps(wl, steps, warmup, device, flush=True):
         stop.synchronize()
         times.append(start.elapsed_time(stop))
     launches = (nat.launch_count() - launches0) / max(1, steps)
+    if getattr(wl, "graph", None) is not None:
+        launches += wl.graph_launches  # replayed from the workload's CUDA graph
     sweep = getattr(wl, "sweep", None)
     if sweep is not None and getattr(sweep, "_graphs", None) is not None:
         launches += sweep.launches_per_run  # kernels replayed from CUDA graphs are not counted by the library

@@ -381,6 +381,147 @@ static int launch_dw_warp(const void* in, const void* w, const void* bias, void*
   return EINCONV_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Vectorised "same" stencil for fp32 rows that are a multiple of 4 wide (stride 1, 2 * p_w = KW - 1,
+// channel multiplier 1: the MobileNet case).  A lane owns FOUR adjacent columns: one 16-byte load per
+// input row, the (KW - 1) halo columns come from the two neighbouring lanes, KH rolling accumulator
+// rows, one 16-byte store per output row.  W / 4 lanes cover a row, so a warp works on 32 / (W / 4)
+// independent (plane, row block) units side by side.  ~11 instructions per output instead of ~36 in
+// dw_warp_kernel, which was issue-bound (70 % issue-active at 0.4 of the HBM roofline).
+// ---------------------------------------------------------------------------------------------
+struct DwVecParams {
+  int planes, chan;
+  int in_h, in_w, out_h, p_h;      // out_w == in_w
+  int lanes_per_row, slots;        // in_w / 4, 32 / lanes_per_row
+  int n_rblocks, rows_per_block;
+  long long total_units;           // planes * n_rblocks
+  FastDiv rblock_div, chan_div, lane_div;
+};
+
+__device__ __forceinline__ float f4_get(const float4& v, int c) {
+  return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+}
+
+template <int KH, int KW, bool FLIP>
+__global__ void __launch_bounds__(128) dw_vec4_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, float* __restrict__ out,
+                                                      const __grid_constant__ DwVecParams p) {
+  constexpr int PW = (KW - 1) / 2;
+  constexpr int NR = kDwWarpRows;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  uint32_t slot, cg;
+  p.lane_div.divmod((uint32_t)lane, slot, cg);
+  const long long unit = warp * p.slots + slot;
+  const bool active = (int)slot < p.slots && unit < p.total_units;
+  uint32_t plane = 0, rblk = 0, b = 0, q = 0;
+  if (active) {
+    p.rblock_div.divmod((uint32_t)unit, plane, rblk);
+    p.chan_div.divmod(plane, b, q);
+  }
+  float wreg[KH * KW];
+#pragma unroll
+  for (int t = 0; t < KH * KW; ++t) wreg[t] = __ldg(w + (int)q * (KH * KW) + (FLIP ? KH * KW - 1 - t : t));
+  const float bv = bias ? __ldg(bias + q) : 0.f;
+
+  const int row_v = p.lanes_per_row;
+  const int oh0 = (int)rblk * p.rows_per_block;
+  const int rows = min(p.rows_per_block, p.out_h - oh0);
+  const int ih0 = oh0 - p.p_h;
+  const float4* base = reinterpret_cast<const float4*>(in + (long long)plane * p.in_h * p.in_w) + cg;
+  float4* dst = reinterpret_cast<float4*>(out + (long long)plane * p.out_h * p.in_w) + cg;
+  const bool first = cg == 0, last = (int)cg == row_v - 1;
+
+  float4 v[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const int ih = ih0 + i;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && i < rows + KH - 1 && ih >= 0 && ih < p.in_h) v[i] = __ldg(base + (long long)ih * row_v);
+  }
+  float acc[KH][4];
+#pragma unroll
+  for (int r = 0; r < KH; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = bv;
+  const int n_in = p.rows_per_block + KH - 1;  // uniform over the grid: shuffles stay convergent
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    if (i < n_in) {
+      float e[4 + KW - 1];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) e[PW + c] = f4_get(v[i], c);
+#pragma unroll
+      for (int j = 0; j < PW; ++j) {
+        const float t = __shfl_up_sync(FULL, f4_get(v[i], 4 - PW + j), 1);
+        e[j] = first ? 0.f : t;
+      }
+#pragma unroll
+      for (int j = 0; j < KW - 1 - PW; ++j) {
+        const float t = __shfl_down_sync(FULL, f4_get(v[i], j), 1);
+        e[PW + 4 + j] = last ? 0.f : t;
+      }
+#pragma unroll
+      for (int kh = 0; kh < KH; ++kh) {
+        const int o = i - kh;
+        if (o >= 0 && o < NR - KH + 1) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int kw = 0; kw < KW; ++kw)
+              acc[o % KH][c] = fmaf(e[c + kw], wreg[kh * KW + kw], acc[o % KH][c]);
+        }
+      }
+      const int oc = i - KH + 1;
+      if (oc >= 0) {
+        if (active && oc < rows)
+          dst[(long long)(oh0 + oc) * row_v] =
+              make_float4(acc[oc % KH][0], acc[oc % KH][1], acc[oc % KH][2], acc[oc % KH][3]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[oc % KH][c] = bv;
+      }
+    }
+  }
+}
+
+template <int KH, int KW>
+static int launch_dw_vec4(const void* in, const void* w, const void* bias, void* out, const DwFastParams& f,
+                          cudaStream_t stream) {
+  DwVecParams p{};
+  p.planes = f.planes_out;
+  p.chan = f.chan_out;
+  p.in_h = f.in_h; p.in_w = f.in_w; p.out_h = f.out_h; p.p_h = f.p_h;
+  p.lanes_per_row = f.in_w / 4;
+  p.slots = 32 / p.lanes_per_row;
+  const int max_rows = kDwWarpRows - KH + 1;
+  p.n_rblocks = ceil_div(p.out_h, max_rows);
+  // enough warps to fill the chip several times over: halve the row blocks while they stay >= 2 * KH
+  auto warps_for = [&](int nrb) { return ((long long)p.planes * nrb + p.slots - 1) / p.slots; };
+  while (warps_for(p.n_rblocks) < 148ll * 32 && ceil_div(p.out_h, p.n_rblocks * 2) >= 2 * KH) p.n_rblocks *= 2;
+  if (const char* e = getenv("EINCONV_DW_VEC_RBLOCKS")) {
+    const int v = atoi(e);
+    if (v >= p.n_rblocks && v <= p.out_h) p.n_rblocks = v;
+  }
+  p.rows_per_block = ceil_div(p.out_h, p.n_rblocks);
+  p.n_rblocks = ceil_div(p.out_h, p.rows_per_block);
+  p.total_units = (long long)p.planes * p.n_rblocks;
+  EINCONV_CHECK_ARG(p.total_units < (1ll << 31), "depthwise: tensor too large");
+  p.rblock_div = FastDiv((uint32_t)p.n_rblocks);
+  p.chan_div = FastDiv((uint32_t)p.chan);
+  p.lane_div = FastDiv((uint32_t)p.lanes_per_row);
+  const long long warps = warps_for(p.n_rblocks);
+  const unsigned grid = (unsigned)((warps + 3) / 4);
+  if (f.flip)
+    dw_vec4_kernel<KH, KW, true><<<grid, 128, 0, stream>>>((const float*)in, (const float*)w,
+                                                            (const float*)bias, (float*)out, p);
+  else
+    dw_vec4_kernel<KH, KW, false><<<grid, 128, 0, stream>>>((const float*)in, (const float*)w,
+                                                             (const float*)bias, (float*)out, p);
+  EINCONV_CHECK_LAUNCH("dw_vec4_kernel");
+  return EINCONV_OK;
+}
+
 template <typename T, int KH, int KW, int S>
 static int launch_dw_direct(const void* in, const void* w, const void* bias, void* out,
                             DwFastParams& p, cudaStream_t stream) {
@@ -411,6 +552,16 @@ static int try_dw_direct(const void* in, const void* w, const void* bias, void* 
                          cudaStream_t stream) {
   if (d_h != 1 || d_w != 1 || s_h != s_w) return 0;
   int st = 1;
+  if constexpr (std::is_same_v<T, float>) {
+    // "same" geometry along W, rows a multiple of 4 wide, 16-byte aligned tensors
+    if (s_h == 1 && p.mult == 1 && k_h == k_w && 2 * p.p_w == k_w - 1 && p.out_w == p.in_w &&
+        p.in_w % 4 == 0 && p.in_w <= 128 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0 &&
+        !getenv("EINCONV_DW_DIRECT") && !getenv("EINCONV_DW_NO_VEC")) {
+      if (k_h == 3) return launch_dw_vec4<3, 3>(in, w, bias, out, p, stream) == EINCONV_OK ? 1 : EINCONV_ERR_CUDA;
+      if (k_h == 5) return launch_dw_vec4<5, 5>(in, w, bias, out, p, stream) == EINCONV_OK ? 1 : EINCONV_ERR_CUDA;
+      if (k_h == 7) return launch_dw_vec4<7, 7>(in, w, bias, out, p, stream) == EINCONV_OK ? 1 : EINCONV_ERR_CUDA;
+    }
+  }
   if (s_h == 1 && p.mult == 1 && !getenv("EINCONV_DW_DIRECT")) {
     if (k_h == 3 && k_w == 3) st = launch_dw_warp<T, 3, 3>(in, w, bias, out, p, stream);
     else if (k_h == 5 && k_w == 5) st = launch_dw_warp<T, 5, 5>(in, w, bias, out, p, stream);

@@ -723,16 +723,26 @@ DW_CASES = [
     ((2, 6, 20, 20), 3, dict(padding=0)),            # no padding: output smaller than input
     ((2, 6, 9, 9), 3, dict(padding=2)),              # padding = K - 1
     ((2, 6, 21, 22), 3, dict(padding=1, stride=2)),  # stride 2: per-column kernel
+    # rows a multiple of 4 wide with "same" padding along W: the 16-byte vectorised kernel (fp32)
+    ((2, 6, 20, 36), 3, dict(padding=1)),            # 9 lanes per row, 3 units per warp
+    ((2, 3, 33, 128), 3, dict(padding=1)),           # 32 lanes per row, three row blocks
+    ((3, 5, 13, 8), 5, dict(padding=2)),             # 2 lanes per row, 16 units per warp
+    ((2, 4, 30, 24), 7, dict(padding=3)),            # 7x7
+    ((2, 6, 10, 12), 3, dict(padding=(2, 1))),       # taller output than input
+    ((2, 6, 10, 12), 3, dict(padding=(0, 1))),       # no padding along H
+    ((1, 3, 5, 4), 3, dict(padding=1)),              # a single lane per row
 ]
 
 
 @pytest.mark.parametrize("case", DW_CASES, ids=lambda c: "x".join(map(str, c[0])) + f"-k{c[1]}")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("variant", ["warp", "column"])
+@pytest.mark.parametrize("variant", ["auto", "warp", "column"])
 def test_depthwise_kernels(case, dtype, variant, monkeypatch):
     """fp32: CUDA-core FMA in a fixed order, rtol 1e-5 like the reference's tests; bf16: 2^-7 max|ref|."""
     if variant == "column":
         monkeypatch.setenv("EINCONV_DW_DIRECT", "1")
+    elif variant == "warp":
+        monkeypatch.setenv("EINCONV_DW_NO_VEC", "1")
     xs, k, kw = case
     C = xs[1]
     ks = (k, k) if isinstance(k, int) else k
