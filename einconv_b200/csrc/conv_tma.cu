@@ -483,6 +483,130 @@ __global__ void __launch_bounds__(256) pack_channels_last_kernel(const T* __rest
   }
 }
 
+// Vectorised variant for innermost extents that are a multiple of 4.  The scalar kernel above was
+// instruction-issue bound (725 warp instructions per 8 KB tile, 73 % issue-active at 3.3 TB/s): here a
+// lane loads FOUR source positions of a channel at once (8 bytes of 16-bit data, 16 bytes of fp32),
+// builds whole 16-byte chunks of the destination rows in registers, and both the shared-memory and the
+// global side move 16 bytes per lane (~130 warp instructions per tile).  The tile is indexed by SOURCE
+// position (aligned loads); the padding columns and the all-padding rows are zero-filled directly.
+// Shared layout: tile[position][16-byte chunk], chunks rotated by (position >> 2) so that the
+// 4-rows-per-lane writes and the row-wise reads are both conflict-free.
+// TS / T: source / destination element; they differ only for the fp32 -> scaled fp16 conversion
+// (TS = float, T = uint16_t, `absmax_bits` given).
+template <typename T, typename TS = T>
+__global__ void __launch_bounds__(256) pack_vec4_kernel(const TS* __restrict__ src, T* __restrict__ xp,
+                                                        const __grid_constant__ PackParams pp,
+                                                        const unsigned* __restrict__ absmax_bits = nullptr) {
+  constexpr int EPW = 4 / sizeof(T);
+  constexpr bool CONVERT = !std::is_same_v<T, TS>;
+  constexpr int TP = 128;            // source positions per tile
+  constexpr int TC = 64;             // channels per tile
+  constexpr int CPR = TC / (4 * EPW);  // 16-byte chunks per destination row: 8 (16-bit) or 16 (fp32)
+  constexpr int RPW = 32 / CPR;      // destination rows per warp instruction
+  constexpr int CCH = 4 * EPW;       // channels per chunk
+  __shared__ uint4 tile[TP][CPR];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x >= pp.x_ctas) {  // fused weight job
+    if (blockIdx.y == 0) pack_weights_block<T>(pp, blockIdx.x - pp.x_ctas);
+    return;
+  }
+  const int W = pp.n_dims - 1;
+  const int c0 = blockIdx.y * TC;
+  const long long orow = blockIdx.x;
+  uint32_t rem = (uint32_t)orow;
+  bool row_real = true;
+  long long src_off = 0, mul = pp.S[W];
+  for (int d = W - 1; d >= 0; --d) {
+    uint32_t q, r;
+    pp.outer_div[d].divmod(rem, q, r);
+    rem = q;
+    const int i = (int)r - pp.pad[d];
+    if (i < 0 || i >= pp.S[d]) row_real = false;
+    src_off += (long long)i * mul;
+    mul *= pp.S[d];
+  }
+  const long long b = rem;
+  const int PW = pp.P[W], SW = pp.S[W], pad = pp.pad[W];
+  const int q = lane & (CPR - 1), rsub = lane / CPR;
+  const bool chunk_ok = c0 + q * CCH < pp.cp;  // cp is a multiple of 16 bytes
+  const long long row_chunks = (long long)pp.cp / CCH;  // 16-byte chunks per destination row
+  uint4* dst = reinterpret_cast<uint4*>(xp + orow * PW * pp.cp + c0) + q;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  if (!row_real) {  // a line inside the padding of an outer dimension
+    if (chunk_ok)
+      for (int w = warp * RPW + rsub; w < PW; w += 8 * RPW) dst[w * row_chunks] = zero;
+    return;
+  }
+  if (chunk_ok) {  // the two margins of the line
+    for (int w = warp * RPW + rsub; w < pad; w += 8 * RPW) dst[w * row_chunks] = zero;
+    for (int w = pad + SW + warp * RPW + rsub; w < PW; w += 8 * RPW) dst[w * row_chunks] = zero;
+  }
+  const TS* row0 = src + (b * pp.ctot + c0 + 8 * warp) * pp.s_total + src_off + 4 * lane;
+  float scale = 1.f;
+  if constexpr (CONVERT) scale = operand_scale(__ldg(absmax_bits));
+  const int n_ch = min(8, pp.ctot - (c0 + 8 * warp));  // channels of this warp that exist (may be <= 0)
+  for (int s0 = 0; s0 < SW; s0 += TP) {
+    const bool ok = s0 + 4 * lane < SW;  // SW % 4 == 0: four positions exist together
+    if constexpr (CONVERT) {
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && i < n_ch) v[i] = __ldg(reinterpret_cast<const float4*>(row0 + i * pp.s_total + s0));
+      }
+      auto h2 = [&](float a, float c) -> uint32_t {
+        const __half2 h = __floats2half2_rn(a * scale, c * scale);
+        return *reinterpret_cast<const uint32_t*>(&h);
+      };
+      uint4* t = &tile[4 * lane][(warp + lane) & (CPR - 1)];
+      t[0 * CPR] = make_uint4(h2(v[0].x, v[1].x), h2(v[2].x, v[3].x), h2(v[4].x, v[5].x), h2(v[6].x, v[7].x));
+      t[1 * CPR] = make_uint4(h2(v[0].y, v[1].y), h2(v[2].y, v[3].y), h2(v[4].y, v[5].y), h2(v[6].y, v[7].y));
+      t[2 * CPR] = make_uint4(h2(v[0].z, v[1].z), h2(v[2].z, v[3].z), h2(v[4].z, v[5].z), h2(v[6].z, v[7].z));
+      t[3 * CPR] = make_uint4(h2(v[0].w, v[1].w), h2(v[2].w, v[3].w), h2(v[4].w, v[5].w), h2(v[6].w, v[7].w));
+    } else if constexpr (EPW == 2) {
+      uint2 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = make_uint2(0u, 0u);
+        if (ok && i < n_ch) v[i] = __ldg(reinterpret_cast<const uint2*>(row0 + i * pp.s_total + s0));
+      }
+      uint4* t = &tile[4 * lane][(warp + lane) & (CPR - 1)];
+      t[0 * CPR] = make_uint4(__byte_perm(v[0].x, v[1].x, 0x5410), __byte_perm(v[2].x, v[3].x, 0x5410),
+                              __byte_perm(v[4].x, v[5].x, 0x5410), __byte_perm(v[6].x, v[7].x, 0x5410));
+      t[1 * CPR] = make_uint4(__byte_perm(v[0].x, v[1].x, 0x7632), __byte_perm(v[2].x, v[3].x, 0x7632),
+                              __byte_perm(v[4].x, v[5].x, 0x7632), __byte_perm(v[6].x, v[7].x, 0x7632));
+      t[2 * CPR] = make_uint4(__byte_perm(v[0].y, v[1].y, 0x5410), __byte_perm(v[2].y, v[3].y, 0x5410),
+                              __byte_perm(v[4].y, v[5].y, 0x5410), __byte_perm(v[6].y, v[7].y, 0x5410));
+      t[3 * CPR] = make_uint4(__byte_perm(v[0].y, v[1].y, 0x7632), __byte_perm(v[2].y, v[3].y, 0x7632),
+                              __byte_perm(v[4].y, v[5].y, 0x7632), __byte_perm(v[6].y, v[7].y, 0x7632));
+    } else {
+      uint4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok && i < n_ch) v[i] = __ldg(reinterpret_cast<const uint4*>(row0 + i * pp.s_total + s0));
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4* t = &tile[4 * lane][(2 * warp + h + lane) & (CPR - 1)];
+        t[0 * CPR] = make_uint4(v[4 * h].x, v[4 * h + 1].x, v[4 * h + 2].x, v[4 * h + 3].x);
+        t[1 * CPR] = make_uint4(v[4 * h].y, v[4 * h + 1].y, v[4 * h + 2].y, v[4 * h + 3].y);
+        t[2 * CPR] = make_uint4(v[4 * h].z, v[4 * h + 1].z, v[4 * h + 2].z, v[4 * h + 3].z);
+        t[3 * CPR] = make_uint4(v[4 * h].w, v[4 * h + 1].w, v[4 * h + 2].w, v[4 * h + 3].w);
+      }
+    }
+    __syncthreads();
+    const int n_rows = min(TP, SW - s0);
+    uint4* d = dst + (long long)(s0 + pad) * row_chunks;
+#pragma unroll
+    for (int it = 0; it < TP / (8 * RPW); ++it) {
+      const int row = it * 8 * RPW + warp * RPW + rsub;
+      if (row < n_rows && chunk_ok) d[row * row_chunks] = tile[row][(q + (row >> 2)) & (CPR - 1)];
+    }
+    __syncthreads();
+  }
+}
+
 // fp32 source -> scaled fp16 destination, same padded channels-last layout (tile: 64 channels x 32 positions)
 __global__ void __launch_bounds__(256) pack_convert_kernel(const float* __restrict__ src, __half* __restrict__ xp,
                                                            const __grid_constant__ PackParams pp,
@@ -564,7 +688,11 @@ int pack_channels_last_f32_to_f16(const float* src, void* xp, int n_dims, int ba
   if (outer == 0 || cp == 0) return EINCONV_OK;
   dim3 grid((unsigned)outer, (unsigned)((cp + 63) / 64));
   EINCONV_CHECK_ARG(grid.y < 65536, "pack_channels_last: too many channels");
-  pack_convert_kernel<<<grid, 256, 0, stream>>>(src, (__half*)xp, pp, absmax_bits);
+  pp.x_ctas = grid.x;
+  if (S[N - 1] % 4 == 0 && ((uintptr_t)src & 15) == 0 && !getenv("EINCONV_PACK_SCALAR"))
+    pack_vec4_kernel<uint16_t, float><<<grid, 256, 0, stream>>>(src, (uint16_t*)xp, pp, absmax_bits);
+  else
+    pack_convert_kernel<<<grid, 256, 0, stream>>>(src, (__half*)xp, pp, absmax_bits);
   EINCONV_CHECK_LAUNCH("pack_convert_kernel");
   return EINCONV_OK;
 }
@@ -609,12 +737,16 @@ int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int bat
     grid.x += pp.w_ctas;
   }
   EINCONV_CHECK_ARG(grid.y < 65536, "pack_channels_last: too many channels");
+  const bool vec4 = S[N - 1] % 4 == 0 && ((uintptr_t)src & 15) == 0 && pp.rows_per_cta == 1 &&
+                    !getenv("EINCONV_PACK_SCALAR");
   switch (es) {
     case 4:
-      pack_channels_last_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)xp, pp);
+      if (vec4) pack_vec4_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)xp, pp);
+      else pack_channels_last_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)xp, pp);
       break;
     default:
-      pack_channels_last_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)src, (uint16_t*)xp, pp);
+      if (vec4) pack_vec4_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)src, (uint16_t*)xp, pp);
+      else pack_channels_last_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)src, (uint16_t*)xp, pp);
       break;
   }
   EINCONV_CHECK_LAUNCH("pack_channels_last_kernel");
