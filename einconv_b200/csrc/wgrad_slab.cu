@@ -49,6 +49,15 @@ struct Params {
   int group_shift[kMaxGroups];
   uint32_t pair_off16[kMaxTpg / 2];  // (row offset of the pair's first tap inside the slab) * 128 / 16
   uint32_t pair_lbo16[kMaxTpg / 2];  // (row distance between the pair's taps) * 128 / 16   (0: single tap)
+  // accumulator block -> tap of the group (-1: unused): [MMA][M half: first / second unit][N block]
+  signed char tap_tbl[kMaxTpg / 2][2][2];
+  // quad mode (BN = 64 only): the B operand is N = 128 with its two 64-column blocks `quad_rows` ROWS
+  // apart in a vp slab that starts quad_rows before the k-block, so one MMA pairs each of its two xp
+  // units with vp[r - quad_rows] (tap shift + quad_rows, N block 0) and vp[r] (N block 1): four taps
+  // per M = 128, N = 128 instruction, which is tensor-bound where N = 64 is shared-memory-read bound.
+  int quad_rows;
+  int v_rows;             // rows of vp staged per 64-channel block (kb_rows, or kb_rows + 64 in quad mode)
+  int acc_cols;           // TMEM columns per MMA accumulator (bn, or 128 in quad mode)
   float* partial;         // [k_splits][groups * cog * cg * taps]
   long long gw_elems;
 };
@@ -109,7 +118,7 @@ wgrad_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     prefetch_tensormap(&map_v);
   }
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(p.n_pairs * p.bn)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(p.n_pairs * p.acc_cols)) tmem_cols <<= 1;
   if (warp == 1) tmem_alloc(&bars->tmem_base, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -120,7 +129,7 @@ wgrad_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     // ------------------------------------------------------------------ TMA producer
     int st = 0;
     uint32_t ph = 0;
-    const uint32_t stage_tx = (uint32_t)(p.slab_rows * kRowBytes + p.n_vblocks * p.kb_rows * kRowBytes);
+    const uint32_t stage_tx = (uint32_t)(p.slab_rows * kRowBytes + p.n_vblocks * p.v_rows * kRowBytes);
     const int col_x = g * p.cg + cblock * kCB;
     const int col_v = g * p.cog + cotile * p.bn;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -132,7 +141,7 @@ wgrad_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         unsigned char* stage = ring + (size_t)st * p.stage_bytes;
         const int r0 = kb * p.kb_rows;
         const int xrow0 = r0 + p.group_shift[tg];
-        const int x_boxes = p.slab_rows / kBoxRows, v_boxes_per_block = p.kb_rows / kBoxRows;
+        const int x_boxes = p.slab_rows / kBoxRows, v_boxes_per_block = p.v_rows / kBoxRows;
         const int n_boxes = x_boxes + p.n_vblocks * v_boxes_per_block;
         unsigned char* vt = stage + p.slab_bytes;
         for (int bx = lane; bx < n_boxes; bx += 32) {
@@ -141,8 +150,9 @@ wgrad_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                         xrow0 + bx * kBoxRows);
           } else {
             const int v = bx - x_boxes, nb = v / v_boxes_per_block, r = (v - nb * v_boxes_per_block) * kBoxRows;
-            tma_load_2d(vt + (size_t)(nb * p.kb_rows + r) * kRowBytes, &map_v, &bars->full[st], col_v + nb * kCB,
-                        r0 + r);
+            // quad mode: the slab starts quad_rows early (negative rows of the first k-block zero-fill)
+            tma_load_2d(vt + (size_t)(nb * p.v_rows + r) * kRowBytes, &map_v, &bars->full[st], col_v + nb * kCB,
+                        r0 - p.quad_rows + r);
           }
         }
       }
@@ -151,10 +161,12 @@ wgrad_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_mn(FMT, 128, p.bn);
+    const uint32_t idesc = make_idesc_mn(FMT, 128, p.acc_cols);
     const uint32_t ring16 = smem_u32(ring) >> 4;
     const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, slab16 = (uint32_t)p.slab_bytes >> 4;
-    const uint32_t vlbo16 = (uint32_t)(p.kb_rows * kRowBytes) >> 4;  // distance between 64-channel blocks of vp
+    // distance between the 64-column blocks of B: the next channel block of vp, or (quad mode) the same
+    // channels quad_rows further down the slab
+    const uint32_t vlbo16 = (uint32_t)((p.quad_rows ? p.quad_rows : p.v_rows) * kRowBytes) >> 4;
     const int k_steps = p.kb_rows / 16;
     int st = 0;
     uint32_t ph = 0;
@@ -166,7 +178,7 @@ wgrad_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const uint64_t b_base = make_desc_mnmajor(a16 + slab16, vlbo16);
         for (int pr = 0; pr < p.n_pairs; ++pr) {
           const uint64_t a_base = make_desc_mnmajor(a16 + p.pair_off16[pr], p.pair_lbo16[pr]);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(pr * p.bn);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(pr * p.acc_cols);
           // 16 rows (two 8-row groups of 1024 bytes) per MMA: + 2048 bytes = + 128 in the address field
           for (int k = 0; k < k_steps; ++k)
             umma<false>(d_tmem, a_base + (uint64_t)(k * 128), b_base + (uint64_t)(k * 128), idesc,
@@ -191,13 +203,15 @@ wgrad_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int ci = cblock * kCB + (row & 63);
     float* part = p.partial + (long long)split * p.gw_elems;
     for (int pr = 0; pr < p.n_pairs; ++pr) {
-      const int tl = 2 * pr + unit;  // tap within the group
-      const bool tap_ok = tl < p.tpg && ci < p.cg;
-      const int t = tg * p.tpg + tl;
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+      for (int c0 = 0; c0 < p.acc_cols; c0 += 16) {
+        const int nblock = p.quad_rows ? (c0 >> 6) : 0;
+        const int tl = p.tap_tbl[pr][unit][nblock];  // tap within the group
+        const bool tap_ok = tl >= 0 && ci < p.cg;
+        const int t = tg * p.tpg + tl;
+        const int cbase = p.quad_rows ? (c0 & 63) : c0;
         uint32_t r[16];
         if (n_kb > 0) {
-          tmem_ld16_nowait(tmem_base + (uint32_t)(pr * p.bn + c0) + ((uint32_t)(quarter * 32) << 16), r);
+          tmem_ld16_nowait(tmem_base + (uint32_t)(pr * p.acc_cols + c0) + ((uint32_t)(quarter * 32) << 16), r);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -206,7 +220,7 @@ wgrad_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         if (tap_ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int co = cotile * p.bn + c0 + j;
+            const int co = cotile * p.bn + cbase + j;
             if (co < p.cog)
               part[(((long long)g * p.cog + co) * p.cg + ci) * p.taps + t] = __uint_as_float(r[j]);
           }
@@ -245,6 +259,7 @@ struct Plan {
   long long P[kMaxDims], pitch[kMaxDims], ptot, rows_total;
   int cxp, cvp;
   int taps, tpg, n_tgroups, n_pairs;
+  int quad_rows = 0, v_rows = 0;  // quad mode: see Params
   int kb_rows, slab_rows, slab_bytes, vtile_bytes, stage_bytes, n_stages;
   int bn, n_vblocks, n_cotiles, n_cblocks, n_kblocks, k_splits;
   long long xp_bytes, vp_bytes, partial_bytes, gw_elems;
@@ -301,26 +316,41 @@ static Plan make_plan(const DevGeom& g, int dtype) {
     }
     if (tpg > kMaxTpg || pl.taps / tpg > kMaxGroups) continue;
     const int pairs = (int)((tpg + 1) / 2);
-    if ((long long)pairs * pl.bn > 512) continue;
+    // quad mode: units of up to two taps adjacent along the innermost dimension, two units per MMA;
+    // worth it when its N = 128 MMAs (64 cycles each) beat the N = 64 pairs (48 cycles, smem-bound)
+    const int kw = level >= 1 ? g.k[N - 1] : 1;
+    const int units = (int)(tpg / kw) * ((kw + 1) / 2);
+    const int quads = (units + 1) / 2;
+    const long long quad_rows = (long long)g.dil[N - 1];
+    const bool quad_ok = pl.bn == 64 && pl.n_vblocks == 1 && kw >= 2 && quads * 128 <= 512 && quad_rows <= kBoxRows &&
+                         quads * 64 < pairs * 48 && !getenv("EINCONV_WGRAD_NO_QUAD");
+    if (!quad_ok && (long long)pairs * pl.bn > 512) continue;
     for (int kb : {256, 128, 64}) {
       const long long rows = (kb + span + kBoxRows - 1) / kBoxRows * kBoxRows;
-      const long long stage = rows * kRowBytes + (long long)pl.n_vblocks * kb * kRowBytes;
-      if (2 * stage > kSmemBudget) continue;
-      pl.tpg = (int)tpg;
-      pl.n_pairs = pairs;
-      pl.n_tgroups = pl.taps / pl.tpg;
-      pl.kb_rows = kb;
-      pl.slab_rows = (int)rows;
-      pl.slab_bytes = (int)(rows * kRowBytes);
-      pl.vtile_bytes = pl.n_vblocks * kb * kRowBytes;
-      pl.stage_bytes = (int)stage;
-      pl.n_stages = (int)std::min<long long>(4, kSmemBudget / stage);
-      pl.ok = true;
-      break;
+      for (int quad = quad_ok ? 1 : 0; quad >= 0 && !pl.ok; --quad) {
+        if (!quad && (long long)pairs * pl.bn > 512) continue;
+        const long long v_rows = quad ? kb + kBoxRows : kb;
+        const long long stage = rows * kRowBytes + (long long)pl.n_vblocks * v_rows * kRowBytes;
+        if (2 * stage > kSmemBudget) continue;
+        pl.tpg = (int)tpg;
+        pl.n_pairs = quad ? quads : pairs;
+        pl.quad_rows = quad ? (int)quad_rows : 0;
+        pl.v_rows = (int)v_rows;
+        pl.n_tgroups = pl.taps / pl.tpg;
+        pl.kb_rows = kb;
+        pl.slab_rows = (int)rows;
+        pl.slab_bytes = (int)(rows * kRowBytes);
+        pl.vtile_bytes = (int)(pl.n_vblocks * v_rows * kRowBytes);
+        pl.stage_bytes = (int)stage;
+        pl.n_stages = (int)std::min<long long>(4, kSmemBudget / stage);
+        pl.ok = true;
+      }
+      if (pl.ok) break;
     }
   }
   if (!pl.ok) return pl;
-  pl.n_kblocks = (int)((pl.rows_total + pl.kb_rows - 1) / pl.kb_rows);
+  // quad mode reads vp[r - quad_rows]: r must run quad_rows past the last row
+  pl.n_kblocks = (int)((pl.rows_total + pl.quad_rows + pl.kb_rows - 1) / pl.kb_rows);
   const long long types = (long long)g.groups * pl.n_cblocks * pl.n_tgroups * pl.n_cotiles;
   // split K to fill whole waves of the 148 SMs (one CTA per SM)
   {
@@ -439,12 +469,42 @@ static int run_t(const Plan& pl, const void* x, const void* v, void* gw, int dty
     if (t % pl.tpg == 0) p.group_shift[t / pl.tpg] = (int)shift;
     if (t < pl.tpg) tap_shift[t] = shift;
   }
+  p.quad_rows = pl.quad_rows;
+  p.v_rows = pl.v_rows;
+  p.acc_cols = pl.quad_rows ? 128 : pl.bn;
+  // units: the M = 64 halves of the MMAs.  Pair mode: one tap each.  Quad mode: the tap at an even
+  // position of the innermost kernel dimension (N block 1, vp[r]) and its right neighbour, if any
+  // (N block 0, vp[r - quad_rows]).
+  int unit_tap[kMaxTpg][2], n_units = 0;
+  if (pl.quad_rows) {
+    const int kw = g.k[N - 1];
+    for (int row = 0; row < pl.tpg / kw; ++row)
+      for (int i = 0; 2 * i < kw; ++i) {
+        unit_tap[n_units][1] = row * kw + 2 * i;
+        unit_tap[n_units][0] = 2 * i + 1 < kw ? row * kw + 2 * i + 1 : -1;
+        ++n_units;
+      }
+  } else {
+    for (int t = 0; t < pl.tpg; ++t) {
+      unit_tap[n_units][0] = t;
+      unit_tap[n_units][1] = -1;
+      ++n_units;
+    }
+  }
+  EINCONV_CHECK_ARG((n_units + 1) / 2 == pl.n_pairs, "wgrad_slab: inconsistent plan");
   for (int pr = 0; pr < pl.n_pairs; ++pr) {
-    const long long s1 = tap_shift[2 * pr];
-    const long long s2 = (2 * pr + 1 < pl.tpg) ? tap_shift[2 * pr + 1] : s1;
+    const int u1 = 2 * pr, u2 = 2 * pr + 1 < n_units ? 2 * pr + 1 : -1;
+    const int first = pl.quad_rows ? 1 : 0;  // the N block that holds the unit's un-shifted tap
+    const long long s1 = tap_shift[unit_tap[u1][first]];
+    const long long s2 = u2 >= 0 ? tap_shift[unit_tap[u2][first]] : s1;
     p.pair_off16[pr] = (uint32_t)((s1 * kRowBytes) >> 4);
     p.pair_lbo16[pr] = (uint32_t)(((s2 - s1) * kRowBytes) >> 4);
-    EINCONV_CHECK_ARG((s2 - s1) * kRowBytes < (1 << 18), "wgrad_slab: tap distance exceeds the descriptor range");
+    EINCONV_CHECK_ARG(s2 >= s1 && (s2 - s1) * kRowBytes < (1 << 18),
+                      "wgrad_slab: tap distance exceeds the descriptor range");
+    for (int nb = 0; nb < 2; ++nb) {
+      p.tap_tbl[pr][0][nb] = (signed char)unit_tap[u1][nb];
+      p.tap_tbl[pr][1][nb] = (signed char)(u2 >= 0 ? unit_tap[u2][nb] : -1);
+    }
   }
   p.partial = partial;
   p.gw_elems = pl.gw_elems;

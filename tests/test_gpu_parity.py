@@ -779,6 +779,13 @@ CTMA_CASES = [
     ((2, 8, 12, 12), (8, 8, 3, 3), dict(padding=0)),
     ((1, 64, 56, 56), (64, 64, 3, 3), dict(padding=1)),                      # C1 shape, one sample
     ((2, 64, 14, 14), (256, 64, 1, 1), dict()),                              # 1x1, BN = 256
+    # 49..64 output channels per group: the weight VJP runs four taps per MMA ("quad" mode)
+    ((2, 32, 10, 11), (64, 32, 3, 3), dict(padding=1)),
+    ((2, 16, 6, 7, 8), (64, 16, 3, 3, 3), dict(padding=1)),                  # tap groups per depth plane
+    ((2, 16, 12, 13), (56, 16, 2, 4), dict(padding=1)),                      # even kernel width, 56 of 64 columns
+    ((2, 16, 11, 12), (64, 16, 3, 5), dict(padding=(1, 6), dilation=(1, 3))),  # dilated pairs, groups per row
+    ((3, 16, 40), (64, 16, 3), dict(padding=1)),                             # N = 1
+    ((2, 32, 9, 9), (128, 16, 3, 3), dict(padding=1, groups=2)),             # two conv groups of 64
 ]
 CTMA_IDS = ["x".join(map(str, c[0])) + "-w" + "x".join(map(str, c[1])) for c in CTMA_CASES]
 
@@ -825,10 +832,13 @@ def test_conv_tma_forward_and_input_vjp(case, mode, ctma_weights):
 
 @pytest.mark.parametrize("case", CTMA_CASES, ids=CTMA_IDS)
 @pytest.mark.parametrize("mode", ["bf16", "fp16", "tf32"])
-def test_slab_weight_vjp(case, mode):
+@pytest.mark.parametrize("taps_per_mma", ["auto", "pairs"])
+def test_slab_weight_vjp(case, mode, taps_per_mma, monkeypatch):
     """csrc/wgrad_slab.cu (MN-major operands from the channels-last padded copies, tap pairs sharing one
     slab): max|d| <= 2^-7 (bf16) / 2^-10 (fp16) of max|ref| against the fp64 oracle on the same bits;
     fp32 tensors in TF32 mode run on scaled fp16 operand copies with the TF32 tolerance 1e-3."""
+    if taps_per_mma == "pairs":
+        monkeypatch.setenv("EINCONV_WGRAD_NO_QUAD", "1")
     dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "tf32": torch.float32}[mode]
     x, w, b, kw = _tc_inputs(case, dtype)
     N = x.dim() - 2
