@@ -800,6 +800,36 @@ int encode_2d(CUtensorMap* map, int dtype, const void* base, long long rows, lon
   return EINCONV_OK;
 }
 
+// Rank-n tiled map of raw 2/4/8-byte elements, no swizzle, zero fill outside the tensor: dims / box /
+// element strides innermost first, byte strides for dims 1..rank-1.
+int encode_tiled_raw(CUtensorMap* map, const void* base, int elem_bytes, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_bytes, const unsigned* box, const unsigned* elem_strides) {
+  EncodeFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return EINCONV_ERR_CUDA;
+  }
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    es[i] = elem_strides[i];
+    if (i > 0) st[i - 1] = strides_bytes[i - 1];
+  }
+  const CUtensorMapDataType dt = elem_bytes == 2   ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                 : elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32
+                                                   : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)r);
+    return EINCONV_ERR_CUDA;
+  }
+  return EINCONV_OK;
+}
+
 // The convolution in "role" form: src channels Cs -> dst channels Cd, stride 1.
 struct Role {
   int n_dims, batch, groups, cs, cd;

@@ -84,6 +84,8 @@ int pack_channels_last_f32_to_f16(const float* src, void* xp, int n_dims, int ba
                                   cudaStream_t stream);
 int encode_2d(CUtensorMap* map, int dtype, const void* base, long long rows, long long cols, int box_cols,
               int box_rows, int swizzle_bytes);
+int encode_tiled_raw(CUtensorMap* map, const void* base, int elem_bytes, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_bytes, const unsigned* box, const unsigned* elem_strides);
 }  // namespace ctma
 
 // wgrad_slab.cu (weight VJP from channels-last padded copies, MN-major tcgen05, stride 1, 16-bit)

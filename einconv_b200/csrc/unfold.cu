@@ -15,9 +15,12 @@
 // written with full-line coalesced stores — the kernel is bound by HBM write bandwidth.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "common.cuh"
+#include "dispatch.cuh"
+#include "tc_ptx.cuh"
 
 namespace einconv {
 
@@ -342,6 +345,12 @@ struct FlatParams {
   // `tile0` output coordinates of dim 0 (all of the other dims) and emits P_loc = rows * rest outputs per tap
   int n_tiles0, tile0, rest, tile_shift;
   FastDiv tile_div;
+  // TMA staging (16-byte aligned contiguous planes): one cp.async.bulk.tensor of rank
+  // ND + 1 with element strides gstep (the innermost dimension cannot be strided and is staged as is)
+  // replaces the software staging loop; `lead` elements at the start of the staged rows are alignment
+  // slack, `tma_c[d]` the start coordinate of dim d for tile 0.
+  int use_tma, lead;
+  int tma_c[ND];
   long long n_planes;
   FastDiv ext_div[ND], out_div[ND], k_div[ND], chan_div, chunk_div, p_div;
 };
@@ -356,16 +365,40 @@ __device__ __forceinline__ void store_stream1(T* dst, T val) {
 
 // One chunk of NI x 256 consecutive outputs for every tap of the CTA: slots 0..NI-2 are valid for
 // all threads, slot NI-1 only where `last_on` (ragged end of the plane; its offset is 0 otherwise).
+// shared-memory load from a 32-bit shared-window byte address
+template <typename T>
+__device__ __forceinline__ T lds_addr(uint32_t addr) {
+  if constexpr (sizeof(T) == 8) {
+    unsigned long long v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return (T)v;
+  } else if constexpr (sizeof(T) == 4) {
+    unsigned int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return (T)v;
+  } else {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return (T)v;
+  }
+}
+
 template <typename T, int NI>
 __device__ __forceinline__ void flat_emit(const T* __restrict__ plane, const int* __restrict__ tap_off,
                                           int n_taps, T* __restrict__ dst, int P,
                                           const int (&off)[kFlatJpt], bool last_on) {
+  // byte addresses in the shared window, slot offsets folded in once per chunk: the tap loop is one
+  // integer add + one shared load + one store per element
+  uint32_t a[NI];
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(plane));
+#pragma unroll
+  for (int i = 0; i < NI; ++i) a[i] = base + (uint32_t)off[i] * (uint32_t)sizeof(T);
 #pragma unroll 2
   for (int t = 0; t < n_taps; ++t, dst += P) {
-    const T* s = plane + tap_off[t];
+    const uint32_t tb = (uint32_t)tap_off[t] * (uint32_t)sizeof(T);
     T v[NI];
 #pragma unroll
-    for (int i = 0; i < NI; ++i) v[i] = s[off[i]];
+    for (int i = 0; i < NI; ++i) v[i] = lds_addr<T>(a[i] + tb);
 #pragma unroll
     for (int i = 0; i < NI - 1; ++i) store_stream1<T>(dst + i * kFlatThreads, v[i]);
     if (last_on) store_stream1<T>(dst + (NI - 1) * kFlatThreads, v[NI - 1]);
@@ -414,10 +447,12 @@ __device__ __forceinline__ void flat_emit_pair(const uint16_t* __restrict__ plan
 template <typename T, int ND>
 __global__ void __launch_bounds__(kFlatThreads, kFlatMinBlocks)
 unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
-                   const __grid_constant__ FlatParams<ND> p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* plane = reinterpret_cast<T*>(smem_raw);
+                   const __grid_constant__ FlatParams<ND> p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* plane_buf = reinterpret_cast<T*>(smem_raw);
+  const T* plane = plane_buf + p.lead;  // first staged element that maps to window coordinate 0
   int* tap_off = reinterpret_cast<int*>(smem_raw + (((size_t)p.box * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15));
+  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(tap_off + ((p.taps_per_chunk + 1) & ~1));
   const int tid = threadIdx.x;
 
   uint32_t bcg, chunk, tile = 0;
@@ -435,6 +470,35 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
   const int t0 = (int)chunk * p.taps_per_chunk;
   const int t1 = min(p.K, t0 + p.taps_per_chunk);
   const int n_taps = t1 - t0;
+
+  if (p.use_tma) {
+    // the whole window of this CTA in one bulk tensor copy; it lands while the threads build their tables
+    if (tid == 0) {
+      ptx::mbar_init(tma_bar, 1);
+      ptx::fence_barrier_init();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      ptx::mbar_expect_tx(tma_bar, (uint32_t)(p.box * (int)sizeof(T)));
+      const int c0 = p.tma_c[0] + cc_shift0 * p.gstep[0];
+      const uint32_t dst = ptx::smem_u32(plane_buf), bar = ptx::smem_u32(tma_bar);
+      const uint64_t map = reinterpret_cast<uint64_t>(&tmap);
+      const int bcp = (int)bcg;
+      if constexpr (ND == 1)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                     "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(bcp) : "memory");
+      else if constexpr (ND == 2)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                     "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(p.tma_c[1]), "r"(c0),
+                     "r"(bcp) : "memory");
+      else if constexpr (ND == 3)
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                     "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(p.tma_c[2]),
+                     "r"(p.tma_c[1]), "r"(c0), "r"(bcp) : "memory");
+      else
+        asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                     "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(p.tma_c[3]),
+                     "r"(p.tma_c[2]), "r"(p.tma_c[1]), "r"(c0), "r"(bcp) : "memory");
+    }
+  }
 
   // tap table: staged offset of tap t relative to tap 0
   for (int t = t0 + tid; t < t1; t += kFlatThreads) {
@@ -573,7 +637,7 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
     // barrier for tens of kilobytes of output instead of one per 7 KB plane
     const long long bc0 = (long long)bcg * p.planes_per_cta;
     const int n_pl = (int)min((long long)p.planes_per_cta, p.n_planes - bc0);
-    for (int pl = 0; pl < n_pl; ++pl) stage_plane(bc0 + pl, plane + pl * p.box);
+    for (int pl = 0; pl < n_pl; ++pl) stage_plane(bc0 + pl, plane_buf + pl * p.box);
     __syncthreads();
     const int total = n_pl * p.P;  // <= kFlatThreads * kFlatJpt by construction on the host
     const int n_i = (total + kFlatThreads - 1) / kFlatThreads;
@@ -631,8 +695,28 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
 
   // ---- one plane per CTA
   const long long bc = bcg;
-  stage_plane(bc, plane);
-  __syncthreads();
+  bool pairs = false;
+  if constexpr (sizeof(T) == 2) pairs = p.pair != 0;
+  // slot offsets of the first chunk
+  int off_first[kFlatJpt], n_i_first = n_i0;
+  bool last_on_first = last_on0;
+  auto first_offsets = [&]() {
+    if (single) {
+#pragma unroll
+      for (int i = 0; i < kFlatJpt; ++i) off_first[i] = off0[i];
+    } else {
+      slot_offsets(0, off_first, n_i_first, last_on_first);
+    }
+  };
+  if (p.use_tma) {
+    if (!pairs) first_offsets();  // computed while the copy is in flight
+    __syncthreads();              // tap table written, barrier initialised
+    ptx::mbar_wait(tma_bar, 0);
+  } else {
+    stage_plane(bc, plane_buf);
+    __syncthreads();
+    if (!pairs) first_offsets();
+  }
   if constexpr (sizeof(T) == 2) {
     if (p.pair) {
       // pairs of consecutive outputs per slot (P even, rows 4-byte aligned)
@@ -689,15 +773,10 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
     }
   }
   T* dst_plane = out + (bc * p.K + t0) * (long long)p.P + dst_tile_off + tid;
-  if (single) {
-    emit_chunk(dst_plane, n_i0, off0, last_on0);
-  } else {
-    for (int jb = 0; jb < P_loc; jb += kChunk) {
-      int off[kFlatJpt], n_i;
-      bool last_on;
-      slot_offsets(jb, off, n_i, last_on);
-      emit_chunk(dst_plane + jb, n_i, off, last_on);
-    }
+  emit_chunk(dst_plane, n_i_first, off_first, last_on_first);
+  for (int jb = kChunk; jb < P_loc; jb += kChunk) {
+    slot_offsets(jb, off_first, n_i_first, last_on_first);
+    emit_chunk(dst_plane + jb, n_i_first, off_first, last_on_first);
   }
 }
 
@@ -934,7 +1013,7 @@ static bool unfold_force_tiled() {
 }
 
 // Whole-plane kernel: returns 1 if it took the job, 0 if the geometry does not qualify, < 0 on error.
-template <typename T, int ND>
+template <typename T, int ND, bool ALLOW_TMA = true>
 static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, const long long* xs,
                                 int C, cudaStream_t stream) {
   FlatParams<ND> p{};
@@ -957,6 +1036,21 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     p.xs[d] = (int)xsd;
     p.gstep[d] = igcd(stride[d], dil[d]);
   }
+  // TMA staging: planes contiguous and 16-byte aligned in every outer stride, window
+  // extents within the 256-element box limit, and planes big enough that neither the persistent nor the
+  // pooled small-plane mode applies.  Costs: the innermost dimension is staged uncompacted.
+  bool tma = false;
+  constexpr long long ES = (long long)sizeof(T);
+  constexpr int A16 = 16 / (int)sizeof(T);  // elements per 16 bytes
+  if constexpr (ND <= 4) {
+    tma = ALLOW_TMA && !getenv("EINCONV_UNFOLD_NO_TMA") && ((uintptr_t)x % 16) == 0 && p.xs[ND - 1] == 1 &&
+          (p.xs_c * ES) % 16 == 0 && p.xs_b == (long long)C * p.xs_c && p.xs_c > 0 &&
+          (long long)g0.k_total * g0.out_total * ES > 64 * 1024 && g0.out_total * 2 > kFlatThreads * kFlatJpt &&
+          (long long)g0.batch * C < (1ll << 31);
+    for (int d = 0; d < ND - 1 && tma; ++d)
+      if (p.in[d] > 1 && (p.xs[d] <= 0 || ((long long)p.xs[d] * ES) % 16 != 0)) tma = false;
+  }
+  if (tma) p.gstep[ND - 1] = 1;
   long long box = 1, span = 0;
   p.n_tiles0 = 1;
   p.tile0 = std::max(1, p.out[0]);
@@ -965,9 +1059,19 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
   for (int d = ND - 1; d >= 0; --d) {
     long long ext = (long long)(stride[d] / p.gstep[d]) * (p.out[d] - 1) +
                     (long long)(dil[d] / p.gstep[d]) * (p.k[d] - 1) + 1;
+    if (tma && d == ND - 1) {
+      // innermost start coordinate must be 16-byte aligned: start `lead` elements early, whole 16-byte rows
+      const int start = -(((p.pad[d] + A16 - 1) / A16) * A16);
+      p.lead = -p.pad[d] - start;
+      p.tma_c[d] = start;
+      ext = (ext + p.lead + A16 - 1) / A16 * A16;
+    } else if (tma) {
+      p.tma_c[d] = -p.pad[d];
+    }
     if (d == 0 && !getenv("EINCONV_UNFOLD_NO_TILE0")) {
-      // cut along the outermost dimension so that the staged window fits ~40 KB
-      const long long budget = (40 * 1024) / (long long)sizeof(T);
+      // cut along the outermost dimension so that the staged window fits ~40 KB (one plane of the
+      // uncompacted TMA layout may take up to 50 KB: still four CTAs per SM)
+      const long long budget = ((tma ? 50 : 40) * 1024) / (long long)sizeof(T);
       const long long sg = stride[0] / p.gstep[0], halo = (long long)(dil[0] / p.gstep[0]) * (p.k[0] - 1) + 1;
       if (ext * box > budget) {
         const long long rows = (budget / std::max<long long>(1, box) - halo) / sg + 1;  // ext(tile0) <= budget / box
@@ -988,6 +1092,12 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
   }
   if (span >= (1ll << 31)) return 0;
   if ((long long)p.tile0 * p.rest >= (1ll << 30)) return 0;
+  if (tma) {
+    bool fits = p.ext[ND - 1] <= 256;
+    for (int d = 0; d < ND - 1; ++d) fits = fits && (long long)p.ext[d] * p.gstep[d] <= 256 && p.gstep[d] <= 8;
+    if (!fits) return launch_unfold_flat_t<T, ND, false>(x, out, g0, xs, C, stream);
+  }
+  p.use_tma = tma ? 1 : 0;
   p.tile_div = FastDiv((uint32_t)p.n_tiles0);
   p.box = (int)box;
   p.P = g0.out_total;
@@ -1013,7 +1123,7 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     // measured: wins for small planes (14x14: 33 -> 27 us for 58 MB), loses ~5% on C2-sized planes, where
     // one CTA per plane already amortises its set-up (EINCONV_UNFOLD_PERSISTENT=1 forces it)
     const bool small_plane = (long long)p.K * p.P * (long long)sizeof(T) <= 64 * 1024;
-    if (p.n_tiles0 == 1 && !getenv("EINCONV_UNFOLD_NO_PERSISTENT") &&
+    if (!tma && p.n_tiles0 == 1 && !getenv("EINCONV_UNFOLD_NO_PERSISTENT") &&
         (small_plane || getenv("EINCONV_UNFOLD_PERSISTENT")) && aligned &&
         p.P > 0 && p.P <= kFlatThreads * kPersJpt &&
         smem_p <= 56 * 1024 && items >= 8ll * grid_p && p.K <= kFlatMaxTaps && n_planes < (1ll << 31)) {
@@ -1037,8 +1147,11 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
   p.taps_per_chunk = ceil_div(p.K, chunks);
   p.tap_chunks = ceil_div(p.K, p.taps_per_chunk);
   if (p.taps_per_chunk > kFlatMaxTaps) return 0;
-  size_t smem = (((size_t)p.box * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4;
-  if (smem > 48 * 1024) return 0;  // keep >= 4 CTAs per SM resident
+  size_t smem = (((size_t)p.box * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4 + 16;
+  if (smem > (size_t)(tma ? 52 : 48) * 1024) {  // keep >= 4 CTAs per SM resident
+    if (tma) return launch_unfold_flat_t<T, ND, false>(x, out, g0, xs, C, stream);
+    return 0;
+  }
   // planes per CTA: small planes only; all their (plane, position) slots must fit the thread's slot
   // registers and their staged windows the shared-memory budget; aim at >= 64 KB of output per CTA
   // while keeping at least ~8 CTAs per SM in the grid
@@ -1058,7 +1171,7 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
             kFlatJpt <= 8 && !getenv("EINCONV_UNFOLD_NO_PAIRS"))
                ? 1
                : 0;
-  smem = (((size_t)p.box * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4;
+  smem = (((size_t)p.box * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4 + 16;
   const long long grid = ((n_planes + p.planes_per_cta - 1) / p.planes_per_cta) * p.n_tiles0 * p.tap_chunks;
   if (grid >= (1ll << 31)) return 0;
   // Too little output per staged element: the tiled kernel amortises its staging better.
@@ -1076,7 +1189,27 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(unfold_flat)");
   }
-  kern<<<(unsigned)grid, kFlatThreads, smem, stream>>>((const T*)x, (T*)out, p);
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if constexpr (ND <= 4) if (tma) {
+    unsigned long long dims[5], strides[4];
+    unsigned box_dims[5], est[5];
+    for (int i = 0; i < ND; ++i) {
+      const int d = ND - 1 - i;
+      dims[i] = (unsigned long long)p.in[d];
+      box_dims[i] = (unsigned)(i == 0 ? p.ext[d] : p.ext[d] * p.gstep[d]);
+      est[i] = (unsigned)(i == 0 ? 1 : p.gstep[d]);
+      // byte stride of dim d (dims of extent 1 take any valid stride)
+      if (i > 0) strides[i - 1] = (unsigned long long)(p.in[d] > 1 ? (long long)p.xs[d] : p.xs_c) * ES;
+    }
+    dims[ND] = (unsigned long long)n_planes;
+    box_dims[ND] = 1;
+    est[ND] = 1;
+    strides[ND - 1] = (unsigned long long)(p.xs_c * ES);
+    const int st = ctma::encode_tiled_raw(&tmap, x, (int)sizeof(T), ND + 1, dims, strides, box_dims, est);
+    if (st != EINCONV_OK) return st;
+  }
+  kern<<<(unsigned)grid, kFlatThreads, smem, stream>>>((const T*)x, (T*)out, p, tmap);
   {
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return cuda_fail(err, "unfold_flat_kernel");

@@ -115,6 +115,47 @@ UNFOLD_EXTRA = [
 ]
 
 
+# planes of > 64 KB of output and > 1024 positions: the whole-plane kernel stages them with ONE bulk
+# tensor copy (element strides = gcd(stride, dilation), zero fill = padding) when the tensor is 16-byte
+# aligned and contiguous; "software" forces the staging loop on the same shapes
+UNFOLD_TMA = [
+    dict(x=(2, 3, 48, 48), kernel_size=3, kwargs=dict(padding=1)),                    # start coordinate -4, 3 slack columns
+    dict(x=(1, 2, 100, 104), kernel_size=3, kwargs=dict(stride=2, dilation=2)),      # rows compacted by the copy
+    dict(x=(2, 2, 10, 24, 28), kernel_size=3, kwargs=dict(stride=2, dilation=2)),    # N = 3 like C2
+    dict(x=(1, 2, 224, 224), kernel_size=7, kwargs=dict(stride=2, padding=3)),       # cut along the outermost dim
+    dict(x=(2, 3, 4000), kernel_size=5, kwargs=dict(padding=2)),                     # window wider than a TMA box
+    dict(x=(2, 3, 46, 46), kernel_size=3, kwargs=dict(padding=1)),                   # rows not 16-byte multiples
+    dict(x=(1, 2, 60, 64), kernel_size=(5, 2), kwargs=dict(padding=(2, 5), dilation=(1, 3))),  # padding > 4
+    dict(x=(2, 1, 3, 3, 40, 44), kernel_size=(2, 2, 3, 3), kwargs=dict(padding=(0, 1, 1, 1))),  # N = 4: rank-5 map
+]
+
+
+@pytest.mark.parametrize("staging", ["tma", "software"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64], ids=["f32", "bf16", "f64"])
+@pytest.mark.parametrize("case", UNFOLD_TMA, ids=lambda c: "x".join(map(str, c["x"])) + f"-k{c['kernel_size']}")
+def test_unfold_bulk_copy_staging(case, dtype, staging, monkeypatch):
+    """Bit-exact on arbitrary bit patterns (NaN payloads, infinities, denormals are copied)."""
+    if staging == "software":
+        monkeypatch.setenv("EINCONV_UNFOLD_NO_TMA", "1")
+    monkeypatch.setenv("EINCONV_UNFOLD_NO_PERSISTENT", "1")
+    torch.manual_seed(3)
+    itype = {torch.float32: torch.int32, torch.bfloat16: torch.int16, torch.float64: torch.int64}[dtype]
+    info = torch.iinfo(itype)
+    bits = torch.randint(info.min, info.max, case["x"], dtype=itype)
+    bits[bits == 0] = 1  # the oracle pads with integer 0 = +0.0
+    want = direct.unfold(bits.numpy(), case["kernel_size"], **case["kwargs"])
+    x = bits.view(dtype).to(DEV)
+    got = unfoldNd(x, case["kernel_size"], **case["kwargs"])
+    assert tuple(got.shape) == want.shape
+    assert np.array_equal(got.cpu().view(itype).numpy(), want)
+    # a view that starts one element into an allocation is not 16-byte aligned: software staging, same result
+    flat = torch.zeros(x.numel() + 1, dtype=dtype, device=DEV)
+    shifted = flat[1:].view(*case["x"])
+    shifted.copy_(x)
+    got2 = unfoldNd(shifted, case["kernel_size"], **case["kwargs"])
+    assert np.array_equal(got2.cpu().view(itype).numpy(), want)
+
+
 @pytest.mark.parametrize("case", UNFOLD_EXTRA, ids=lambda c: "x".join(map(str, c["x"])) + f"-k{c['kernel_size']}")
 def test_unfold_edge_cases(case, unfold_variant):
     torch.manual_seed(1)
