@@ -412,12 +412,16 @@ __device__ __forceinline__ void flat_emit_multi(const T* __restrict__ plane, con
                                                 int n_taps, T* __restrict__ dst, int P,
                                                 const int (&soff)[kFlatJpt], const int (&doff)[kFlatJpt],
                                                 bool last_on) {
+  uint32_t a[NI];
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(plane));
+#pragma unroll
+  for (int i = 0; i < NI; ++i) a[i] = base + (uint32_t)soff[i] * (uint32_t)sizeof(T);
 #pragma unroll 2
   for (int t = 0; t < n_taps; ++t, dst += P) {
-    const T* s = plane + tap_off[t];
+    const uint32_t tb = (uint32_t)tap_off[t] * (uint32_t)sizeof(T);
     T v[NI];
 #pragma unroll
-    for (int i = 0; i < NI; ++i) v[i] = s[soff[i]];
+    for (int i = 0; i < NI; ++i) v[i] = lds_addr<T>(a[i] + tb);
 #pragma unroll
     for (int i = 0; i < NI - 1; ++i) store_stream1<T>(dst + doff[i], v[i]);
     if (last_on) store_stream1<T>(dst + doff[NI - 1], v[NI - 1]);
@@ -431,12 +435,20 @@ __device__ __forceinline__ void flat_emit_pair(const uint16_t* __restrict__ plan
                                                int n_taps, uint16_t* __restrict__ dst, int P,
                                                const int (&offa)[kFlatJpt], const int (&offb)[kFlatJpt],
                                                bool last_on) {
+  uint32_t aa[NI], ab[NI];
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(plane));
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    aa[i] = base + 2u * (uint32_t)offa[i];
+    ab[i] = base + 2u * (uint32_t)offb[i];
+  }
 #pragma unroll 2
   for (int t = 0; t < n_taps; ++t, dst += P) {
-    const uint16_t* s = plane + tap_off[t];
+    const uint32_t tb = 2u * (uint32_t)tap_off[t];
     uint32_t v[NI];
 #pragma unroll
-    for (int i = 0; i < NI; ++i) v[i] = (uint32_t)s[offa[i]] | ((uint32_t)s[offb[i]] << 16);
+    for (int i = 0; i < NI; ++i)
+      v[i] = (uint32_t)lds_addr<uint16_t>(aa[i] + tb) | ((uint32_t)lds_addr<uint16_t>(ab[i] + tb) << 16);
     uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
 #pragma unroll
     for (int i = 0; i < NI - 1; ++i) __stcs(d32 + i * kFlatThreads, v[i]);
