@@ -351,6 +351,12 @@ struct FlatParams {
   // slack, `tma_c[d]` the start coordinate of dim d for tile 0.
   int use_tma, lead;
   int tma_c[ND];
+  // gcd(stride, dilation) > 1 along the innermost dimension: the copy lands rows of `tma_ext` elements,
+  // of which every tma_g-th (from `lead`) is kept; the CTA compacts them in place to rows of ext[ND-1]
+  // before the tap loop (stride-g shared loads would be g-way bank conflicts for every output).
+  // box_t = elements of the staged buffer (== box unless compacting).
+  int tma_compact, tma_ext, tma_g, box_t;
+  FastDiv extc_div;
   long long n_planes;
   FastDiv ext_div[ND], out_div[ND], k_div[ND], chan_div, chunk_div, p_div;
 };
@@ -462,8 +468,9 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
                    const __grid_constant__ FlatParams<ND> p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* plane_buf = reinterpret_cast<T*>(smem_raw);
-  const T* plane = plane_buf + p.lead;  // first staged element that maps to window coordinate 0
-  int* tap_off = reinterpret_cast<int*>(smem_raw + (((size_t)p.box * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15));
+  // first staged element that maps to window coordinate 0 (after the in-place compaction: element 0)
+  const T* plane = plane_buf + (p.tma_compact ? 0 : p.lead);
+  int* tap_off = reinterpret_cast<int*>(smem_raw + (((size_t)p.box_t * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15));
   uint64_t* tma_bar = reinterpret_cast<uint64_t*>(tap_off + ((p.taps_per_chunk + 1) & ~1));
   const int tid = threadIdx.x;
 
@@ -489,7 +496,7 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
       ptx::mbar_init(tma_bar, 1);
       ptx::fence_barrier_init();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      ptx::mbar_expect_tx(tma_bar, (uint32_t)(p.box * (int)sizeof(T)));
+      ptx::mbar_expect_tx(tma_bar, (uint32_t)(p.box_t * (int)sizeof(T)));
       const int c0 = p.tma_c[0] + cc_shift0 * p.gstep[0];
       const uint32_t dst = ptx::smem_u32(plane_buf), bar = ptx::smem_u32(tma_bar);
       const uint64_t map = reinterpret_cast<uint64_t>(&tmap);
@@ -724,6 +731,32 @@ unfold_flat_kernel(const T* __restrict__ x, T* __restrict__ out,
     if (!pairs) first_offsets();  // computed while the copy is in flight
     __syncthreads();              // tap table written, barrier initialised
     ptx::mbar_wait(tma_bar, 0);
+    if (p.tma_compact) {
+      // in place, in batches of 16 elements per thread held in registers: the destination index of an
+      // element never exceeds its source index, so batches in increasing order never overwrite unread data
+      constexpr int CU = 16;
+      const int dr = kFlatThreads / p.ext[ND - 1], dc = kFlatThreads - dr * p.ext[ND - 1];
+      for (int e0 = 0; e0 < p.box; e0 += kFlatThreads * CU) {
+        uint32_t row, col;
+        p.extc_div.divmod((uint32_t)(e0 + tid), row, col);
+        T v[CU];
+#pragma unroll
+        for (int u = 0; u < CU; ++u) {
+          if (e0 + tid + u * kFlatThreads < p.box) v[u] = plane_buf[(int)row * p.tma_ext + p.lead + (int)col * p.tma_g];
+          col += dc;
+          row += dr;
+          if ((int)col >= p.ext[ND - 1]) {
+            col -= p.ext[ND - 1];
+            row += 1;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < CU; ++u)
+          if (e0 + tid + u * kFlatThreads < p.box) plane_buf[e0 + tid + u * kFlatThreads] = v[u];
+        __syncthreads();
+      }
+    }
   } else {
     stage_plane(bc, plane_buf);
     __syncthreads();
@@ -1062,8 +1095,13 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     for (int d = 0; d < ND - 1 && tma; ++d)
       if (p.in[d] > 1 && (p.xs[d] <= 0 || ((long long)p.xs[d] * ES) % 16 != 0)) tma = false;
   }
-  if (tma) p.gstep[ND - 1] = 1;
-  long long box = 1, span = 0;
+  // innermost gcd > 1: the rows stay as copied (stride-g shared loads in the tap loop).  Compacting them in
+  // shared memory after the copy (EINCONV_UNFOLD_COMPACT=1) removes the g-way bank conflicts but was
+  // measured neutral on C2 (49.8 vs 48.9 us): the tap loop is not bound by the shared-memory pipe.
+  const int g_last = p.gstep[ND - 1];
+  const bool compact = tma && g_last > 1 && getenv("EINCONV_UNFOLD_COMPACT") != nullptr;
+  if (tma && !compact) p.gstep[ND - 1] = 1;
+  long long box = 1, box_t = 1, span = 0;
   p.n_tiles0 = 1;
   p.tile0 = std::max(1, p.out[0]);
   p.rest = 1;
@@ -1071,12 +1109,20 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
   for (int d = ND - 1; d >= 0; --d) {
     long long ext = (long long)(stride[d] / p.gstep[d]) * (p.out[d] - 1) +
                     (long long)(dil[d] / p.gstep[d]) * (p.k[d] - 1) + 1;
+    long long ext_t = ext;  // staged extent of this dim in the copy's layout
     if (tma && d == ND - 1) {
       // innermost start coordinate must be 16-byte aligned: start `lead` elements early, whole 16-byte rows
       const int start = -(((p.pad[d] + A16 - 1) / A16) * A16);
       p.lead = -p.pad[d] - start;
       p.tma_c[d] = start;
-      ext = (ext + p.lead + A16 - 1) / A16 * A16;
+      if (compact) {
+        ext_t = ((ext - 1) * g_last + 1 + p.lead + A16 - 1) / A16 * A16;
+        p.tma_ext = (int)ext_t;
+        p.tma_g = g_last;
+      } else {
+        ext = (ext + p.lead + A16 - 1) / A16 * A16;
+        ext_t = ext;
+      }
     } else if (tma) {
       p.tma_c[d] = -p.pad[d];
     }
@@ -1085,33 +1131,38 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
       // uncompacted TMA layout may take up to 50 KB: still four CTAs per SM)
       const long long budget = ((tma ? 50 : 40) * 1024) / (long long)sizeof(T);
       const long long sg = stride[0] / p.gstep[0], halo = (long long)(dil[0] / p.gstep[0]) * (p.k[0] - 1) + 1;
-      if (ext * box > budget) {
-        const long long rows = (budget / std::max<long long>(1, box) - halo) / sg + 1;  // ext(tile0) <= budget / box
+      if (ext * box_t > budget) {
+        const long long rows = (budget / std::max<long long>(1, box_t) - halo) / sg + 1;  // ext(tile0) <= budget / box
         if (rows < 1) return 0;
         p.tile0 = (int)std::min<long long>(rows, p.out[0]);
         p.n_tiles0 = ceil_div(p.out[0], p.tile0);
         p.tile0 = ceil_div(p.out[0], p.n_tiles0);  // even split
         ext = sg * (p.tile0 - 1) + halo;
+        ext_t = ext;
       }
       p.tile_shift = (int)(sg * p.tile0);
     }
-    if (ext * box > (1 << 20)) return 0;
+    if (ext_t * box_t > (1 << 20)) return 0;
     p.ext[d] = (int)ext;
     p.so[d] = (int)((stride[d] / p.gstep[d]) * box);
     p.ko[d] = (int)((dil[d] / p.gstep[d]) * box);
     box *= ext;
+    box_t *= ext_t;
     span += (long long)(p.in[d] - 1) * (p.xs[d] < 0 ? -(long long)p.xs[d] : (long long)p.xs[d]);
   }
   if (span >= (1ll << 31)) return 0;
   if ((long long)p.tile0 * p.rest >= (1ll << 30)) return 0;
   if (tma) {
-    bool fits = p.ext[ND - 1] <= 256;
+    bool fits = (compact ? p.tma_ext : p.ext[ND - 1]) <= 256;
     for (int d = 0; d < ND - 1; ++d) fits = fits && (long long)p.ext[d] * p.gstep[d] <= 256 && p.gstep[d] <= 8;
     if (!fits) return launch_unfold_flat_t<T, ND, false>(x, out, g0, xs, C, stream);
   }
   p.use_tma = tma ? 1 : 0;
+  p.tma_compact = compact ? 1 : 0;
+  p.extc_div = FastDiv((uint32_t)std::max(1, p.ext[ND - 1]));
   p.tile_div = FastDiv((uint32_t)p.n_tiles0);
   p.box = (int)box;
+  p.box_t = (int)box_t;
   p.P = g0.out_total;
   p.K = g0.k_total;
   const long long n_planes = (long long)g0.batch * C;
@@ -1159,7 +1210,7 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
   p.taps_per_chunk = ceil_div(p.K, chunks);
   p.tap_chunks = ceil_div(p.K, p.taps_per_chunk);
   if (p.taps_per_chunk > kFlatMaxTaps) return 0;
-  size_t smem = (((size_t)p.box * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4 + 16;
+  size_t smem = (((size_t)p.box_t * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4 + 16;
   if (smem > (size_t)(tma ? 52 : 48) * 1024) {  // keep >= 4 CTAs per SM resident
     if (tma) return launch_unfold_flat_t<T, ND, false>(x, out, g0, xs, C, stream);
     return 0;
@@ -1183,7 +1234,7 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
             kFlatJpt <= 8 && !getenv("EINCONV_UNFOLD_NO_PAIRS"))
                ? 1
                : 0;
-  smem = (((size_t)p.box * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4 + 16;
+  smem = (((size_t)p.box_t * p.planes_per_cta * sizeof(T) + 15) & ~(size_t)15) + (size_t)p.taps_per_chunk * 4 + 16;
   const long long grid = ((n_planes + p.planes_per_cta - 1) / p.planes_per_cta) * p.n_tiles0 * p.tap_chunks;
   if (grid >= (1ll << 31)) return 0;
   // Too little output per staged element: the tiled kernel amortises its staging better.
@@ -1209,7 +1260,7 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     for (int i = 0; i < ND; ++i) {
       const int d = ND - 1 - i;
       dims[i] = (unsigned long long)p.in[d];
-      box_dims[i] = (unsigned)(i == 0 ? p.ext[d] : p.ext[d] * p.gstep[d]);
+      box_dims[i] = (unsigned)(i == 0 ? (compact ? p.tma_ext : p.ext[d]) : p.ext[d] * p.gstep[d]);
       est[i] = (unsigned)(i == 0 ? 1 : p.gstep[d]);
       // byte stride of dim d (dims of extent 1 take any valid stride)
       if (i > 0) strides[i - 1] = (unsigned long long)(p.in[d] > 1 ? (long long)p.xs[d] : p.xs_c) * ES;

@@ -125,18 +125,21 @@ UNFOLD_TMA = [
     dict(x=(1, 2, 224, 224), kernel_size=7, kwargs=dict(stride=2, padding=3)),       # cut along the outermost dim
     dict(x=(2, 3, 4000), kernel_size=5, kwargs=dict(padding=2)),                     # window wider than a TMA box
     dict(x=(2, 3, 46, 46), kernel_size=3, kwargs=dict(padding=1)),                   # rows not 16-byte multiples
+    dict(x=(1, 2, 90, 200), kernel_size=(3, 2), kwargs=dict(stride=(1, 3), dilation=(2, 6), padding=(1, 2))),  # gcd 3, two compaction batches
     dict(x=(1, 2, 60, 64), kernel_size=(5, 2), kwargs=dict(padding=(2, 5), dilation=(1, 3))),  # padding > 4
     dict(x=(2, 1, 3, 3, 40, 44), kernel_size=(2, 2, 3, 3), kwargs=dict(padding=(0, 1, 1, 1))),  # N = 4: rank-5 map
 ]
 
 
-@pytest.mark.parametrize("staging", ["tma", "software"])
+@pytest.mark.parametrize("staging", ["tma", "tma-compacted", "software"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64], ids=["f32", "bf16", "f64"])
 @pytest.mark.parametrize("case", UNFOLD_TMA, ids=lambda c: "x".join(map(str, c["x"])) + f"-k{c['kernel_size']}")
 def test_unfold_bulk_copy_staging(case, dtype, staging, monkeypatch):
     """Bit-exact on arbitrary bit patterns (NaN payloads, infinities, denormals are copied)."""
     if staging == "software":
         monkeypatch.setenv("EINCONV_UNFOLD_NO_TMA", "1")
+    elif staging == "tma-compacted":
+        monkeypatch.setenv("EINCONV_UNFOLD_COMPACT", "1")  # in-place compaction of strided windows after the copy
     monkeypatch.setenv("EINCONV_UNFOLD_NO_PERSISTENT", "1")
     torch.manual_seed(3)
     itype = {torch.float32: torch.int32, torch.bfloat16: torch.int16, torch.float64: torch.int64}[dtype]
