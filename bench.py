@@ -26,7 +26,13 @@ import sys
 import time
 from pathlib import Path
 
-import torch
+if "reference" in sys.argv:
+    # the CPU arm uses every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, and the OpenMP /
+    # MKL pools read it when torch is imported
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
+import torch  # noqa: E402
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
