@@ -402,12 +402,11 @@ __device__ __forceinline__ float f4_get(const float4& v, int c) {
   return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
 }
 
-template <int KH, int KW, bool FLIP>
+template <int KH, int KW, bool FLIP, int NR>
 __global__ void __launch_bounds__(128) dw_vec4_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ out,
                                                       const __grid_constant__ DwVecParams p) {
-  constexpr int PW = (KW - 1) / 2;
-  constexpr int NR = kDwWarpRows;
+  constexpr int PW = (KW - 1) / 2;  // NR: input rows held in registers per unit
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -499,6 +498,10 @@ static int launch_dw_vec4(const void* in, const void* w, const void* bias, void*
   // enough warps to fill the chip several times over: halve the row blocks while they stay >= 2 * KH
   auto warps_for = [&](int nrb) { return ((long long)p.planes * nrb + p.slots - 1) / p.slots; };
   while (warps_for(p.n_rblocks) < 148ll * 32 && ceil_div(p.out_h, p.n_rblocks * 2) >= 2 * KH) p.n_rblocks *= 2;
+  // small problems (C3: 51 MB per direction) are latency-bound: blocks of 4 output rows use the variant
+  // that holds KH + 3 input rows (56 registers, 8 CTAs per SM); measured 10.2 us against 10.8 (7-row blocks)
+  // and 12.3 (14-row blocks).  Large ones keep the long blocks (less halo re-reading).
+  if (p.out_h > 4 && warps_for(ceil_div(p.out_h, 4)) <= 148ll * 32 * 8) p.n_rblocks = ceil_div(p.out_h, 4);
   if (const char* e = getenv("EINCONV_DW_VEC_RBLOCKS")) {
     const int v = atoi(e);
     if (v >= p.n_rblocks && v <= p.out_h) p.n_rblocks = v;
@@ -512,12 +515,24 @@ static int launch_dw_vec4(const void* in, const void* w, const void* bias, void*
   p.lane_div = FastDiv((uint32_t)p.lanes_per_row);
   const long long warps = warps_for(p.n_rblocks);
   const unsigned grid = (unsigned)((warps + 3) / 4);
-  if (f.flip)
-    dw_vec4_kernel<KH, KW, true><<<grid, 128, 0, stream>>>((const float*)in, (const float*)w,
-                                                            (const float*)bias, (float*)out, p);
-  else
-    dw_vec4_kernel<KH, KW, false><<<grid, 128, 0, stream>>>((const float*)in, (const float*)w,
-                                                             (const float*)bias, (float*)out, p);
+  // short row blocks: a variant that holds fewer input rows needs fewer registers (more resident warps)
+  constexpr int NRS = KH + 7, NRT = KH + 3;
+  const int n_in = p.rows_per_block + KH - 1;
+  const bool big = getenv("EINCONV_DW_VEC_NR16") != nullptr;
+  const bool tiny = !big && n_in <= NRT;
+  const bool small = !big && !tiny && n_in <= NRS && NRS < kDwWarpRows;
+  auto go = [&](auto kern) {
+    kern<<<grid, 128, 0, stream>>>((const float*)in, (const float*)w, (const float*)bias, (float*)out, p);
+  };
+  if (f.flip) {
+    if (tiny) go(dw_vec4_kernel<KH, KW, true, NRT>);
+    else if (small) go(dw_vec4_kernel<KH, KW, true, NRS>);
+    else go(dw_vec4_kernel<KH, KW, true, kDwWarpRows>);
+  } else {
+    if (tiny) go(dw_vec4_kernel<KH, KW, false, NRT>);
+    else if (small) go(dw_vec4_kernel<KH, KW, false, NRS>);
+    else go(dw_vec4_kernel<KH, KW, false, kDwWarpRows>);
+  }
   EINCONV_CHECK_LAUNCH("dw_vec4_kernel");
   return EINCONV_OK;
 }
