@@ -425,9 +425,9 @@ def to_value(wl, ms, n_units=1):
 # ncu --set full captures of the dominant kernel of each workload (summaries committed under profiles/)
 NCU_PROFILES = {
     "unfold": "profiles/r01_unfold_c2_ncu_full_v10_tma.txt",
-    "depthwise": "profiles/r01_depthwise_c3_ncu_full_v4_vec4.txt",
+    "depthwise": "profiles/r01_depthwise_c3_ncu_full_v5_vec4_nr6.txt",
     "conv_fwd": "profiles/r01_conv_fwd_c1_ncu_full_v3.txt",
-    "weight_vjp": "profiles/r01_wgrad_c4_ncu_full_v2_slab.txt",
+    "weight_vjp": "profiles/r01_wgrad_c4_ncu_full_v3_quad.txt",
 }
 
 
