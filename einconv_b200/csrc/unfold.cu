@@ -1269,8 +1269,9 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     box_dims[ND] = 1;
     est[ND] = 1;
     strides[ND - 1] = (unsigned long long)(p.xs_c * ES);
-    const int st = ctma::encode_tiled_raw(&tmap, x, (int)sizeof(T), ND + 1, dims, strides, box_dims, est);
-    if (st != EINCONV_OK) return st;
+    // a map the driver rejects is not an error of the call: the software staging loop handles every layout
+    if (ctma::encode_tiled_raw(&tmap, x, (int)sizeof(T), ND + 1, dims, strides, box_dims, est) != EINCONV_OK)
+      return launch_unfold_flat_t<T, ND, false>(x, out, g0, xs, C, stream);
   }
   kern<<<(unsigned)grid, kFlatThreads, smem, stream>>>((const T*)x, (T*)out, p, tmap);
   {

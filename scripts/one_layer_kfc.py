@@ -12,7 +12,7 @@ evaluator.set_fp32_math("tf32")
 for c, h, k, s, p, n in RESNET50_LAYERS:
     x = torch.rand(256, c, h, h, device="cuda")
     for _ in range(2):
-        evaluator.kfc(x, k, stride=s, padding=p)
+        (evaluator.kfac_reduce if len(sys.argv) > 1 and sys.argv[1] == "kfacr" else evaluator.kfc)(x, k, stride=s, padding=p)
     torch.cuda.synchronize()
     del x
 print("ok")
