@@ -805,7 +805,10 @@ __global__ void __launch_bounds__(256) window_sum_flat_kernel(const T* __restric
   const int lane = threadIdx.x & 31;
   const int warps_per_cta = blockDim.x >> 5;
   const int chans = g.groups * g.c_in_g;
-  constexpr int U = 4;
+#ifndef EINCONV_WSUM_U
+#define EINCONV_WSUM_U 8
+#endif
+  constexpr int U = EINCONV_WSUM_U;  // independent loads in flight per lane
   for (int plane = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); plane < planes;
        plane += gridDim.x * warps_per_cta) {
     const T* src = x + (long long)plane * n;
