@@ -68,6 +68,9 @@ struct Params {
   long long out_total;
   const void* bias;
   void* dst;
+  // fp32 tensors on scaled fp16 operand copies: [0] max|src|, [1] max|w| (bit patterns); the epilogue
+  // multiplies the accumulator by 1 / (s_src * s_w).  nullptr otherwise.
+  const unsigned* absmax;
   long long* trace;  // bring-up only (EINCONV_CTMA_TRACE): clock64() stamps of CTA 0, 16 per tile
 };
 
@@ -110,7 +113,9 @@ __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint64_t a_base, ui
     if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(tile - tile_begin) * 16 + (slot)] = clock64(); \
   } while (0)
 
-template <typename T>
+// T: operand type of the MMAs; TO: type of the destination and the bias (differs only for fp32 tensors on
+// scaled fp16 operands)
+template <typename T, typename TO = T>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ Params p) {
@@ -272,8 +277,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lanes 32 * quarter .. + 31 are visible to this warp
     const int etid = threadIdx.x - 64;
-    T* dst = reinterpret_cast<T*>(p.dst);
-    const T* bias = reinterpret_cast<const T*>(p.bias);
+    TO* dst = reinterpret_cast<TO*>(p.dst);
+    const TO* bias = reinterpret_cast<const TO*>(p.bias);
+    float unscale = 1.f;
+    if (p.absmax) unscale = 1.f / (operand_scale(__ldg(p.absmax)) * operand_scale(__ldg(p.absmax + 1)));
     uint32_t it = 0;
     long long cur_class = -1;
     for (long long tile = tile_begin; tile < tile_end; ++tile, ++it) {
@@ -288,7 +295,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         cur_class = cls;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int c = etid; c < p.bn; c += 128)
-          bars->bias[c] = (bias && n0 + c < p.cd) ? Cvt<T>::load(bias + (long long)g * p.cd + n0 + c) : 0.f;
+          bars->bias[c] = (bias && n0 + c < p.cd) ? (float)Cvt<TO>::load(bias + (long long)g * p.cd + n0 + c) : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       // decode this thread's row
@@ -304,7 +311,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         valid = valid && (int)od < p.out[d];
         oflat = oflat * p.out[d] + od;
       }
-      T* dst_row = dst + ((long long)b * p.cd_total + (long long)g * p.cd + n0) * p.out_total + oflat;
+      TO* dst_row = dst + ((long long)b * p.cd_total + (long long)g * p.cd + n0) * p.out_total + oflat;
 
       if (warp == 2) CTMA_TRACE(10);
       mbar_wait_relaxed(&bars->tmem_full[acc], acc_phase);
@@ -323,16 +330,18 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (warp == 2) CTMA_TRACE(12);
         }
         if (valid) {
-          T* d0 = dst_row + (long long)c0 * p.out_total;
+          TO* d0 = dst_row + (long long)c0 * p.out_total;
           if (n0 + c0 + 16 <= p.cd) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              Cvt<T>::store(d0 + (long long)j * p.out_total, __uint_as_float(r[j]) + bars->bias[c0 + j]);
+              Cvt<TO>::store(d0 + (long long)j * p.out_total,
+                             fmaf(__uint_as_float(r[j]), unscale, bars->bias[c0 + j]));
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (n0 + c0 + j < p.cd)
-                Cvt<T>::store(d0 + (long long)j * p.out_total, __uint_as_float(r[j]) + bars->bias[c0 + j]);
+                Cvt<TO>::store(d0 + (long long)j * p.out_total,
+                               fmaf(__uint_as_float(r[j]), unscale, bars->bias[c0 + j]));
           }
         }
       }
@@ -393,6 +402,31 @@ __device__ __forceinline__ void pack_weights_block(const PackParams& pp, unsigne
       if (n < cg && c < cog) v = w[(((long long)g * cog + c) * cg + n) * taps + (taps - 1 - t)];
     }
     wp[idx] = v;
+  }
+}
+
+// fp32 weights -> scaled fp16 packed weights (scale from absmax_w), same layout as pack_weights_block
+__device__ __forceinline__ void pack_weights_block_convert(const PackParams& pp, unsigned block,
+                                                           const unsigned* __restrict__ absmax_w) {
+  const float* __restrict__ w = reinterpret_cast<const float*>(pp.w_src);
+  __half* __restrict__ wp = reinterpret_cast<__half*>(pp.w_dst);
+  const float scale = operand_scale(__ldg(absmax_w));
+  const int taps = pp.w_taps, np = pp.w_np, cgp = pp.w_cgp, cog = pp.w_cog, cg = pp.w_cg;
+  for (long long idx = (long long)block * 1024 + threadIdx.x; idx < min(pp.w_total, ((long long)block + 1) * 1024);
+       idx += 256) {
+    const int c = (int)(idx % cgp);
+    long long r = idx / cgp;
+    const int n = (int)(r % np);
+    r /= np;
+    const int t = (int)(r % taps);
+    const int g = (int)(r / taps);
+    float v = 0.f;
+    if (!pp.w_transpose) {
+      if (n < cog && c < cg) v = w[(((long long)g * cog + n) * cg + c) * taps + t];
+    } else {
+      if (n < cg && c < cog) v = w[(((long long)g * cog + c) * cg + n) * taps + (taps - 1 - t)];
+    }
+    wp[idx] = __float2half_rn(v * scale);
   }
 }
 
@@ -507,7 +541,10 @@ __global__ void __launch_bounds__(256) pack_vec4_kernel(const TS* __restrict__ s
   __shared__ uint4 tile[TP][CPR];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (blockIdx.x >= pp.x_ctas) {  // fused weight job
-    if (blockIdx.y == 0) pack_weights_block<T>(pp, blockIdx.x - pp.x_ctas);
+    if (blockIdx.y == 0) {
+      if constexpr (CONVERT) pack_weights_block_convert(pp, blockIdx.x - pp.x_ctas, absmax_bits + 1);
+      else pack_weights_block<T>(pp, blockIdx.x - pp.x_ctas);
+    }
     return;
   }
   const int W = pp.n_dims - 1;
@@ -614,6 +651,10 @@ __global__ void __launch_bounds__(256) pack_convert_kernel(const float* __restri
   constexpr int TW = 32, TC = 64, NW = TC / 2;
   __shared__ uint32_t tile[TW][NW + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x >= pp.x_ctas) {  // fused weight job
+    if (blockIdx.y == 0) pack_weights_block_convert(pp, blockIdx.x - pp.x_ctas, absmax_bits + 1);
+    return;
+  }
   const float scale = operand_scale(__ldg(absmax_bits));
   const int W = pp.n_dims - 1;
   const int c0 = blockIdx.y * TC;
@@ -665,7 +706,7 @@ __global__ void __launch_bounds__(256) pack_convert_kernel(const float* __restri
 
 int pack_channels_last_f32_to_f16(const float* src, void* xp, int n_dims, int batch, int ctot, int cp, const int* S,
                                   const long long* P, const int* pad, const unsigned* absmax_bits,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, const WeightJob* wj) {
   const int N = n_dims;
   PackParams pp{};
   pp.n_dims = N;
@@ -685,10 +726,19 @@ int pack_channels_last_f32_to_f16(const float* src, void* xp, int n_dims, int ba
   }
   EINCONV_CHECK_ARG(outer < (1ll << 31), "pack_channels_last: too many rows");
   EINCONV_CHECK_ARG(cp % 8 == 0, "pack_channels_last: channel pitch must be a multiple of 16 bytes");
-  if (outer == 0 || cp == 0) return EINCONV_OK;
-  dim3 grid((unsigned)outer, (unsigned)((cp + 63) / 64));
+  if ((outer == 0 || cp == 0) && !(wj && wj->total > 0)) return EINCONV_OK;
+  dim3 grid((unsigned)outer, (unsigned)std::max(1, (cp + 63) / 64));
   EINCONV_CHECK_ARG(grid.y < 65536, "pack_channels_last: too many channels");
   pp.x_ctas = grid.x;
+  if (wj && wj->total > 0) {
+    pp.w_src = wj->src; pp.w_dst = wj->dst;
+    pp.w_groups = wj->groups; pp.w_taps = wj->taps; pp.w_np = wj->np; pp.w_cgp = wj->cgp;
+    pp.w_cog = wj->cog; pp.w_cg = wj->cg; pp.w_transpose = wj->transpose;
+    pp.w_total = wj->total;
+    pp.w_ctas = (unsigned)((wj->total + 1023) / 1024);
+    EINCONV_CHECK_ARG((long long)grid.x + pp.w_ctas < (1ll << 31), "pack_channels_last: grid too large");
+    grid.x += pp.w_ctas;
+  }
   if (S[N - 1] % 4 == 0 && ((uintptr_t)src & 15) == 0 && !getenv("EINCONV_PACK_SCALAR"))
     pack_vec4_kernel<uint16_t, float><<<grid, 256, 0, stream>>>(src, (uint16_t*)xp, pp, absmax_bits);
   else
@@ -992,14 +1042,28 @@ int64_t workspace_bytes(int op, const DevGeom& g, int dtype) {
   if (!make_role(op, g, &r)) return 0;
   const CPlan pl = make_cplan(r, dtype);
   if (!pl.ok) return 0;
-  return pl.xp_bytes + pl.wp_bytes + 1024;
+  int64_t need = pl.xp_bytes + pl.wp_bytes + 1024;
+  if (dtype == EINCONV_F32) {  // scaled fp16 operand copies: [absmax header][xp][wp]
+    const CPlan ph = make_cplan(r, EINCONV_F16);
+    if (ph.ok) need = std::max<int64_t>(need, ph.xp_bytes + ph.wp_bytes + 2048);
+  }
+  return need;
 }
 
-template <typename T>
+// T: operand type of the MMAs (`dtype` is ITS enum); TO: tensor type.  TO = float with T = __half is the
+// TF32-mode route on power-of-two-scaled fp16 operand copies (same 10-bit mantissa as TF32, round to
+// nearest instead of truncation, twice the MMA rate on half the bytes; see convert.cu).
+template <typename T, typename TO = T>
 static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w, const void* bias, void* dst,
                  int dtype, void* workspace, cudaStream_t stream) {
+  constexpr bool CONVERT = !std::is_same<T, TO>::value;
   // workspace may be arbitrarily aligned: TMA needs 16 bytes for the global address
   uintptr_t base = ((uintptr_t)workspace + 1023) & ~(uintptr_t)1023;
+  unsigned* absmax = nullptr;
+  if (CONVERT) {
+    absmax = reinterpret_cast<unsigned*>(base);  // [0] max|src|, [1] max|w|
+    base += 1024;
+  }
   T* xp = reinterpret_cast<T*>(base);
   T* wp = reinterpret_cast<T*>(base + pl.xp_bytes);
   const int N = r.n_dims;
@@ -1013,7 +1077,22 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
     wj.cg = r.transpose ? r.cd : r.cs;
     wj.transpose = r.transpose;
     wj.total = (long long)r.groups * pl.taps * pl.np * pl.cgp;
-    int st0 = pack_channels_last(src, xp, dtype, N, r.batch, r.groups * r.cs, pl.cp, r.S, pl.P, r.pad, stream, &wj);
+    int st0;
+    if (CONVERT) {
+      long long n_src = (long long)r.batch * r.groups * r.cs, n_w = (long long)r.groups * r.cs * r.cd;
+      for (int d = 0; d < N; ++d) {
+        n_src *= r.S[d];
+        n_w *= r.K[d];
+      }
+      cudaError_t e = cudaMemsetAsync(absmax, 0, 8, stream);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(absmax)");
+      st0 = launch_absmax2((const float*)src, n_src, (const float*)w, n_w, absmax, stream);
+      if (st0) return st0;
+      st0 = pack_channels_last_f32_to_f16((const float*)src, xp, N, r.batch, r.groups * r.cs, pl.cp, r.S, pl.P,
+                                          r.pad, absmax, stream, &wj);
+    } else {
+      st0 = pack_channels_last(src, xp, dtype, N, r.batch, r.groups * r.cs, pl.cp, r.S, pl.P, r.pad, stream, &wj);
+    }
     if (st0) return st0;
   }
   // ---- tensor maps
@@ -1072,8 +1151,9 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
   p.cd_total = r.groups * r.cd;
   p.bias = bias;
   p.dst = dst;
+  p.absmax = absmax;
 
-  auto kern = conv_tma_kernel<T>;
+  auto kern = conv_tma_kernel<T, TO>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tma)");
   const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, kNumSMs);
@@ -1125,6 +1205,19 @@ int run(int op, const void* src, const void* w, const void* bias, void* dst, int
     return EINCONV_ERR_WORKSPACE;
   }
   if ((long long)r.batch * r.groups * r.cd == 0 || pl.rows_total == 0) return EINCONV_OK;
+  // fp32 tensors (TF32 mode): scaled fp16 operand copies run the main kernel a third faster (C1: 25.0 -> 16.7 us
+  // under ncu) but cost an extra pass over the source for its maximum (13 us for C1's 25.7 MB), so the route
+  // pays only when the GEMM outweighs the packing: many output channels x taps per source element.
+  // EINCONV_CTMA_HALF=1 / EINCONV_CTMA_TF32=1 force either route.
+  long long taps_total = 1;
+  for (int d = 0; d < r.n_dims; ++d) taps_total *= r.K[d];
+  const bool want_half = getenv("EINCONV_CTMA_HALF") != nullptr || (long long)r.cd * taps_total >= 2048;
+  if (dtype == EINCONV_F32 && want_half && !getenv("EINCONV_CTMA_TF32") && ((uintptr_t)src % 16) == 0 &&
+      ((uintptr_t)w % 16) == 0) {
+    const CPlan ph = make_cplan(r, EINCONV_F16);
+    if (ph.ok && workspace_bytes_given >= ph.xp_bytes + ph.wp_bytes + 2048)
+      return run_t<__half, float>(r, ph, src, w, bias, dst, EINCONV_F16, workspace, stream);
+  }
   switch (dtype) {
     case EINCONV_F32: return run_t<float>(r, pl, src, w, bias, dst, dtype, workspace, stream);
     case EINCONV_BF16: return run_t<__nv_bfloat16>(r, pl, src, w, bias, dst, dtype, workspace, stream);

@@ -54,6 +54,39 @@ __global__ void __launch_bounds__(256) scale_to_half_kernel(const float* __restr
     y[i] = __float2half_rn(__ldg(x + i) * s);
 }
 
+// two tensors in one launch: blocks [0, blocks_a) reduce a into out_bits[0], the others b into out_bits[1]
+__global__ void __launch_bounds__(256) absmax2_kernel(const float* __restrict__ a, long long na, unsigned blocks_a,
+                                                      const float* __restrict__ b, long long nb,
+                                                      unsigned* __restrict__ out_bits) {
+  const bool first = blockIdx.x < blocks_a;
+  const float* x = first ? a : b;
+  const long long n = first ? na : nb;
+  const long long bid = first ? blockIdx.x : blockIdx.x - blocks_a;
+  const long long nblk = first ? blocks_a : gridDim.x - blocks_a;
+  float m = 0.f;
+  const long long n4 = n / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = bid * blockDim.x + threadIdx.x; i < n4; i += nblk * blockDim.x) {
+    const float4 v = __ldg(x4 + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  for (long long i = n4 * 4 + bid * blockDim.x + threadIdx.x; i < n; i += nblk * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(x + i)));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits + (first ? 0 : 1), __float_as_uint(m));
+}
+
+int launch_absmax2(const float* a, long long na, const float* b, long long nb, unsigned* out_bits,
+                   cudaStream_t stream) {
+  EINCONV_CHECK_ARG(((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0, "absmax: misaligned tensor");
+  const unsigned blocks_a = (unsigned)std::min<long long>((na / 4 + 255) / 256 + 1, 8ll * kNumSMs);
+  const unsigned blocks_b = (unsigned)std::min<long long>((nb / 4 + 255) / 256 + 1, 2ll * kNumSMs);
+  absmax2_kernel<<<blocks_a + blocks_b, 256, 0, stream>>>(a, na, blocks_a, b, nb, out_bits);
+  EINCONV_CHECK_LAUNCH("absmax2_kernel");
+  return EINCONV_OK;
+}
+
 // max |x| of an fp32 tensor as float bits, atomically maxed into *out_bits (caller zeroes it first)
 int launch_absmax(const float* x, long long n, unsigned* out_bits, cudaStream_t stream) {
   if (n == 0) return EINCONV_OK;

@@ -50,6 +50,8 @@ int tc_kfc(const void* x, void* out, int dtype, const DevGeom& g, double scale, 
 // convert.cu
 int scaled_half_copy(const float* x, __half* y, long long n, void* header, cudaStream_t stream);
 int launch_absmax(const float* x, long long n, unsigned* out_bits, cudaStream_t stream);
+int launch_absmax2(const float* a, long long na, const float* b, long long nb, unsigned* out_bits,
+                   cudaStream_t stream);
 
 // tc_tma.cu (TMA-fed tcgen05 kernels for the reduction networks)
 namespace tma {
@@ -79,9 +81,10 @@ int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int bat
                        const int* S, const long long* P, const int* pad, cudaStream_t stream,
                        const WeightJob* wj = nullptr);
 // same layout, fp32 source -> fp16 destination scaled by operand_scale(*absmax_bits) (convert.cu)
+// an optional weight job is converted with the scale of absmax_bits[1]
 int pack_channels_last_f32_to_f16(const float* src, void* xp, int n_dims, int batch, int ctot, int cp, const int* S,
                                   const long long* P, const int* pad, const unsigned* absmax_bits,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, const WeightJob* wj = nullptr);
 int encode_2d(CUtensorMap* map, int dtype, const void* base, long long rows, long long cols, int box_cols,
               int box_rows, int swizzle_bytes);
 int encode_tiled_raw(CUtensorMap* map, const void* base, int elem_bytes, int rank, const unsigned long long* dims,

@@ -845,10 +845,18 @@ def ctma_weights(request, monkeypatch):
 
 
 @pytest.mark.parametrize("case", CTMA_CASES, ids=CTMA_IDS)
-@pytest.mark.parametrize("mode", ["bf16", "fp16", "tf32"])
-def test_conv_tma_forward_and_input_vjp(case, mode, ctma_weights):
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "tf32", "tf32-native", "tf32-half"])
+def test_conv_tma_forward_and_input_vjp(case, mode, ctma_weights, monkeypatch):
     """Same tolerances as the other tensor-core tests: against the fp64 oracle on the same rounded
-    inputs, max|d| <= 2^-7 (bf16) / 2^-10 (fp16) / 1e-3 (TF32) of max|ref|."""
+    inputs, max|d| <= 2^-7 (bf16) / 2^-10 (fp16) / 1e-3 (TF32) of max|ref|.  fp32 tensors in TF32 mode:
+    "tf32" = the dispatcher's choice, "tf32-native" = kind::tf32 MMAs, "tf32-half" = power-of-two-scaled
+    fp16 operand copies (same 10-bit mantissa)."""
+    if mode == "tf32-native":
+        monkeypatch.setenv("EINCONV_CTMA_TF32", "1")
+        mode = "tf32"
+    elif mode == "tf32-half":
+        monkeypatch.setenv("EINCONV_CTMA_HALF", "1")
+        mode = "tf32"
     dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "tf32": torch.float32}[mode]
     tol = {"bf16": 2.0**-7, "fp16": 2.0**-10, "tf32": 1e-3}[mode]
     x, w, b, kw = _tc_inputs(case, dtype)
