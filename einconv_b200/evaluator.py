@@ -305,13 +305,21 @@ def kfc(x, kernel_size, stride=1, padding=0, dilation=1, groups=1, simplify=True
     """KFC factor ``[G, A, A]`` (``convNd_kfc.py:75-116``).  ``scale`` defaults to ``1/B``; pass the
     global ``1/B`` when ``x`` is a batch shard whose factors will be summed across ranks.  ``out``
     (optional) receives the result in place."""
-    return _factor(nat.OP_KFC, x, kernel_size, stride, padding, dilation, groups, simplify, scale, out)
+    return _factor_entry(nat.OP_KFC, x, kernel_size, stride, padding, dilation, groups, simplify, scale, out)
 
 
 def kfac_reduce(x, kernel_size, stride=1, padding=0, dilation=1, groups=1, simplify=True, scale=None,
                 out=None) -> Tensor:
     """KFAC-reduce factor ``[G, A, A]`` (``convNd_kfac_reduce.py:77-119``)."""
-    return _factor(nat.OP_KFAC_REDUCE, x, kernel_size, stride, padding, dilation, groups, simplify, scale, out)
+    return _factor_entry(nat.OP_KFAC_REDUCE, x, kernel_size, stride, padding, dilation, groups, simplify, scale, out)
+
+
+def _factor_entry(op, x, kernel_size, stride, padding, dilation, groups, simplify, scale, out):
+    if _needs_grad(x):
+        if out is not None:
+            raise RuntimeError("kfc / kfac_reduce: `out=` cannot be combined with an input that requires grad.")
+        return _FactorFunction.apply(x, op, kernel_size, stride, padding, dilation, groups, simplify, scale)
+    return _factor(op, x, kernel_size, stride, padding, dilation, groups, simplify, scale, out)
 
 
 # --------------------------------------------------------------------------------------------
@@ -372,6 +380,14 @@ def kfac_reduce_transpose(x, kernel_size, stride=1, padding=0, output_padding=0,
         i_total *= i
     B = x.shape[0]
     A = x.shape[1] // groups * k_total
+    if _needs_grad(x):
+        # differentiable by composition: native (differentiable) gather, then the definition
+        if scale is None:
+            denom = B * i_total**2
+            scale = float(torch.tensor([1.0 / denom]).to(x.dtype)) if denom > 0 else 0.0
+        u = unfold_transpose_autograd(x, kernel_size, stride, padding, output_padding, dilation)
+        m = u.reshape(B, groups, A, i_total).sum(-1)
+        return torch.einsum("ngi,ngj->gij", m, m) * scale
     if scale is None:
         denom = B * i_total**2
         scale = float(torch.tensor([1.0 / denom]).to(x.dtype)) if denom > 0 else 0.0
@@ -390,8 +406,21 @@ def kfac_reduce_transpose(x, kernel_size, stride=1, padding=0, output_padding=0,
 
 
 # --------------------------------------------------------------------------------------------
-# differentiable wrappers (the reference's einsum is differentiable, modules/conv.py:173-182)
+# differentiable wrappers.  The reference evaluates every network with ``torch.einsum``, which is
+# differentiable to any order (``modules/conv.py:173-182``, ``README.md:64-73``).  The kernels are
+# each other's derivatives, so every backward below is written with the differentiable wrappers
+# again: with ``create_graph=True`` the graph of the backward pass is recorded like einsum's would be.
+#   y  = fwd(x, w):        dx = ivjp(w, c)        dw = wvjp(x, c)
+#   gx = ivjp(w, v):       dw = wvjp(c, v)        dv = fwd(c, w)
+#   gw = wvjp(x, v):       dx = ivjp(c, v)        dv = fwd(x, c)
+#   u  = unfold(x):        dx = fold(c)           (and fold's backward is unfold)
+#   K  = s sum_n U U^T:    dU = s (C + C^T) U     dx = fold(dU)
+#   R  = s sum_n m m^T:    dm = s (C + C^T) m,  m = sum_o U,  dU = dm broadcast over o,  dx = fold(dU)
 # --------------------------------------------------------------------------------------------
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 class _ConvNdFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, dilation, groups, simplify):
@@ -407,16 +436,52 @@ class _ConvNdFunction(torch.autograd.Function):
         gx = gw = gb = None
         v = v.contiguous()
         if ctx.needs_input_grad[0]:
-            gx = conv_input_vjp_raw(
-                weight, v, tuple(x.shape[2:]), stride, padding, dilation, groups, simplify
-            )
+            gx = conv_input_vjp(weight, v, tuple(x.shape[2:]), stride, padding, dilation, groups, simplify)
         if ctx.needs_input_grad[1]:
-            gw = conv_weight_vjp_raw(
-                x, v, tuple(weight.shape[2:]), dilation, padding, stride, groups, simplify
-            )
+            gw = conv_weight_vjp(x, v, tuple(weight.shape[2:]), dilation, padding, stride, groups, simplify)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = v.sum(dim=[0] + list(range(2, v.dim())))
         return gx, gw, gb, None, None, None, None, None
+
+
+class _InputVjpFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weight, v, input_size, stride, padding, dilation, groups, simplify):
+        ctx.save_for_backward(weight, v)
+        ctx.hyper = (stride, padding, dilation, groups, simplify)
+        return conv_input_vjp_raw(weight, v, input_size, stride, padding, dilation, groups, simplify)
+
+    @staticmethod
+    def backward(ctx, c):
+        weight, v = ctx.saved_tensors
+        stride, padding, dilation, groups, simplify = ctx.hyper
+        gw = gv = None
+        c = c.contiguous()
+        if ctx.needs_input_grad[0]:
+            gw = conv_weight_vjp(c, v, tuple(weight.shape[2:]), dilation, padding, stride, groups, simplify)
+        if ctx.needs_input_grad[1]:
+            gv = conv_forward(c, weight, None, stride, padding, dilation, groups, simplify)
+        return gw, gv, None, None, None, None, None, None
+
+
+class _WeightVjpFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, v, kernel_size, dilation, padding, stride, groups, simplify):
+        ctx.save_for_backward(x, v)
+        ctx.hyper = (stride, padding, dilation, groups, simplify)
+        return conv_weight_vjp_raw(x, v, kernel_size, dilation, padding, stride, groups, simplify)
+
+    @staticmethod
+    def backward(ctx, c):
+        x, v = ctx.saved_tensors
+        stride, padding, dilation, groups, simplify = ctx.hyper
+        gx = gv = None
+        c = c.contiguous()
+        if ctx.needs_input_grad[0]:
+            gx = conv_input_vjp(c, v, tuple(x.shape[2:]), stride, padding, dilation, groups, simplify)
+        if ctx.needs_input_grad[1]:
+            gv = conv_forward(x, c, None, stride, padding, dilation, groups, simplify)
+        return gx, gv, None, None, None, None, None, None
 
 
 class _UnfoldNdFunction(torch.autograd.Function):
@@ -428,24 +493,154 @@ class _UnfoldNdFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gu):
         channels, input_size, kernel_size, dilation, padding, stride = ctx.geometry
-        return fold(gu, channels, input_size, kernel_size, dilation, padding, stride), None, None, None, None
+        return fold_autograd(gu, channels, input_size, kernel_size, dilation, padding, stride), None, None, None, None
+
+
+class _FoldFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gu, channels, input_size, kernel_size, dilation, padding, stride):
+        ctx.geometry = (kernel_size, dilation, padding, stride)
+        return fold(gu, channels, input_size, kernel_size, dilation, padding, stride)
+
+    @staticmethod
+    def backward(ctx, c):
+        kernel_size, dilation, padding, stride = ctx.geometry
+        return unfold_autograd(c.contiguous(), kernel_size, dilation, padding, stride), None, None, None, None, None, None
+
+
+def _factor_scale(op: int, x: Tensor, out: Sequence[int], scale) -> float:
+    """The scalar the reference multiplies with (``convNd_kfc.py:105``, ``convNd_kfac_reduce.py:106-108``),
+    rounded through ``x.dtype`` like its ``Tensor([..]).to(x.dtype)``."""
+    if scale is not None:
+        return float(scale)
+    B = x.shape[0]
+    denom = B
+    if op != nat.OP_KFC:
+        o_total = 1
+        for o in out:
+            o_total *= o
+        denom = B * o_total**2
+    return float(torch.tensor([1.0 / denom]).to(x.dtype)) if denom > 0 else 0.0
+
+
+class _FactorFunction(torch.autograd.Function):
+    """KFC / KFAC-reduce with the backward of the definition: unfold -> outer products -> fold."""
+
+    @staticmethod
+    def forward(ctx, x, op, kernel_size, stride, padding, dilation, groups, simplify, scale):
+        ctx.save_for_backward(x)
+        _, _, _, _, _, out = resolve_geometry(tuple(x.shape[2:]), kernel_size, stride, padding, dilation)
+        ctx.scale = _factor_scale(op, x, out, scale)
+        ctx.hyper = (op, kernel_size, stride, padding, dilation, groups)
+        return _factor(op, x, kernel_size, stride, padding, dilation, groups, simplify, ctx.scale)
+
+    @staticmethod
+    def backward(ctx, c):
+        (x,) = ctx.saved_tensors
+        op, kernel_size, stride, padding, dilation, groups = ctx.hyper
+        B, channels = x.shape[0], x.shape[1]
+        u = unfold_autograd(x, kernel_size, dilation, padding, stride)  # [B, G*A, O]
+        A, O = u.shape[1] // groups, u.shape[2]
+        u = u.reshape(B, groups, A, O)
+        sym = (c + c.transpose(1, 2)) * ctx.scale
+        if op == nat.OP_KFC:
+            gu = torch.einsum("gij,ngjo->ngio", sym, u)
+        else:
+            gm = torch.einsum("gij,ngj->ngi", sym, u.sum(-1))
+            gu = gm.unsqueeze(-1).expand(B, groups, A, O)
+        gx = fold_autograd(gu.reshape(B, groups * A, O).contiguous(), channels, tuple(x.shape[2:]), kernel_size,
+                           dilation, padding, stride)
+        return gx, None, None, None, None, None, None, None, None
+
+
+class _UnfoldTransposeFunction(torch.autograd.Function):
+    """Backward of the transpose-convolution unfolding: ``gx[b,c,o] = sum_k gu[b,(c,k), s o + d k - p]`` — a
+    grouped convolution of ``gu`` (``C*K -> C`` channels, ``groups = C``) with a one-hot kernel."""
+
+    @staticmethod
+    def forward(ctx, x, kernel_size, stride, padding, output_padding, dilation):
+        ctx.hyper = (kernel_size, stride, padding, dilation)
+        ctx.x_shape = tuple(x.shape)
+        return unfold_transpose(x, kernel_size, stride, padding, output_padding, dilation)
+
+    @staticmethod
+    def backward(ctx, gu):
+        kernel_size, stride, padding, dilation = ctx.hyper
+        B, C = ctx.x_shape[:2]
+        N = len(ctx.x_shape) - 2
+        t_k = _tuple(kernel_size, N)
+        k_total = 1
+        for k in t_k:
+            k_total *= k
+        # spatial sizes of gu's last axis: the associated convolution's input sizes
+        t_s, t_p, t_d = _tuple(stride, N), _tuple(padding, N), _tuple(dilation, N)
+        total = gu.shape[2]
+        base = [get_conv_input_size(o, k, s, p, 0, d) for o, k, s, p, d in zip(ctx.x_shape[2:], t_k, t_s, t_p, t_d)]
+        # output_padding only enlarges the input sizes; recover it from the element count dimension by dimension
+        in_sizes = _recover_sizes(base, t_s, total)
+        onehot = torch.eye(k_total, dtype=gu.dtype, device=gu.device).reshape(1, k_total, *t_k)
+        onehot = onehot.expand(C, k_total, *t_k).contiguous()
+        gx = conv_forward(gu.reshape(B, C * k_total, *in_sizes), onehot, None, stride, padding, dilation, C, True)
+        return gx, None, None, None, None, None
+
+
+def _recover_sizes(base: Sequence[int], strides: Sequence[int], total: int) -> Tuple[int, ...]:
+    """Input sizes ``base_d + output_padding_d`` (``0 <= output_padding_d < stride_d``) whose product is ``total``."""
+    def search(d, rest):
+        if d == len(base):
+            return () if rest == 1 else None
+        for extra in range(max(1, strides[d])):
+            size = base[d] + extra
+            if size > 0 and rest % size == 0:
+                tail = search(d + 1, rest // size)
+                if tail is not None:
+                    return (size,) + tail
+        return None
+
+    sizes = search(0, total)
+    if sizes is None:
+        raise RuntimeError("unfoldNd_transpose backward: cannot recover the unfolded sizes")
+    return sizes
 
 
 def conv_forward(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, simplify=True) -> Tensor:
     """Differentiable N-d convolution on the native kernels (``functionals/conv.py:11-69``)."""
     _conv_check(x, weight, bias, groups)
-    needs_grad = torch.is_grad_enabled() and any(
-        t is not None and t.requires_grad for t in (x, weight, bias)
-    )
-    if needs_grad:
+    if _needs_grad(x, weight, bias):
         return _ConvNdFunction.apply(x, weight, bias, stride, padding, dilation, groups, simplify)
     return conv_forward_raw(x, weight, bias, stride, padding, dilation, groups, simplify)
 
 
+def conv_input_vjp(weight, v, input_size, stride=1, padding=0, dilation=1, groups=1, simplify=True) -> Tensor:
+    """Differentiable input VJP (network of ``convNd_input_vjp.py:53-60``)."""
+    if _needs_grad(weight, v):
+        return _InputVjpFunction.apply(weight, v, input_size, stride, padding, dilation, groups, simplify)
+    return conv_input_vjp_raw(weight, v, input_size, stride, padding, dilation, groups, simplify)
+
+
+def conv_weight_vjp(x, v, kernel_size, dilation=1, padding=0, stride=1, groups=1, simplify=True) -> Tensor:
+    """Differentiable weight VJP (network of ``convNd_weight_vjp.py:51-58``)."""
+    if _needs_grad(x, v):
+        return _WeightVjpFunction.apply(x, v, kernel_size, dilation, padding, stride, groups, simplify)
+    return conv_weight_vjp_raw(x, v, kernel_size, dilation, padding, stride, groups, simplify)
+
+
 def unfold_autograd(x, kernel_size, dilation=1, padding=0, stride=1) -> Tensor:
-    if torch.is_grad_enabled() and x.requires_grad:
+    if _needs_grad(x):
         return _UnfoldNdFunction.apply(x, kernel_size, dilation, padding, stride)
     return unfold(x, kernel_size, dilation, padding, stride)
+
+
+def fold_autograd(gu, channels, input_size, kernel_size, dilation=1, padding=0, stride=1) -> Tensor:
+    if _needs_grad(gu):
+        return _FoldFunction.apply(gu, channels, input_size, kernel_size, dilation, padding, stride)
+    return fold(gu, channels, input_size, kernel_size, dilation, padding, stride)
+
+
+def unfold_transpose_autograd(x, kernel_size, stride=1, padding=0, output_padding=0, dilation=1) -> Tensor:
+    if _needs_grad(x):
+        return _UnfoldTransposeFunction.apply(x, kernel_size, stride, padding, output_padding, dilation)
+    return unfold_transpose(x, kernel_size, stride, padding, output_padding, dilation)
 
 
 # --------------------------------------------------------------------------------------------
@@ -468,11 +663,11 @@ class Plan:
             return conv_forward(t["x"], t["weight"], None, h["stride"], h["padding"], h["dilation"],
                                 h["groups"], self.simplify)
         if self.kind == "input_vjp":
-            return conv_input_vjp_raw(t["weight"], t["v"], h["input_size"], h["stride"], h["padding"],
-                                      h["dilation"], h["groups"], self.simplify)
+            return conv_input_vjp(t["weight"], t["v"], h["input_size"], h["stride"], h["padding"],
+                                  h["dilation"], h["groups"], self.simplify)
         if self.kind == "weight_vjp":
-            return conv_weight_vjp_raw(t["x"], t["v"], h["kernel_size"], h["dilation"], h["padding"],
-                                       h["stride"], h["groups"], self.simplify)
+            return conv_weight_vjp(t["x"], t["v"], h["kernel_size"], h["dilation"], h["padding"],
+                                   h["stride"], h["groups"], self.simplify)
         if self.kind == "unfold":
             return unfold_autograd(t["x"], h["kernel_size"], h["dilation"], h["padding"], h["stride"])
         if self.kind == "kfc":
@@ -482,8 +677,8 @@ class Plan:
             return kfac_reduce(t["x"], h["kernel_size"], h["stride"], h["padding"], h["dilation"],
                                h["groups"], self.simplify)
         if self.kind == "unfold_transpose":
-            return unfold_transpose(t["x"], h["kernel_size"], h["stride"], h["padding"],
-                                    h["output_padding"], h["dilation"])
+            return unfold_transpose_autograd(t["x"], h["kernel_size"], h["stride"], h["padding"],
+                                             h["output_padding"], h["dilation"])
         if self.kind == "kfac_reduce_transpose":
             return kfac_reduce_transpose(t["x"], h["kernel_size"], h["stride"], h["padding"],
                                          h["output_padding"], h["dilation"], h["groups"], self.simplify)

@@ -28,6 +28,6 @@ def unfoldNd_transpose(
     is one kernel for every geometry.
     """
     del simplify
-    return evaluator.unfold_transpose(
+    return evaluator.unfold_transpose_autograd(
         x, kernel_size, stride=stride, padding=padding, output_padding=output_padding, dilation=dilation
     )
