@@ -1,6 +1,7 @@
 // extern "C" boundary of libeinconv_b200.so: argument validation, kernel selection, workspace
 // accounting.  See include/einconv_b200.h for the contract of each entry point and the reference
 // call site it replaces.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -26,6 +27,18 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t err, const char* what) {
   set_error("%s: %s", what, cudaGetErrorString(err));
   return EINCONV_ERR_CUDA;
+}
+
+int num_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -90,12 +103,17 @@ static int resolve_math(int dtype, int math) {
   return math;
 }
 
-static Path select_path(int op, const DevGeom& g, int dtype, int math, int kernels) {
+// `aligned`: every tensor pointer of the call is 16-byte aligned.  The tensor-core routes move data with
+// TMA boxes and 16-byte vector accesses; a misaligned base (e.g. the batch-shard view x_all[1:] of a
+// tensor with an odd per-sample element count) takes the CUDA-core path instead of failing.
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static Path select_path(int op, const DevGeom& g, int dtype, int math, int kernels, bool aligned = true) {
   if (kernels == EINCONV_KERNELS_GENERIC) return Path::FFMA;
   if ((op == EINCONV_OP_CONV_FWD || op == EINCONV_OP_CONV_INPUT_VJP) && depthwise_supported(g, dtype))
     return Path::DEPTHWISE;
   const int m = resolve_math(dtype, math);
-  if (m == EINCONV_MATH_TF32 || m == EINCONV_MATH_HALF) {
+  if (aligned && (m == EINCONV_MATH_TF32 || m == EINCONV_MATH_HALF)) {
     // reduction networks: TMA-fed tcgen05 kernel when the layout allows it (16-byte aligned rows);
     // the software-gather tensor-core kernel is kept for the forward pass only (for the reduction
     // networks it is slower than the CUDA-core kernel)
@@ -234,19 +252,26 @@ const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype,
   }
 }
 
+static int64_t workspace_for(int op, DevGeom g, int dtype, int math, int kernels, bool aligned);
+
 int64_t einconv_workspace_bytes(int op, const einconv_geom* geom, int dtype, int math, int kernels) {
   DevGeom g;
   const bool no_cout = op == EINCONV_OP_UNFOLD || op == EINCONV_OP_FOLD || op == EINCONV_OP_UNFOLD_TRANSPOSE ||
                        op == EINCONV_OP_KFAC_REDUCE_TRANSPOSE;
   if (make_dev_geom(geom, &g, !no_cout)) return -1;
   if (check_math(dtype, math)) return -1;
+  // the route depends on the alignment of the pointers, which this query does not see: enough for either
+  return std::max(workspace_for(op, g, dtype, math, kernels, true), workspace_for(op, g, dtype, math, kernels, false));
+}
+
+static int64_t workspace_for(int op, DevGeom g, int dtype, int math, int kernels, bool aligned) {
   if (op == EINCONV_OP_UNFOLD || op == EINCONV_OP_FOLD || op == EINCONV_OP_UNFOLD_TRANSPOSE) return 0;
   if (op == EINCONV_OP_KFAC_REDUCE_TRANSPOSE) {
     // same two stages as KFAC-reduce, on the transpose-convolution view of the geometry
     op = EINCONV_OP_KFAC_REDUCE;
     g = swap_io(g);
   }
-  if (op == EINCONV_OP_KFC) {
+  if (op == EINCONV_OP_KFC && aligned) {
     DevGeom g1;
     int64_t ub, hb;
     if (kfc_half_route(g, dtype, math, kernels, &hb)) {
@@ -256,7 +281,7 @@ int64_t einconv_workspace_bytes(int op, const einconv_geom* geom, int dtype, int
     }
     if (kfc_via_unfold(g, dtype, math, kernels, &g1, &ub)) return ub + tma::tma_workspace_bytes(op, g1, dtype);
   }
-  const Path path = select_path(op, g, dtype, math, kernels);
+  const Path path = select_path(op, g, dtype, math, kernels, aligned);
   if (path == Path::DEPTHWISE) return 0;
   if (path == Path::TENSOR) return tc_workspace_bytes(op, g, dtype, resolve_math(dtype, math));
   if (path == Path::TMA) return tma::tma_workspace_bytes(op, g, dtype);
@@ -265,6 +290,7 @@ int64_t einconv_workspace_bytes(int op, const einconv_geom* geom, int dtype, int
   switch (op) {
     case EINCONV_OP_KFAC_REDUCE: {
       DevGeom g2;
+      // stage 1 writes u into the (256-byte aligned) workspace, so stage 2 never sees the caller's pointer
       if (kfac_reduce_tensor(g, dtype, math, kernels, &g2))
         return kfac_u_bytes(g) + tma::tma_workspace_bytes(EINCONV_OP_KFC, g2, EINCONV_F32);
       return ffma_splitk_workspace(op, g, dtype, nullptr);
@@ -296,7 +322,8 @@ int einconv_conv_fwd(const void* x, const void* w, const void* bias, void* y, in
   if ((st = check_math(dtype, math))) return st;
   if ((long long)g.batch * g.groups * g.c_out_g * g.out_total == 0) return EINCONV_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  switch (select_path(EINCONV_OP_CONV_FWD, g, dtype, math, kernels)) {
+  const bool al = aligned16(x) && aligned16(w) && aligned16(y) && aligned16(bias);
+  switch (select_path(EINCONV_OP_CONV_FWD, g, dtype, math, kernels, al)) {
     case Path::DEPTHWISE: return dw_conv_fwd(x, w, bias, y, dtype, g, s);
     case Path::CONV_TMA:
       return ctma::run(EINCONV_OP_CONV_FWD, x, w, bias, y, dtype, g, workspace, workspace_bytes, s);
@@ -316,7 +343,8 @@ int einconv_conv_input_vjp(const void* w, const void* v, void* gx, int dtype,
   if ((st = check_math(dtype, math))) return st;
   if ((long long)g.batch * g.groups * g.c_in_g * g.in_total == 0) return EINCONV_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  switch (select_path(EINCONV_OP_CONV_INPUT_VJP, g, dtype, math, kernels)) {
+  const bool al = aligned16(w) && aligned16(v) && aligned16(gx);
+  switch (select_path(EINCONV_OP_CONV_INPUT_VJP, g, dtype, math, kernels, al)) {
     case Path::DEPTHWISE: return dw_conv_input_vjp(w, v, gx, dtype, g, s);
     case Path::CONV_TMA:
       return ctma::run(EINCONV_OP_CONV_INPUT_VJP, v, w, nullptr, gx, dtype, g, workspace, workspace_bytes, s);
@@ -334,7 +362,8 @@ int einconv_conv_weight_vjp(const void* x, const void* v, void* gw, int dtype,
   if ((st = check_math(dtype, math))) return st;
   if ((long long)g.groups * g.c_out_g * g.c_in_g * g.k_total == 0) return EINCONV_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  switch (select_path(EINCONV_OP_CONV_WEIGHT_VJP, g, dtype, math, kernels)) {
+  const bool al = aligned16(x) && aligned16(v) && aligned16(gw);
+  switch (select_path(EINCONV_OP_CONV_WEIGHT_VJP, g, dtype, math, kernels, al)) {
     case Path::WGRAD_SLAB: return wslab::run(x, v, gw, dtype, g, workspace, workspace_bytes, s);
     case Path::TMA:
       return tma::tma_run(EINCONV_OP_CONV_WEIGHT_VJP, x, v, gw, dtype, g, 1.0, workspace, workspace_bytes, s);
@@ -353,7 +382,8 @@ int einconv_kfc(const void* x, void* out, int dtype, const einconv_geom* geom, d
   if ((st = check_math(dtype, math))) return st;
   if ((long long)g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  {
+  const bool al = aligned16(x) && aligned16(out);
+  if (al) {
     int64_t hb;
     if (kfc_half_route(g, dtype, math, kernels, &hb)) {
       DevGeom g1;
@@ -380,7 +410,7 @@ int einconv_kfc(const void* x, void* out, int dtype, const einconv_geom* geom, d
                                     workspace_bytes - hb, s, inv_s2);
     }
   }
-  {
+  if (al) {
     DevGeom g1;
     int64_t ub;
     if (kfc_via_unfold(g, dtype, math, kernels, &g1, &ub)) {
@@ -395,7 +425,7 @@ int einconv_kfc(const void* x, void* out, int dtype, const einconv_geom* geom, d
                           workspace_bytes - ub, s);
     }
   }
-  switch (select_path(EINCONV_OP_KFC, g, dtype, math, kernels)) {
+  switch (select_path(EINCONV_OP_KFC, g, dtype, math, kernels, al)) {
     case Path::TMA:
       return tma::tma_run(EINCONV_OP_KFC, x, nullptr, out, dtype, g, scale, workspace, workspace_bytes, s);
     case Path::TENSOR:
@@ -409,7 +439,7 @@ static int kfac_reduce_impl(const void* x, void* out, int dtype, const DevGeom& 
   if ((long long)g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
   int st;
   DevGeom g2;
-  if (kfac_reduce_tensor(g, dtype, math, kernels, &g2)) {
+  if (aligned16(out) && kfac_reduce_tensor(g, dtype, math, kernels, &g2)) {
     const int64_t u_bytes = kfac_u_bytes(g);
     const int64_t need = u_bytes + tma::tma_workspace_bytes(EINCONV_OP_KFC, g2, EINCONV_F32);
     if (workspace_bytes < need || !workspace) {

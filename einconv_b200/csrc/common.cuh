@@ -11,7 +11,9 @@
 namespace einconv {
 
 constexpr int kMaxDims = EINCONV_MAX_DIMS;
-constexpr int kNumSMs = 148;  // B200
+// SMs of the current device (cudaDevAttrMultiProcessorCount, cached per device; 148 on B200): grid sizing and
+// the split-K heuristics count in units of it
+int num_sms();
 
 // ---------------------------------------------------------------------------------------------
 // error reporting (thread-local message, C status codes)

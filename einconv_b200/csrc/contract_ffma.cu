@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(256) window_sum_flat_kernel(const T* __restric
 // ---------------------------------------------------------------------------------------------
 static int pick_splits(long long tiles, int k_chunks) {
   // enough CTAs for ~3 waves, but keep >= 8 chunks per split
-  long long want = (3ll * kNumSMs + tiles - 1) / tiles;
+  long long want = (3ll * num_sms() + tiles - 1) / tiles;
   long long cap = std::max(1, k_chunks / 8);
   return (int)std::max<long long>(1, std::min<long long>(std::min(want, cap), 512));
 }
@@ -1029,7 +1029,7 @@ int kfac_window_sums(const void* x, void* u_out, int dtype, const DevGeom& g, in
     }
     if (g.in_total <= 12288 && g.k_total <= 32 && !getenv("EINCONV_WINDOW_SUM_ROWS")) {
       const size_t smem = (size_t)g.in_total * 4;
-      const unsigned blocks = (unsigned)std::min<long long>((planes + 7) / 8, 4ll * kNumSMs);
+      const unsigned blocks = (unsigned)std::min<long long>((planes + 7) / 8, 4ll * num_sms());
       auto launch_flat = [&](auto kt) -> int {
         constexpr int KT = decltype(kt)::value;
         auto kern = window_sum_flat_kernel<T, KT>;

@@ -1156,15 +1156,17 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
   auto kern = conv_tma_kernel<T, TO>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tma)");
-  const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, kNumSMs);
+  const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, num_sms());
   // (programmatic dependent launch was measured here: no gain, the GEMM's CTAs need the whole SM)
   long long* trace = nullptr;
   const int trace_tiles = 16;
+#ifdef EINCONV_BRINGUP  // allocates, synchronises and frees: never inside a product build (breaks graph capture)
   if (getenv("EINCONV_CTMA_TRACE")) {
     cudaMalloc(&trace, trace_tiles * 16 * sizeof(long long));
     cudaMemset(trace, 0, trace_tiles * 16 * sizeof(long long));
     p.trace = trace;
   }
+#endif
   kern<<<grid, kThreads, pl.smem, stream>>>(map_a, map_b, p);
   EINCONV_CHECK_LAUNCH("conv_tma_kernel");
   if (trace) {  // bring-up only: synchronises and prints the pipeline timeline of CTA 0

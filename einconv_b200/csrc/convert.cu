@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(256) absmax2_kernel(const float* __restrict__ 
 int launch_absmax2(const float* a, long long na, const float* b, long long nb, unsigned* out_bits,
                    cudaStream_t stream) {
   EINCONV_CHECK_ARG(((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0, "absmax: misaligned tensor");
-  const unsigned blocks_a = (unsigned)std::min<long long>((na / 4 + 255) / 256 + 1, 8ll * kNumSMs);
-  const unsigned blocks_b = (unsigned)std::min<long long>((nb / 4 + 255) / 256 + 1, 2ll * kNumSMs);
+  const unsigned blocks_a = (unsigned)std::min<long long>((na / 4 + 255) / 256 + 1, 8ll * num_sms());
+  const unsigned blocks_b = (unsigned)std::min<long long>((nb / 4 + 255) / 256 + 1, 2ll * num_sms());
   absmax2_kernel<<<blocks_a + blocks_b, 256, 0, stream>>>(a, na, blocks_a, b, nb, out_bits);
   EINCONV_CHECK_LAUNCH("absmax2_kernel");
   return EINCONV_OK;
@@ -100,7 +100,7 @@ int launch_absmax2(const float* a, long long na, const float* b, long long nb, u
 int launch_absmax(const float* x, long long n, unsigned* out_bits, cudaStream_t stream) {
   if (n == 0) return EINCONV_OK;
   EINCONV_CHECK_ARG(((uintptr_t)x % 16) == 0, "absmax: misaligned tensor");
-  const unsigned blocks = (unsigned)std::min<long long>((n / 4 + 255) / 256 + 1, 8ll * kNumSMs);
+  const unsigned blocks = (unsigned)std::min<long long>((n / 4 + 255) / 256 + 1, 8ll * num_sms());
   absmax_kernel<<<blocks, 256, 0, stream>>>(x, n, out_bits);
   EINCONV_CHECK_LAUNCH("absmax_kernel");
   return EINCONV_OK;
@@ -112,7 +112,7 @@ int scaled_half_copy(const float* x, __half* y, long long n, void* header, cudaS
   cudaError_t e = cudaMemsetAsync(header, 0, 8, stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(absmax)");
   if (n == 0) return EINCONV_OK;
-  const unsigned blocks = (unsigned)std::min<long long>((n / 4 + 255) / 256 + 1, 8ll * kNumSMs);
+  const unsigned blocks = (unsigned)std::min<long long>((n / 4 + 255) / 256 + 1, 8ll * num_sms());
   absmax_kernel<<<blocks, 256, 0, stream>>>(x, n, (unsigned*)header);
   EINCONV_CHECK_LAUNCH("absmax_kernel");
   scale_to_half_kernel<<<blocks, 256, 0, stream>>>(x, y, n, (const unsigned*)header, (float*)header + 1);

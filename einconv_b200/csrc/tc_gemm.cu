@@ -651,7 +651,7 @@ static TcPlan tc_plan(int op, const DevGeom& g, int dtype) {
   pl.n_tiles = ceil_div(pl.N, pl.bn);
   if (op != EINCONV_OP_CONV_FWD) {
     const long long tiles = (long long)pl.m_tiles * pl.n_tiles * g.groups;
-    long long want = (2ll * kNumSMs + tiles - 1) / tiles;
+    long long want = (2ll * num_sms() + tiles - 1) / tiles;
     long long cap = std::max(1, pl.k_blocks / 8);
     pl.k_splits = (int)std::max<long long>(1, std::min<long long>(std::min(want, cap), 256));
   }

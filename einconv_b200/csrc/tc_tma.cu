@@ -711,7 +711,7 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
       (pl.tri ? (long long)pl.m_tiles * (pl.m_tiles + 1) / 2 : (long long)pl.m_tiles * pl.n_tiles) * g.groups;
   const int stage_bytes = (kTileM + pl.bn) * kRowBytes;
   const int ctas_per_sm = std::max(1, (227 * 1024) / (kStages * stage_bytes + 2048));
-  const long long resident = (long long)kNumSMs * ctas_per_sm;
+  const long long resident = (long long)num_sms() * ctas_per_sm;
   // Split K so that the CTAs fill whole waves of the resident slots: with `s` splits the main kernel
   // takes ceil(tiles * s / resident) rounds of 1/s of the reduction each, and the finish kernel reads
   // s partial copies.  Pick the s with the least estimated time (300 TFLOP/s per round of full
@@ -811,8 +811,10 @@ static int encode_map(CUtensorMap* map, int dtype, const void* base, const int e
                            : line_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                               : CU_TENSOR_MAP_SWIZZLE_32B;
   CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-  if (const char* e = getenv("EINCONV_TMA_SWZ")) swz = (CUtensorMapSwizzle)atoi(e);   // bring-up only
+#ifdef EINCONV_BRINGUP  // unchecked overrides that corrupt results: compiled out of product builds
+  if (const char* e = getenv("EINCONV_TMA_SWZ")) swz = (CUtensorMapSwizzle)atoi(e);
   if (const char* e = getenv("EINCONV_TMA_L2P")) l2p = (CUtensorMapL2promotion)atoi(e);
+#endif
   CUresult r = encode_fn()(map, dt, 5, const_cast<void*>(base), dims, strides, bx, st,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -939,10 +941,12 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   p.is_kfc = kfc ? 1 : 0;
   p.tri = pl.tri ? 1 : 0;
   p.scale_dev = scale_dev;
+#ifdef EINCONV_BRINGUP
   {
     const char* dbg = getenv("EINCONV_TMA_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+#endif
   for (int kw = 0; kw < q.k[0]; ++kw) {
     if (pl.per_tap) {
       // copy_kw[j] = x[s*(j - A) + t_kw]  =>  x[s*w + t_kw] = copy_kw[w + A]

@@ -1181,7 +1181,7 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     const size_t buf_bytes = ((size_t)p.box * sizeof(T) + 15) & ~(size_t)15;
     const size_t smem_p = 2 * buf_bytes + (size_t)p.K * 4;
     const long long items = n_planes * p.K;
-    const int grid_p = 4 * kNumSMs;
+    const int grid_p = 4 * num_sms();
     bool aligned = ((uintptr_t)x % sizeof(T)) == 0;
     // measured: wins for small planes (14x14: 33 -> 27 us for 58 MB), loses ~5% on C2-sized planes, where
     // one CTA per plane already amortises its set-up (EINCONV_UNFOLD_PERSISTENT=1 forces it)
@@ -1205,7 +1205,7 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
 
   // CTAs per plane: split the taps while there are fewer CTAs than ~4 per SM
   int chunks = 1;
-  while (n_planes * p.n_tiles0 * chunks < 4ll * kNumSMs && chunks * 2 <= p.K) chunks *= 2;
+  while (n_planes * p.n_tiles0 * chunks < 4ll * num_sms() && chunks * 2 <= p.K) chunks *= 2;
   if (const char* e = getenv("EINCONV_UNFOLD_CHUNKS")) chunks = std::max(1, std::min(p.K, atoi(e)));
   p.taps_per_chunk = ceil_div(p.K, chunks);
   p.tap_chunks = ceil_div(p.K, p.taps_per_chunk);
@@ -1226,7 +1226,7 @@ static int launch_unfold_flat_t(const void* x, void* out, const DevGeom& g0, con
     long long pc = std::max<long long>(1, std::min<long long>(32, (64 * 1024 + per_plane_bytes - 1) / per_plane_bytes));
     pc = std::min<long long>(pc, (kFlatThreads * kFlatJpt) / p.P);
     pc = std::min<long long>(pc, (long long)(40 * 1024) / std::max<long long>(1, (long long)p.box * (long long)sizeof(T)));
-    while (pc > 1 && ((n_planes + pc - 1) / pc) * p.tap_chunks < 8ll * kNumSMs) pc /= 2;
+    while (pc > 1 && ((n_planes + pc - 1) / pc) * p.tap_chunks < 8ll * num_sms()) pc /= 2;
     p.planes_per_cta = (int)std::max<long long>(1, pc);
   }
   p.pair = (sizeof(T) == 2 && p.planes_per_cta == 1 && p.P % 2 == 0 && (p.n_tiles0 == 1 || p.rest % 2 == 0) &&
@@ -1423,7 +1423,7 @@ int launch_unfold(const void* x, const int64_t* x_strides, void* out, int dtype,
   cb = std::min<long long>(cb, 64);
   // Prefer more, smaller CTAs (shorter tail) while there are fewer than ~4 waves of the
   // 148 x 8 resident slots: fewer planes per CTA.
-  const long long want_ctas = 4ll * kNumSMs * 8;
+  const long long want_ctas = 4ll * num_sms() * 8;
   auto n_ctas = [&](long long cb_, int th_) {
     return (long long)ceil_div((long long)g.batch * C, cb_) * p.v_total * ceil_div(g.out[H], th_);
   };
@@ -1680,7 +1680,7 @@ static int launch_unfold_transpose_tab(const void* x, void* out, const DevGeom& 
     smem += (size_t)g.out_total * sizeof(T);
   }
   const long long chunks = (g.in_total + 255) / 256;
-  const long long per_plane = std::max<long long>(1, std::min<long long>(chunks, (16ll * kNumSMs + planes - 1) / planes));
+  const long long per_plane = std::max<long long>(1, std::min<long long>(chunks, (16ll * num_sms() + planes - 1) / planes));
   dim3 grid((unsigned)per_plane, (unsigned)planes);
   unfold_transpose_tab_kernel<T, ND><<<grid, 256, smem, stream>>>((const T*)x, (T*)out, g, lead, (int)tab_total,
                                                                   plane_in_smem);

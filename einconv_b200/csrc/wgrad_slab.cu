@@ -364,8 +364,8 @@ static Plan make_plan(const DevGeom& g, int dtype) {
     int best_s = 1;
     for (long long s = 1; s <= cap; ++s) {
       const long long ctas = types * s;
-      const long long rounds = (ctas + kNumSMs - 1) / kNumSMs;
-      const double t = (double)rounds * kNumSMs / (double)ctas + w_partial * (double)s;
+      const long long rounds = (ctas + num_sms() - 1) / num_sms();
+      const double t = (double)rounds * num_sms() / (double)ctas + w_partial * (double)s;
       if (t < best) {
         best = t;
         best_s = (int)s;

@@ -78,13 +78,108 @@ def _check_sizes(out: Sequence[int], what: str) -> None:
         )
 
 
+def _hashable(h):
+    return tuple(h) if isinstance(h, list) else h
+
+
+class CallPlan:
+    """Everything about one (operation, geometry, dtype, math mode, kernel family) that does not depend on
+    the tensors' contents: the resolved ``einconv_geom``, output sizes, workspace bytes and (lazily) the
+    name of the kernel the dispatcher picks.
+
+    This is the tensor-free plan the reference's symbolic simplifier aims at
+    (``einconv/simplifications/symbolic.py:518-544``, ``README.md:110-117``): the reference re-derives
+    equation, patterns and simplifications from the tensors at every call; here a repeated call costs one
+    dictionary lookup before the kernel launch."""
+
+    __slots__ = ("op", "geom", "kernel_size", "out", "code", "math", "kern", "ws_bytes", "_kernel")
+
+    def __init__(self, op, geom, kernel_size, out, code, math, kern):
+        self.op, self.geom, self.kernel_size, self.out = op, geom, kernel_size, out
+        self.code, self.math, self.kern = code, math, kern
+        self.ws_bytes = 0
+        self._kernel = None
+
+    @property
+    def kernel(self) -> str:
+        if self._kernel is None:
+            name = nat.lib().einconv_selected_kernel(self.op, self.geom, self.code, self.math, self.kern)
+            self._kernel = name.decode() if name else ""
+        return self._kernel
+
+    def workspace(self, device) -> Tuple[Optional[Tensor], int]:
+        if self.ws_bytes == 0:
+            return None, 0
+        return torch.empty(self.ws_bytes, dtype=torch.uint8, device=device), self.ws_bytes
+
+
+_PLANS: Dict[tuple, CallPlan] = {}
+_PLAN_STATS = {"hits": 0, "misses": 0}
+_PLAN_CAPACITY = 8192
+
+
+def plan_cache_info() -> Dict[str, int]:
+    """``{"hits", "misses", "size"}`` of the call-plan cache."""
+    return dict(_PLAN_STATS, size=len(_PLANS))
+
+
+def clear_plan_cache() -> None:
+    _PLANS.clear()
+    _PLAN_STATS["hits"] = _PLAN_STATS["misses"] = 0
+
+
+def call_plan(op, batch, groups, c_in_g, c_out_g, input_size, kernel_size, stride, padding, dilation, dtype,
+              simplify=True) -> CallPlan:
+    """Cached :class:`CallPlan`; geometry errors are raised (not cached) exactly as without the cache."""
+    math = _math_for(dtype)
+    key = (op, batch, groups, c_in_g, c_out_g, tuple(input_size), _hashable(kernel_size), _hashable(stride),
+           _hashable(padding), _hashable(dilation), dtype, math, simplify)
+    plan = _PLANS.get(key)
+    if plan is not None:
+        _PLAN_STATS["hits"] += 1
+        return plan
+    _PLAN_STATS["misses"] += 1
+    t_in, t_k, t_s, t_d, p_left, out = resolve_geometry(input_size, kernel_size, stride, padding, dilation)
+    _check_sizes(out, "convolution geometry")
+    g = nat.make_geom(batch, groups, c_in_g, c_out_g, t_in, t_k, t_s, t_d, p_left, out)
+    plan = CallPlan(op, g, t_k, out, nat.dtype_code(dtype), math, _kernels_for(simplify))
+    if op not in (nat.OP_UNFOLD, nat.OP_FOLD, nat.OP_UNFOLD_TRANSPOSE):
+        nbytes = nat.lib().einconv_workspace_bytes(op, g, plan.code, plan.math, plan.kern)
+        if nbytes < 0:
+            nat.check(-1, "einconv_workspace_bytes")
+        plan.ws_bytes = int(nbytes)
+    if len(_PLANS) >= _PLAN_CAPACITY:
+        _PLANS.pop(next(iter(_PLANS)))
+    _PLANS[key] = plan
+    return plan
+
+
 def _geom(batch, groups, c_in_g, c_out_g, input_size, kernel_size, stride, padding, dilation):
+    """Uncached geometry (tests and tools): ``(einconv_geom, kernel sizes, output sizes)``."""
     t_in, t_k, t_s, t_d, p_left, out = resolve_geometry(
         input_size, kernel_size, stride, padding, dilation
     )
     _check_sizes(out, "convolution geometry")
     g = nat.make_geom(batch, groups, c_in_g, c_out_g, t_in, t_k, t_s, t_d, p_left, out)
     return g, t_k, out
+
+
+class _on_device:
+    """``torch.cuda.device(device)`` only when it is not already current (saves ~3 us per call)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if device.index is None or torch.cuda.current_device() == device.index \
+            else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
 
 
 def _workspace(op: int, g, dtype_code: int, math: int, kernels: int, device) -> Tuple[Optional[Tensor], int]:
@@ -121,7 +216,8 @@ def unfold(x: Tensor, kernel_size, dilation=1, padding=0, stride=1) -> Tensor:
     if x.dim() < 3:
         raise ValueError(f"unfoldNd expects [batch, channels, *spatial]. Got shape {tuple(x.shape)}.")
     B, C = x.shape[:2]
-    g, t_k, out = _geom(B, 1, C, 0, x.shape[2:], kernel_size, stride, padding, dilation)
+    plan = call_plan(nat.OP_UNFOLD, B, 1, C, 0, x.shape[2:], kernel_size, stride, padding, dilation, x.dtype)
+    g, t_k, out = plan.geom, plan.kernel_size, plan.out
     k_total = 1
     for k in t_k:
         k_total *= k
@@ -131,10 +227,10 @@ def unfold(x: Tensor, kernel_size, dilation=1, padding=0, stride=1) -> Tensor:
     result = torch.empty((B, C * k_total, o_total), dtype=x.dtype, device=device)
     if result.numel() == 0:
         return result
-    strides = (nat.ctypes.c_int64 * x.dim())(*x.stride())
-    with torch.cuda.device(device):
+    strides = None if x.is_contiguous() else (nat.ctypes.c_int64 * x.dim())(*x.stride())
+    with _on_device(device):
         st = nat.lib().einconv_unfold(
-            x.data_ptr(), strides, result.data_ptr(), nat.dtype_code(x.dtype), g, nat.stream_ptr(device)
+            x.data_ptr(), strides, result.data_ptr(), plan.code, g, nat.stream_ptr(device)
         )
     nat.check(st, "einconv_unfold")
     return result
@@ -181,16 +277,15 @@ def conv_forward_raw(x, weight, bias, stride, padding, dilation, groups, simplif
     x, weight = x.contiguous(), weight.contiguous()
     bias = None if bias is None else bias.contiguous()
     B, c_out = x.shape[0], weight.shape[0]
-    g, _, out = _geom(
-        B, groups, weight.shape[1], c_out // groups, x.shape[2:], tuple(weight.shape[2:]),
-        stride, padding, dilation,
-    )
+    plan = call_plan(nat.OP_CONV_FWD, B, groups, weight.shape[1], c_out // groups, x.shape[2:],
+                     tuple(weight.shape[2:]), stride, padding, dilation, dtype, simplify)
+    g, out = plan.geom, plan.out
     y = torch.empty((B, c_out, *out), dtype=dtype, device=device)
     if y.numel() == 0:
         return y
-    code, math, kern = nat.dtype_code(dtype), _math_for(dtype), _kernels_for(simplify)
-    ws, ws_bytes = _workspace(nat.OP_CONV_FWD, g, code, math, kern, device)
-    with torch.cuda.device(device):
+    code, math, kern = plan.code, plan.math, plan.kern
+    ws, ws_bytes = plan.workspace(device)
+    with _on_device(device):
         st = nat.lib().einconv_conv_fwd(
             x.data_ptr(), weight.data_ptr(), nat.ptr(bias), y.data_ptr(), code, g, math, kern,
             nat.ptr(ws), ws_bytes, nat.stream_ptr(device),
@@ -207,9 +302,9 @@ def conv_input_vjp_raw(weight, v, input_size, stride, padding, dilation, groups,
     t_input = _tuple(input_size if isinstance(input_size, int) else tuple(input_size), N)
     B, c_out = v.shape[0], weight.shape[0]
     c_in_g = weight.shape[1]
-    g, _, out = _geom(
-        B, groups, c_in_g, c_out // groups, t_input, tuple(weight.shape[2:]), stride, padding, dilation
-    )
+    plan = call_plan(nat.OP_CONV_INPUT_VJP, B, groups, c_in_g, c_out // groups, t_input, tuple(weight.shape[2:]),
+                     stride, padding, dilation, dtype, simplify)
+    g, out = plan.geom, plan.out
     if tuple(v.shape[2:]) != tuple(out) or v.shape[1] != c_out:
         raise ValueError(
             f"Cotangent has shape {tuple(v.shape)}, expected {(B, c_out, *out)} for this geometry."
@@ -219,9 +314,9 @@ def conv_input_vjp_raw(weight, v, input_size, stride, padding, dilation, groups,
         return gx
     if v.numel() == 0:
         return gx.zero_()
-    code, math, kern = nat.dtype_code(dtype), _math_for(dtype), _kernels_for(simplify)
-    ws, ws_bytes = _workspace(nat.OP_CONV_INPUT_VJP, g, code, math, kern, device)
-    with torch.cuda.device(device):
+    code, math, kern = plan.code, plan.math, plan.kern
+    ws, ws_bytes = plan.workspace(device)
+    with _on_device(device):
         st = nat.lib().einconv_conv_input_vjp(
             weight.data_ptr(), v.data_ptr(), gx.data_ptr(), code, g, math, kern,
             nat.ptr(ws), ws_bytes, nat.stream_ptr(device),
@@ -236,9 +331,9 @@ def conv_weight_vjp_raw(x, v, kernel_size, dilation, padding, stride, groups, si
     x, v = x.contiguous(), v.contiguous()
     N = x.dim() - 2
     B, c_in, c_out = x.shape[0], x.shape[1], v.shape[1]
-    g, t_k, out = _geom(
-        B, groups, c_in // groups, c_out // groups, x.shape[2:], kernel_size, stride, padding, dilation
-    )
+    plan = call_plan(nat.OP_CONV_WEIGHT_VJP, B, groups, c_in // groups, c_out // groups, x.shape[2:], kernel_size,
+                     stride, padding, dilation, dtype, simplify)
+    g, t_k, out = plan.geom, plan.kernel_size, plan.out
     if tuple(v.shape[2:]) != tuple(out) or v.shape[0] != B:
         raise ValueError(
             f"Cotangent has shape {tuple(v.shape)}, expected {(B, c_out, *out)} for this geometry."
@@ -246,9 +341,9 @@ def conv_weight_vjp_raw(x, v, kernel_size, dilation, padding, stride, groups, si
     gw = torch.empty((c_out, c_in // groups, *t_k), dtype=dtype, device=device)
     if gw.numel() == 0:
         return gw
-    code, math, kern = nat.dtype_code(dtype), _math_for(dtype), _kernels_for(simplify)
-    ws, ws_bytes = _workspace(nat.OP_CONV_WEIGHT_VJP, g, code, math, kern, device)
-    with torch.cuda.device(device):
+    code, math, kern = plan.code, plan.math, plan.kern
+    ws, ws_bytes = plan.workspace(device)
+    with _on_device(device):
         st = nat.lib().einconv_conv_weight_vjp(
             x.data_ptr(), v.data_ptr(), gw.data_ptr(), code, g, math, kern,
             nat.ptr(ws), ws_bytes, nat.stream_ptr(device),
@@ -263,7 +358,9 @@ def _factor(op: int, x, kernel_size, stride, padding, dilation, groups, simplify
     B, c_in = x.shape[0], x.shape[1]
     if c_in % groups != 0:
         raise ValueError(f"Groups ({groups}) must divide in_channels ({c_in}).")
-    g, t_k, out = _geom(B, groups, c_in // groups, 0, x.shape[2:], kernel_size, stride, padding, dilation)
+    plan = call_plan(op, B, groups, c_in // groups, 0, x.shape[2:], kernel_size, stride, padding, dilation, x.dtype,
+                     simplify)
+    g, t_k, out = plan.geom, plan.kernel_size, plan.out
     k_total = 1
     for k in t_k:
         k_total *= k
@@ -289,10 +386,10 @@ def _factor(op: int, x, kernel_size, stride, padding, dilation, groups, simplify
         result = dest
     if result.numel() == 0:
         return result
-    code, math, kern = nat.dtype_code(x.dtype), _math_for(x.dtype), _kernels_for(simplify)
-    ws, ws_bytes = _workspace(op, g, code, math, kern, device)
+    code, math, kern = plan.code, plan.math, plan.kern
+    ws, ws_bytes = plan.workspace(device)
     fn = nat.lib().einconv_kfc if op == nat.OP_KFC else nat.lib().einconv_kfac_reduce
-    with torch.cuda.device(device):
+    with _on_device(device):
         st = fn(
             x.data_ptr(), result.data_ptr(), code, g, float(scale), math, kern,
             nat.ptr(ws), ws_bytes, nat.stream_ptr(device),

@@ -63,10 +63,9 @@ class ConvNd(Module):
         self.dilation = _tuple(dilation, N)
         self.groups = groups
 
-        factory = dict(
-            device=torch.device("cpu") if device is None else device,
-            dtype=torch.float32 if dtype is None else dtype,
-        )
+        # None passes through to torch.empty like in the reference and torch.nn.Conv: torch.set_default_dtype,
+        # set_default_device and meta / device contexts then apply (modules/conv.py:108 of the reference)
+        factory = dict(device=device, dtype=dtype)
         self.weight = Parameter(
             torch.empty((out_channels, in_channels // groups, *self.kernel_size), **factory)
         )

@@ -346,3 +346,42 @@ def test_geometry_struct_roundtrip():
     assert p_left == (1, 1) and out == (9, 8)
     g = nat.make_geom(2, 1, 3, 4, t_in, t_k, t_s, t_d, p_left, out)
     assert g.n_dims == 2 and list(g.out)[:2] == [9, 8] and list(g.pad_left)[:2] == [1, 1]
+
+
+# =============================================================================================
+# call-plan cache (tensor-free planning, cached per geometry)
+# =============================================================================================
+def test_call_plan_cache_hits_and_keys():
+    """Same (op, geometry, dtype, math, kernel family) -> the same plan object; anything else -> a new one.
+    Needs the shared library (for the workspace query) but no GPU."""
+    from einconv_b200 import _native as nat
+    from einconv_b200 import evaluator
+
+    evaluator.clear_plan_cache()
+    args = (nat.OP_CONV_FWD, 4, 1, 8, 8, (12, 12), (3, 3), 1, 1, 1, torch.float32)
+    a = evaluator.call_plan(*args)
+    b = evaluator.call_plan(*args)
+    assert a is b and evaluator.plan_cache_info() == {"hits": 1, "misses": 1, "size": 1}
+    assert tuple(a.out) == (12, 12) and a.geom.n_dims == 2 and a.ws_bytes >= 0
+    # list-valued hyper-parameters hash like tuples; 'same' padding is a different key with the same geometry
+    c = evaluator.call_plan(nat.OP_CONV_FWD, 4, 1, 8, 8, (12, 12), [3, 3], 1, 1, 1, torch.float32)
+    assert c is a
+    d = evaluator.call_plan(nat.OP_CONV_FWD, 4, 1, 8, 8, (12, 12), (3, 3), 1, "same", 1, torch.float32)
+    assert d is not a and tuple(d.out) == (12, 12)
+    e = evaluator.call_plan(nat.OP_CONV_FWD, 4, 1, 8, 8, (12, 12), (3, 3), 1, 1, 1, torch.float32, False)
+    assert e is not a and e.kern == nat.KERNELS_GENERIC
+    # the math mode is part of the key
+    evaluator.set_fp32_math("tf32")
+    try:
+        f = evaluator.call_plan(*args)
+        assert f is not a and f.math == nat.MATH_TF32
+    finally:
+        evaluator.set_fp32_math("auto")
+    # invalid geometries raise every time and are never cached
+    size = evaluator.plan_cache_info()["size"]
+    for _ in range(2):
+        with pytest.raises(RuntimeError):
+            evaluator.call_plan(nat.OP_CONV_FWD, 1, 1, 1, 1, (2, 2), (5, 5), 1, 0, 1, torch.float32)
+    assert evaluator.plan_cache_info()["size"] == size
+    assert isinstance(a.kernel, str) and a.kernel
+    evaluator.clear_plan_cache()
