@@ -2,19 +2,27 @@
 """Benchmark of the einconv hot path on B200 (see BASELINE.md for workloads and algorithmic work).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload unfold|conv_fwd|depthwise|weight_vjp|factors]
-                    [--impl ours|reference] [--no-suite]
+                    [--impl ours|reference] [--no-suite] [--no-cpu-baseline]
 
 Prints ONE JSON line.  The headline workload is BASELINE.json ``configs[1]`` (C2: unfoldNd 3-d,
 N=16 C=32 16x56x56 k=3 stride=2 dilation=2, fp32, bit-exact gather) with metric "unfoldNd HBM GB/s"
 = algorithmic bytes (249.97 MB per call: 224.28 MB written + 25.69 MB compulsory read) / time.
-A "step" is one call over one synthetic batch.  ``value`` is timed with CUDA events on the launch
-stream with inputs resident in HBM and L2 flushed between steps; ``e2e`` is the same call through
-``einconv_b200.functionals`` with HOST (pinned) buffers, host<->device copies inside the timed
-region.  ``suite`` carries the other BASELINE configs measured the same way (kernel-only).
+A "step" is one call over one synthetic batch.
+
+* ``value``: CUDA events on the launch stream, inputs resident in HBM, L2 flushed between steps.
+* ``e2e``: the same call through the public API with HOST (pinned) buffers — the host->device copy
+  of the inputs and the device->host copy of the result are inside the timed region.
+* ``roofline``: algorithmic bytes / flops over the measured time against MEASURED_PEAKS.json (HBM,
+  bf16) and a TF32 cuBLAS peak measured live in this run; ``traffic`` from the committed ncu captures.
+* ``cpu_baseline``: the reference's own CPU einsum path (``oracle/_ref`` = the unmodified reference,
+  byte-compiled; falls back to the port ``oracle/einsum_port.py`` if it was not built) on the box's
+  host cores, on a bounded sample of the same workload.
+* ``suite``: the other BASELINE configs (C1, C3, C4, C5), each with the same four measurements.
+
 With ``--gpus N`` (launched by torchrun) every rank runs the workload on its own batch shard
-("weak" scaling; the factor workload adds the NCCL all-reduce of SURVEY.md 8e) and the time is the
-max over ranks.  ``--impl reference`` times the reference's CPU algorithm (oracle/einsum_port.py:
-one-hot patterns + torch.einsum) on the host cores for the same workload and metric.
+("weak" scaling); the factor workload splits a fixed batch of 256 and adds the exchange step of
+SURVEY.md 8e.  Times are the max over ranks.  ``--impl reference`` times the reference's CPU path
+on the full C2 batch with every host thread.
 """
 
 import argparse
@@ -47,20 +55,106 @@ RESNET50_LAYERS = [
 ]
 
 
-PEAK_TF32_MEASURED = 734.7  # TFLOP/s
-
-
 def peaks():
     path = ROOT / "MEASURED_PEAKS.json"
     if path.exists():
         p = json.loads(path.read_text())
         return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained"),
-                    source="measured")
-    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+                    source="MEASURED_PEAKS.json")
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+_TF32_PEAK = {}
+
+
+def tf32_peak(device):
+    """Dense TF32 throughput of THIS box, measured like MEASURED_PEAKS.json's bf16 figure:
+    torch.matmul fp32 with allow_tf32, 8192^3, best of 10, CUDA events."""
+    key = str(device)
+    if key not in _TF32_PEAK:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            n = 8192
+            a = torch.randn(n, n, device=device)
+            b = torch.randn(n, n, device=device)
+            for _ in range(3):
+                a @ b
+            best = None
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                a @ b
+                e1.record()
+                e1.synchronize()
+                t = e0.elapsed_time(e1)
+                best = t if best is None else min(best, t)
+            _TF32_PEAK[key] = 2 * n**3 / (best * 1e-3) / 1e12
+            del a, b
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        torch.cuda.empty_cache()
+    return _TF32_PEAK[key]
 
 
 # ------------------------------------------------------------------------------------------------
-# workloads: build(device, batch_scale) -> dict(run=callable, unit, work per step, ...)
+# the reference's CPU path (oracle/_ref = unmodified reference; oracle/einsum_port.py = port)
+# ------------------------------------------------------------------------------------------------
+class ReferenceCPU:
+    """Uniform front over the reference's public API for the five workloads."""
+
+    def __init__(self):
+        from oracle import ref_build
+
+        self.pkg = ref_build.load()
+        self.kind = "reference" if self.pkg is not None else "port"
+        if self.pkg is not None:
+            import importlib
+
+            self.F = importlib.import_module("einconv.functionals")
+            self.E = {n: importlib.import_module(f"einconv.expressions.{n}")
+                      for n in ("convNd_input_vjp", "convNd_weight_vjp", "convNd_kfc", "convNd_kfac_reduce")}
+        else:
+            from oracle import einsum_port
+
+            self.port = einsum_port
+        self.source = ("oracle/_ref (unmodified reference, byte-compiled; torch.einsum on the host cores)"
+                       if self.pkg is not None else "oracle/einsum_port.py (port of the reference's einsum path)")
+
+    def _expr(self, name, *args, **kw):
+        eq, ops, shape = self.E[name].einsum_expression(*args, **kw)
+        return torch.einsum(eq, *ops).reshape(shape)
+
+    def unfold(self, x, **kw):
+        return self.F.unfoldNd(x, **kw) if self.pkg else self.port.unfoldNd(x, **kw)
+
+    def conv(self, x, w, **kw):
+        return self.F.convNd(x, w, **kw) if self.pkg else self.port.convNd(x, w, **kw)
+
+    def input_vjp(self, w, v, input_size, **kw):
+        if self.pkg:
+            return self._expr("convNd_input_vjp", w, v, input_size, **kw)
+        return self.port.evaluate(self.port.input_vjp_expression(w, v, input_size, **kw))
+
+    def weight_vjp(self, x, v, k, **kw):
+        if self.pkg:
+            return self._expr("convNd_weight_vjp", x, v, k, **kw)
+        return self.port.evaluate(self.port.weight_vjp_expression(x, v, k, **kw))
+
+    def kfc(self, x, k, **kw):
+        if self.pkg:
+            return self._expr("convNd_kfc", x, k, **kw)
+        return self.port.evaluate(self.port.kfc_expression(x, k, **kw))
+
+    def kfac_reduce(self, x, k, **kw):
+        if self.pkg:
+            return self._expr("convNd_kfac_reduce", x, k, **kw)
+        return self.port.evaluate(self.port.kfac_reduce_expression(x, k, **kw))
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
 # ------------------------------------------------------------------------------------------------
 class Workload:
     name = ""
@@ -69,6 +163,9 @@ class Workload:
     bound = "hbm"
     dtype = "f32"
     fp32_math = "fp32"  # how fp32 contractions run: "fp32" (CUDA cores, exact) or "tf32" (tcgen05)
+    graph = None
+    graph_launches = 0
+    ncu_profiles = ()   # committed ncu --set full summaries whose DRAM bytes make up `roofline.traffic`
 
     def setup(self, device, seed=0):
         raise NotImplementedError
@@ -79,12 +176,6 @@ class Workload:
     def work(self):
         """Algorithmic units per step (bytes for GB/s metrics, flops for TFLOP/s, factors)."""
         raise NotImplementedError
-
-    def host_inputs(self):
-        return []
-
-    graph = None
-    graph_launches = 0
 
     def capture(self, body):
         """Capture `body` (public API calls on fixed buffers) in a CUDA graph: a step of a few ~10 us
@@ -107,8 +198,26 @@ class Workload:
         torch.cuda.current_stream().wait_stream(side)
         self.graph = g
 
-    def e2e_step(self, dev_inputs):
+    # ---- end to end: host buffers in, host buffers out, through the public API -----------------
+    def e2e_setup(self, device):
         raise NotImplementedError
+
+    def e2e_step(self, device):
+        """One call with pinned host inputs and outputs; returns (h2d bytes, d2h bytes)."""
+        raise NotImplementedError
+
+    # ---- the reference on the host cores --------------------------------------------------------
+    def cpu_run(self, ref):
+        """Returns (seconds, algorithmic units processed, description of the bounded sample)."""
+        raise NotImplementedError
+
+
+def _pinned(t):
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+def _nbytes(*tensors):
+    return sum(t.numel() * t.element_size() for t in tensors)
 
 
 class UnfoldC2(Workload):
@@ -118,14 +227,16 @@ class UnfoldC2(Workload):
     bound = "hbm"
     shape = (16, 32, 16, 56, 56)
     kw = dict(kernel_size=3, dilation=2, padding=0, stride=2)
+    ncu_profiles = ("profiles/r01_unfold_c2_ncu_full_v10_tma.txt",)
 
     def setup(self, device, seed=0):
-        from einconv_b200.functionals import unfoldNd
-
         torch.manual_seed(seed)
-        self.fn = unfoldNd
-        self.x_host = torch.rand(*self.shape).pin_memory() if device.type == "cuda" else torch.rand(*self.shape)
-        self.x = self.x_host.to(device)
+        self.x_host = _pinned(torch.rand(*self.shape))
+        if device.type == "cuda":
+            from einconv_b200.functionals import unfoldNd
+
+            self.fn = unfoldNd
+            self.x = self.x_host.to(device)
         self.out = None
 
     def step(self):
@@ -160,25 +271,21 @@ class UnfoldC2(Workload):
             best = t if best is None else min(best, t)
         return best
 
-    def e2e(self, device, out_host):
+    def e2e_setup(self, device):
+        self.out_host = torch.empty(16, 864, 4056).pin_memory()
+
+    def e2e_step(self, device):
         # public host-buffer API: batch chunks alternate between two streams so that uploads and the
         # gather overlap the (dominant) download of the previous chunk
         from einconv_b200.functionals import unfoldNd_host
 
-        unfoldNd_host(self.x_host, out=out_host, device=device, **self.kw)
-        return self.x_host.numel() * 4, out_host.numel() * 4
+        unfoldNd_host(self.x_host, out=self.out_host, device=device, **self.kw)
+        return _nbytes(self.x_host), _nbytes(self.out_host)
 
-    def e2e_out(self):
-        return torch.empty(16, 864, 4056).pin_memory()
-
-    def cpu_run(self, frac=1.0):
-        from oracle import einsum_port
-
-        n = max(1, int(round(16 * frac)))
-        x = self.x_host[:n]
+    def cpu_run(self, ref):
         t0 = time.perf_counter()
-        einsum_port.unfoldNd(x, 3, dilation=2, padding=0, stride=2)
-        return time.perf_counter() - t0, self.work() * n / 16, f"{n}/16 samples of the C2 batch"
+        ref.unfold(self.x_host, **self.kw)
+        return time.perf_counter() - t0, self.work(), "the full C2 batch (16/16 samples), simplify=True"
 
 
 class ConvFwdC1(Workload):
@@ -186,18 +293,20 @@ class ConvFwdC1(Workload):
     metric = "convNd fwd TFLOP/s"
     unit = "TFLOP/s"
     bound = "tensor"
-
-    def setup(self, device, seed=0):
-        from einconv_b200.functionals import convNd
-
-        torch.manual_seed(seed)
-        self.fn = convNd
-        self.x = torch.rand(32, 64, 56, 56).to(device)
-        self.w = torch.rand(64, 64, 3, 3).to(device)
-        self.capture(self._calls)
-
     dtype = "f32 (tf32 MMA, fp32 accumulate)"
     fp32_math = "tf32"
+    ncu_profiles = ("profiles/r01_conv_fwd_c1_ncu_full_v3.txt",)
+
+    def setup(self, device, seed=0):
+        torch.manual_seed(seed)
+        self.x_host = _pinned(torch.rand(32, 64, 56, 56))
+        self.w_host = _pinned(torch.rand(64, 64, 3, 3))
+        if device.type == "cuda":
+            from einconv_b200.functionals import convNd
+
+            self.fn = convNd
+            self.x, self.w = self.x_host.to(device), self.w_host.to(device)
+            self.capture(self._calls)
 
     def _calls(self):
         self.out = self.fn(self.x, self.w, padding=1)
@@ -208,31 +317,56 @@ class ConvFwdC1(Workload):
         else:
             self._calls()
 
+    def eager_step(self):
+        self._calls()
+
     def work(self):
         return 2 * 32 * 64 * 64 * 9 * 56 * 56
 
+    def bytes_algorithmic(self):
+        return (2 * 32 * 64 * 56 * 56 + 64 * 64 * 9) * 4
+
+    def e2e_setup(self, device):
+        self.y_host = torch.empty(32, 64, 56, 56).pin_memory()
+
+    def e2e_step(self, device):
+        x = self.x_host.to(device, non_blocking=True)
+        w = self.w_host.to(device, non_blocking=True)
+        self.y_host.copy_(self.fn(x, w, padding=1), non_blocking=True)
+        return _nbytes(self.x_host, self.w_host), _nbytes(self.y_host)
+
+    def cpu_run(self, ref):
+        t0 = time.perf_counter()
+        ref.conv(self.x_host, self.w_host, padding=1)
+        return time.perf_counter() - t0, self.work(), "the full C1 batch (32/32 samples), fp32, simplify=True"
+
 
 class DepthwiseC3(Workload):
-    name = "C3 depthwise 2d fwd + input VJP N=32 C=256 28x28 k3 p1 fp32 (step = one CUDA-graph replay of the two calls, forked streams)"
+    name = ("C3 depthwise 2d fwd + input VJP N=32 C=256 28x28 k3 p1 fp32 (step = one CUDA-graph replay of the two "
+            "calls, forked streams)")
     metric = "depthwise fwd+input-VJP HBM GB/s"
     unit = "GB/s"
     bound = "hbm"
+    ncu_profiles = ("profiles/r01_depthwise_c3_ncu_full_v5_vec4_nr6.txt",)
+    traffic_launches = 2  # the step is two launches of the profiled kernel
 
     def setup(self, device, seed=0):
-        from einconv_b200 import evaluator
-        from einconv_b200.functionals import convNd
-
         torch.manual_seed(seed)
-        self.fwd, self.vjp = convNd, evaluator.conv_input_vjp_raw
-        self.x = torch.rand(32, 256, 28, 28).to(device)
-        self.w = torch.rand(256, 1, 3, 3).to(device)
-        self.v = torch.rand(32, 256, 28, 28).to(device)
-        self.side = None
-        self.capture(self._calls)
+        self.x_host = _pinned(torch.rand(32, 256, 28, 28))
+        self.w_host = _pinned(torch.rand(256, 1, 3, 3))
+        self.v_host = _pinned(torch.rand(32, 256, 28, 28))
+        if device.type == "cuda":
+            from einconv_b200 import evaluator
+            from einconv_b200.functionals import convNd
+
+            self.fwd, self.vjp = convNd, evaluator.conv_input_vjp_raw
+            self.x, self.w, self.v = self.x_host.to(device), self.w_host.to(device), self.v_host.to(device)
+            self.side = None
+            self.capture(self._calls)
 
     def _calls(self):
         # the two directions are independent: the input VJP runs on a forked stream, so that inside the
-        # captured graph the two ~12 us kernels overlap instead of queueing behind each other
+        # captured graph the two ~10 us kernels overlap instead of queueing behind each other
         cur = torch.cuda.current_stream()
         if self.side is None:
             self.side = torch.cuda.Stream()
@@ -248,9 +382,32 @@ class DepthwiseC3(Workload):
         else:
             self._calls()
 
+    def eager_step(self):
+        # plain user code: two calls on the current stream
+        self.gx = self.vjp(self.w, self.v, (28, 28), 1, 1, 1, 256)
+        self.y = self.fwd(self.x, self.w, padding=1, groups=256)
+
     def work(self):
         one = 2 * 32 * 256 * 28 * 28 * 4 + 256 * 9 * 4
         return 2 * one
+
+    def e2e_setup(self, device):
+        self.y_host = torch.empty(32, 256, 28, 28).pin_memory()
+        self.gx_host = torch.empty(32, 256, 28, 28).pin_memory()
+
+    def e2e_step(self, device):
+        x = self.x_host.to(device, non_blocking=True)
+        w = self.w_host.to(device, non_blocking=True)
+        v = self.v_host.to(device, non_blocking=True)
+        self.y_host.copy_(self.fwd(x, w, padding=1, groups=256), non_blocking=True)
+        self.gx_host.copy_(self.vjp(w, v, (28, 28), 1, 1, 1, 256), non_blocking=True)
+        return _nbytes(self.x_host, self.w_host, self.v_host), _nbytes(self.y_host, self.gx_host)
+
+    def cpu_run(self, ref):
+        t0 = time.perf_counter()
+        ref.conv(self.x_host, self.w_host, padding=1, groups=256)
+        ref.input_vjp(self.w_host, self.v_host, (28, 28), padding=1, groups=256)
+        return time.perf_counter() - t0, self.work(), "the full C3 batch (32/32 samples), both directions"
 
 
 class WeightVjpC4(Workload):
@@ -259,20 +416,44 @@ class WeightVjpC4(Workload):
     unit = "TFLOP/s"
     bound = "tensor"
     dtype = "bf16"
+    # main kernel + the two channels-last packing launches (x and v) that precede it in every call
+    ncu_profiles = ("profiles/r01_wgrad_c4_ncu_full_v3_quad.txt", "profiles/r01_pack_channels_last_c4_ncu_full_v3_vec4.txt",
+                    "profiles/r01_pack_channels_last_c4_ncu_full_v3_vec4.txt")
 
     def setup(self, device, seed=0):
-        from einconv_b200 import evaluator
-
         torch.manual_seed(seed)
-        self.fn = evaluator.conv_weight_vjp_raw
-        self.x = torch.rand(8, 64, 16, 112, 112).bfloat16().to(device)
-        self.v = torch.rand(8, 64, 16, 112, 112).bfloat16().to(device)
+        self.x_host = _pinned(torch.rand(8, 64, 16, 112, 112).bfloat16())
+        self.v_host = _pinned(torch.rand(8, 64, 16, 112, 112).bfloat16())
+        if device.type == "cuda":
+            from einconv_b200 import evaluator
+
+            self.fn = evaluator.conv_weight_vjp_raw
+            self.x, self.v = self.x_host.to(device), self.v_host.to(device)
 
     def step(self):
         self.out = self.fn(self.x, self.v, 3, 1, 1, 1, 1)
 
     def work(self):
         return 2 * 8 * 64 * 64 * 27 * 16 * 112 * 112
+
+    def bytes_algorithmic(self):
+        return 2 * 8 * 64 * 16 * 112 * 112 * 2 + 64 * 64 * 27 * 2
+
+    def e2e_setup(self, device):
+        self.gw_host = torch.empty(64, 64, 3, 3, 3, dtype=torch.bfloat16).pin_memory()
+
+    def e2e_step(self, device):
+        x = self.x_host.to(device, non_blocking=True)
+        v = self.v_host.to(device, non_blocking=True)
+        self.gw_host.copy_(self.fn(x, v, 3, 1, 1, 1, 1), non_blocking=True)
+        return _nbytes(self.x_host, self.v_host), _nbytes(self.gw_host)
+
+    def cpu_run(self, ref):
+        # one of the 8 samples (the reference's bf16 temporaries for N=8 need > 5 GB)
+        x, v = self.x_host[:1], self.v_host[:1]
+        t0 = time.perf_counter()
+        ref.weight_vjp(x, v, 3, padding=1)
+        return time.perf_counter() - t0, self.work() / 8, "1/8 samples of the C4 batch (full 16x112x112 volume), bf16"
 
 
 class FactorsC5(Workload):
@@ -282,37 +463,48 @@ class FactorsC5(Workload):
     metric = "KFC+KFAC-reduce factors/s"
     unit = "factors/s"
     bound = "tensor"
-    dtype = "f32 (KFC: tf32 MMA, fp32 accumulate; KFAC-reduce: fp32)"
+    dtype = "f32 (KFC: tf32 / scaled-fp16 MMA, fp32 accumulate; KFAC-reduce: fp32 sums + tf32 MMA)"
     fp32_math = "tf32"
+    ncu_profiles = ()
 
     def __init__(self, world=1, rank=0, global_batch=256):
         self.world, self.rank, self.global_batch = world, rank, global_batch
 
+    @staticmethod
+    def layer_input(n, c, h, lo, hi, device="cpu"):
+        """Samples [lo, hi) of the synthetic input of distinct geometry `n`: every sample has its own seed, so
+        any rank (and the parity check) can draw any slice of the global batch of 256."""
+        gen = torch.Generator(device="cpu")
+        out = torch.empty(hi - lo, c, h, h)
+        for i in range(lo, hi):
+            gen.manual_seed(1000 * n + i)
+            out[i - lo] = torch.rand(c, h, h, generator=gen)
+        return out.to(device)
+
     def setup(self, device, seed=0):
         from einconv_b200 import distributed as D
+        from einconv_b200 import evaluator
 
         self.D = D
         lo, hi = D.shard_bounds(self.global_batch, self.world, self.rank)
-        self.local = hi - lo
+        self.lo, self.hi = lo, hi
         self.inputs, self.specs, self.index = [], [], []
         for n, (c, h, k, s, p, count) in enumerate(RESNET50_LAYERS):
-            torch.manual_seed(seed + n)
             # one tensor per distinct geometry (layers sharing it see the same synthetic input)
-            x = torch.rand(self.local, c, h, h, device=device)
+            torch.manual_seed(seed * 100 + n)
+            x = torch.rand(hi - lo, c, h, h, device=device)
             self.inputs.append(x)
             self.specs.append(D.LayerSpec(kernel_size=k, stride=s, padding=p))
             self.index.append(count)
-
-        # fixed inputs -> the sweep is built once: factors written in place into flat all-reduce
-        # buckets, one CUDA graph per bucket, bucket b's all-reduce overlapping bucket b+1's compute
+        # fixed inputs -> the sweep is built once: factors written in place into flat exchange buckets, one
+        # CUDA graph per bucket, bucket b's collective overlapping bucket b+1's compute
         xs, specs = [], []
         for x, spec, count in zip(self.inputs, self.specs, self.index):
             xs += [x] * count
             specs += [spec] * count
-        from einconv_b200 import evaluator
-
         evaluator.set_fp32_math(self.fp32_math)
-        self.sweep = D.FactorSweep(xs, specs, self.global_batch, use_graphs=not os.environ.get("EINCONV_BENCH_NO_GRAPHS"))
+        self.sweep = D.FactorSweep(xs, specs, self.global_batch,
+                                   use_graphs=not os.environ.get("EINCONV_BENCH_NO_GRAPHS"))
 
     def step(self):
         self.out = self.sweep.run()
@@ -320,13 +512,62 @@ class FactorsC5(Workload):
     def work(self):
         return 106
 
-    def flops(self):
+    def flops(self, triangle=False):
         total = 0
         for c, h, k, s, p, count in RESNET50_LAYERS:
             o = (h + 2 * p - k) // s + 1
             a = c * k * k
-            total += count * 2 * self.global_batch * o * o * a * a
+            total += count * 2 * self.global_batch * o * o * (a * (a + 1) // 2 if triangle else a * a)
         return total
+
+    def e2e_setup(self, device):
+        self.x_hosts = [torch.empty(x.shape, dtype=x.dtype).pin_memory().copy_(x) for x in self.inputs]
+        out = self.sweep.run()
+        self.f_hosts = {k: [torch.empty(f.shape, dtype=f.dtype).pin_memory() for f in fs] for k, fs in out.items()}
+
+    def e2e_step(self, device):
+        for x, xh in zip(self.inputs, self.x_hosts):
+            x.copy_(xh, non_blocking=True)
+        out = self.sweep.run()
+        d2h = 0
+        for kind, fs in out.items():
+            for f, fh in zip(fs, self.f_hosts[kind]):
+                fh.copy_(f, non_blocking=True)
+                d2h += _nbytes(fh)
+        return _nbytes(*self.x_hosts), d2h
+
+    CHUNK = 2
+
+    def cpu_run(self, ref):
+        """the reference cannot run N=256 (24 GB of temporaries per layer, 370 GB for the
+        stem); it runs in batch chunks whose factors are summed.  Timed: ONE chunk of CHUNK samples through all
+        106 factors; a sweep of 256 samples is 256 / CHUNK such chunks."""
+        t_total = 0.0
+        self.cpu_chunk = []
+        for n, (c, h, k, s, p, count) in enumerate(RESNET50_LAYERS):
+            x = self.inputs[n][: self.CHUNK].cpu()
+            t0 = time.perf_counter()
+            kf = ref.kfc(x, k, stride=s, padding=p)
+            kr = ref.kfac_reduce(x, k, stride=s, padding=p)
+            t_total += (time.perf_counter() - t0) * count
+            self.cpu_chunk.append((kf, kr))
+        chunks = self.global_batch / self.CHUNK
+        return t_total * chunks, self.work(), (
+            f"one chunk of {self.CHUNK}/256 samples through all 106 factors, timed once per distinct geometry and "
+            f"multiplied by the layer count, extrapolated x{chunks:.0f} chunks (the reference cannot hold N=256)")
+
+    def chunk_parity(self):
+        """The GPU factors of the chunk the CPU baseline just computed, against those CPU results
+        (the chunk term of the chunk-summed oracle of SURVEY.md 8d).  Max error relative to max|ref|."""
+        from einconv_b200 import evaluator
+
+        worst = 0.0
+        for n, (c, h, k, s, p, count) in enumerate(RESNET50_LAYERS):
+            x = self.inputs[n][: self.CHUNK]
+            for fn, want in zip((evaluator.kfc, evaluator.kfac_reduce), self.cpu_chunk[n]):
+                got = fn(x, k, stride=s, padding=p).double().cpu()
+                worst = max(worst, float((got - want.double()).abs().max() / want.double().abs().max()))
+        return worst
 
 
 WORKLOADS = dict(unfold=UnfoldC2, conv_fwd=ConvFwdC1, depthwise=DepthwiseC3, weight_vjp=WeightVjpC4,
@@ -384,13 +625,14 @@ def flush_l2(buf):
     buf[half:].sum()
 
 
-def time_steps(wl, steps, warmup, device, flush=True):
+def time_steps(wl, steps, warmup, device, flush=True, step=None):
     """Per-step CUDA-event timing on the current stream; returns (list of ms, launches per step)."""
     from einconv_b200 import _native as nat
 
+    step = step or wl.step
     buf = torch.zeros(512 << 20, dtype=torch.uint8, device=device).view(torch.int32) if flush else None
     for _ in range(warmup):
-        wl.step()
+        step()
     torch.cuda.synchronize(device)
     times = []
     launches0 = nat.launch_count()
@@ -400,16 +642,17 @@ def time_steps(wl, steps, warmup, device, flush=True):
         start = torch.cuda.Event(enable_timing=True)
         stop = torch.cuda.Event(enable_timing=True)
         start.record()
-        wl.step()
+        step()
         stop.record()
         stop.synchronize()
         times.append(start.elapsed_time(stop))
     launches = (nat.launch_count() - launches0) / max(1, steps)
-    if getattr(wl, "graph", None) is not None:
-        launches += wl.graph_launches  # replayed from the workload's CUDA graph
-    sweep = getattr(wl, "sweep", None)
-    if sweep is not None and getattr(sweep, "_graphs", None) is not None:
-        launches += sweep.launches_per_run  # kernels replayed from CUDA graphs are not counted by the library
+    if step == wl.step:
+        if getattr(wl, "graph", None) is not None:
+            launches += wl.graph_launches  # replayed from the workload's CUDA graph
+        sweep = getattr(wl, "sweep", None)
+        if sweep is not None and getattr(sweep, "_graphs", None) is not None:
+            launches += sweep.launches_per_run  # kernels replayed from CUDA graphs are not counted by the library
     return times, launches
 
 
@@ -422,80 +665,113 @@ def to_value(wl, ms, n_units=1):
     return wl.work() / (ms * 1e-3)  # factors/s: the sweep is shared by all ranks
 
 
-# ncu --set full captures of the dominant kernel of each workload (summaries committed under profiles/)
-NCU_PROFILES = {
-    "unfold": "profiles/r01_unfold_c2_ncu_full_v10_tma.txt",
-    "depthwise": "profiles/r01_depthwise_c3_ncu_full_v5_vec4_nr6.txt",
-    "conv_fwd": "profiles/r01_conv_fwd_c1_ncu_full_v3.txt",
-    "weight_vjp": "profiles/r01_wgrad_c4_ncu_full_v3_quad.txt",
-}
-
-
-def ncu_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the workload's dominant kernel,
-    read from the committed ncu summary; None if there is no capture."""
-    rel = NCU_PROFILES.get(workload)
-    if not rel or not (ROOT / rel).exists():
-        return None
+def ncu_traffic(wl):
+    """Sum over the workload's committed ncu captures of dram__bytes_read.sum + dram__bytes_write.sum
+    (bytes per launch): every kernel of one step, not just the dominant one.  None without captures."""
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    total, seen = 0.0, 0
-    for line in (ROOT / rel).read_text().splitlines():
-        parts = line.split()
-        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and seen < 2:
-            total += float(parts[1]) * scale.get(parts[2], 1.0)
-            seen += 1
-    return dict(bytes=total, source=rel) if seen == 2 else None
+    total, sources = 0.0, []
+    for rel in wl.ncu_profiles:
+        if not (ROOT / rel).exists():
+            return None
+        seen = 0
+        for line in (ROOT / rel).read_text().splitlines():
+            parts = line.split()
+            if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and seen < 2:
+                total += float(parts[1]) * scale.get(parts[2], 1.0)
+                seen += 1
+        if seen != 2:
+            return None
+        sources.append(rel)
+    if not sources:
+        return None
+    total *= getattr(wl, "traffic_launches", 1)
+    return dict(bytes=total, source=" + ".join(sources))
 
 
-def roofline(wl, ms_kernel, pk):
-    r = _roofline(wl, ms_kernel, pk)
-    key = next((k for k, c in WORKLOADS.items() if isinstance(wl, c)), None)
-    t = ncu_traffic(key)
+def roofline(wl, ms, pk, device, n_gpus=1):
+    """`ms` = time of one step of ONE rank; the peak is one GPU's, so a per-rank figure goes in."""
+    if wl.bound == "hbm":
+        achieved = wl.work() / (ms * 1e-3) / 1e9
+        r = dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"],
+                 traffic=None, peak_source=pk["source"])
+    else:
+        # per-GPU share of the algorithmic flops (the factor sweep splits a fixed batch over the ranks)
+        flops = (wl.flops() / n_gpus) if hasattr(wl, "flops") else wl.work()
+        achieved = flops / (ms * 1e-3) / 1e12
+        r = dict(bound="tensor", achieved=achieved, peak=pk["bf16"], unit="TFLOP/s", frac=achieved / pk["bf16"],
+                 traffic=None, peak_source=pk["source"], per_gpu=True,
+                 note="peak = measured dense bf16 cuBLAS of one GPU; achieved = this rank's share of the algorithmic "
+                      "flops / its step time")
+        if wl.fp32_math == "tf32":
+            r["peak_tf32"] = tf32_peak(device)
+            r["peak_tf32_source"] = "measured live in this run: torch.matmul fp32 allow_tf32 8192^3, best of 10, CUDA events"
+            r["frac_tf32"] = achieved / r["peak_tf32"]
+        if hasattr(wl, "flops"):
+            tri = wl.flops(triangle=True) / n_gpus / (ms * 1e-3) / 1e12
+            r["flop_convention"] = ("achieved counts the FULL A x A GEMM of every KFC factor (what the reference "
+                                    "computes); the kernels compute only the upper triangle tiles and mirror them")
+            r["achieved_triangle_flops"] = tri
+            r["frac_triangle_tf32"] = tri / r["peak_tf32"]
+        if hasattr(wl, "bytes_algorithmic"):
+            r["algorithmic_bytes"] = wl.bytes_algorithmic()
+    t = ncu_traffic(wl)
     if t:
         r["traffic"] = t["bytes"]
-        r["traffic_source"] = t["source"] + " (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        r["traffic_source"] = t["source"] + " (dram__bytes_read.sum + dram__bytes_write.sum per launch, every kernel of the step)"
     return r
 
 
-def _roofline(wl, ms_kernel, pk):
-    if wl.bound == "hbm":
-        achieved = wl.work() / (ms_kernel * 1e-3) / 1e9
-        return dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"],
-                    traffic=None, peak_source=pk["source"])
-    flops = wl.flops() if hasattr(wl, "flops") else wl.work()
-    achieved = flops / (ms_kernel * 1e-3) / 1e12
-    r = dict(bound="tensor", achieved=achieved, peak=pk["bf16"], unit="TFLOP/s", frac=achieved / pk["bf16"],
-             traffic=None, peak_source=pk["source"],
-             note="peak = measured dense bf16 cuBLAS; fp32 runs on CUDA cores / tf32 at half that rate")
-    if wl.fp32_math == "tf32":
-        # dense TF32 cuBLAS on this pool's B200 (scripts/measure_tf32_peak.py, 4096^3, best of 5 x 10)
-        r["peak_tf32"] = PEAK_TF32_MEASURED
-        r["frac_tf32"] = achieved / PEAK_TF32_MEASURED
-    return r
+def config_for(wl, world):
+    return dict(workload=wl.name,
+                l2="flushed between steps (256 MiB write + 256 MiB read, outside the timed events)",
+                timing="CUDA events per step on the launch stream, max over ranks",
+                parallelism=f"batch shards x{world}, no collective" if not isinstance(wl, FactorsC5)
+                else f"batch 256 split x{world}, KFC all-reduce + KFAC-reduce all-gather over NCCL")
+
+
+def measure_cpu(wl, ref, repeats=3):
+    """Median of `repeats` runs after one warm-up (workloads whose sample is long run once)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    t, units, sample = wl.cpu_run(ref)  # warm-up (builds the index patterns' caches, if any)
+    if t < 5.0:
+        runs = [wl.cpu_run(ref) for _ in range(repeats)]
+        t = statistics.median(r[0] for r in runs)
+        sample += f", median of {repeats} after 1 warm-up"
+    else:
+        sample += ", single run"
+    if wl.unit == "GB/s":
+        value = units / t / 1e9
+    elif wl.unit == "TFLOP/s":
+        value = units / t / 1e12
+    else:
+        value = units / t
+    return dict(value=value, unit=wl.unit, cores=torch.get_num_threads(), kind=ref.kind,
+                sample=sample + f" ({ref.source})", seconds=t)
 
 
 def run_reference(args):
-    """The reference's CPU algorithm (oracle port) on the host cores, same workload and metric."""
+    """The reference's own CPU implementation on the host cores: full C2 batch, same metric and config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    wl = UnfoldC2()
+    ref = ReferenceCPU()
+    wl = WORKLOADS[args.workload]()
     wl.setup(torch.device("cpu"))
-    frac = 0.25  # bounded sample: 4 of the 16 batch elements per step
     for _ in range(max(1, args.warmup)):
-        wl.cpu_run(frac)
-    times, work, sample = [], 0, ""
+        wl.cpu_run(ref)
+    times, units, sample = [], 0, ""
     for _ in range(args.steps):
-        t, work, sample = wl.cpu_run(frac)
+        t, units, sample = wl.cpu_run(ref)
         times.append(t)
     ms = statistics.mean(times) * 1e3
-    value = work / (ms * 1e-3) / 1e9
+    value = units / (ms * 1e-3) / (1e9 if wl.unit == "GB/s" else 1e12 if wl.unit == "TFLOP/s" else 1)
     line = dict(
         metric=wl.metric, value=value, unit=wl.unit, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-        impl="reference", config=dict(workload=wl.name, sample=sample),
-        cpu_baseline=dict(value=value, unit=wl.unit, cores=torch.get_num_threads(), kind="port", sample=sample),
+        impl="reference", config=config_for(wl, args.gpus),
+        cpu_baseline=dict(value=value, unit=wl.unit, cores=torch.get_num_threads(), kind=ref.kind,
+                          sample=sample + f" ({ref.source})"),
         e2e=dict(value=value, unit=wl.unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         gpu_launches=0,
     )
@@ -538,86 +814,129 @@ def main():
     if world > 1:
         dist.barrier()
     from einconv_b200 import _native as nat
+    from einconv_b200 import evaluator
 
     nat.lib()
     pk = peaks()
+    ref = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = ReferenceCPU()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return ms
 
     def make(name):
         cls = WORKLOADS[name]
         return cls(world, rank) if name == "factors" else cls()
 
-    def measure(name, steps, warmup):
-        from einconv_b200 import evaluator
-
+    def measure(name, steps, warmup, sample_clocks=False):
+        """Everything about one workload: device-timed value, roofline, e2e, eager latency, cpu baseline."""
         wl = make(name)
         evaluator.set_fp32_math(wl.fp32_math)
         wl.setup(device, seed=rank)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
         times, launches = time_steps(wl, steps, warmup, device)
         clocks = sampler.stop() if sampler else None
-        ms = statistics.mean(times)
-        if world > 1:
-            t = torch.tensor([ms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return wl, ms, launches, clocks, times
+        step_ms = statistics.mean(times)
+        ms = max_over_ranks(step_ms)
+        n_units = world if name != "factors" else 1
+        res = dict(wl=wl, ms=ms, launches=launches, clocks=clocks, value=to_value(wl, ms, n_units))
 
-    wl, ms, launches, clocks, times = measure(args.workload, args.steps, args.warmup)
-    n_units = world if args.workload != "factors" else 1
-    value = to_value(wl, ms, n_units)
-    # roofline of the dominant kernel: its average launch duration (CUDA events around back-to-back
-    # launches on rotating cold buffers) where the workload provides that measurement, else the per-step time
-    step_ms = statistics.mean(times)
-    kern_ms = wl.kernel_ms(device) if hasattr(wl, "kernel_ms") else None
-    if kern_ms is not None and world > 1:
-        t = torch.tensor([kern_ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        kern_ms = float(t)
-    roof = roofline(wl, kern_ms if kern_ms is not None else step_ms, pk)
-    roof["kernel_ms"] = kern_ms
-    roof["timing"] = ("8 launches back to back in one CUDA-event pair, rotating input/output buffers (2.6 GB >> L2), "
-                      "best of 3" if kern_ms is not None else "per-step CUDA events (includes the launch gap)")
-    roof["frac_per_step"] = wl.work() / (step_ms * 1e-3) / 1e9 / pk["hbm"] if wl.bound == "hbm" else None
-    if hasattr(wl, "naive_bytes"):
-        roof["achieved_naive_bytes"] = wl.naive_bytes() / ((kern_ms or step_ms) * 1e-3) / 1e9
+        # roofline of the dominant kernel: its average launch duration (CUDA events around back-to-back
+        # launches on rotating cold buffers) where the workload provides that measurement, else the step time
+        kern_ms = wl.kernel_ms(device) if hasattr(wl, "kernel_ms") else None
+        if kern_ms is not None:
+            kern_ms = max_over_ranks(kern_ms)
+        roof = roofline(wl, kern_ms if kern_ms is not None else ms, pk, device, n_gpus=world if name == "factors" else 1)
+        roof["kernel_ms"] = kern_ms
+        roof["timing"] = ("8 launches back to back in one CUDA-event pair, rotating input/output buffers (2.6 GB >> L2), "
+                          "best of 3" if kern_ms is not None else "per-step CUDA events (includes the launch gaps)")
+        if wl.bound == "hbm":
+            roof["frac_per_step"] = wl.work() / (step_ms * 1e-3) / 1e9 / pk["hbm"]
+        if hasattr(wl, "naive_bytes"):
+            roof["achieved_naive_bytes"] = wl.naive_bytes() / ((kern_ms or step_ms) * 1e-3) / 1e9
+        res["roofline"] = roof
 
-    # ---- end to end through the public API with host buffers --------------------------------
-    e2e = None
-    if hasattr(wl, "e2e"):
-        out_host = wl.e2e_out()
+        # eager (no CUDA graph) latency of the same calls through the public API, L2 flushed like the steps
+        if hasattr(wl, "eager_step"):
+            et, _ = time_steps(wl, min(steps, 10), 3, device, step=wl.eager_step)
+            res["eager_ms_per_step"] = max_over_ranks(statistics.mean(et))
+            res["plan_cache"] = evaluator.plan_cache_info()
+
+        # ---- end to end through the public API with host buffers -------------------------------
+        wl.e2e_setup(device)
         for _ in range(2):
-            wl.e2e(device, out_host)
+            wl.e2e_step(device)
         torch.cuda.synchronize(device)
         if world > 1:
             dist.barrier()
+        n_e2e = max(3, min(steps, 10))
         t0 = time.perf_counter()
         h2d = d2h = 0
-        n_e2e = max(3, min(args.steps, 10))
         for _ in range(n_e2e):
-            h2d, d2h = wl.e2e(device, out_host)
+            h2d, d2h = wl.e2e_step(device)
             torch.cuda.synchronize(device)
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
-        if world > 1:
-            t = torch.tensor([e2e_ms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t)
-        e2e = dict(value=to_value(wl, e2e_ms, n_units), unit=wl.unit, h2d_bytes_per_step=h2d,
-                   d2h_bytes_per_step=d2h, ms_per_step=e2e_ms)
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_e2e)
+        res["e2e"] = dict(value=to_value(wl, e2e_ms, n_units), unit=wl.unit, h2d_bytes_per_step=h2d,
+                          d2h_bytes_per_step=d2h, ms_per_step=e2e_ms,
+                          api="pinned host tensors -> .to(device) -> public API call -> copy into pinned host tensors, "
+                              "synchronised every step")
 
-    # ---- CPU baseline (oracle port = the reference's algorithm) on rank 0, N=1 only ----------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and hasattr(wl, "cpu_run"):
-        torch.set_num_threads(os.cpu_count() or 1)
-        wl.cpu_run(0.25)
-        runs = [wl.cpu_run(0.25) for _ in range(3)]
-        t = statistics.median(r[0] for r in runs)
-        cpu = dict(value=runs[0][1] / t / 1e9, unit=wl.unit, cores=torch.get_num_threads(), kind="port",
-                   sample=runs[0][2] + ", median of 3 after 1 warm-up (oracle/einsum_port.py)")
+        # ---- CPU baseline (the reference's own einsum path) on rank 0, N=1 only ------------------
+        res["cpu_baseline"] = None
+        if ref is not None:
+            try:
+                res["cpu_baseline"] = measure_cpu(wl, ref)
+                if hasattr(wl, "chunk_parity"):
+                    err = wl.chunk_parity()
+                    res["cpu_baseline"]["parity_checked"] = bool(err <= 1e-3)
+                    res["cpu_baseline"]["parity_max_err_rel_to_max"] = err
+                    res["cpu_baseline"]["parity_tolerance"] = 1e-3
+            except Exception as e:  # a failing baseline must not lose the GPU numbers
+                res["cpu_baseline"] = dict(error=f"{type(e).__name__}: {e}", kind=ref.kind)
+        return res
 
-    # ---- the other BASELINE configs, kernel-only, same timing rules ----------------------------
+    def factor_exchange_parity(wl):
+        """N > 1: the exchanged factors of this job against a single-GPU full-batch run on rank 0 (outside any
+        timed region).  Rank 0 re-draws every rank's shard (seed = rank * 100 + geometry) and evaluates the
+        concatenated batch of 256 with the single-process API."""
+        out = wl.sweep.run()
+        torch.cuda.synchronize(device)
+        worst, checked = 0.0, 0
+        if rank == 0:
+            layer = 0
+            for n, (c, h, k, s, p, count) in enumerate(RESNET50_LAYERS):
+                if n % 3 == 0 or c * k * k >= 2304:  # a third of the geometries plus every large factor
+                    parts = []
+                    for r in range(world):
+                        lo, hi = wl.D.shard_bounds(wl.global_batch, world, r)
+                        torch.manual_seed(r * 100 + n)
+                        parts.append(torch.rand(hi - lo, c, h, h, device=device))
+                    full = torch.cat(parts)
+                    del parts
+                    for kind, fn in (("kfc", evaluator.kfc), ("kfac_reduce", evaluator.kfac_reduce)):
+                        want = fn(full, k, stride=s, padding=p).double()
+                        got = out[kind][layer].double()
+                        worst = max(worst, float((got - want).abs().max() / want.abs().max()))
+                        checked += 1
+                    del full
+                layer += count
+        return dict(parity_checked=bool(worst <= 1e-3) if rank == 0 else None, factors_compared=checked,
+                    max_err_rel_to_max=worst, tolerance=1e-3,
+                    against="single-GPU evaluation of the concatenated batch of 256 on rank 0")
+
+    head = measure(args.workload, args.steps, args.warmup, sample_clocks=True)
+    wl = head["wl"]
+    exchange = factor_exchange_parity(wl) if (args.workload == "factors" and world > 1) else None
+
+    # ---- the other BASELINE configs, measured the same way ---------------------------------------
     suite = {}
     if not args.no_suite:
         names = [n for n in ("conv_fwd", "depthwise", "weight_vjp", "factors") if n != args.workload]
@@ -626,33 +945,45 @@ def main():
         for name in names:
             if world > 1 and name != "factors":
                 continue  # only the factor path has an exchange step; the rest is replicas
-            steps = 3 if name == "factors" else min(args.steps, 10)
+            steps = min(args.steps, 10)
             try:
-                w2, ms2, l2, _, t2 = measure(name, steps, 3)
-                entry = dict(workload=w2.name, metric=w2.metric, value=to_value(w2, ms2), unit=w2.unit,
-                             ms_per_step=ms2, gpu_launches=l2, dtype=w2.dtype,
-                             roofline=roofline(w2, statistics.mean(t2), pk))
+                torch.cuda.empty_cache()
+                r = measure(name, steps, 3)
+                w2 = r["wl"]
+                entry = dict(workload=w2.name, metric=w2.metric, value=r["value"], unit=w2.unit, steps=steps,
+                             ms_per_step=r["ms"], gpu_launches=r["launches"], dtype=w2.dtype,
+                             scaling="strong" if name == "factors" else "weak",
+                             roofline=r["roofline"], e2e=r["e2e"], cpu_baseline=r["cpu_baseline"])
+                for key in ("eager_ms_per_step", "plan_cache"):
+                    if key in r:
+                        entry[key] = r[key]
+                if name == "factors" and world > 1:
+                    entry["exchange_parity"] = factor_exchange_parity(w2)
                 suite[name] = entry
+                del r, w2
             except Exception as e:  # keep the headline line even if a suite entry fails
                 suite[name] = dict(error=f"{type(e).__name__}: {e}")
             torch.cuda.empty_cache()
 
     if rank == 0:
         line = dict(
-            metric=wl.metric, value=value, unit=wl.unit, n_gpus=world, steps=args.steps, warmup=args.warmup,
-            ms_per_step=ms, higher_is_better=True,
+            metric=wl.metric, value=head["value"], unit=wl.unit, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=head["ms"], higher_is_better=True,
             # the factor workload splits a FIXED batch of 256 over the ranks; every other workload gives
             # each rank its own full batch
             scaling="strong" if args.workload == "factors" else "weak", vs_baseline=None, dtype=wl.dtype,
-            data="synthetic",
-            config=dict(workload=wl.name, l2="flushed between steps (256 MiB write + 256 MiB read, outside the timed events)",
-                        timing="CUDA events per step on the launch stream, max over ranks",
-                        parallelism=f"batch shards x{world}, no collective" if args.workload != "factors"
-                        else f"batch 256 split x{world}, NCCL all-reduce of factors"),
-            roofline=roof, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks, suite=suite,
+            data="synthetic", config=config_for(wl, world),
+            roofline=head["roofline"], cpu_baseline=head["cpu_baseline"], e2e=head["e2e"],
+            gpu_launches=head["launches"], clocks=head["clocks"], suite=suite,
         )
+        for key in ("eager_ms_per_step", "plan_cache"):
+            if key in head:
+                line[key] = head[key]
+        if exchange is not None:
+            line["exchange_parity"] = exchange
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -168,7 +168,12 @@ def require_cuda(*tensors: torch.Tensor) -> torch.device:
 
 
 def stream_ptr(device: torch.device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """``cudaStream_t`` of torch's current stream on ``device`` (raw handle: 0.1 us instead of the 2 us of
+    building a ``torch.cuda.Stream`` object per call)."""
+    index = device.index
+    if index is None:
+        index = torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(index)
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

@@ -382,7 +382,8 @@ int einconv_kfc(const void* x, void* out, int dtype, const einconv_geom* geom, d
   if ((st = check_math(dtype, math))) return st;
   if ((long long)g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool al = aligned16(x) && aligned16(out);
+  // the factor itself is written with scalar stores: only the input pointer matters
+  const bool al = aligned16(x);
   if (al) {
     int64_t hb;
     if (kfc_half_route(g, dtype, math, kernels, &hb)) {
@@ -439,7 +440,7 @@ static int kfac_reduce_impl(const void* x, void* out, int dtype, const DevGeom& 
   if ((long long)g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
   int st;
   DevGeom g2;
-  if (aligned16(out) && kfac_reduce_tensor(g, dtype, math, kernels, &g2)) {
+  if (kfac_reduce_tensor(g, dtype, math, kernels, &g2)) {
     const int64_t u_bytes = kfac_u_bytes(g);
     const int64_t need = u_bytes + tma::tma_workspace_bytes(EINCONV_OP_KFC, g2, EINCONV_F32);
     if (workspace_bytes < need || !workspace) {

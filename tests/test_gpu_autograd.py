@@ -86,12 +86,15 @@ def test_factor_gradients(kind):
         eq, ops, shape = mod.einsum_expression(x, 3, **kw)
         return torch.einsum(eq, *ops).reshape(shape)
 
+    # the reference's scale is ``Tensor([1 / B]).to(x.dtype)``: rounded through fp32 (convNd_kfc.py:105)
+    scale = float(torch.tensor([1.0 / 3]))
+
     def definition(x):
         u = F.unfold(x, 3, padding=1).reshape(3, 2, 18, -1)
         if kind == "kfc":
-            return torch.einsum("ngik,ngjk->gij", u, u) / 3
-        m = u.mean(-1)
-        return torch.einsum("ngi,ngj->gij", m, m) / 3
+            return torch.einsum("ngik,ngjk->gij", u, u) * scale
+        m = u.sum(-1)
+        return torch.einsum("ngi,ngj->gij", m, m) * float(torch.tensor([1.0 / (3 * 30**2)]))
 
     out = ours(x)
     assert out.grad_fn is not None
