@@ -180,7 +180,9 @@ static bool kfc_half_route(const DevGeom& g, int dtype, int math, int kernels, i
   // measured on the ResNet-50 layer table (scripts/time_factors.py): the copy pays off for kernels with
   // several taps (the operand is re-read per tap) up to A = 2304; 1x1 layers and the A = 4608 layers are
   // faster on kind::tf32 without the extra pass
-  if (g.k_total == 1 || (long long)g.c_in_g * g.k_total > 2304) return false;
+  long long max_a = 2304;
+  if (const char* e = getenv("EINCONV_KFC_HALF_MAXA")) max_a = atoll(e);  // A/B measurements
+  if (g.k_total == 1 || (long long)g.c_in_g * g.k_total > max_a) return false;
   DevGeom g1;
   int64_t ub;
   if (!tma::tma_supported(EINCONV_OP_KFC, g, EINCONV_F16) &&

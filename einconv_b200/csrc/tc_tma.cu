@@ -197,6 +197,7 @@ struct Params {
   float* direct_out;                   // KFC, one split, fp32 output: the epilogue writes the (un-permuted) factor itself
   float direct_scale;
   int direct_a;                        // A = c_in_g * k_total (rows / columns of the factor)
+  int s_tiles;                         // KFC super-tile kernel: ceil(m_tiles / 2) super-tiles (256 rows) per side
 };
 
 template <typename T> struct Elem;
@@ -499,6 +500,310 @@ tma_reduce_gemm_kernel(const __grid_constant__ MapArray map_array, const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
+// KFC with 256 x 256 super-tiles.
+//
+// The 128 x 128 kernel above pulls (128 + 128) rows x 128 B from L2 for every 4 x 64 tensor cycles:
+// 128 B/clk/SM, three times what the L2 can deliver to 148 SMs at once (~42 B/clk/SM, measured ~6300 B/clk
+// chip-wide), so it ran at a third of the tensor rate.  Here a CTA owns TWO row tiles and TWO column tiles
+// of the factor: a K block brings (256 + 256) rows and feeds 2 MMAs of N = 256 per 32-byte K step (the whole
+// 512-column TMEM: accumulator (mi) = columns [256 mi, 256 mi + 256)), i.e. 64 KB per 1024 tensor cycles =
+// 64 B/clk/SM; an N = 256 instruction also halves the shared-memory read per flop (12 KB per 128 cycles).
+// Super-tiles on the diagonal use their row operand as the column operand too (the column operand's maps,
+// whose positions beyond the output width read as zero, are used for both) and load nothing else.
+// Only super-tiles (I, J >= I) exist; inside a diagonal one the mirror block (2I+1, 2I) is not computed.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStagesS = 3;
+constexpr int kSuperRows = 2 * kTileM;                       // 256
+constexpr int kSuperOperandBytes = kSuperRows * kRowBytes;   // 32 KB per operand and stage
+constexpr int kSuperStageBytes = 2 * kSuperOperandBytes;     // 64 KB
+constexpr int kSuperSmem = kStagesS * kSuperStageBytes + 1024 + 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+kfc_super_kernel(const __grid_constant__ MapArray map_array, const __grid_constant__ Params p) {
+  const CUtensorMap* maps = map_array.m;
+  using E = Elem<T>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                                         ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesS * kSuperStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStagesS;
+  uint64_t* accum_bar = bars + 2 * kStagesS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStagesS + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  // blockIdx.x enumerates the super-tiles (I, J >= I) row by row
+  int sI = 0, sJ = 0;
+  {
+    int rest = blockIdx.x, i = 0;
+    while (rest >= p.s_tiles - i) {
+      rest -= p.s_tiles - i;
+      ++i;
+    }
+    sI = i;
+    sJ = i + rest;
+  }
+  const bool diag = sI == sJ;
+  const int grp = blockIdx.z / p.k_splits;
+  const int split = blockIdx.z - grp * p.k_splits;
+  const int kb_per_split = (p.k_blocks + p.k_splits - 1) / p.k_splits;
+  const int kb_begin = split * kb_per_split;
+  const int kb_end = min(p.k_blocks, kb_begin + kb_per_split);
+  const int n_kb = max(0, kb_end - kb_begin);
+  // row tiles 2I, 2I+1 and column tiles 2J, 2J+1 (the second of each may not exist)
+  const bool m1 = 2 * sI + 1 < p.m_tiles;
+  const bool n1 = 2 * sJ + 1 < p.m_tiles;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStagesS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  struct Walker {
+    int wt, ht, dt, b;
+    __device__ void init(const Params& p, int kb) {
+      uint32_t rest = (uint32_t)kb, a, c, d, e;
+      p.wt_div.divmod(rest, rest, a);
+      p.ht_div.divmod(rest, rest, c);
+      p.dt_div.divmod(rest, e, d);
+      wt = (int)a; ht = (int)c; dt = (int)d; b = (int)e;
+    }
+    __device__ void next(const Params& p) {
+      if (++wt == p.n_wt) { wt = 0; if (++ht == p.n_ht) { ht = 0; if (++dt == p.n_dt) { dt = 0; ++b; } } }
+    }
+  };
+
+  if (warp == 0) {
+    // ================================= TMA producer ==========================================
+    // boxes of one K block: per patch line (piece), per operand tile (A0, A1, B0, B1 as far as they exist
+    // and are needed), per tap of the tile.  Lane l owns boxes l, l + 32, ...; everything that does not
+    // depend on the patch position is computed once.
+    constexpr int kLoadsPerLane = 4;
+    const int tiles_a = m1 ? 2 : 1;
+    const int tiles_b = diag ? 0 : (n1 ? 2 : 1);
+    const int n_tiles_cta = tiles_a + tiles_b;
+    const int tpt = p.taps_per_tile;
+    const int per_piece = n_tiles_cta * tpt;   // slots; slots of taps beyond k_total are skipped
+    const int n_loads = p.n_pieces * per_piece;
+    const int bh_shift = 31 - __clz(p.BH);
+
+    const CUtensorMap* l_map[kLoadsPerLane];
+    int l_dst[kLoadsPerLane], l_cw[kLoadsPerLane], l_ch[kLoadsPerLane], l_cd[kLoadsPerLane];
+    int l_hh[kLoadsPerLane], l_dd[kLoadsPerLane], l_chan[kLoadsPerLane];
+    bool l_on[kLoadsPerLane];
+    int boxes_per_piece = 0;  // valid boxes of one patch line (same for every piece)
+#pragma unroll
+    for (int q = 0; q < kLoadsPerLane; ++q) {
+      const int li = lane + 32 * q;
+      bool on = li < n_loads;
+      const int pc = on ? li / per_piece : 0;
+      const int slot = on ? li - pc * per_piece : 0;
+      const int t_idx = slot / tpt;            // operand tile of this CTA: [A0, A1, B0, B1] compacted
+      const int tl = slot - t_idx * tpt;       // tap slot inside the tile
+      const bool is_a = t_idx < tiles_a;
+      const int sub = is_a ? t_idx : t_idx - tiles_a;      // 0 / 1 within the operand
+      const int tile = is_a ? 2 * sI + sub : 2 * sJ + sub;  // row / column tile of the factor
+      const int cblock = tile % p.c_blocks, tapgroup = tile / p.c_blocks;
+      const int tap = tapgroup * tpt + tl;
+      on = on && tap < p.k_total;
+      l_on[q] = on;
+      l_hh[q] = pc & (p.BH - 1);
+      l_dd[q] = pc >> bh_shift;
+      uint32_t kd = 0, kh = 0, kw = 0, r2;
+      if (on) {
+        p.kw_div.divmod((uint32_t)tap, r2, kw);
+        p.kh_div.divmod(r2, kd, kh);
+      }
+      // the row operand may hold anything beyond the output width only if the column operand is zero there;
+      // on the diagonal the row operand IS the column operand, so it uses the clipped maps as well
+      l_map[q] = maps + ((is_a && !diag) ? p.kw_map[kw] : p.kw_map_b[kw]);
+      l_cw[q] = p.kw_c0[kw];
+      l_ch[q] = (int)kh * p.dil[1] - p.pad[1];
+      l_cd[q] = (int)kd * p.dil[2] - p.pad[2];
+      l_dst[q] = (is_a ? 0 : kSuperOperandBytes) + pc * (kSuperRows * p.PB) + sub * (kTileM * p.PB) + tl * p.CB * p.PB;
+      l_chan[q] = grp * p.c_in_g + cblock * p.CB;
+    }
+    for (int slot = 0; slot < per_piece; ++slot) {
+      const int t_idx = slot / tpt, tl = slot - t_idx * tpt;
+      const bool is_a = t_idx < tiles_a;
+      const int sub = is_a ? t_idx : t_idx - tiles_a;
+      const int tile = is_a ? 2 * sI + sub : 2 * sJ + sub;
+      boxes_per_piece += ((tile / p.c_blocks) * tpt + tl) < p.k_total;
+    }
+    const uint32_t line_tx = (uint32_t)boxes_per_piece * p.CB * p.PB;
+    const int sw = p.stride[0], sh = p.stride[1], sd = p.stride[2];
+
+    Walker wk;
+    wk.init(p, kb_begin);
+    for (int i = 0; i < n_kb; ++i, wk.next(p)) {
+      const int s = i % kStagesS;
+      const uint32_t ph = (uint32_t)(i / kStagesS) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      const int ow0 = wk.wt * p.BW, oh0 = wk.ht * p.BH, od0 = wk.dt * p.BD;
+      if (lane == 0) {
+        int n_valid = 0;
+        for (int pc = 0; pc < p.n_pieces; ++pc)
+          n_valid += (oh0 + (pc & (p.BH - 1)) < p.out_h) && (od0 + (pc >> bh_shift) < p.out_d);
+        mbar_expect_tx(&full_bar[s], line_tx * n_valid);
+      }
+      __syncwarp();
+      unsigned char* stage = smem + s * kSuperStageBytes;
+#pragma unroll
+      for (int q = 0; q < kLoadsPerLane; ++q) {
+        if (!l_on[q]) continue;
+        const int oh = oh0 + l_hh[q], od = od0 + l_dd[q];
+        if (oh >= p.out_h || od >= p.out_d) continue;
+        tma_load_5d(stage + l_dst[q], l_map[q], &full_bar[s], ow0 * sw + l_cw[q], oh * sh + l_ch[q],
+                    od * sd + l_cd[q], l_chan[q], wk.b);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================= MMA issuer ============================================
+    constexpr uint32_t idesc256 = make_idesc(E::FMT, kTileM, 256);
+    constexpr uint32_t idesc128 = make_idesc(E::FMT, kTileM, 128);
+    const int steps_per_line = p.PB / 32;  // 32 bytes of K per instruction (16 fp16 / 8 tf32)
+    const int bh_shift = 31 - __clz(p.BH);
+    // taps beyond k_total leave rows of a tile unloaded: stale shared memory.  Their products land in rows /
+    // columns of the accumulator that the epilogue never reads, but they must be finite garbage-free for the
+    // rows that ARE read: rows only mix within their own (row, column) pair, so no masking is needed.
+    uint32_t first = 1u;
+    Walker wk;
+    wk.init(p, kb_begin);
+    for (int i = 0; i < n_kb; ++i, wk.next(p)) {
+      const int s = i % kStagesS;
+      const uint32_t ph = (uint32_t)(i / kStagesS) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * kSuperStageBytes);
+        const uint32_t b_addr = diag ? a_addr : a_addr + kSuperOperandBytes;
+        const int oh0 = wk.ht * p.BH, od0 = wk.dt * p.BD;
+        for (int pc = 0; pc < p.n_pieces; ++pc) {
+          if (oh0 + (pc & (p.BH - 1)) >= p.out_h || od0 + (pc >> bh_shift) >= p.out_d) continue;
+          const uint32_t a_pc = a_addr + pc * (kSuperRows * p.PB);
+          const uint32_t b_pc = b_addr + pc * (kSuperRows * p.PB);
+          for (int j = 0; j < steps_per_line; ++j) {
+            // row tile 0 against both column tiles (or the only one)
+            if (n1)
+              umma<E::TF32>(tmem_base, make_desc_kmajor(a_pc + j * 32, p.PB), make_desc_kmajor(b_pc + j * 32, p.PB),
+                            idesc256, first ? 0u : 1u);
+            else
+              umma<E::TF32>(tmem_base, make_desc_kmajor(a_pc + j * 32, p.PB), make_desc_kmajor(b_pc + j * 32, p.PB),
+                            idesc128, first ? 0u : 1u);
+            if (m1) {
+              const uint32_t a1 = a_pc + kTileM * p.PB + j * 32;
+              if (diag)  // the block (2I+1, 2I) is the mirror of (2I, 2I+1): only column tile 1
+                umma<E::TF32>(tmem_base + 256 + 128, make_desc_kmajor(a1, p.PB),
+                              make_desc_kmajor(b_pc + kTileM * p.PB + j * 32, p.PB), idesc128, first ? 0u : 1u);
+              else if (n1)
+                umma<E::TF32>(tmem_base + 256, make_desc_kmajor(a1, p.PB), make_desc_kmajor(b_pc + j * 32, p.PB),
+                              idesc256, first ? 0u : 1u);
+              else
+                umma<E::TF32>(tmem_base + 256, make_desc_kmajor(a1, p.PB), make_desc_kmajor(b_pc + j * 32, p.PB),
+                              idesc128, first ? 0u : 1u);
+            }
+            first = 0u;
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (i == n_kb - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ================================= epilogue ==============================================
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    if (n_kb > 0) {
+      mbar_wait_relaxed(accum_bar, 0);
+      tc_fence_after();
+    }
+    const int cb_shift = 31 - __clz(p.CB);
+    const int Kt = p.k_total;
+    for (int mi = 0; mi < (m1 ? 2 : 1); ++mi) {
+      for (int nj = 0; nj < (n1 ? 2 : 1); ++nj) {
+        const int m_tile = 2 * sI + mi, n_tile = 2 * sJ + nj;
+        if (m_tile > n_tile) continue;  // mirror block of a diagonal super-tile: not computed
+        const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(mi * 256 + nj * 128);
+        if (p.direct_out) {
+          const float scale = p.scale_dev ? p.direct_scale * __ldg(p.scale_dev) : p.direct_scale;
+          const int A = p.direct_a;
+          const int m_tg = m_tile / p.c_blocks, m_cb = m_tile - m_tg * p.c_blocks;
+          const int n_tg = n_tile / p.c_blocks, n_cb = n_tile - n_tg * p.c_blocks;
+          const int r_tap = m_tg * p.taps_per_tile + (row >> cb_shift);
+          const int r_ci = m_cb * p.CB + (row & (p.CB - 1));
+          const bool r_ok = r_tap < Kt && r_ci < p.c_in_g;
+          const long long a = (long long)r_ci * Kt + r_tap;
+          float* og = p.direct_out + (long long)grp * A * A;
+#pragma unroll 1
+          for (int n0 = 0; n0 < 128; n0 += 16) {
+            uint32_t r[16];
+            if (n_kb > 0) {
+              tmem_ld16(lane_base + n0, r);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = 0u;
+            }
+            const int c_tap = n_tg * p.taps_per_tile + (n0 >> cb_shift);
+            const int c_ci0 = n_cb * p.CB + (n0 & (p.CB - 1));
+            if (r_ok && c_tap < Kt) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int c_ci = c_ci0 + j;
+                if (c_ci < p.c_in_g) {
+                  const long long a2 = (long long)c_ci * Kt + c_tap;
+                  const float v = __uint_as_float(r[j]) * scale;
+                  og[a * A + a2] = v;
+                  if (m_tile != n_tile) og[a2 * A + a] = v;
+                }
+              }
+            }
+          }
+        } else {
+          float* dst = p.partial + (((long long)grp * p.k_splits + split) * p.Mp + (m_tile * kTileM + row)) * p.Np +
+                       n_tile * 128;
+#pragma unroll 1
+          for (int n0 = 0; n0 < 128; n0 += 16) {
+            uint32_t r[16];
+            if (n_kb > 0) {
+              tmem_ld16(lane_base + n0, r);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = 0u;
+            }
+            float4* d4 = reinterpret_cast<float4*>(dst + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // pre-pass: aligned shifted copies.  copy_r[row][j] = x[row][j - A + r] (zero outside [0, W)), rows =
 // (b, c, d, h), j in [0, Wp), A = 16 / sizeof(T) elements, Wp a multiple of A.  A conv tap whose offset
 // along the innermost dimension is t = A*q + r then reads copy_r at the ALIGNED coordinate
@@ -611,6 +916,8 @@ struct Plan {
   int CB, taps_per_tile, tap_groups, c_blocks;
   int bn, m_tiles, n_tiles, k_blocks, k_splits;
   bool tri = false;  // KFC: compute only the tiles on or above the diagonal
+  bool super = false;  // KFC: 256 x 256 super-tiles (kfc_super_kernel)
+  int s_tiles = 0;
   int n_wt, n_ht, n_dt;
   long long Mp, Np;
   // shifted copies of the input (and an aligned copy of the cotangent when its rows are not
@@ -707,10 +1014,13 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
   // split-K so that the grid is exactly one wave of resident CTAs (a partial second wave would
   // double the run time): resident = 148 SMs x CTAs that fit in shared memory
   pl.tri = (op == EINCONV_OP_KFC) && !getenv("EINCONV_KFC_FULL");
+  pl.super = pl.tri && !getenv("EINCONV_KFC_TILE128");
+  pl.s_tiles = (pl.m_tiles + 1) / 2;
   const long long tiles =
-      (pl.tri ? (long long)pl.m_tiles * (pl.m_tiles + 1) / 2 : (long long)pl.m_tiles * pl.n_tiles) * g.groups;
+      (pl.super ? (long long)pl.s_tiles * (pl.s_tiles + 1) / 2
+                : pl.tri ? (long long)pl.m_tiles * (pl.m_tiles + 1) / 2 : (long long)pl.m_tiles * pl.n_tiles) * g.groups;
   const int stage_bytes = (kTileM + pl.bn) * kRowBytes;
-  const int ctas_per_sm = std::max(1, (227 * 1024) / (kStages * stage_bytes + 2048));
+  const int ctas_per_sm = pl.super ? 1 : std::max(1, (227 * 1024) / (kStages * stage_bytes + 2048));
   const long long resident = (long long)num_sms() * ctas_per_sm;
   // Split K so that the CTAs fill whole waves of the resident slots: with `s` splits the main kernel
   // takes ceil(tiles * s / resident) rounds of 1/s of the reduction each, and the finish kernel reads
@@ -719,7 +1029,9 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
   {
     const long long cap = std::max<long long>(1, std::min<long long>(pl.k_blocks / 8, 512));
     const double k_total_pos = (double)pl.k_blocks * (kRowBytes / es);
-    const double t_main = 2.0 * kTileM * pl.bn * k_total_pos * (double)tiles / 300e12;  // all tiles, one pass
+    // all tiles, one pass: 128 x 128 tiles run at ~300 TFLOP/s (L2-bound), super-tiles at ~2-3x that
+    const double t_main = pl.super ? 2.0 * 256 * 256 * k_total_pos * (double)tiles / (es == 2 ? 900e12 : 450e12)
+                                   : 2.0 * kTileM * pl.bn * k_total_pos * (double)tiles / 300e12;
     const double t_partial = (double)g.groups * pl.Mp * pl.Np * 4.0 / 4e12;          // per split copy
     double best_t = 1e30;
     int best_s = 1;
@@ -941,6 +1253,7 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   p.is_kfc = kfc ? 1 : 0;
   p.tri = pl.tri ? 1 : 0;
   p.scale_dev = scale_dev;
+  p.s_tiles = pl.s_tiles;
 #ifdef EINCONV_BRINGUP
   {
     const char* dbg = getenv("EINCONV_TMA_DEBUG");
@@ -1006,6 +1319,15 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   }
   auto run_main = [&](auto* tag) -> int {
     using T = std::remove_pointer_t<decltype(tag)>;
+    if (pl.super) {
+      auto kern = kfc_super_kernel<T>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSuperSmem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(kfc_super)");
+      dim3 grid(pl.s_tiles * (pl.s_tiles + 1) / 2, 1, g.groups * pl.k_splits);
+      kern<<<grid, kThreads, kSuperSmem, stream>>>(map_array, p);
+      EINCONV_CHECK_LAUNCH("kfc_super_kernel");
+      return EINCONV_OK;
+    }
     if (pl.bn == 256) return launch<T, 256>(map_array, p, pl, g.groups, stream);
     if (pl.bn == 128) return launch<T, 128>(map_array, p, pl, g.groups, stream);
     return launch<T, 64>(map_array, p, pl, g.groups, stream);

@@ -82,3 +82,14 @@ def forward_out_shape(case):
     g = direct.geometry(x[0], kw.get("groups", 1), w[1], w[0] // kw.get("groups", 1), x[2:], w[2:],
                         kw.get("stride", 1), kw.get("padding", 0), kw.get("dilation", 1))
     return (x[0], w[0], *[g.out[d] for d in range(len(x) - 2)])
+
+
+@pytest.fixture(autouse=True)
+def _fresh_plan_cache():
+    """Call plans cache the workspace size of the route chosen when they were made; tests that flip the
+    library's diagnostic EINCONV_* switches (monkeypatch.setenv) must not see a plan made under another
+    setting."""
+    from einconv_b200 import evaluator
+
+    evaluator.clear_plan_cache()
+    yield
