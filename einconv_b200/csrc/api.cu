@@ -193,6 +193,21 @@ static bool kfc_half_route(const DevGeom& g, int dtype, int math, int kernels, i
   return true;
 }
 
+// Dense rule of the simplifier (simplifications/opt.py:196-240: kernel size 1, stride 1, no padding => the
+// index pattern is the identity): a 1x1 KFC factor is the plain Gram matrix X X^T over ALL positions of a
+// sample, so the spatial dimensions collapse into one.  The TMA kernel then reads whole 128-byte lines of the
+// contiguous (H W) axis instead of one short box per image row (14 x 14: 56-byte rows needed shifted copies).
+static DevGeom kfc_canonical(const DevGeom& g) {
+  if (g.k_total != 1 || g.n_dims == 1) return g;
+  for (int i = 0; i < g.n_dims; ++i)
+    if (g.stride[i] != 1 || g.pad[i] != 0 || g.out[i] != g.in[i]) return g;
+  einconv_geom e{};
+  e.n_dims = 1; e.groups = g.groups; e.batch = g.batch; e.c_in_g = g.c_in_g; e.c_out_g = 0;
+  e.in[0] = g.in_total; e.k[0] = 1; e.stride[0] = 1; e.dilation[0] = 1; e.pad_left[0] = 0; e.out[0] = g.in_total;
+  DevGeom d;
+  return make_dev_geom(&e, &d, false) == EINCONV_OK ? d : g;
+}
+
 static int64_t kfac_u_bytes(const DevGeom& g) {
   return (((int64_t)g.batch * g.groups * g.c_in_g * g.k_total * 4 + 255) / 256) * 256;
 }
@@ -237,6 +252,7 @@ const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype,
     default: break;
   }
   if (op == EINCONV_OP_KFC) {
+    g = kfc_canonical(g);
     DevGeom g1;
     int64_t ub, hb;
     if (kfc_half_route(g, dtype, math, kernels, &hb))
@@ -273,6 +289,7 @@ static int64_t workspace_for(int op, DevGeom g, int dtype, int math, int kernels
     op = EINCONV_OP_KFAC_REDUCE;
     g = swap_io(g);
   }
+  if (op == EINCONV_OP_KFC) g = kfc_canonical(g);
   if (op == EINCONV_OP_KFC && aligned) {
     DevGeom g1;
     int64_t ub, hb;
@@ -383,6 +400,7 @@ int einconv_kfc(const void* x, void* out, int dtype, const einconv_geom* geom, d
   if (st) return st;
   if ((st = check_math(dtype, math))) return st;
   if ((long long)g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
+  g = kfc_canonical(g);
   cudaStream_t s = (cudaStream_t)stream;
   // the factor itself is written with scalar stores: only the input pointer matters
   const bool al = aligned16(x);

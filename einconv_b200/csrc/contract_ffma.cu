@@ -846,6 +846,107 @@ __global__ void __launch_bounds__(256) window_sum_flat_kernel(const T* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Window sums of a 2-d plane, separable form.  Tap (kh, kw) sums x over rows(kh) x cols(kw) where both
+// membership relations depend on one coordinate only, so
+//     u[kh][kw] = sum_{j in cols(kw)}  ( sum_{i in rows(kh)} x[i][j] ).
+// A lane owns columns j (and, for planes narrower than a warp, one of 32 / Wl row phases): per element it
+// adds into at most K_h lane-local accumulators (row membership is a table bit), 3 FADD for a 3 x 3 kernel
+// instead of the 9 masked adds + table look-up of the flat kernel.  The column relation is applied once
+// per plane, when the K_h x K_w sums are reduced across the warp.  Loads are coalesced row segments, 4
+// row steps in flight.  No atomics: deterministic.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int KH, int Q>
+__global__ void __launch_bounds__(256) window_sum_sep_kernel(const T* __restrict__ x,
+                                                             typename Cvt<T>::acc_t* __restrict__ u,
+                                                             const __grid_constant__ DevGeom g, int planes,
+                                                             int transposed, int Wl, int rpw) {
+  using acc_t = typename Cvt<T>::acc_t;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned* rowmask = reinterpret_cast<unsigned*>(smem_raw);  // [H]: bit kh set iff row i is under tap kh
+  const int H = g.in[0], W = g.in[1], k_h = g.k[0], k_w = g.k[1];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    unsigned m = 0;
+    for (int k = 0; k < k_h; ++k)
+      if (tap_member(g, 0, i, k)) m |= 1u << k;
+    rowmask[i] = m;
+  }
+  const int lane = threadIdx.x & 31;
+  const int ri = lane / Wl;        // row phase of this lane (0 when the plane is at least a warp wide)
+  const int jl = lane - ri * Wl;
+  unsigned cm[Q];                  // column masks of this lane's columns
+  bool col_ok[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int j = jl + Wl * q;
+    col_ok[q] = j < W && ri < rpw;
+    unsigned m = 0;
+    if (col_ok[q])
+      for (int k = 0; k < k_w; ++k)
+        if (tap_member(g, 1, j, k)) m |= 1u << k;
+    cm[q] = m;
+    col_ok[q] = col_ok[q] && m != 0u;  // columns under no tap are never read
+  }
+  __syncthreads();
+
+  const int warps_per_cta = blockDim.x >> 5;
+  const int chans = g.groups * g.c_in_g;
+  const long long n = (long long)H * W;
+  constexpr int RU = 4;  // row steps in flight
+  for (int plane = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); plane < planes;
+       plane += gridDim.x * warps_per_cta) {
+    const T* src = x + (long long)plane * n;
+    acc_t acc[Q][KH];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+      for (int k = 0; k < KH; ++k) acc[q][k] = acc_t(0);
+    for (int i0 = 0; i0 < H; i0 += rpw * RU) {
+      acc_t v[RU][Q];
+      unsigned rm[RU];
+#pragma unroll
+      for (int r = 0; r < RU; ++r) {
+        const int i = i0 + r * rpw + ri;
+        rm[r] = i < H ? rowmask[i] : 0u;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          v[r][q] = acc_t(0);
+          if (rm[r] != 0u && col_ok[q]) v[r][q] = Cvt<T>::load(src + (long long)i * W + jl + Wl * q);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RU; ++r)
+#pragma unroll
+        for (int k = 0; k < KH; ++k)
+          if (rm[r] >> k & 1u) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) acc[q][k] += v[r][q];
+          }
+    }
+    const int b = plane / chans, c = plane - b * chans;
+    acc_t mine = acc_t(0);  // lane t ends up holding tap t
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh) {
+      if (kh >= k_h) break;
+      for (int kw = 0; kw < k_w; ++kw) {
+        acc_t sum = acc_t(0);
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+          if (cm[q] >> kw & 1u) sum += acc[q][kh];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const int t = kh * k_w + kw;
+        if ((t & 31) == lane) mine = sum;
+        if ((t & 31) == 31 || t == g.k_total - 1) {  // flush up to 32 taps with one store instruction
+          const int tt = (t & ~31) + lane;
+          if (tt <= t)
+            u[transposed ? ((long long)c * g.k_total + tt) * g.batch + b : (long long)plane * g.k_total + tt] = mine;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
 static int pick_splits(long long tiles, int k_chunks) {
@@ -1026,6 +1127,35 @@ int kfac_window_sums(const void* x, void* u_out, int dtype, const DevGeom& g, in
     for (int d = 0; d <= W; ++d) {
       table += g.in[d];
       masks_fit = masks_fit && g.k[d] <= 32;
+    }
+    // 2-d planes up to 224 columns and 7 rows of taps: separable kernel (column-owning lanes)
+    // (1 x 1 kernels keep the flat kernel: with one tap it is a plain coalesced plane sum, measured faster)
+    if (g.n_dims == 2 && g.k_total > 1 && g.in[1] <= 224 && g.k[0] <= 7 && g.k[1] <= 32 && g.in[0] <= 8192 &&
+        !getenv("EINCONV_WINDOW_SUM_FLAT")) {
+      const int W_ = g.in[1];
+      int Wl = 32;
+      while (Wl / 2 >= W_ && Wl > 1) Wl /= 2;  // smallest power of two >= W (<= 32)
+      const int rpw = 32 / Wl;                  // rows covered by one warp step
+      const int Q = (W_ + 31) / 32;
+      const size_t smem = (size_t)g.in[0] * 4;
+      // enough warps to fill the machine, persistent over planes beyond that
+      const unsigned blocks = (unsigned)std::min<long long>((planes + 7) / 8, 8ll * num_sms());
+      auto launch_sep = [&](auto kh_tag, auto q_tag) -> int {
+        constexpr int KH = decltype(kh_tag)::value;
+        constexpr int QQ = decltype(q_tag)::value;
+        window_sum_sep_kernel<T, KH, QQ><<<blocks, 256, smem, stream>>>((const T*)x, u, g, planes, transposed, Wl, rpw);
+        EINCONV_CHECK_LAUNCH("window_sum_sep_kernel");
+        return EINCONV_OK;
+      };
+      auto with_q = [&](auto kh_tag) -> int {
+        if (Q <= 1) return launch_sep(kh_tag, std::integral_constant<int, 1>{});
+        if (Q <= 2) return launch_sep(kh_tag, std::integral_constant<int, 2>{});
+        if (Q <= 4) return launch_sep(kh_tag, std::integral_constant<int, 4>{});
+        return launch_sep(kh_tag, std::integral_constant<int, 7>{});
+      };
+      if (g.k[0] == 1) return with_q(std::integral_constant<int, 1>{});
+      if (g.k[0] <= 3) return with_q(std::integral_constant<int, 3>{});
+      return with_q(std::integral_constant<int, 7>{});
     }
     if (g.in_total <= 12288 && g.k_total <= 32 && !getenv("EINCONV_WINDOW_SUM_ROWS")) {
       const size_t smem = (size_t)g.in_total * 4;

@@ -723,31 +723,33 @@ kfc_super_kernel(const __grid_constant__ MapArray map_array, const __grid_consta
       }
       __syncwarp();
     }
-  } else if (warp >= 4) {
-    // ================================= epilogue ==============================================
+  }
+
+  // ================================= epilogue (all 8 warps) ====================================
+  // Every thread of warps 4-7 holds one ROW of the accumulator (its TMEM lane).  Storing rows from there
+  // makes each instruction touch 32 different rows (32 lone sectors: ~1 sector per clock and SM, 34 us per
+  // super-tile measured).  Instead a 128 x 128 block goes through shared memory (the pipeline stages are
+  // free by now; row pitch 129 floats is conflict-free for row-wise and column-wise accesses) and all 8
+  // warps write whole 512-byte rows: the split-K partial tile, or — for single-tap kernels with one split,
+  // where the factor index is the channel — the factor block and its mirror image directly.
+  {
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
-    if (n_kb > 0) {
+    if (warp >= 4 && n_kb > 0) {
       mbar_wait_relaxed(accum_bar, 0);
       tc_fence_after();
     }
-    const int cb_shift = 31 - __clz(p.CB);
     const int Kt = p.k_total;
+    float* tile_s = reinterpret_cast<float*>(smem);
+    constexpr int kPitch = 129;
+    const bool direct = p.direct_out != nullptr;  // host sets it only for k_total == 1, one split, fp32 output
+    const float scale = direct ? (p.scale_dev ? p.direct_scale * __ldg(p.scale_dev) : p.direct_scale) : 1.0f;
     for (int mi = 0; mi < (m1 ? 2 : 1); ++mi) {
       for (int nj = 0; nj < (n1 ? 2 : 1); ++nj) {
         const int m_tile = 2 * sI + mi, n_tile = 2 * sJ + nj;
         if (m_tile > n_tile) continue;  // mirror block of a diagonal super-tile: not computed
-        const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(mi * 256 + nj * 128);
-        if (p.direct_out) {
-          const float scale = p.scale_dev ? p.direct_scale * __ldg(p.scale_dev) : p.direct_scale;
-          const int A = p.direct_a;
-          const int m_tg = m_tile / p.c_blocks, m_cb = m_tile - m_tg * p.c_blocks;
-          const int n_tg = n_tile / p.c_blocks, n_cb = n_tile - n_tg * p.c_blocks;
-          const int r_tap = m_tg * p.taps_per_tile + (row >> cb_shift);
-          const int r_ci = m_cb * p.CB + (row & (p.CB - 1));
-          const bool r_ok = r_tap < Kt && r_ci < p.c_in_g;
-          const long long a = (long long)r_ci * Kt + r_tap;
-          float* og = p.direct_out + (long long)grp * A * A;
+        if (warp >= 4) {
+          const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(mi * 256 + nj * 128);
 #pragma unroll 1
           for (int n0 = 0; n0 < 128; n0 += 16) {
             uint32_t r[16];
@@ -757,40 +759,64 @@ kfc_super_kernel(const __grid_constant__ MapArray map_array, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 16; ++j) r[j] = 0u;
             }
-            const int c_tap = n_tg * p.taps_per_tile + (n0 >> cb_shift);
-            const int c_ci0 = n_cb * p.CB + (n0 & (p.CB - 1));
-            if (r_ok && c_tap < Kt) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int c_ci = c_ci0 + j;
-                if (c_ci < p.c_in_g) {
-                  const long long a2 = (long long)c_ci * Kt + c_tap;
-                  const float v = __uint_as_float(r[j]) * scale;
-                  og[a * A + a2] = v;
-                  if (m_tile != n_tile) og[a2 * A + a] = v;
-                }
-              }
-            }
-          }
-        } else {
-          float* dst = p.partial + (((long long)grp * p.k_splits + split) * p.Mp + (m_tile * kTileM + row)) * p.Np +
-                       n_tile * 128;
-#pragma unroll 1
-          for (int n0 = 0; n0 < 128; n0 += 16) {
-            uint32_t r[16];
-            if (n_kb > 0) {
-              tmem_ld16(lane_base + n0, r);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) r[j] = 0u;
-            }
-            float4* d4 = reinterpret_cast<float4*>(dst + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            for (int j = 0; j < 16; ++j) tile_s[row * kPitch + n0 + j] = __uint_as_float(r[j]) * scale;
           }
         }
+        __syncthreads();
+        int rows_valid = 128, cols_valid = 128;
+        long long row_pitch;
+        float* dst0;     // element (row 0, column 0) of the block in its destination
+        float* mir0 = nullptr;
+        if (direct) {
+          // single tap: tile row r <-> channel tile * CB + r, only the first CB rows / columns of a tile exist
+          const long long A = p.direct_a;
+          rows_valid = min(p.CB, p.c_in_g - m_tile * p.CB);
+          cols_valid = min(p.CB, p.c_in_g - n_tile * p.CB);
+          float* og = p.direct_out + (long long)grp * A * A;
+          row_pitch = A;
+          dst0 = og + (long long)m_tile * p.CB * A + (long long)n_tile * p.CB;
+          if (m_tile != n_tile) mir0 = og + (long long)n_tile * p.CB * A + (long long)m_tile * p.CB;
+        } else {
+          row_pitch = p.Np;
+          dst0 = p.partial + (((long long)grp * p.k_splits + split) * p.Mp + (long long)m_tile * kTileM) * p.Np +
+                 (long long)n_tile * 128;
+        }
+        // 4 rows x 4 column segments = 16 independent shared loads in flight per lane
+        for (int r0 = warp * 4; r0 < rows_valid; r0 += 32) {
+          float v[4][4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[a][k] = tile_s[min(r0 + a, 127) * kPitch + lane + 32 * k];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            if (r0 + a >= rows_valid) break;
+            float* dst = dst0 + (long long)(r0 + a) * row_pitch;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (lane + 32 * k < cols_valid) dst[lane + 32 * k] = v[a][k];
+          }
+        }
+        if (mir0) {
+          for (int c0 = warp * 4; c0 < cols_valid; c0 += 32) {
+            float v[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[a][k] = tile_s[(lane + 32 * k) * kPitch + min(c0 + a, 127)];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              if (c0 + a >= cols_valid) break;
+              float* dst = mir0 + (long long)(c0 + a) * row_pitch;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (lane + 32 * k < rows_valid) dst[lane + 32 * k] = v[a][k];
+            }
+          }
+        }
+        __syncthreads();  // the block is out: shared memory may be refilled
+        (void)Kt;
       }
     }
   }
@@ -888,6 +914,95 @@ __global__ void __launch_bounds__(256) tma_finish_kernel(const float* __restrict
   float s = 0.f;
   for (int k = 0; k < p.k_splits; ++k) s += src[(long long)k * tile];
   Cvt<T>::store(out + idx, s * scale);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finish pass of the symmetric (upper-triangular) KFC tiling, in TILE space: one CTA per computed
+// 128 x 128 block (mt <= nt).  Reads are whole 512-byte partial rows (one float4 per lane, independent
+// loads over the splits), all index arithmetic is per CTA / per lane / per row (no per-element division);
+// the block and its mirror image are scattered into the factor, whose order is channel-major
+// (a = ci * Kt + tap) while tile rows are tap-major.  Replaces the element-space kernel, which spent its
+// time on ~8 integer divisions per output element and ran at ~1 TB/s.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) kfc_finish_tri_kernel(const float* __restrict__ partial, T* __restrict__ out,
+                                                             const __grid_constant__ Params p, float scale_host,
+                                                             int rows_per_cta) {
+  __shared__ float4 red[8][32];
+  const float scale = p.scale_dev ? scale_host * __ldg(p.scale_dev) : scale_host;
+  int mt = 0, nt = 0;
+  {
+    int rest = blockIdx.x, i = 0;
+    while (rest >= p.m_tiles - i) {
+      rest -= p.m_tiles - i;
+      ++i;
+    }
+    mt = i;
+    nt = i + rest;
+  }
+  const int grp = blockIdx.z;
+  const int Kt = p.k_total;
+  const long long A = (long long)p.c_in_g * Kt;
+  const int cb_shift = 31 - __clz(p.CB);
+  const int m_tg = mt / p.c_blocks, m_cb = mt - m_tg * p.c_blocks;
+  const int n_tg = nt / p.c_blocks, n_cb = nt - n_tg * p.c_blocks;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.y: chunk of rows_per_cta (1, 2, 4 or 8) rows; the 8 warps are 8 / rows_per_cta split lanes per row,
+  // so that a factor with few tiles and many splits still spreads over the machine
+  const int row_local = warp % rows_per_cta;
+  const int split_lane = warp / rows_per_cta, split_lanes = 8 / rows_per_cta;
+  const int r = blockIdx.y * rows_per_cta + row_local;
+  // this lane's four columns: same tap slot, consecutive channels
+  const int c0 = 4 * lane;
+  const int c_tap = n_tg * p.taps_per_tile + (c0 >> cb_shift);
+  const int c_ci0 = n_cb * p.CB + (c0 & (p.CB - 1));
+  const long long a2_0 = (long long)c_ci0 * Kt + c_tap;
+  const long long tile = (long long)p.Mp * p.Np;
+  const int r_tap = m_tg * p.taps_per_tile + (r >> cb_shift);
+  const int r_ci = m_cb * p.CB + (r & (p.CB - 1));
+  const bool ok = r_tap < Kt && r_ci < p.c_in_g && c_tap < Kt;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) {
+    const float* src = partial + (long long)grp * p.k_splits * tile + (long long)(mt * kTileM + r) * p.Np +
+                       nt * kTileM + c0;
+    int k = split_lane;
+    for (; k + 3 * split_lanes < p.k_splits; k += 4 * split_lanes) {
+      const float4 v0 = __ldcs(reinterpret_cast<const float4*>(src + (long long)k * tile));
+      const float4 v1 = __ldcs(reinterpret_cast<const float4*>(src + (long long)(k + split_lanes) * tile));
+      const float4 v2 = __ldcs(reinterpret_cast<const float4*>(src + (long long)(k + 2 * split_lanes) * tile));
+      const float4 v3 = __ldcs(reinterpret_cast<const float4*>(src + (long long)(k + 3 * split_lanes) * tile));
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x);
+      acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z);
+      acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; k < p.k_splits; k += split_lanes) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (long long)k * tile));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  if (split_lanes > 1) {
+    red[warp][lane] = acc;
+    __syncthreads();
+    if (split_lane != 0) return;
+    for (int q = 1; q < split_lanes; ++q) {
+      const float4 v = red[q * rows_per_cta + row_local][lane];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  if (!ok) return;
+  T* og = out + (long long)grp * A * A;
+  const bool mirror = mt != nt;
+  const long long a = (long long)r_ci * Kt + r_tap;
+  const float vals[4] = {acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (c_ci0 + e < p.c_in_g) {
+      const long long a2 = a2_0 + (long long)e * Kt;
+      Cvt<T>::store(og + a * A + a2, vals[e]);
+      if (mirror) Cvt<T>::store(og + a2 * A + a, vals[e]);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1041,7 +1156,8 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
       // a round processes `resident` CTA-slots of 1/s of the K range each
       // one split writes the factor from the epilogue (KFC); more splits pay the partial copies, the
       // finish kernel's output pass and its launch
-      const double t_fin = (op == EINCONV_OP_KFC && s == 1) ? 0.0 : t_partial * (double)(s + 1) + 4e-6;
+      const bool fused = op == EINCONV_OP_KFC && s == 1 && (!pl.super || g.k_total == 1);
+      const double t_fin = fused ? 0.0 : t_partial * (double)(s + 1) + 4e-6;
       const double t = t_main * ((double)rounds * resident / (double)ctas) + t_fin + 2e-6 * rounds;
       if (t < best_t) {
         best_t = t;
@@ -1310,8 +1426,11 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   p.partial = partial;
   // fused finish: KFC with one split, a 1x1 kernel whose partial rows are the channels in order
   // (one channel block, or full 128-channel blocks), upper-triangular tiling and fp32 output
+  // (with several taps the factor's channel-major order makes every epilogue store a lone 4-byte sector write,
+  // ~1 sector per clock and SM and serialised with the MMAs: measured 160 us per wave for A = 4608 against
+  // 26 us of tensor work; the tile-space finish kernel does the same scatter from all SMs at once)
   const bool direct = kfc && pl.tri && pl.k_splits == 1 && out_dtype == EINCONV_F32 &&
-                      !getenv("EINCONV_KFC_NO_DIRECT");
+                      (!pl.super || g.k_total == 1) && !getenv("EINCONV_KFC_NO_DIRECT");
   if (direct) {
     p.direct_out = (float*)out;
     p.direct_scale = (float)scale;
@@ -1345,6 +1464,15 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   const long long total = (kfc ? Atot * Atot : (long long)g.c_out_g * Atot) * g.groups;
   auto run_finish = [&](auto* tag) -> int {
     using T = std::remove_pointer_t<decltype(tag)>;
+    if (kfc && pl.tri && !getenv("EINCONV_KFC_FINISH_ELEMENTWISE")) {
+      const long long n_tri = (long long)pl.m_tiles * (pl.m_tiles + 1) / 2 * g.groups;
+      int rows = 8;  // rows per CTA: fewer when there are few tiles, so that >= ~4 CTAs per SM exist
+      while (rows > 1 && n_tri * (kTileM / rows) < 4ll * num_sms()) rows /= 2;
+      dim3 grid((unsigned)(pl.m_tiles * (pl.m_tiles + 1) / 2), (unsigned)(kTileM / rows), (unsigned)g.groups);
+      kfc_finish_tri_kernel<T><<<grid, 256, 0, stream>>>(p.partial, (T*)out, p, (float)scale, rows);
+      EINCONV_CHECK_LAUNCH("kfc_finish_tri_kernel");
+      return EINCONV_OK;
+    }
     tma_finish_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p.partial, (T*)out, p, (float)scale);
     EINCONV_CHECK_LAUNCH("tma_finish_kernel");
     return EINCONV_OK;
