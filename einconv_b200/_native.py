@@ -98,6 +98,12 @@ SIGNATURES = {
         _INT,
         [_VOIDP, _VOIDP, _INT, _GEOMP, _DBL, _INT, _INT, _VOIDP, _I64, _VOIDP],
     ),
+    "einconv_kfac_reduce_sums": (_INT, [_VOIDP, _VOIDP, _INT, _GEOMP, _VOIDP]),
+    "einconv_kfac_reduce_from_sums": (
+        _INT,
+        [_VOIDP, _INT, _I64, _VOIDP, _INT, _GEOMP, _DBL, _INT, _INT, _VOIDP, _I64, _VOIDP],
+    ),
+    "einconv_kfac_reduce_from_sums_workspace": (_I64, [_INT, _INT, _GEOMP, _INT, _INT]),
     "einconv_unfold_transpose": (_INT, [_VOIDP, _VOIDP, _INT, _GEOMP, _VOIDP]),
     "einconv_kfac_reduce_transpose": (
         _INT,

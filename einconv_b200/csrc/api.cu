@@ -260,6 +260,12 @@ const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype,
                                                                                    : "f16scaled+tcgen05_tma_kfc";
     if (kfc_via_unfold(g, dtype, math, kernels, &g1, &ub)) return "unfold+tcgen05_tma_kfc";
   }
+  if (op == EINCONV_OP_KFAC_REDUCE || op == EINCONV_OP_KFAC_REDUCE_TRANSPOSE) {
+    DevGeom g2;
+    return kfac_reduce_tensor(op == EINCONV_OP_KFAC_REDUCE ? g : swap_io(g), dtype, math, kernels, &g2)
+               ? "window_sums+tcgen05_tma_kfc"
+               : "window_sums+ffma_outer";
+  }
   switch (select_path(op, g, dtype, math, kernels)) {
     case Path::DEPTHWISE: return "depthwise_stencil";
     case Path::TENSOR: return tc_kernel_name(op, g, dtype, resolve_math(dtype, math));
@@ -487,6 +493,63 @@ int einconv_kfac_reduce(const void* x, void* out, int dtype, const einconv_geom*
   if (st) return st;
   if ((st = check_math(dtype, math))) return st;
   return kfac_reduce_impl(x, out, dtype, g, scale, math, kernels, workspace, workspace_bytes, stream);
+}
+
+// stage-2 geometry over `n_shards` gathered blocks: a 1x1 "convolution" over 1-d images of B_shard positions
+static bool kfac_shard_geom(const DevGeom& g, int n_shards, DevGeom* g2) {
+  const long long A = (long long)g.c_in_g * g.k_total;
+  if (A >= (1ll << 24) || g.batch < 1 || n_shards < 1) return false;
+  einconv_geom e{};
+  e.n_dims = 1; e.groups = g.groups; e.batch = n_shards; e.c_in_g = A; e.c_out_g = 0;
+  e.in[0] = g.batch; e.k[0] = 1; e.stride[0] = 1; e.dilation[0] = 1; e.pad_left[0] = 0; e.out[0] = g.batch;
+  return make_dev_geom(&e, g2, false) == EINCONV_OK;
+}
+
+static bool kfac_from_sums_route(const DevGeom& g, int n_shards, int dtype, int math, int kernels, DevGeom* g2) {
+  DevGeom tmp;
+  if (!kfac_reduce_tensor(g, dtype, math, kernels, &tmp)) return false;  // same conditions as the fused call
+  if (!kfac_shard_geom(g, n_shards, g2)) return false;
+  if ((g.batch * 4) % 16 != 0) return false;  // rows of u must be directly readable by TMA
+  return tma::tma_supported(EINCONV_OP_KFC, *g2, EINCONV_F32);
+}
+
+int einconv_kfac_reduce_sums(const void* x, void* u, int dtype, const einconv_geom* geom, void* stream) {
+  EINCONV_CHECK_ARG(x && u, "kfac_reduce_sums: NULL tensor pointer");
+  DevGeom g;
+  int st = make_dev_geom(geom, &g, false);
+  if (st) return st;
+  EINCONV_CHECK_ARG(elem_size(dtype) > 0, "unknown dtype %d", dtype);
+  if ((long long)g.batch * g.groups * g.c_in_g * g.k_total == 0) return EINCONV_OK;
+  return kfac_window_sums(x, u, dtype, g, /*transposed=*/1, (cudaStream_t)stream);
+}
+
+int64_t einconv_kfac_reduce_from_sums_workspace(int n_shards, int dtype, const einconv_geom* geom, int math,
+                                                int kernels) {
+  DevGeom g, g2;
+  if (make_dev_geom(geom, &g, false)) return -1;
+  if (check_math(dtype, math)) return -1;
+  if (!kfac_from_sums_route(g, n_shards, dtype, math, kernels, &g2)) return -1;
+  return tma::tma_workspace_bytes(EINCONV_OP_KFC, g2, EINCONV_F32);
+}
+
+int einconv_kfac_reduce_from_sums(const void* u, int n_shards, int64_t shard_stride, void* out, int dtype,
+                                  const einconv_geom* geom, double scale, int math, int kernels, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+  EINCONV_CHECK_ARG(u && out, "kfac_reduce_from_sums: NULL tensor pointer");
+  DevGeom g, g2;
+  int st = make_dev_geom(geom, &g, false);
+  if (st) return st;
+  if ((st = check_math(dtype, math))) return st;
+  if (!kfac_from_sums_route(g, n_shards, dtype, math, kernels, &g2) || !aligned16(u) || (shard_stride * 4) % 16 != 0) {
+    set_error("kfac_reduce_from_sums: no tensor-core route for this geometry / math mode / alignment");
+    return EINCONV_ERR_UNSUPPORTED;
+  }
+  const long long block = (long long)g.groups * g.c_in_g * g.k_total * g.batch;
+  EINCONV_CHECK_ARG(n_shards == 1 || shard_stride >= block, "kfac_reduce_from_sums: shard_stride %lld < block of %lld",
+                    (long long)shard_stride, block);
+  return tma::tma_run_typed_out(EINCONV_OP_KFC, u, nullptr, out, EINCONV_F32, dtype, g2, scale, workspace,
+                                workspace_bytes, (cudaStream_t)stream, nullptr,
+                                (n_shards > 1 && shard_stride != block) ? shard_stride : 0);
 }
 
 int einconv_unfold_transpose(const void* x, void* out, int dtype, const einconv_geom* g, void* stream) {

@@ -61,7 +61,7 @@ int tma_run(int op, const void* x, const void* v, void* out, int dtype, const De
             void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype, int out_dtype, const DevGeom& g,
                       double scale, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
-                      const float* scale_dev = nullptr);
+                      const float* scale_dev = nullptr, long long x_batch_stride = 0);
 }  // namespace tma
 
 // conv_tma.cu (TMA-fed tcgen05 implicit GEMM for forward / input VJP, stride 1)

@@ -1219,7 +1219,8 @@ int64_t tma_workspace_bytes(int op, const DevGeom& g, int dtype) {
 }
 
 static int encode_map(CUtensorMap* map, int dtype, const void* base, const int extent[5],
-                      const int box[5], const int estride[5], int line_bytes, int pitch_w = 0) {
+                      const int box[5], const int estride[5], int line_bytes, int pitch_w = 0,
+                      long long batch_stride_elems = 0) {
   const int es = (int)elem_size(dtype);
   CUtensorMapDataType dt = dtype == EINCONV_F32    ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
                            : dtype == EINCONV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
@@ -1235,6 +1236,8 @@ static int encode_map(CUtensorMap* map, int dtype, const void* base, const int e
     bx[i] = (cuuint32_t)box[i];
     st[i] = (cuuint32_t)estride[i];
   }
+  // samples may be further apart than their extent (blocks of gathered window sums, api.cu)
+  if (batch_stride_elems > 0) strides[3] = (unsigned long long)batch_stride_elems * es;
   CUtensorMapSwizzle swz = line_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
                            : line_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                               : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -1267,9 +1270,13 @@ static int launch(const MapArray& maps, const Params& p, const Plan& pl, int gro
 
 int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype, int out_dtype, const DevGeom& g,
                       double scale, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
-                      const float* scale_dev) {
+                      const float* scale_dev, long long x_batch_stride) {
   const Plan pl = make_plan(op, g, dtype);
   EINCONV_CHECK_ARG(pl.ok, "tma path not available for this geometry");
+  if (x_batch_stride > 0) {
+    EINCONV_CHECK_ARG(pl.x_direct && pl.n_copies == 0 && (x_batch_stride * (long long)elem_size(dtype)) % 16 == 0,
+                      "strided samples need a directly readable operand (16-byte multiples)");
+  }
   const int64_t need = tma_workspace_bytes(op, g, dtype);
   if (workspace_bytes < need || !workspace) {
     set_error("workspace of %lld bytes required, got %lld", (long long)need, (long long)workspace_bytes);
@@ -1336,7 +1343,7 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
       const int extent[5] = {Wext, q.in[1], q.in[2], g.groups * g.c_in_g, g.batch};
       const int box[5] = {pl.BW, 1, 1, pl.CB, 1};
       const int est[5] = {1, 1, 1, 1, 1};
-      int st = encode_map(&host_maps[n_maps++], dtype, base, extent, box, est, pl.PB);
+      int st = encode_map(&host_maps[n_maps++], dtype, base, extent, box, est, pl.PB, 0, direct ? x_batch_stride : 0);
       if (st) return st;
     }
   }
@@ -1417,7 +1424,7 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
       const int est[5] = {1, 1, 1, 1, 1};
       EINCONV_CHECK_ARG(n_maps < kMaxMaps, "kfc: too many tensor maps");
       p.kw_map_b[kw] = (signed char)n_maps;
-      int st = encode_map(&host_maps[n_maps++], dtype, base, extent, box, est, pl.PB, pitch);
+      int st = encode_map(&host_maps[n_maps++], dtype, base, extent, box, est, pl.PB, pitch, direct ? x_batch_stride : 0);
       if (st) return st;
     }
   }

@@ -10,7 +10,8 @@ the package (unfold, forward, input VJP) is independent per sample and needs no 
 Layers are processed as a pipeline: the all-reduce of layer ``l`` is issued asynchronously on
 NCCL's stream as soon as its factor kernel has been enqueued, while the compute stream goes on
 with layer ``l+1``; small factors are coalesced into flat buckets so the collective count stays
-low.  ``backend="gloo"`` with CPU tensors is supported for the host-side logic only (tests inject
+low.  KFAC-reduce factors need no all-reduce at all: they are Gram matrices of the window sums, so
+ranks all-gather those (``FactorSweep``) and each forms the full-batch factor.  ``backend="gloo"`` with CPU tensors is supported for the host-side logic only (tests inject
 the compute function); the product compute path is CUDA-only.
 """
 
@@ -40,10 +41,11 @@ def shard_bounds(batch: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def global_scales(global_batch: int, output_total: int) -> Tuple[float, float]:
-    """``(1/B, 1/(B * prod(O)^2))`` rounded through fp32 like the reference's ``Tensor([..])``."""
-    kfc = float(torch.tensor([1.0 / global_batch]))
-    red = float(torch.tensor([1.0 / (global_batch * output_total**2)]))
+def global_scales(global_batch: int, output_total: int, dtype: torch.dtype = torch.float32) -> Tuple[float, float]:
+    """``(1/B, 1/(B * prod(O)^2))`` rounded like the reference's ``Tensor([..]).to(x.dtype)``
+    (``convNd_kfc.py:105``, ``convNd_kfac_reduce.py:106-108``): through fp32, then through ``dtype``."""
+    kfc = float(torch.tensor([1.0 / global_batch]).to(dtype))
+    red = float(torch.tensor([1.0 / (global_batch * output_total**2)]).to(dtype))
     return kfc, red
 
 
@@ -133,7 +135,7 @@ def sharded_factors(
         o_total = 1
         for o in out:
             o_total *= o
-        scale_kfc, scale_red = global_scales(global_batch, o_total)
+        scale_kfc, scale_red = global_scales(global_batch, o_total, x.dtype)
         for kind in kinds:
             factor = fns[kind](
                 x,
@@ -153,25 +155,37 @@ def sharded_factors(
     return results
 
 
-class FactorSweep:
-    """Repeated factor sweeps over fixed layer inputs, with the launch-bound part in CUDA graphs.
+def _align(n: int, to: int = 64) -> int:
+    return (n + to - 1) // to * to
 
-    ``sharded_factors`` pays ~25 us of host work and 4-8 kernel launches per factor; at 8 ranks the
-    per-rank batch of a ResNet-50 sweep is so small that this, not the arithmetic, sets the time.
+
+class FactorSweep:
+    """Repeated factor sweeps over fixed layer inputs: CUDA graphs for the launch-bound part, and an exchange
+    step that moves as few bytes as the mathematics allows.
+
     A ``FactorSweep`` is built once for a fixed list of input tensors (their storage is read at every
     ``run()``, like the static inputs of any CUDA-graph training loop):
 
-    * every factor is written in place into a slice of a flat fp bucket (no ``cat`` / copy-back);
-    * the calls that fill one bucket are captured into one CUDA graph;
-    * ``run()`` replays graph ``b`` and immediately issues the asynchronous SUM all-reduce of bucket
-      ``b`` on NCCL's stream, so the collective of one bucket overlaps the compute of the next.
+    * **KFC** factors are sums over samples of ``A x A`` matrices: every factor is written in place into a
+      256-byte aligned slice of a flat bucket (no ``cat`` / copy-back), the calls that fill one bucket are
+      one CUDA graph, and ``run()`` issues the asynchronous SUM all-reduce of bucket ``b`` right after
+      replaying graph ``b``, so the collective of one bucket overlaps the compute of the next.
+    * **KFAC-reduce** factors are Gram matrices of the window sums ``u`` (``B x A`` numbers per layer against
+      ``A x A`` for the factor).  Ranks exchange ``u`` with ONE all-gather for all layers (6 MB instead of
+      482 MB per sweep of ResNet-50) and every rank forms the full-batch factor from the gathered sums
+      (``evaluator.kfac_reduce_from_sums``): bit-identical on all ranks and to a single-process evaluation
+      of the concatenated batch.  Stage 1 of all layers is one graph at the start of ``run()``; stage 2 is
+      one graph at the end, where it covers the tail of the KFC all-reduces.  Layers without a tensor-core
+      route for stage 2 (``A < 256``, exact fp32 / fp64 math) use the fused call and the bucket all-reduce.
 
-    The numbers are those of ``sharded_factors`` (same kernels, same order of operations).
+    Buckets are per dtype; factors are summed in the dtype of their layer input (like the reference, whose
+    einsum emits ``x.dtype``): reduce fp32 inputs if the last bits of a 16-bit sum across ranks matter.
     """
 
     def __init__(self, x_shards: Sequence[Tensor], layers: Sequence[LayerSpec], global_batch: int,
                  kinds: Sequence[str] = ("kfc", "kfac_reduce"), group=None, simplify: bool = True,
-                 bucket_bytes: int = 64 << 20, use_graphs: bool = True):
+                 bucket_bytes: int = 64 << 20, use_graphs: bool = True, two_stage: Optional[bool] = None):
+        from einconv_b200 import _native as nat
         from einconv_b200 import evaluator
         from einconv_b200.utils import _tuple, resolve_geometry
 
@@ -179,92 +193,172 @@ class FactorSweep:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.kinds = tuple(kinds)
         device = x_shards[0].device
-        dtype = x_shards[0].dtype
-        # ---- work items and their output shapes
-        items = []  # (kind, x, spec, scale, numel, shape)
+        on_gpu = device.type == "cuda"
+        if two_stage is None:
+            two_stage = on_gpu
+        # ---- work items ---------------------------------------------------------------------------
+        fused = []     # (kind, x, spec, scale, numel, shape, dtype): fused call into an all-reduce bucket
+        staged = []    # (x, spec, scale, plan, A, groups): KFAC-reduce through window sums + all-gather
+        order = []     # per (layer, kind): ("fused", index) | ("staged", index) to restore the layer order
         for x, spec in zip(x_shards, layers):
             N = x.dim() - 2
-            _, t_k, _, _, _, out = resolve_geometry(tuple(x.shape[2:]), spec.kernel_size, spec.stride,
-                                                    spec.padding, spec.dilation)
+            _, _, _, _, _, out = resolve_geometry(tuple(x.shape[2:]), spec.kernel_size, spec.stride,
+                                                  spec.padding, spec.dilation)
             o_total = k_total = 1
             for o in out:
                 o_total *= o
             for k in _tuple(spec.kernel_size, N):
                 k_total *= k
             A = x.shape[1] // spec.groups * k_total
-            scale_kfc, scale_red = global_scales(global_batch, o_total)
+            scale_kfc, scale_red = global_scales(global_batch, o_total, x.dtype)
             for kind in self.kinds:
-                items.append((kind, x, spec, scale_kfc if kind == "kfc" else scale_red,
-                              spec.groups * A * A, (spec.groups, A, A)))
-        # ---- flat buckets
-        esz = torch.empty((), dtype=dtype).element_size()
+                plan = None
+                if kind == "kfac_reduce" and two_stage and x.shape[0] > 0:
+                    plan = evaluator.call_plan(nat.OP_KFAC_REDUCE, x.shape[0], spec.groups, x.shape[1] // spec.groups,
+                                               0, x.shape[2:], spec.kernel_size, spec.stride, spec.padding,
+                                               spec.dilation, x.dtype, simplify)
+                    if not evaluator.kfac_reduce_from_sums_supported(plan, self.world):
+                        plan = None
+                if plan is not None:
+                    order.append(("staged", len(staged), kind))
+                    staged.append((x, spec, scale_red, plan, A, spec.groups))
+                else:
+                    order.append(("fused", len(fused), kind))
+                    fused.append((kind, x, spec, scale_kfc if kind == "kfc" else scale_red,
+                                  spec.groups * A * A, (spec.groups, A, A), x.dtype))
+        # ---- flat all-reduce buckets (per dtype, 256-byte aligned slices) ----------------------------
         self.buckets: List[Tensor] = []
-        self._segments: List[List[Tuple]] = []
-        seg, seg_elems = [], 0
-        for it in items:
-            seg.append(it)
-            seg_elems += it[4]
-            if seg_elems * esz >= bucket_bytes:
-                self._segments.append(seg)
-                self.buckets.append(torch.empty(seg_elems, dtype=dtype, device=device))
-                seg, seg_elems = [], 0
-        if seg:
-            self._segments.append(seg)
-            self.buckets.append(torch.empty(seg_elems, dtype=dtype, device=device))
-        self.results: Dict[str, List[Tensor]] = {k: [] for k in self.kinds}
         self._calls: List[List[Callable]] = []
+        fused_views: List[Optional[Tensor]] = [None] * len(fused)
         fns = {"kfc": evaluator.kfc, "kfac_reduce": evaluator.kfac_reduce}
-        for seg, bucket in zip(self._segments, self.buckets):
+
+        def close(seg, dtype):
+            if not seg:
+                return
+            total = sum(_align(it[1][4]) for it in seg)
+            bucket = torch.empty(total, dtype=dtype, device=device)
             calls, offset = [], 0
-            for kind, x, spec, scale, numel, shape in seg:
-                view = bucket[offset : offset + numel].view(shape)
-                offset += numel
-                self.results[kind].append(view)
+            for idx, (kind, x, spec, scale, numel, shape, _) in seg:
+                view = bucket[offset: offset + numel].view(shape)
+                offset += _align(numel)
+                fused_views[idx] = view
 
                 def call(fn=fns[kind], x=x, spec=spec, scale=scale, view=view):
                     fn(x, spec.kernel_size, stride=spec.stride, padding=spec.padding, dilation=spec.dilation,
                        groups=spec.groups, simplify=simplify, scale=scale, out=view)
 
                 calls.append(call)
+            self.buckets.append(bucket)
             self._calls.append(calls)
-        # ---- warm up eagerly (lazy module loading, cudaFuncSetAttribute), then capture one graph per bucket
-        self._graphs = None
-        self.launches_per_run = 0  # kernels of this library inside one run() (graph replays hide them)
-        if use_graphs and device.type == "cuda":
-            from einconv_b200 import _native as nat
 
+        for dtype in dict.fromkeys(it[6] for it in fused):
+            esz = torch.empty((), dtype=dtype).element_size()
+            seg, seg_bytes = [], 0
+            for idx, it in enumerate(fused):
+                if it[6] != dtype:
+                    continue
+                seg.append((idx, it))
+                seg_bytes += _align(it[4]) * esz
+                if seg_bytes >= bucket_bytes:
+                    close(seg, dtype)
+                    seg, seg_bytes = [], 0
+            close(seg, dtype)
+        # ---- window sums of the staged layers: one flat block per rank, all-gathered ------------------
+        self._stage1: List[Callable] = []
+        self._stage2: List[Callable] = []
+        staged_out: List[Tensor] = []
+        self.u_all = self.u_local = None
+        if staged:
+            offsets, total = [], 0
+            for x, spec, scale, plan, A, groups in staged:
+                offsets.append(total)
+                total += _align(groups * A * x.shape[0])
+            u_dtype = torch.float32
+            self.u_all = torch.zeros((self.world, total), dtype=u_dtype, device=device)
+            rank = dist.get_rank(group) if self.world > 1 else 0
+            self.u_local = self.u_all[rank]
+            for (x, spec, scale, plan, A, groups), off in zip(staged, offsets):
+                rows, b_local = groups * A, x.shape[0]
+                u_view = self.u_local[off: off + rows * b_local].view(rows, b_local)
+                out = torch.empty((groups, A, A), dtype=x.dtype, device=device)
+                staged_out.append(out)
+
+                def s1(x=x, spec=spec, u_view=u_view):
+                    evaluator.kfac_reduce_sums(x, spec.kernel_size, stride=spec.stride, padding=spec.padding,
+                                               dilation=spec.dilation, groups=spec.groups, out=u_view)
+
+                def s2(plan=plan, scale=scale, out=out, off=off, total=total):
+                    evaluator.kfac_reduce_from_sums(self.u_all.view(-1)[off:], plan, self.world, total, scale, out)
+
+                self._stage1.append(s1)
+                self._stage2.append(s2)
+        # ---- results in layer order ---------------------------------------------------------------------
+        self.results: Dict[str, List[Tensor]] = {k: [] for k in self.kinds}
+        for where, idx, kind in order:
+            self.results[kind].append(fused_views[idx] if where == "fused" else staged_out[idx])
+        # ---- warm up eagerly (lazy module loading, cudaFuncSetAttribute), then capture the graphs ------
+        self._graphs = None
+        self._graph_s1 = self._graph_s2 = None
+        self.launches_per_run = 0  # kernels of this library inside one run() (graph replays hide them)
+        if use_graphs and on_gpu:
             side = torch.cuda.Stream(device)
             side.wait_stream(torch.cuda.current_stream(device))
             n0 = nat.launch_count()
             with torch.cuda.stream(side):
+                for call in self._stage1:
+                    call()
                 for calls in self._calls:
                     for call in calls:
                         call()
+                for call in self._stage2:
+                    call()
             self.launches_per_run = nat.launch_count() - n0
             torch.cuda.current_stream(device).wait_stream(side)
             torch.cuda.synchronize(device)
             self._graphs = []
             pool = None
-            for calls in self._calls:
+
+            def capture(calls):
+                nonlocal pool
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, pool=pool):
                     for call in calls:
                         call()
                 pool = graph.pool()
-                self._graphs.append(graph)
+                return graph
+
+            if self._stage1:
+                self._graph_s1 = capture(self._stage1)
+            for calls in self._calls:
+                self._graphs.append(capture(calls))
+            if self._stage2:
+                self._graph_s2 = capture(self._stage2)
+
+    def _play(self, graph, calls):
+        if graph is not None:
+            graph.replay()
+        else:
+            for call in calls:
+                call()
 
     def run(self) -> Dict[str, List[Tensor]]:
-        """One sweep: returns ``{kind: [factor per layer]}`` (views into the buckets, overwritten by
-        the next ``run()``), identical on every rank."""
+        """One sweep: returns ``{kind: [factor per layer]}`` (views into the buckets / fixed tensors,
+        overwritten by the next ``run()``), identical on every rank."""
         works = []
+        gather = None
+        if self._stage1:
+            self._play(self._graph_s1, self._stage1)
+            if self.world > 1:
+                # in place: rank r's block is row r of u_all
+                gather = dist.all_gather_into_tensor(self.u_all.view(-1), self.u_local, group=self.group, async_op=True)
         for b, bucket in enumerate(self.buckets):
-            if self._graphs is not None:
-                self._graphs[b].replay()
-            else:
-                for call in self._calls[b]:
-                    call()
+            self._play(self._graphs[b] if self._graphs is not None else None, self._calls[b])
             if self.world > 1:
                 works.append(dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if self._stage2:
+            if gather is not None:
+                gather.wait()
+            self._play(self._graph_s2, self._stage2)
         for work in works:
             work.wait()
         return self.results

@@ -420,6 +420,77 @@ def _factor_entry(op, x, kernel_size, stride, padding, dilation, groups, simplif
 
 
 # --------------------------------------------------------------------------------------------
+# KFAC-reduce in two stages (batch-sharded evaluation): window sums, then their Gram matrix
+# --------------------------------------------------------------------------------------------
+_STAGE2_WS: Dict[tuple, int] = {}
+
+
+def kfac_reduce_sums(x, kernel_size, stride=1, padding=0, dilation=1, groups=1, out=None) -> Tensor:
+    """Stage 1 of KFAC-reduce: ``u[g * A + a, b] = sum_o U[b, g, a, o]`` as ``[G * A, B]`` (fp32; fp64 for
+    fp64 input), the unfolded input summed over output positions without ever being written
+    (``convNd_kfac_reduce.py:77-108``: the network factorises over these sums)."""
+    device = nat.require_cuda(x)
+    x = x.contiguous()
+    B, c_in = x.shape[0], x.shape[1]
+    if c_in % groups != 0:
+        raise ValueError(f"Groups ({groups}) must divide in_channels ({c_in}).")
+    plan = call_plan(nat.OP_KFAC_REDUCE, B, groups, c_in // groups, 0, x.shape[2:], kernel_size, stride, padding,
+                     dilation, x.dtype, True)
+    k_total = 1
+    for k in plan.kernel_size:
+        k_total *= k
+    rows = c_in * k_total
+    u_dtype = torch.float64 if x.dtype == torch.float64 else torch.float32
+    if out is None:
+        out = torch.empty((rows, B), dtype=u_dtype, device=device)
+    elif tuple(out.shape) != (rows, B) or out.dtype != u_dtype or not out.is_contiguous() or out.device != x.device:
+        raise ValueError(f"out must be a contiguous {u_dtype} tensor of shape {(rows, B)} on {x.device}.")
+    if out.numel() == 0:
+        return out
+    with _on_device(device):
+        st = nat.lib().einconv_kfac_reduce_sums(x.data_ptr(), out.data_ptr(), plan.code, plan.geom,
+                                                nat.stream_ptr(device))
+    nat.check(st, "einconv_kfac_reduce_sums")
+    return out
+
+
+def kfac_reduce_from_sums_supported(plan: CallPlan, n_shards: int) -> bool:
+    """Whether stage 2 can run on ``n_shards`` gathered blocks of window sums for this call plan."""
+    return _stage2_workspace(plan, n_shards) >= 0
+
+
+def _stage2_workspace(plan: CallPlan, n_shards: int) -> int:
+    key = (n_shards, plan.code, plan.math, plan.kern, bytes(plan.geom))
+    ws = _STAGE2_WS.get(key)
+    if ws is None:
+        ws = int(nat.lib().einconv_kfac_reduce_from_sums_workspace(n_shards, plan.code, plan.geom, plan.math,
+                                                                     plan.kern))
+        if len(_STAGE2_WS) > _PLAN_CAPACITY:
+            _STAGE2_WS.clear()
+        _STAGE2_WS[key] = ws
+    return ws
+
+
+def kfac_reduce_from_sums(u: Tensor, plan: CallPlan, n_shards: int, shard_stride: int, scale: float,
+                          out: Tensor) -> Tensor:
+    """Stage 2: ``out[g, a, a'] = scale * sum_s sum_b u_s[g, a, b] u_s[g, a', b]`` over ``n_shards`` blocks of
+    window sums, block ``s`` starting ``s * shard_stride`` elements into ``u`` (e.g. the result of an
+    all-gather over ranks), each ``[G * A, B_shard]`` with ``B_shard = plan.geom.batch``.  ``plan`` is the
+    KFAC-reduce call plan of ONE shard (``call_plan(OP_KFAC_REDUCE, B_shard, ...)``)."""
+    device = nat.require_cuda(u, out)
+    ws_bytes = _stage2_workspace(plan, n_shards)
+    if ws_bytes < 0:
+        raise NotImplementedError("kfac_reduce_from_sums: no tensor-core route for this geometry / math mode")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device) if ws_bytes else None
+    with _on_device(device):
+        st = nat.lib().einconv_kfac_reduce_from_sums(
+            u.data_ptr(), n_shards, shard_stride, out.data_ptr(), plan.code, plan.geom, float(scale), plan.math,
+            plan.kern, nat.ptr(ws), ws_bytes, nat.stream_ptr(device))
+    nat.check(st, "einconv_kfac_reduce_from_sums")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # transpose convolutions (SURVEY.md 8f, row f2).  Hyper-parameters are those of the ASSOCIATED
 # convolution; ``x`` has that convolution's OUTPUT sizes.
 # --------------------------------------------------------------------------------------------

@@ -159,6 +159,27 @@ int einconv_kfac_reduce(const void* x, void* out, int dtype, const einconv_geom*
                         int math, int kernels, void* workspace, int64_t workspace_bytes,
                         void* stream);
 
+/* ---- KFAC-reduce in two stages, for batch-sharded evaluation.  The factor is
+ *   out = scale * sum_b u_b u_b^T,   u[b, g, (ci,k..)] = sum_{o..} U[b,g,ci,k..,o..]
+ * (expressions/convNd_kfac_reduce.py:77-108: the second pattern copy shares no index with the first, so
+ * the network factorises over the window sums u).  u is tiny (B x A numbers against A x A for the factor):
+ * ranks exchange u (all-gather) instead of all-reducing factors, and every rank then forms the full-batch
+ * factor — bit-identical on all ranks and to a single-process evaluation of the concatenated batch.
+ *
+ * Stage 1: u[g*A + a][b] (fp32; fp64 for f64 input), contiguous [G*A][B] — positions b innermost. */
+int einconv_kfac_reduce_sums(const void* x, void* u, int dtype, const einconv_geom* g, void* stream);
+
+/* Stage 2 over `n_shards` blocks of window sums, block s at u + s * shard_stride (elements), each laid out
+ * [G*A][B_shard] with B_shard = g->batch:  out[g,a,a'] = scale * sum_s sum_b u_s[g,a,b] u_s[g,a',b].
+ * Tensor-core route only (math TF32 / HALF, A >= 256, 4 * B_shard and 4 * shard_stride multiples of 16
+ * bytes); otherwise EINCONV_ERR_UNSUPPORTED and the caller sums factors instead.  out: [G, A, A] in `dtype`. */
+int einconv_kfac_reduce_from_sums(const void* u, int n_shards, int64_t shard_stride, void* out, int dtype,
+                                  const einconv_geom* g, double scale, int math, int kernels, void* workspace,
+                                  int64_t workspace_bytes, void* stream);
+/* Workspace of stage 2 (bytes), or -1 if the tensor-core route does not apply. */
+int64_t einconv_kfac_reduce_from_sums_workspace(int n_shards, int dtype, const einconv_geom* g, int math,
+                                                int kernels);
+
 /* ---- transpose convolutions.  The geometry always describes the ASSOCIATED
  * convolution: `in` = its input sizes (the transpose convolution's output), `out` = its output sizes
  * (the spatial sizes of the tensor x passed here), with out = 1 + floor((in + 2p - d(k-1) - 1) / s);
