@@ -166,10 +166,13 @@ def require_cuda(*tensors: torch.Tensor) -> torch.device:
                 "einconv_b200 evaluates convolution tensor networks with sm_100a CUDA kernels "
                 f"only; got a tensor on {t.device}. There is no CPU fallback."
             )
+        dev = t.device
+        if dev.index is None:  # e.g. a lazy index pattern created with device="cuda": the current device
+            dev = torch.device("cuda", torch.cuda.current_device())
         if device is None:
-            device = t.device
-        elif t.device != device:
-            raise RuntimeError(f"Tensors on different devices: {device} and {t.device}.")
+            device = dev
+        elif dev != device:
+            raise RuntimeError(f"Tensors on different devices: {device} and {dev}.")
     return device
 
 

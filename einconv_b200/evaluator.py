@@ -942,8 +942,93 @@ def einsum(equation, *operands):
         result = plan.run()
         return result.reshape(_einsum_output_shape(str(equation), operands))
 
+    return _pattern_aware_einsum(str(equation), list(operands))
+
+
+# --------------------------------------------------------------------------------------------
+# user-composed networks: index patterns as native gathers, never as one-hot GEMMs
+# --------------------------------------------------------------------------------------------
+def _apply_pattern(tensor: Tensor, axis: int, pattern, transpose: bool) -> Optional[Tensor]:
+    """Contract ``tensor``'s ``axis`` with an index pattern ``Pi[k, o, i]`` without forming ``Pi``.
+
+    ``transpose=False``: the axis is ``i``; result axes ``(k, o)`` hold ``tensor[i = s o + d k - p]`` (0 outside):
+    the 1-d ``unfoldNd`` gather.  ``transpose=True``: the axis is ``o``; result axes ``(k, i)`` hold
+    ``tensor[o]`` where ``i = s o + d k - p``: the transpose-convolution gather.  Both run the bit-exact native
+    kernels and are differentiable.  Returns None when the pattern cannot be expressed (asymmetric padding in
+    the transpose direction)."""
+    h = pattern._pattern_hyperparams
+    K, S, D, P = h["kernel_size"], h["stride"], h["dilation"], h["padding"]
+    moved = tensor.movedim(axis, -1)
+    rest = moved.shape[:-1]
+    flat = moved.reshape(-1, 1, moved.shape[-1])
+    if not transpose:
+        out = unfold_autograd(flat, K, dilation=D, padding=P, stride=S)          # [R, K, O]
+    else:
+        from einconv_b200.utils import get_conv_paddings
+
+        p_left, p_right = get_conv_paddings(K, S, P, D)
+        if p_left != p_right:
+            return None
+        base = get_conv_input_size(flat.shape[-1], K, S, p_left, 0, D)
+        extra = h["input_size"] - base
+        if extra < 0 or extra >= max(S, D):
+            return None
+        out = unfold_transpose_autograd(flat, K, stride=S, padding=p_left, output_padding=extra, dilation=D)
+    out = out.reshape(*rest, out.shape[-2], out.shape[-1])
+    n = out.dim()
+    return out.movedim((n - 2, n - 1), (axis, axis + 1))
+
+
+def _pattern_aware_einsum(equation: str, operands: List[Any]) -> Tensor:
+    """``torch.einsum`` for networks that mix lazy index patterns with ordinary tensors.
+
+    The reference evaluates such a network as dense GEMMs against the one-hot ``Pi`` tensors
+    (``conv_index_pattern.py:12-85``).  Here every pattern whose input index ``i`` (or, in the transpose
+    direction, output index ``o``) is shared with exactly one data operand and is summed out is *applied* to
+    that operand as an indexed gather (the native 1-d unfold kernels): the operand trades its ``i`` axis for a
+    ``(k, o)`` pair and the pattern disappears from the network.  What is left is an ordinary contraction of
+    data tensors.  Patterns that do not fit (their index survives into the output, is shared by several
+    operands, ...) are written out densely like before."""
+    from einconv_b200.conv_index_pattern import IndexPattern
+
+    eq = equation.replace(" ", "")
+    if "->" not in eq or "." in eq:
+        with torch._C.DisableTorchFunctionSubclass():
+            return torch.einsum(equation, *[_dense(op) for op in operands])
+    lhs, rhs = eq.split("->")
+    terms = lhs.split(",")
+    ops = [op.as_subclass(Tensor) if isinstance(op, PlannedOperand) else op for op in operands]
+    if len(terms) != len(ops):
+        with torch._C.DisableTorchFunctionSubclass():
+            return torch.einsum(equation, *[_dense(op) for op in operands])
+    changed = True
+    while changed:
+        changed = False
+        for pos, (term, op) in enumerate(zip(terms, ops)):
+            if not isinstance(op, IndexPattern) or len(term) != 3 or len(set(term)) != 3:
+                continue
+            k, o, i = term
+            for letter, transpose in ((i, False), (o, True)):
+                others = [q for q, t in enumerate(terms) if q != pos and letter in t]
+                if letter in rhs or len(others) != 1:
+                    continue
+                q = others[0]
+                t = terms[q]
+                new_pair = (k + o) if not transpose else (k + i)
+                if isinstance(ops[q], IndexPattern) or t.count(letter) != 1 or any(c in t for c in new_pair):
+                    continue
+                applied = _apply_pattern(ops[q], t.index(letter), op, transpose)
+                if applied is None:
+                    continue
+                ops[q] = applied
+                terms[q] = t.replace(letter, new_pair)
+                del ops[pos], terms[pos]
+                changed = True
+                break
+            if changed:
+                break
     with torch._C.DisableTorchFunctionSubclass():
-        return torch.einsum(str(equation), *[_dense(op) for op in operands])
+        return torch.einsum(",".join(terms) + "->" + rhs, *[_dense(op) for op in ops])
 
 
 def evaluate(equation, operands, shape=None) -> Tensor:

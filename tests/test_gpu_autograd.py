@@ -145,3 +145,68 @@ def test_fp32_training_step_uses_native_backward_kernels():
     before = nat.launch_count()
     y.sum().backward()
     assert nat.launch_count() > before and w.grad is not None
+
+
+# =============================================================================================
+# user-composed networks with index patterns
+# =============================================================================================
+def _dense_einsum(eq, ops):
+    return torch.einsum(eq, *evaluator.plain(ops))
+
+
+def test_user_composed_networks_apply_patterns_as_gathers(monkeypatch):
+    """Networks built by hand from ``einconv_b200.index_pattern`` never materialise the one-hot tensor when the
+    pattern's input (or output) index is contracted with one data operand: same values as the dense route."""
+    import einconv_b200
+    from einconv_b200 import conv_index_pattern as cip
+
+    torch.manual_seed(6)
+    x = torch.rand(3, 5, 11, 9, dtype=torch.float64, device=DEV)
+    w = torch.rand(4, 5, 3, 2, dtype=torch.float64, device=DEV)
+    pat_h = einconv_b200.index_pattern(11, 3, stride=2, padding=1, dilation=1, device=DEV, dtype=x.dtype)
+    pat_w = einconv_b200.index_pattern(9, 2, stride=1, padding=0, dilation=2, device=DEV, dtype=x.dtype)
+    calls = []
+    real = cip.IndexPattern.materialize
+    monkeypatch.setattr(cip.IndexPattern, "materialize", lambda self: calls.append(1) or real(self))
+
+    # a convolution written by hand, with an extra per-channel gate the library has no plan for
+    gate = torch.rand(5, dtype=torch.float64, device=DEV)
+    eq = "ncab,kxa,lyb,dckl,c->ndxy"
+    got = torch.einsum(eq, x, pat_h, pat_w, w, gate)
+    assert not calls, "the index patterns were written out"
+    want = F.conv2d(x * gate.view(1, -1, 1, 1), w, stride=(2, 1), padding=(1, 0), dilation=(1, 2))
+    torch.testing.assert_close(got, want, rtol=1e-10, atol=1e-12)
+    torch.testing.assert_close(got, _dense_einsum(eq, [x, pat_h, pat_w, w, gate]), rtol=1e-10, atol=1e-12)
+
+    # second-moment of the unfolded input along one axis only (a "lens" onto the network)
+    calls.clear()
+    eq2 = "ncab,kxa,lxa_->nckl".replace("a_", "e").replace("ncab", "ncab")
+    eq2 = "ncab,kxa,lxe,nceb->nckl"
+    got2 = torch.einsum(eq2, x, pat_h, pat_h, x)
+    assert not calls
+    torch.testing.assert_close(got2, _dense_einsum(eq2, [x, pat_h, pat_h, x]), rtol=1e-10, atol=1e-12)
+
+    # transpose direction: the OUTPUT index is contracted (a transpose convolution written by hand)
+    calls.clear()
+    y = torch.rand(3, 4, 6, dtype=torch.float64, device=DEV)   # [n, d, x]: 6 = output size of pat_h
+    wt = torch.rand(4, 5, 3, dtype=torch.float64, device=DEV)   # [d, c, k]
+    eq3 = "ndx,kxa,dck->nca"
+    got3 = torch.einsum(eq3, y, pat_h, wt)
+    assert not calls
+    want3 = F.conv_transpose1d(y, wt, stride=2, padding=1)
+    torch.testing.assert_close(got3, want3[..., :11], rtol=1e-10, atol=1e-12)
+    torch.testing.assert_close(got3, _dense_einsum(eq3, [y, pat_h, wt]), rtol=1e-10, atol=1e-12)
+
+    # a pattern whose indices all survive is written out (nothing to apply it to): still correct
+    calls.clear()
+    got4 = torch.einsum("kxa,a->kx", pat_h, torch.ones(11, dtype=torch.float64, device=DEV))
+    torch.testing.assert_close(got4, _dense_einsum("kxa,a->kx", [pat_h, torch.ones(11, dtype=torch.float64, device=DEV)]))
+
+    # gradients flow through the gathers
+    xg = x.clone().requires_grad_()
+    out = torch.einsum(eq, xg, pat_h, pat_w, w, gate)
+    (gx,) = torch.autograd.grad(out.sum(), xg)
+    xr = x.clone().requires_grad_()
+    (gr,) = torch.autograd.grad(F.conv2d(xr * gate.view(1, -1, 1, 1), w, stride=(2, 1), padding=(1, 0),
+                                         dilation=(1, 2)).sum(), xr)
+    torch.testing.assert_close(gx, gr, rtol=1e-10, atol=1e-12)
