@@ -182,7 +182,11 @@ static bool kfc_half_route(const DevGeom& g, int dtype, int math, int kernels, i
   // faster on kind::tf32 without the extra pass
   long long max_a = 2304;
   if (const char* e = getenv("EINCONV_KFC_HALF_MAXA")) max_a = atoll(e);  // A/B measurements
-  if (g.k_total == 1 || (long long)g.c_in_g * g.k_total > max_a) return false;
+  // narrow images (rows shorter than a 128-byte box in fp16) use the flat-plane operand layout of tc_tma.cu,
+  // where fp16 positions are as densely packed as fp32 ones: the copy pays off for every A
+  const bool flat = g.n_dims == 2 && g.k_total > 1 && g.k_total <= 25 && g.out[1] * 2 < 128 &&
+                    !getenv("EINCONV_KFC_NO_FLAT");
+  if (g.k_total == 1 || (!flat && (long long)g.c_in_g * g.k_total > max_a)) return false;
   DevGeom g1;
   int64_t ub;
   if (!tma::tma_supported(EINCONV_OP_KFC, g, EINCONV_F16) &&

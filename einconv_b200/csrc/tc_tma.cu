@@ -200,6 +200,10 @@ struct Params {
   float direct_scale;
   int direct_a;                        // A = c_in_g * k_total (rows / columns of the factor)
   int s_tiles;                         // KFC super-tile kernel: ceil(m_tiles / 2) super-tiles (256 rows) per side
+  // flat-plane mode (see flat_copy_kernel): per-tap tensor map (row / column operand) and start coordinate
+  int flat;
+  signed char tap_map_a[kMaxMaps], tap_map_b[kMaxMaps];
+  int tap_c0[kMaxMaps];
 };
 
 template <typename T> struct Elem;
@@ -646,6 +650,13 @@ kfc_super_kernel(const __grid_constant__ MapArray map_array, const __grid_consta
       l_cw[q] = p.kw_c0[kw];
       l_ch[q] = (int)kh * p.dil[1] - p.pad[1];
       l_cd[q] = (int)kd * p.dil[2] - p.pad[2];
+      if (p.flat) {  // one flat coordinate per tap, its own (clipped) map
+        const int tt = on ? tap : 0;
+        l_map[q] = maps + ((is_a && !diag) ? p.tap_map_a[tt] : p.tap_map_b[tt]);
+        l_cw[q] = p.tap_c0[tt];
+        l_ch[q] = 0;
+        l_cd[q] = 0;
+      }
       l_dst[q] = (is_a ? 0 : kSuperOperandBytes) + pc * (kSuperRows * p.PB) + sub * (kTileM * p.PB) + tl * p.CB * p.PB;
       l_chan[q] = grp * p.c_in_g + cblock * p.CB;
     }
@@ -840,6 +851,63 @@ kfc_super_kernel(const __grid_constant__ MapArray map_array, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass of the flat-plane mode (2-d KFC whose output rows are shorter than a 128-byte box: 28, 14, 7
+// wide images).  Per-row boxes waste the TMA unit there (a 14-wide fp16 row is a 32-byte request; the
+// kernel measured 24 % tensor activity on 14 x 14 planes).  Instead every (sample, channel) plane is
+// re-laid as ONE flat array per kernel column kw (stride 1) or per tap (stride > 1):
+//     copy[q = r * pitch + j] = (j < O_w) ? x[r * s_h + kh_off - p_h][j * s_w + kw * d_w - p_w] : 0
+// with pitch = O_w rounded up to 16 bytes.  Output position (oh, ow) is q = oh * pitch + ow; tap (kh, kw)
+// of a stride-1 layer reads the kw-copy at q + kh * d_h * pitch (rows are shared between the kh), a strided
+// layer reads its own copy at q.  A K block is then 128 contiguous bytes per channel whatever the image
+// width (one box of CB x 128 B per tap and tile), columns j >= O_w are zero in the copy, and rows beyond
+// the last output row are cut off by the extent of the column operand's tensor map (zero fill).
+// One thread writes one 16-byte unit.
+// ---------------------------------------------------------------------------------------------
+struct FlatCopyParams {
+  int W, H;               // input plane
+  int pitch, rows;        // flat plane: rows x pitch elements (+ tail up to plane_stride)
+  long long plane_stride; // elements between consecutive planes of one copy
+  long long copy_stride;  // elements between copies
+  int n_copies, per_tap;
+  int k_w;                // kernel width (tap -> (kh, kw))
+  int s_h, s_w, d_h, d_w, p_h, p_w, out_w;
+  long long planes;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) flat_copy_kernel(const T* __restrict__ x, T* __restrict__ out,
+                                                        const __grid_constant__ FlatCopyParams fp) {
+  constexpr int A = 16 / sizeof(T);
+  const int units = (int)(fp.plane_stride / A);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_copy = fp.planes * units;
+  if (idx >= per_copy * fp.n_copies) return;
+  const int copy = (int)(idx / per_copy);
+  const long long rem = idx - (long long)copy * per_copy;
+  const long long plane = rem / units;
+  const int u = (int)(rem - plane * units);
+  const int q0 = u * A;
+  const int r = q0 / fp.pitch, j0 = q0 - r * fp.pitch;  // pitch is a multiple of A: one unit stays in one row
+  int kh = 0, kw = copy;
+  if (fp.per_tap) {
+    kh = copy / fp.k_w;
+    kw = copy - kh * fp.k_w;
+  }
+  const int i = fp.per_tap ? r * fp.s_h + kh * fp.d_h - fp.p_h : r - fp.p_h;
+  const bool row_ok = r < fp.rows && i >= 0 && i < fp.H;
+  const T* src = x + plane * ((long long)fp.W * fp.H) + (long long)(row_ok ? i : 0) * fp.W;
+  alignas(16) T vals[A];
+#pragma unroll
+  for (int e = 0; e < A; ++e) {
+    const int j = j0 + e;
+    const int c = j * fp.s_w + kw * fp.d_w - fp.p_w;
+    vals[e] = (row_ok && j < fp.out_w && c >= 0 && c < fp.W) ? src[c] : T(0);
+  }
+  *reinterpret_cast<uint4*>(out + (long long)copy * fp.copy_stride + plane * fp.plane_stride + (long long)u * A) =
+      *reinterpret_cast<const uint4*>(vals);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1046,6 +1114,10 @@ struct Plan {
   bool tri = false;  // KFC: compute only the tiles on or above the diagonal
   bool super = false;  // KFC: 256 x 256 super-tiles (kfc_super_kernel)
   int s_tiles = 0;
+  bool flat = false;          // KFC: flat-plane operand copies (flat_copy_kernel)
+  bool flat_per_tap = false;  // one copy per tap (strided layers) instead of one per kernel column
+  int flat_pitch = 0, flat_rows = 0;
+  long long flat_plane = 0;   // elements per (sample, channel) plane of a copy
   int n_wt, n_ht, n_dt;
   long long Mp, Np;
   // shifted copies of the input (and an aligned copy of the cotangent when its rows are not
@@ -1090,6 +1162,17 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
   const long long x_elems = (long long)g.batch * g.groups * g.c_in_g * g.in_total;
   if (x_elems >= (1ll << 40)) return pl;
   pl.kpos = kRowBytes / es;
+  pl.flat = op == EINCONV_OP_KFC && g.n_dims == 2 && g.k_total > 1 && g.k_total <= 25 &&
+            q.out[0] * es < kRowBytes && !getenv("EINCONV_KFC_FULL") && !getenv("EINCONV_KFC_TILE128") &&
+            !getenv("EINCONV_KFC_NO_FLAT");
+  if (pl.flat) {
+    const int A_ = 16 / es;
+    pl.flat_per_tap = q.stride[0] > 1 || q.stride[1] > 1;
+    pl.flat_pitch = ((q.out[0] + A_ - 1) / A_) * A_;
+    pl.flat_rows = pl.flat_per_tap ? q.out[1] : q.out[1] + (q.k[1] - 1) * q.dil[1];
+    pl.flat_plane = (long long)pl.flat_rows * pl.flat_pitch;
+    if (pl.flat_plane >= (1ll << 30)) pl.flat = false;
+  }
   // patch shape: one (d, h) line of the patch is PB = 128 / 64 / 32 bytes per channel (BW = PB / es
   // positions, the TMA box's inner extent and the swizzle span); 128 / PB lines (BH x BD) make one
   // 128-byte K block.  Minimise out-of-range positions; prefer long lines on ties.
@@ -1112,6 +1195,11 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
   pl.n_wt = ceil_div(q.out[0], pl.BW);
   pl.n_ht = ceil_div(q.out[1], pl.BH);
   pl.n_dt = ceil_div(q.out[2], pl.BD);
+  if (pl.flat) {  // K blocks are 128-byte runs of the flat output grid of one sample
+    pl.PB = kRowBytes; pl.BW = kRowBytes / es; pl.BH = 1; pl.BD = 1;
+    pl.n_wt = ceil_div(q.out[1] * pl.flat_pitch, pl.BW);
+    pl.n_ht = 1; pl.n_dt = 1;
+  }
   const long long kb = (long long)g.batch * pl.n_wt * pl.n_ht * pl.n_dt;
   if (kb >= (1ll << 31) || kb == 0) return pl;
   pl.k_blocks = (int)kb;
@@ -1209,6 +1297,15 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
   if (n_maps + q.k[0] + 1 >= kMaxMaps) return pl;
   pl.x_rows = (long long)g.batch * g.groups * g.c_in_g * q.in[2] * q.in[1];
   pl.copy_x_bytes = (((long long)pl.x_rows * pl.Wp_x * es + 255) / 256) * 256;
+  if (pl.flat) {
+    if (!pl.super) { pl.flat = false; }
+  }
+  if (pl.flat) {
+    pl.per_tap = false; pl.x_direct = false;
+    pl.n_copies = pl.flat_per_tap ? g.k_total : q.k[0];
+    const long long planes = (long long)g.batch * g.groups * g.c_in_g;
+    pl.copy_x_bytes = ((planes * pl.flat_plane * es + 255) / 256) * 256;
+  }
   pl.v_copy = (op == EINCONV_OP_CONV_WEIGHT_VJP) && (q.out[0] * es) % 16 != 0;
   pl.Wp_v = ((q.out[0] + A - 1) / A) * A + A;
   pl.v_rows = (long long)g.batch * g.groups * std::max(1, g.c_out_g) * q.out[2] * q.out[1];
@@ -1319,7 +1416,26 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
     EINCONV_CHECK_LAUNCH("shift_copy_kernel");
     return EINCONV_OK;
   };
-  for (int i = 0; i < pl.n_copies; ++i) {
+  if (pl.flat) {
+    FlatCopyParams fp{};
+    fp.W = q.in[0]; fp.H = q.in[1];
+    fp.pitch = pl.flat_pitch; fp.rows = pl.flat_rows;
+    fp.plane_stride = pl.flat_plane;
+    fp.copy_stride = pl.copy_x_bytes / es;
+    fp.n_copies = pl.n_copies; fp.per_tap = pl.flat_per_tap ? 1 : 0;
+    fp.k_w = q.k[0];
+    fp.s_h = q.stride[1]; fp.s_w = q.stride[0]; fp.d_h = q.dil[1]; fp.d_w = q.dil[0];
+    fp.p_h = q.pad[1]; fp.p_w = q.pad[0]; fp.out_w = q.out[0];
+    fp.planes = (long long)g.batch * g.groups * g.c_in_g;
+    const long long units = fp.planes * (fp.plane_stride / A) * fp.n_copies;
+    const unsigned blocks = (unsigned)((units + 255) / 256);
+    if (es == 2)
+      flat_copy_kernel<uint16_t><<<blocks, 256, 0, stream>>>((const uint16_t*)x, (uint16_t*)copies_x, fp);
+    else
+      flat_copy_kernel<uint32_t><<<blocks, 256, 0, stream>>>((const uint32_t*)x, (uint32_t*)copies_x, fp);
+    EINCONV_CHECK_LAUNCH("flat_copy_kernel");
+  }
+  for (int i = 0; i < (pl.flat ? 0 : pl.n_copies); ++i) {
     int st = shift_copy(x, copies_x + i * pl.copy_x_bytes, pl.x_rows, q.in[0], pl.Wp_x, pl.copy_res[i],
                         pl.per_tap ? q.stride[0] : 1);
     if (st) return st;
@@ -1334,8 +1450,48 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   memset(&map_array, 0, sizeof(map_array));
   CUtensorMap* host_maps = map_array.m;
   int n_maps = 0, copy_i = 0;
-  int res_margin[16];  // coordinate margin of the map serving residue r: A for copies, 0 for x itself
-  if (pl.per_tap) {
+  int res_margin[16] = {0};  // coordinate margin of the map serving residue r: A for copies, 0 for x itself
+  signed char flat_map_a[kMaxMaps] = {0}, flat_map_b[kMaxMaps] = {0};
+  int flat_c0[kMaxMaps] = {0};
+  if (pl.flat) {
+    const int chans = g.groups * g.c_in_g;
+    const int box[5] = {pl.BW, 1, 1, pl.CB, 1};
+    const int est[5] = {1, 1, 1, 1, 1};
+    const int plane = (int)pl.flat_plane;
+    if (pl.flat_per_tap) {
+      // one copy per tap, every tap reads its copy at the output position itself; rows >= O_h do not exist
+      for (int t = 0; t < g.k_total; ++t) {
+        const void* base = copies_x + (long long)t * pl.copy_x_bytes;
+        const int extent[5] = {plane, 1, 1, chans, g.batch};
+        int st = encode_map(&host_maps[n_maps], dtype, base, extent, box, est, pl.PB, plane);
+        if (st) return st;
+        flat_map_a[t] = flat_map_b[t] = (signed char)n_maps++;
+        flat_c0[t] = 0;
+      }
+    } else {
+      // one copy per kernel column; tap (kh, kw) starts kh * d_h rows further down.  Row operand: the whole
+      // plane.  Column operand: cut off after the last output row as seen through this kh (zero fill).
+      for (int kw = 0; kw < q.k[0]; ++kw) {
+        const void* base = copies_x + (long long)kw * pl.copy_x_bytes;
+        const int extent[5] = {plane, 1, 1, chans, g.batch};
+        int st = encode_map(&host_maps[n_maps++], dtype, base, extent, box, est, pl.PB, plane);
+        if (st) return st;
+      }
+      for (int kh = 0; kh < q.k[1]; ++kh)
+        for (int kw = 0; kw < q.k[0]; ++kw) {
+          const int t = kh * q.k[0] + kw;
+          const void* base = copies_x + (long long)kw * pl.copy_x_bytes;
+          const int clipped = std::min(plane, (q.out[1] + kh * q.dil[1]) * pl.flat_pitch);
+          const int extent[5] = {clipped, 1, 1, chans, g.batch};
+          EINCONV_CHECK_ARG(n_maps < kMaxMaps, "kfc: too many tensor maps");
+          int st = encode_map(&host_maps[n_maps], dtype, base, extent, box, est, pl.PB, plane);
+          if (st) return st;
+          flat_map_a[t] = (signed char)kw;
+          flat_map_b[t] = (signed char)n_maps++;
+          flat_c0[t] = kh * q.dil[1] * pl.flat_pitch;
+        }
+    }
+  } else if (pl.per_tap) {
     for (int kw = 0; kw < q.k[0]; ++kw) {
       const void* base = copies_x + (long long)kw * pl.copy_x_bytes;
       const int extent[5] = {pl.Wp_x, q.in[1], q.in[2], g.groups * g.c_in_g, g.batch};
@@ -1416,7 +1572,15 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   p.out_h = q.out[1];
   p.out_d = q.out[2];
   for (int kw = 0; kw < q.k[0]; ++kw) p.kw_map_b[kw] = p.kw_map[kw];
-  if (kfc) {
+  if (pl.flat) {
+    p.flat = 1;
+    for (int t = 0; t < g.k_total; ++t) {
+      p.tap_map_a[t] = flat_map_a[t]; p.tap_map_b[t] = flat_map_b[t]; p.tap_c0[t] = flat_c0[t];
+    }
+    for (int i = 0; i < 3; ++i) { p.stride[i] = 1; p.dil[i] = 0; p.pad[i] = 0; }
+    p.out_h = 1; p.out_d = 1;
+  }
+  if (kfc && !pl.flat) {
     // column operand of KFC: positions beyond the output width must read as zero (the row operand
     // may then hold anything there).  Same memory as the row operand's map for this tap, with the
     // innermost extent clipped to the last valid output; rows keep their pitch.

@@ -254,7 +254,9 @@ class FactorSweep:
         for dtype in dict.fromkeys(it[6] for it in fused):
             esz = torch.empty((), dtype=dtype).element_size()
             seg, seg_bytes = [], 0
-            for idx, it in enumerate(fused):
+            # largest factors first: their all-reduces start early and the LAST bucket, whose collective
+            # nothing but stage 2 can hide, holds the small ones
+            for idx, it in sorted(enumerate(fused), key=lambda pair: -pair[1][4]):
                 if it[6] != dtype:
                     continue
                 seg.append((idx, it))
