@@ -465,7 +465,9 @@ class FactorsC5(Workload):
     bound = "tensor"
     dtype = "f32 (KFC: tf32 / scaled-fp16 MMA, fp32 accumulate; KFAC-reduce: fp32 sums + tf32 MMA)"
     fp32_math = "tf32"
-    ncu_profiles = ()
+    # dominant kernel of the sweep: kfc_super_kernel<__half> (a third of the GPU time,
+    # profiles/r02_factors_c5_launches_b256_weighted.txt), captured on its most frequent layer
+    ncu_profiles = ("profiles/r02_kfc_super_a2304_ncu_full.txt",)
 
     def __init__(self, world=1, rank=0, global_batch=256):
         self.world, self.rank, self.global_batch = world, rank, global_batch
@@ -519,6 +521,32 @@ class FactorsC5(Workload):
             a = c * k * k
             total += count * 2 * self.global_batch * o * o * (a * (a + 1) // 2 if triangle else a * a)
         return total
+
+    def dominant_kernel(self, device, reps=10):
+        """The KFC call of the most frequent 3x3 geometry (C=256, 14x14, k3 p1: 5 of the 16 3x3 layers, each
+        532.7 GFLOP in the full-GEMM convention) timed alone with CUDA events on this rank's batch shard: the
+        call is absmax + fp16 scaling + flat-plane copies + kfc_super_kernel<__half> + the finish pass; the
+        committed ncu capture gives the share of the main kernel (347 of ~460 us at batch 256)."""
+        from einconv_b200 import evaluator
+
+        x = torch.rand(self.hi - self.lo, 256, 14, 14, device=device)
+        for _ in range(3):
+            evaluator.kfc(x, 3, padding=1)
+        torch.cuda.synchronize(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            evaluator.kfc(x, 3, padding=1)
+        b.record()
+        b.synchronize()
+        ms = a.elapsed_time(b) / reps
+        A, pos = 2304, (self.hi - self.lo) * 196
+        full = 2.0 * pos * A * A
+        return dict(call="evaluator.kfc(x[B,256,14,14], 3, padding=1), fp32 tensors in TF32 mode", batch=self.hi - self.lo,
+                    ms_per_call=ms, achieved_full_gemm_tflops=full / (ms * 1e-3) / 1e12,
+                    achieved_triangle_tflops=full * (A + 1) / (2 * A) / (ms * 1e-3) / 1e12,
+                    main_kernel="kfc_super_kernel<__half> (tcgen05 kind::f16 on power-of-two-scaled fp16 copies)",
+                    timing=f"{reps} calls back to back in one CUDA-event pair")
 
     def e2e_setup(self, device):
         self.x_hosts = [torch.empty(x.shape, dtype=x.dtype).pin_memory().copy_(x) for x in self.inputs]
@@ -858,6 +886,11 @@ def main():
         roof["kernel_ms"] = kern_ms
         roof["timing"] = ("8 launches back to back in one CUDA-event pair, rotating input/output buffers (2.6 GB >> L2), "
                           "best of 3" if kern_ms is not None else "per-step CUDA events (includes the launch gaps)")
+        if hasattr(wl, "dominant_kernel"):
+            roof["dominant_kernel"] = wl.dominant_kernel(device)
+            roof["dominant_kernel"]["frac_of_bf16_peak_full_gemm"] = roof["dominant_kernel"]["achieved_full_gemm_tflops"] / pk["bf16"]
+            roof["dominant_kernel"]["frac_of_bf16_peak_triangle"] = roof["dominant_kernel"]["achieved_triangle_tflops"] / pk["bf16"]
+            roof["traffic_note"] = "traffic = DRAM bytes of ONE launch of the dominant kernel (kfc_super_kernel on the C=256 14x14 layer, batch 256)"
         if wl.bound == "hbm":
             roof["frac_per_step"] = wl.work() / (step_ms * 1e-3) / 1e9 / pk["hbm"]
         if hasattr(wl, "naive_bytes"):

@@ -22,6 +22,12 @@ KEYS = [
     "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_subunit_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_tensor.sum",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct",
+    "lts__t_sectors_srcunit_tex_op_write.sum",
+    "sm__cycles_active.avg",
+    "gpc__cycles_elapsed.max",
     "launch__grid_size",
     "launch__block_size",
     "launch__registers_per_thread",
@@ -54,8 +60,10 @@ def main():
             continue
         print(f"kernel: {name}")
         for k in KEYS:
-            if k in hdr:
-                i = hdr.index(k)
+            # some sections prefix their metrics ("TPC.TriageCompute.sm__pipe_tensor_...")
+            hits = [i for i, h in enumerate(hdr) if h == k or h.endswith("." + k)]
+            if hits:
+                i = hits[0]
                 print(f"  {k:<85s} {r[i]:>16s} {units[i]}")
         print()
 
