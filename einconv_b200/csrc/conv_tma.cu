@@ -177,6 +177,19 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         pw ^= 1;
       }
       CTMA_TRACE(0);
+      if (load_w && n_wbars == 1) {
+        // more stages per tile than weight barriers: ONE barrier for the whole class, so every tile must be
+        // requested before the first slab (the MMA warp waits for all of them before it frees a ring slot;
+        // requesting them stage by stage dead-locks as soon as the ring is full)
+        if (lane == 0) mbar_expect_tx(&bars->w_full[0], (uint32_t)(p.n_slices * p.taps * p.bn * p.cb_bytes));
+        __syncwarp();
+        for (int idx = lane; idx < p.n_slices * p.taps; idx += 32) {
+          const int s = idx / p.taps, tap = idx - s * p.taps;
+          tma_load_2d(w_region + (size_t)idx * p.btile_bytes, &map_b, &bars->w_full[0], s * p.cb_elems,
+                      wrow0 + tap * p.np);
+        }
+        load_w = false;
+      }
       int sg = 0;
       for (int s = 0; s < p.n_slices; ++s) {
         for (int grp = 0; grp < p.n_groups; ++grp, ++sg) {
@@ -364,6 +377,9 @@ struct PackParams {
   int n_dims;
   int ctot, cp;
   int S[kMaxDims], P[kMaxDims], pad[kMaxDims];
+  // phase sub-images of a strided convolution (scalar kernel only): padded-grid position r of dimension d
+  // reads source index sstep[d] * (r - pad[d]) + soff[d]; sstep = 1, soff = 0 otherwise
+  int sstep[kMaxDims], soff[kMaxDims];
   long long s_total;  // prod(S)
   long long outer_rows;  // B * prod(P[0..N-2])
   int rows_per_cta;
@@ -461,7 +477,7 @@ __global__ void __launch_bounds__(256) pack_channels_last_kernel(const T* __rest
       uint32_t q, r;
       pp.outer_div[d].divmod(rem, q, r);
       rem = q;
-      const int i = (int)r - pp.pad[d];
+      const int i = ((int)r - pp.pad[d]) * pp.sstep[d] + pp.soff[d];
       if (i < 0 || i >= pp.S[d]) row_real = false;
       src_off += (long long)i * mul;
       mul *= pp.S[d];
@@ -480,7 +496,7 @@ __global__ void __launch_bounds__(256) pack_channels_last_kernel(const T* __rest
       T vals[8][EPW];
 #pragma unroll
       for (int e = 0; e < EPW; ++e) {
-        const int iw = w0 + lane + 32 * e - pp.pad[W];
+        const int iw = (w0 + lane + 32 * e - pp.pad[W]) * pp.sstep[W] + pp.soff[W];
         const bool ok = iw >= 0 && iw < pp.S[W];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -718,6 +734,8 @@ int pack_channels_last_f32_to_f16(const float* src, void* xp, int n_dims, int ba
     pp.S[d] = S[d];
     pp.P[d] = (int)P[d];
     pp.pad[d] = pad[d];
+    pp.sstep[d] = 1;
+    pp.soff[d] = 0;
     pp.s_total *= S[d];
     if (d < N - 1) {
       outer *= P[d];
@@ -750,9 +768,15 @@ int pack_channels_last_f32_to_f16(const float* src, void* xp, int n_dims, int ba
 // src [B, ctot, S..] -> xp [B, P_0.., P_{N-1}, cp]: zero-padded by pad[d] in front, channels-last
 int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int batch, int ctot, int cp,
                        const int* S, const long long* P, const int* pad, cudaStream_t stream,
-                       const WeightJob* wj) {
+                       const WeightJob* wj, const int* sstep, const int* soff) {
   const int N = n_dims;
   PackParams pp{};
+  bool strided = false;
+  for (int d = 0; d < kMaxDims; ++d) {
+    pp.sstep[d] = (sstep && d < N) ? sstep[d] : 1;
+    pp.soff[d] = (soff && d < N) ? soff[d] : 0;
+    strided = strided || pp.sstep[d] != 1 || pp.soff[d] != 0;
+  }
   pp.n_dims = N;
   pp.ctot = ctot;
   pp.cp = cp;
@@ -787,7 +811,7 @@ int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int bat
     grid.x += pp.w_ctas;
   }
   EINCONV_CHECK_ARG(grid.y < 65536, "pack_channels_last: too many channels");
-  const bool vec4 = S[N - 1] % 4 == 0 && ((uintptr_t)src & 15) == 0 && pp.rows_per_cta == 1 &&
+  const bool vec4 = !strided && S[N - 1] % 4 == 0 && ((uintptr_t)src & 15) == 0 && pp.rows_per_cta == 1 &&
                     !getenv("EINCONV_PACK_SCALAR");
   switch (es) {
     case 4:
@@ -885,17 +909,30 @@ struct Role {
   int n_dims, batch, groups, cs, cd;
   int S[kMaxDims], O[kMaxDims], K[kMaxDims], dil[kMaxDims], pad[kMaxDims];
   int transpose;  // weights packed for the input VJP
+  // Strided forward (stride > 1 in some dimension): the source is packed as PHASE SUB-IMAGES
+  //   sub_phi[i'] = x[st * i' + phi],   phi in [0, st)^N,
+  // each zero-padded channels-last like a stride-1 source and stacked along the rows of ONE matrix.  Tap k
+  // reads x[st * o + dil * k - pad] = sub_phi(k)[o + m(k)] with dil * k - pad = st * m + phi: a stride-1 row
+  // shift inside its own sub-image.  The GEMM kernel is unchanged: every tap is its own group whose
+  // group shift = (row block of its phase) + (m(k) - m_min) . pitch; only phases that some tap uses exist
+  // (a 1x1 stride-2 convolution packs one quarter of x and nothing else: the down-sampling rule of
+  // simplifications/opt.py:250-300).
+  int strided;
+  int st[kMaxDims];
 };
 
 static bool make_role(int op, const DevGeom& g, Role* r) {
   r->n_dims = g.n_dims;
   r->batch = g.batch;
   r->groups = g.groups;
+  r->strided = 0;
   for (int d = 0; d < g.n_dims; ++d) {
-    if (g.stride[d] != 1) return false;
+    r->st[d] = g.stride[d];
+    if (g.stride[d] != 1) r->strided = 1;
     r->K[d] = g.k[d];
     r->dil[d] = g.dil[d];
   }
+  if (r->strided && (op != EINCONV_OP_CONV_FWD || getenv("EINCONV_CTMA_NO_STRIDE"))) return false;
   if (op == EINCONV_OP_CONV_FWD) {
     r->cs = g.c_in_g;
     r->cd = g.c_out_g;
@@ -933,7 +970,47 @@ struct CPlan {
   long long P[kMaxDims], pitch[kMaxDims], ptot, rows_total;
   int n_mtiles;
   long long xp_bytes, wp_bytes;
+  // strided forward: phases in use, per-dimension smallest row offset, sub-image padding
+  int n_phases = 1;
+  int m_min[kMaxDims] = {0};
+  long long xp_rows = 0;  // rows of the packed source matrix (all phase sub-images)
 };
+
+// dil * k - pad = st * m + phi with 0 <= phi < st
+static inline void phase_of(int off, int st, int* m, int* phi) {
+  int q = off / st, r = off - q * st;
+  if (r < 0) { r += st; --q; }
+  *m = q; *phi = r;
+}
+
+// compact index of the phase tuple of tap t among the phases that occur (row-major over taps); -1 = count only
+static int phase_index(const Role& r, int tap, int* n_phases_out) {
+  const int N = r.n_dims;
+  int seen[kMaxGroups], n_seen = 0, result = -1;
+  int taps = 1;
+  for (int d = 0; d < N; ++d) taps *= r.K[d];
+  for (int t = 0; t < taps; ++t) {
+    int rem = t, code = 0, mul = 1;
+    for (int d = N - 1; d >= 0; --d) {
+      const int kd = rem % r.K[d];
+      rem /= r.K[d];
+      int m, phi;
+      phase_of(r.dil[d] * kd - r.pad[d], r.st[d], &m, &phi);
+      code += phi * mul;
+      mul *= r.st[d];
+    }
+    int idx = -1;
+    for (int i = 0; i < n_seen; ++i)
+      if (seen[i] == code) idx = i;
+    if (idx < 0 && n_seen < kMaxGroups) {
+      idx = n_seen;
+      seen[n_seen++] = code;
+    }
+    if (t == tap) result = idx;
+  }
+  if (n_phases_out) *n_phases_out = n_seen;
+  return result;
+}
 
 static CPlan make_cplan(const Role& r, int dtype) {
   CPlan pl;
@@ -970,8 +1047,22 @@ static CPlan make_cplan(const Role& r, int dtype) {
   pl.btile_bytes = (pl.bn * pl.cb_bytes + 1023) / 1024 * 1024;
 
   pl.ptot = 1;
+  int m_span[kMaxDims] = {0};
   for (int d = N - 1; d >= 0; --d) {
-    pl.P[d] = std::max<long long>(r.S[d] + r.pad[d], (long long)(r.O[d] - 1) + (long long)r.dil[d] * (r.K[d] - 1) + 1);
+    if (r.strided) {
+      int lo = 1 << 30, hi = -(1 << 30);
+      for (int k = 0; k < r.K[d]; ++k) {
+        int m, phi;
+        phase_of(r.dil[d] * k - r.pad[d], r.st[d], &m, &phi);
+        lo = std::min(lo, m);
+        hi = std::max(hi, m);
+      }
+      pl.m_min[d] = lo;
+      m_span[d] = hi - lo;
+      pl.P[d] = (long long)r.O[d] + m_span[d];  // sub-image index o + m - m_min for every output and tap
+    } else {
+      pl.P[d] = std::max<long long>(r.S[d] + r.pad[d], (long long)(r.O[d] - 1) + (long long)r.dil[d] * (r.K[d] - 1) + 1);
+    }
     pl.pitch[d] = pl.ptot;
     pl.ptot *= pl.P[d];
     if (pl.ptot >= (1ll << 31)) return pl;
@@ -980,16 +1071,23 @@ static CPlan make_cplan(const Role& r, int dtype) {
   long long max_shift = 0;
   pl.taps = 1;
   for (int d = 0; d < N; ++d) {
-    max_shift += (long long)r.dil[d] * (r.K[d] - 1) * pl.pitch[d];
+    max_shift += (r.strided ? (long long)m_span[d] : (long long)r.dil[d] * (r.K[d] - 1)) * pl.pitch[d];
     pl.taps *= r.K[d];
   }
-  if (pl.rows_total + max_shift + 4096 >= (1ll << 31)) return pl;
+  pl.n_phases = 1;
+  if (r.strided) {
+    if (pl.taps > kMaxGroups) return pl;
+    phase_index(r, -1, &pl.n_phases);
+  }
+  pl.xp_rows = pl.rows_total * pl.n_phases;
+  if (pl.xp_rows + max_shift + 4096 >= (1ll << 31)) return pl;
   pl.n_mtiles = (int)((pl.rows_total + kTileM - 1) / kTileM);
   pl.box_rows = std::min(256, 8192 / pl.cb_bytes);
 
   // tap grouping: the trailing `level` dims of a group share one slab; one pipeline stage holds the
   // slab of a (slice, group) and, unless the weights are resident, the group's weight tiles
-  for (int level = N; level >= 0 && !pl.ok; --level) {
+  // (strided: every tap is its own group — taps of different phases read different sub-images)
+  for (int level = r.strided ? 0 : N; level >= 0 && !pl.ok; --level) {
     long long tpg = 1, span = 0;
     for (int d = N - level; d < N; ++d) {
       tpg *= r.K[d];
@@ -1023,7 +1121,7 @@ static CPlan make_cplan(const Role& r, int dtype) {
   }
   if (!pl.ok) return pl;
   pl.smem = (size_t)pl.w_bytes + (size_t)pl.n_stages * pl.stage_bytes + sizeof(Bars) + 64;
-  pl.xp_bytes = ((pl.rows_total * pl.cp * es) + 1023) / 1024 * 1024;
+  pl.xp_bytes = ((pl.xp_rows * pl.cp * es) + 1023) / 1024 * 1024;
   pl.wp_bytes = (((long long)r.groups * pl.taps * pl.np * pl.cgp * es) + 1023) / 1024 * 1024;
   return pl;
 }
@@ -1090,14 +1188,36 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
       if (st0) return st0;
       st0 = pack_channels_last_f32_to_f16((const float*)src, xp, N, r.batch, r.groups * r.cs, pl.cp, r.S, pl.P,
                                           r.pad, absmax, stream, &wj);
-    } else {
+    } else if (!r.strided) {
       st0 = pack_channels_last(src, xp, dtype, N, r.batch, r.groups * r.cs, pl.cp, r.S, pl.P, r.pad, stream, &wj);
+    } else {
+      // one packing launch per phase in use: sub-image index i' = (padded position) + m_min reads x[st * i' + phi]
+      st0 = EINCONV_OK;
+      bool done[kMaxGroups] = {false};
+      for (int t = 0; t < pl.taps && !st0; ++t) {
+        const int ph = phase_index(r, t, nullptr);
+        if (ph < 0 || done[ph]) continue;
+        done[ph] = true;
+        int pad_sub[kMaxDims], soff[kMaxDims];
+        int rem = t;
+        for (int d = N - 1; d >= 0; --d) {
+          const int kd = rem % r.K[d];
+          rem /= r.K[d];
+          int m, phi;
+          phase_of(r.dil[d] * kd - r.pad[d], r.st[d], &m, &phi);
+          pad_sub[d] = -pl.m_min[d];
+          soff[d] = phi;
+        }
+        T* dst_phase = xp + (long long)ph * pl.rows_total * pl.cp;
+        st0 = pack_channels_last(src, dst_phase, dtype, N, r.batch, r.groups * r.cs, pl.cp, r.S, pl.P, pad_sub, stream,
+                                 ph == 0 ? &wj : nullptr, r.st, soff);
+      }
     }
     if (st0) return st0;
   }
   // ---- tensor maps
   CUtensorMap map_a, map_b;
-  int st = encode_2d(&map_a, dtype, xp, pl.rows_total, pl.cp, pl.cb_elems, pl.box_rows, pl.cb_bytes);
+  int st = encode_2d(&map_a, dtype, xp, pl.xp_rows, pl.cp, pl.cb_elems, pl.box_rows, pl.cb_bytes);
   if (st) return st;
   st = encode_2d(&map_b, dtype, wp, (long long)r.groups * pl.taps * pl.np, pl.cgp, pl.cb_elems, pl.bn, pl.cb_bytes);
   if (st) return st;
@@ -1131,8 +1251,15 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
     for (int d = N - 1; d >= 0; --d) {
       const int kd = rem % r.K[d];
       rem /= r.K[d];
-      shift += (long long)r.dil[d] * kd * pl.pitch[d];
+      if (r.strided) {
+        int m, phi;
+        phase_of(r.dil[d] * kd - r.pad[d], r.st[d], &m, &phi);
+        shift += (long long)(m - pl.m_min[d]) * pl.pitch[d];
+      } else {
+        shift += (long long)r.dil[d] * kd * pl.pitch[d];
+      }
     }
+    if (r.strided) shift += (long long)phase_index(r, t, nullptr) * pl.rows_total;
     if (t % pl.tpg == 0) p.group_shift[t / pl.tpg] = (int)shift;
     // group 0: offsets relative to its first tap (shift 0)
     if (t < pl.tpg) p.tap_off16[t] = (uint32_t)((shift * pl.cb_bytes) >> 4);
@@ -1214,7 +1341,7 @@ int run(int op, const void* src, const void* w, const void* bias, void* dst, int
   long long taps_total = 1;
   for (int d = 0; d < r.n_dims; ++d) taps_total *= r.K[d];
   const bool want_half = getenv("EINCONV_CTMA_HALF") != nullptr || (long long)r.cd * taps_total >= 2048;
-  if (dtype == EINCONV_F32 && want_half && !getenv("EINCONV_CTMA_TF32") && ((uintptr_t)src % 16) == 0 &&
+  if (dtype == EINCONV_F32 && want_half && !r.strided && !getenv("EINCONV_CTMA_TF32") && ((uintptr_t)src % 16) == 0 &&
       ((uintptr_t)w % 16) == 0) {
     const CPlan ph = make_cplan(r, EINCONV_F16);
     if (ph.ok && workspace_bytes_given >= ph.xp_bytes + ph.wp_bytes + 2048)

@@ -79,7 +79,7 @@ struct WeightJob {  // optional weight packing fused into the same launch (conv_
 };
 int pack_channels_last(const void* src, void* xp, int dtype, int n_dims, int batch, int ctot, int cp,
                        const int* S, const long long* P, const int* pad, cudaStream_t stream,
-                       const WeightJob* wj = nullptr);
+                       const WeightJob* wj = nullptr, const int* sstep = nullptr, const int* soff = nullptr);
 // same layout, fp32 source -> fp16 destination scaled by operand_scale(*absmax_bits) (convert.cu)
 // an optional weight job is converted with the scale of absmax_bits[1]
 int pack_channels_last_f32_to_f16(const float* src, void* xp, int n_dims, int batch, int ctot, int cp, const int* S,

@@ -737,10 +737,18 @@ def test_tc_kernels_are_selected():
     assert lib.einconv_selected_kernel(nat.OP_CONV_INPUT_VJP, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_conv_input_vjp"
     assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 0, nat.MATH_FP32, 0) == b"ffma_gather_gemm"
     assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 1, nat.MATH_AUTO, 1) == b"ffma_gather_gemm"
-    # stride 2: software-gather tcgen05 kernel
+    # stride 2 forward: the same TMA kernel over phase sub-images of the source (csrc/conv_tma.cu, Role::strided);
+    # the software-gather tcgen05 kernel is only the fallback (EINCONV_CTMA_NO_STRIDE=1)
     gs = nat.make_geom(2, 1, 32, 48, (20, 20), (3, 3), (2, 2), (1, 1), (1, 1), (10, 10))
-    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, gs, 1, nat.MATH_AUTO, 0) == b"tcgen05_fwd_f16"
-    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, gs, 0, nat.MATH_TF32, 0) == b"tcgen05_fwd_tf32"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, gs, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_conv_fwd"
+    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, gs, 0, nat.MATH_TF32, 0) == b"tcgen05_tma_conv_fwd"
+    import os
+    os.environ["EINCONV_CTMA_NO_STRIDE"] = "1"
+    try:
+        assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, gs, 1, nat.MATH_AUTO, 0) == b"tcgen05_fwd_f16"
+        assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, gs, 0, nat.MATH_TF32, 0) == b"tcgen05_fwd_tf32"
+    finally:
+        del os.environ["EINCONV_CTMA_NO_STRIDE"]
     # reduction networks: TMA-fed kernel (aligned shifted copies make any row length usable)
     assert lib.einconv_selected_kernel(nat.OP_KFC, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_kfc"
     # fp32 in TF32 mode: scaled fp16 operand copies (same 10-bit mantissa) for kernels with several taps
@@ -994,3 +1002,41 @@ def test_tensor_core_kfac_reduce(case, mode):
     finally:
         evaluator.set_fp32_math("auto")
     _rel_to_max(got, want, 2.0**-7 if mode == "bf16" else 1e-3, f"kfac_reduce {mode}")
+
+
+# =============================================================================================
+# strided forward on the TMA kernel (phase sub-images, csrc/conv_tma.cu Role::strided)
+# =============================================================================================
+CTMA_STRIDED = [
+    ((2, 32, 20, 20), (48, 32, 3, 3), dict(padding=1, stride=2)),              # ResNet down-sampling 3x3
+    ((2, 64, 14, 14), (128, 64, 1, 1), dict(stride=2)),                        # 1x1 stride 2: one phase only
+    ((2, 3, 38, 37), (24, 3, 7, 7), dict(padding=3, stride=2)),                # stem: C_in = 3, 49 taps
+    ((3, 16, 23, 17), (40, 16, 3, 3), dict(padding=1, stride=(2, 1))),         # mixed strides
+    ((2, 24, 19, 21), (16, 12, 5, 3), dict(padding=(2, 0), dilation=(1, 2), stride=(3, 2), groups=2)),
+    ((2, 8, 300), (24, 8, 7), dict(padding=3, stride=4)),                      # N = 1, stride > kernel/2
+    ((1, 8, 9, 12, 10), (16, 8, 3, 3, 3), dict(padding=1, stride=2)),          # N = 3
+    ((2, 16, 16, 16), (32, 16, 4, 4), dict(stride=4)),                         # patchify: K == S, one tap per phase
+    ((2, 16, 15, 15), (32, 16, 2, 2), dict(stride=3, padding=1)),              # stride > kernel: skipped inputs
+]
+
+
+@pytest.mark.parametrize("case", CTMA_STRIDED, ids=["x".join(map(str, c[0])) + "-w" + "x".join(map(str, c[1])) for c in CTMA_STRIDED])
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_conv_tma_strided_forward(case, mode):
+    dtype = {"bf16": torch.bfloat16, "tf32": torch.float32}[mode]
+    tol = {"bf16": 2.0**-7, "tf32": 1e-3}[mode]
+    x, w, b, kw = _tc_inputs(case, dtype)
+    want = direct.conv_forward(x.double().numpy(), w.double().numpy(), b.double().numpy(), **kw)
+    evaluator.set_fp32_math("tf32" if mode == "tf32" else "auto")
+    try:
+        B, groups = x.shape[0], kw.get("groups", 1)
+        plan = evaluator.call_plan(nat.OP_CONV_FWD, B, groups, w.shape[1], w.shape[0] // groups, x.shape[2:],
+                                   tuple(w.shape[2:]), kw.get("stride", 1), kw.get("padding", 0),
+                                   kw.get("dilation", 1), dtype)
+        # (grouped layers whose per-group channel block is not 16-byte aligned keep the software-gather kernel)
+        aligned = groups == 1 or (w.shape[1] * x.element_size()) % 16 == 0
+        assert plan.kernel == ("tcgen05_tma_conv_fwd" if aligned else plan.kernel), plan.kernel
+        got = convNd(x.to(DEV), w.to(DEV), b.to(DEV), **kw)
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, tol, f"strided conv_tma fwd {mode}")
