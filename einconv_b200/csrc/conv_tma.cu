@@ -25,6 +25,7 @@
 #include <cstring>
 #include <mutex>
 #include <type_traits>
+#include <vector>
 
 #include "dispatch.cuh"
 #include "tc_ptx.cuh"
@@ -66,6 +67,14 @@ struct Params {
   int out[kMaxDims];
   int cd, cd_total;      // dst channels per group / in total
   long long out_total;
+  // destination element of output coordinates (o_0, .., o_{N-1}) of channel c of sample b:
+  //   dst[(b * cd_total + c) * chan_stride + dst_off + sum_d o_d * dst_mul[d]]
+  // (dense output: dst_mul = row-major strides of `out`, dst_off = 0, chan_stride = out_total; one phase of a
+  // strided input VJP: the sub-grid i = st * o + phi of the full input)
+  long long dst_mul[kMaxDims], dst_off, chan_stride;
+  // tap subset (strided input VJP, tpg = 1): group g is tap group_tap[g] of the packed weights
+  int sub;
+  int group_tap[kMaxGroups];
   const void* bias;
   void* dst;
   // fp32 tensors on scaled fp16 operand copies: [0] max|src|, [1] max|w| (bit patterns); the epilogue
@@ -181,10 +190,12 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // more stages per tile than weight barriers: ONE barrier for the whole class, so every tile must be
         // requested before the first slab (the MMA warp waits for all of them before it frees a ring slot;
         // requesting them stage by stage dead-locks as soon as the ring is full)
-        if (lane == 0) mbar_expect_tx(&bars->w_full[0], (uint32_t)(p.n_slices * p.taps * p.bn * p.cb_bytes));
+        const int per_slice = p.n_groups * p.tpg;  // tiles of one slice (= taps unless a tap subset is in use)
+        if (lane == 0) mbar_expect_tx(&bars->w_full[0], (uint32_t)(p.n_slices * per_slice * p.bn * p.cb_bytes));
         __syncwarp();
-        for (int idx = lane; idx < p.n_slices * p.taps; idx += 32) {
-          const int s = idx / p.taps, tap = idx - s * p.taps;
+        for (int idx = lane; idx < p.n_slices * per_slice; idx += 32) {
+          const int s = idx / per_slice, gj = idx - s * per_slice;
+          const int tap = p.sub ? p.group_tap[gj] : gj;
           tma_load_2d(w_region + (size_t)idx * p.btile_bytes, &map_b, &bars->w_full[0], s * p.cb_elems,
                       wrow0 + tap * p.np);
         }
@@ -205,9 +216,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             __syncwarp();
             for (int j = lane; j < p.tpg; j += 32) {
-              const int tap = grp * p.tpg + j;
-              tma_load_2d(w_region + (size_t)(s * p.taps + tap) * p.btile_bytes, &map_b, wb, s * p.cb_elems,
-                          wrow0 + tap * p.np);
+              const int tap = p.sub ? p.group_tap[grp] : grp * p.tpg + j;
+              tma_load_2d(w_region + (size_t)((s * p.n_groups + grp) * p.tpg + j) * p.btile_bytes, &map_b, wb,
+                          s * p.cb_elems, wrow0 + tap * p.np);
             }
           }
           mbar_wait(&bars->empty[st], ph ^ 1);
@@ -226,7 +237,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               unsigned char* bt = stage + p.slab_bytes;
               for (int j = lane; j < p.tpg; j += 32)
                 tma_load_2d(bt + (size_t)j * p.btile_bytes, &map_b, &bars->full[st], s * p.cb_elems,
-                            wrow0 + (grp * p.tpg + j) * p.np);
+                            wrow0 + (p.sub ? p.group_tap[grp] : grp * p.tpg + j) * p.np);
             }
           }
           __syncwarp();
@@ -316,15 +327,15 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       bool valid = row < p.rows_total;
       uint32_t b = 0, rem = 0;
       if (valid) p.ptot_div.divmod((uint32_t)row, b, rem);
-      long long oflat = 0;
+      long long oflat = p.dst_off;
       for (int d = 0; d < p.n_dims; ++d) {
         uint32_t od, r2;
         p.pitch_div[d].divmod(rem, od, r2);
         rem = r2;
         valid = valid && (int)od < p.out[d];
-        oflat = oflat * p.out[d] + od;
+        oflat += (long long)od * p.dst_mul[d];
       }
-      TO* dst_row = dst + ((long long)b * p.cd_total + (long long)g * p.cd + n0) * p.out_total + oflat;
+      TO* dst_row = dst + ((long long)b * p.cd_total + (long long)g * p.cd + n0) * p.chan_stride + oflat;
 
       if (warp == 2) CTMA_TRACE(10);
       mbar_wait_relaxed(&bars->tmem_full[acc], acc_phase);
@@ -343,17 +354,17 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (warp == 2) CTMA_TRACE(12);
         }
         if (valid) {
-          TO* d0 = dst_row + (long long)c0 * p.out_total;
+          TO* d0 = dst_row + (long long)c0 * p.chan_stride;
           if (n0 + c0 + 16 <= p.cd) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              Cvt<TO>::store(d0 + (long long)j * p.out_total,
+              Cvt<TO>::store(d0 + (long long)j * p.chan_stride,
                              fmaf(__uint_as_float(r[j]), unscale, bars->bias[c0 + j]));
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (n0 + c0 + j < p.cd)
-                Cvt<TO>::store(d0 + (long long)j * p.out_total,
+                Cvt<TO>::store(d0 + (long long)j * p.chan_stride,
                                fmaf(__uint_as_float(r[j]), unscale, bars->bias[c0 + j]));
           }
         }
@@ -415,7 +426,7 @@ __device__ __forceinline__ void pack_weights_block(const PackParams& pp, unsigne
     if (!pp.w_transpose) {
       if (n < cog && c < cg) v = w[(((long long)g * cog + n) * cg + c) * taps + t];
     } else {
-      if (n < cg && c < cog) v = w[(((long long)g * cog + c) * cg + n) * taps + (taps - 1 - t)];
+      if (n < cg && c < cog) v = w[(((long long)g * cog + c) * cg + n) * taps + (pp.w_transpose == 2 ? t : taps - 1 - t)];
     }
     wp[idx] = v;
   }
@@ -440,7 +451,7 @@ __device__ __forceinline__ void pack_weights_block_convert(const PackParams& pp,
     if (!pp.w_transpose) {
       if (n < cog && c < cg) v = w[(((long long)g * cog + n) * cg + c) * taps + t];
     } else {
-      if (n < cg && c < cog) v = w[(((long long)g * cog + c) * cg + n) * taps + (taps - 1 - t)];
+      if (n < cg && c < cog) v = w[(((long long)g * cog + c) * cg + n) * taps + (pp.w_transpose == 2 ? t : taps - 1 - t)];
     }
     wp[idx] = __float2half_rn(v * scale);
   }
@@ -932,7 +943,22 @@ static bool make_role(int op, const DevGeom& g, Role* r) {
     r->K[d] = g.k[d];
     r->dil[d] = g.dil[d];
   }
-  if (r->strided && (op != EINCONV_OP_CONV_FWD || getenv("EINCONV_CTMA_NO_STRIDE"))) return false;
+  if (r->strided && getenv("EINCONV_CTMA_NO_STRIDE")) return false;
+  if (r->strided && op == EINCONV_OP_CONV_INPUT_VJP) {
+    // Strided input VJP: gx[st i' + phi] = sum_{k : (phi + p - dil k) % st == 0} v[i' + c(phi, k)] w[k],
+    // c = (phi + p - dil k) / st.  One launch of the GEMM kernel per output phase phi over the SAME packed
+    // cotangent, with the subset of taps that reach this phase and a strided destination (Params::dst_mul).
+    r->strided = 2;
+    r->cs = g.c_out_g;
+    r->cd = g.c_in_g;
+    r->transpose = 2;  // transposed weights, taps in their original order
+    for (int d = 0; d < g.n_dims; ++d) {
+      r->S[d] = g.out[d];   // spatial sizes of v
+      r->O[d] = g.in[d];    // spatial sizes of gx
+      r->pad[d] = g.pad[d]; // the convolution's own padding (phase arithmetic)
+    }
+    return true;
+  }
   if (op == EINCONV_OP_CONV_FWD) {
     r->cs = g.c_in_g;
     r->cd = g.c_out_g;
@@ -1049,7 +1075,23 @@ static CPlan make_cplan(const Role& r, int dtype) {
   pl.ptot = 1;
   int m_span[kMaxDims] = {0};
   for (int d = N - 1; d >= 0; --d) {
-    if (r.strided) {
+    if (r.strided == 2) {
+      // c(phi, k) over every phase and tap that reaches it; sub-grid sizes ceil((I - phi) / st) <= ceil(I / st)
+      int lo = 1 << 30, hi = -(1 << 30);
+      for (int phi = 0; phi < r.st[d]; ++phi)
+        for (int k = 0; k < r.K[d]; ++k) {
+          const int num = phi + r.pad[d] - r.dil[d] * k;
+          if (((num % r.st[d]) + r.st[d]) % r.st[d] != 0) continue;
+          const int c = (num - (((num % r.st[d]) + r.st[d]) % r.st[d])) / r.st[d];
+          lo = std::min(lo, c);
+          hi = std::max(hi, c);
+        }
+      if (lo > hi) { lo = hi = 0; }
+      pl.m_min[d] = std::min(lo, 0);                       // rows of zero padding in front: -m_min
+      m_span[d] = std::max(hi, 0) - pl.m_min[d];
+      const long long n_sub = (r.O[d] + r.st[d] - 1) / r.st[d];
+      pl.P[d] = std::max<long long>((long long)r.S[d] - pl.m_min[d], n_sub + m_span[d]);
+    } else if (r.strided) {
       int lo = 1 << 30, hi = -(1 << 30);
       for (int k = 0; k < r.K[d]; ++k) {
         int m, phi;
@@ -1077,7 +1119,7 @@ static CPlan make_cplan(const Role& r, int dtype) {
   pl.n_phases = 1;
   if (r.strided) {
     if (pl.taps > kMaxGroups) return pl;
-    phase_index(r, -1, &pl.n_phases);
+    if (r.strided == 1) phase_index(r, -1, &pl.n_phases);
   }
   pl.xp_rows = pl.rows_total * pl.n_phases;
   if (pl.xp_rows + max_shift + 4096 >= (1ll << 31)) return pl;
@@ -1190,6 +1232,10 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
                                           r.pad, absmax, stream, &wj);
     } else if (!r.strided) {
       st0 = pack_channels_last(src, xp, dtype, N, r.batch, r.groups * r.cs, pl.cp, r.S, pl.P, r.pad, stream, &wj);
+    } else if (r.strided == 2) {
+      int pad_v[kMaxDims];
+      for (int d = 0; d < N; ++d) pad_v[d] = -pl.m_min[d];
+      st0 = pack_channels_last(src, xp, dtype, N, r.batch, r.groups * r.cs, pl.cp, r.S, pl.P, pad_v, stream, &wj);
     } else {
       // one packing launch per phase in use: sub-image index i' = (padded position) + m_min reads x[st * i' + phi]
       st0 = EINCONV_OK;
@@ -1259,7 +1305,8 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
         shift += (long long)r.dil[d] * kd * pl.pitch[d];
       }
     }
-    if (r.strided) shift += (long long)phase_index(r, t, nullptr) * pl.rows_total;
+    if (r.strided == 1) shift += (long long)phase_index(r, t, nullptr) * pl.rows_total;
+    if (r.strided == 2) shift = 0;  // set per output phase below
     if (t % pl.tpg == 0) p.group_shift[t / pl.tpg] = (int)shift;
     // group 0: offsets relative to its first tap (shift 0)
     if (t < pl.tpg) p.tap_off16[t] = (uint32_t)((shift * pl.cb_bytes) >> 4);
@@ -1279,6 +1326,15 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
   p.bias = bias;
   p.dst = dst;
   p.absmax = absmax;
+  p.chan_stride = p.out_total;
+  p.dst_off = 0;
+  {
+    long long mul = 1;
+    for (int d = N - 1; d >= 0; --d) {
+      p.dst_mul[d] = mul;
+      mul *= r.O[d];
+    }
+  }
 
   auto kern = conv_tma_kernel<T, TO>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
@@ -1294,6 +1350,64 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
     p.trace = trace;
   }
 #endif
+  if (r.strided == 2) {
+    // one launch per output phase; phases no tap reaches stay zero
+    int n_phase_total = 1;
+    for (int d = 0; d < N; ++d) n_phase_total *= r.st[d];
+    bool need_zero = false;
+    std::vector<Params> launches;
+    for (int ph = 0; ph < n_phase_total; ++ph) {
+      int phi[kMaxDims], rem_ph = ph;
+      for (int d = N - 1; d >= 0; --d) {
+        phi[d] = rem_ph % r.st[d];
+        rem_ph /= r.st[d];
+      }
+      Params q = p;
+      q.sub = 1;
+      q.n_groups = 0;
+      bool empty = false;
+      q.dst_off = 0;
+      for (int d = 0; d < N; ++d) {
+        q.out[d] = (r.O[d] - phi[d] + r.st[d] - 1) / r.st[d];
+        if (q.out[d] <= 0) empty = true;
+        q.dst_mul[d] = p.dst_mul[d] * r.st[d];
+        q.dst_off += (long long)phi[d] * p.dst_mul[d];
+      }
+      if (empty) continue;
+      for (int t = 0; t < pl.taps; ++t) {
+        long long shift = 0;
+        int rem = t;
+        bool ok = true;
+        for (int d = N - 1; d >= 0; --d) {
+          const int kd = rem % r.K[d];
+          rem /= r.K[d];
+          const int num = phi[d] + r.pad[d] - r.dil[d] * kd;
+          const int mod = ((num % r.st[d]) + r.st[d]) % r.st[d];
+          if (mod != 0) { ok = false; break; }
+          shift += (long long)(num / r.st[d] - pl.m_min[d]) * pl.pitch[d];
+        }
+        if (!ok) continue;
+        q.group_tap[q.n_groups] = t;
+        q.group_shift[q.n_groups] = (int)shift;
+        ++q.n_groups;
+      }
+      if (q.n_groups == 0) {
+        need_zero = true;
+        continue;
+      }
+      launches.push_back(q);
+    }
+    if (need_zero) {
+      long long n_dst = (long long)r.batch * r.groups * r.cd * p.out_total;
+      cudaError_t ez = cudaMemsetAsync(dst, 0, (size_t)n_dst * sizeof(TO), stream);
+      if (ez != cudaSuccess) return cuda_fail(ez, "cudaMemsetAsync(gx)");
+    }
+    for (const Params& q : launches) {
+      kern<<<grid, kThreads, pl.smem, stream>>>(map_a, map_b, q);
+      EINCONV_CHECK_LAUNCH("conv_tma_kernel");
+    }
+    return EINCONV_OK;
+  }
   kern<<<grid, kThreads, pl.smem, stream>>>(map_a, map_b, p);
   EINCONV_CHECK_LAUNCH("conv_tma_kernel");
   if (trace) {  // bring-up only: synchronises and prints the pipeline timeline of CTA 0

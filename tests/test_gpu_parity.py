@@ -1037,6 +1037,18 @@ def test_conv_tma_strided_forward(case, mode):
         aligned = groups == 1 or (w.shape[1] * x.element_size()) % 16 == 0
         assert plan.kernel == ("tcgen05_tma_conv_fwd" if aligned else plan.kernel), plan.kernel
         got = convNd(x.to(DEV), w.to(DEV), b.to(DEV), **kw)
+        # input VJP of the same layer: one launch per output phase over the packed cotangent
+        torch.manual_seed(1)
+        v = (torch.rand(*want.shape) - 0.5).to(dtype)
+        want_gx = direct.conv_input_vjp(w.double().numpy(), v.double().numpy(), tuple(x.shape[2:]), **kw)
+        vplan = evaluator.call_plan(nat.OP_CONV_INPUT_VJP, B, groups, w.shape[1], w.shape[0] // groups, x.shape[2:],
+                                    tuple(w.shape[2:]), kw.get("stride", 1), kw.get("padding", 0),
+                                    kw.get("dilation", 1), dtype)
+        aligned_v = groups == 1 or ((w.shape[0] // groups) * x.element_size()) % 16 == 0
+        assert vplan.kernel == ("tcgen05_tma_conv_input_vjp" if aligned_v else vplan.kernel), vplan.kernel
+        gx = evaluator.conv_input_vjp_raw(w.to(DEV), v.to(DEV), tuple(x.shape[2:]), kw.get("stride", 1),
+                                          kw.get("padding", 0), kw.get("dilation", 1), groups)
     finally:
         evaluator.set_fp32_math("auto")
     _rel_to_max(got, want, tol, f"strided conv_tma fwd {mode}")
+    _rel_to_max(gx, want_gx, tol, f"strided conv_tma input vjp {mode}")
