@@ -85,6 +85,16 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// one lane of a converged warp (single-thread issue from warp-uniform code, see the MMA issuer of kfc_super_kernel)
+__device__ __forceinline__ bool ptx_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -201,6 +211,8 @@ struct Params {
   int direct_a;                        // A = c_in_g * k_total (rows / columns of the factor)
   int s_tiles;                         // KFC super-tile kernel: ceil(m_tiles / 2) super-tiles (256 rows) per side
   // flat-plane mode (see flat_copy_kernel): per-tap tensor map (row / column operand) and start coordinate
+  int st_n, st_bytes, st_a_bytes, st_rows;  // pipeline stages of the super-tile kernel (see kMaxStagesS)
+  int box_split;                            // channel parts per TMA box (1, 2 or 4)
   int flat;
   signed char tap_map_a[kMaxMaps], tap_map_b[kMaxMaps];
   int tap_c0[kMaxMaps];
@@ -394,10 +406,14 @@ tma_reduce_gemm_kernel(const __grid_constant__ MapArray map_array, const __grid_
     }
   } else if (warp == 1) {
     // ================================= MMA issuer ============================================
+    // warp-uniform loop, one elected lane issues: operands stay in uniform registers (see kfc_super_kernel)
     constexpr uint32_t idesc = make_idesc(E::FMT, kTileM, BN);
     const int steps_per_line = p.PB / 32;  // 32 bytes of K per instruction (16 bf16 / 8 tf32)
     const int bh_shift = 31 - __clz(p.BH);
-    uint32_t first = 1u;                   // the first MMA of the tile overwrites the accumulator
+    const uint64_t desc_const = make_desc_kmajor(0, p.PB);
+    const uint32_t smem16 = smem_u32(smem) >> 4;
+    constexpr uint32_t stage16 = (uint32_t)S::stage_bytes >> 4, oper16 = (uint32_t)S::a_bytes >> 4;
+    const uint32_t a_piece16 = (uint32_t)(kTileM * p.PB) >> 4, b_piece16 = (uint32_t)(BN * p.PB) >> 4;
     Walker wk;
     wk.init(p, kb_begin);
     for (int i = 0; i < n_kb; ++i, wk.next(p)) {
@@ -405,21 +421,14 @@ tma_reduce_gemm_kernel(const __grid_constant__ MapArray map_array, const __grid_
       const uint32_t ph = (uint32_t)(i / kStages) & 1u;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      if (lane == 0 && p.debug != 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
-        if (i == n_kb - 1)
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(accum_bar)) : "memory");
-      } else if (lane == 0) {
-        const uint32_t a_addr = smem_u32(smem + s * S::stage_bytes);
-        const uint32_t b_addr = a_addr + S::a_bytes;
-        const int oh0 = wk.ht * p.BH, od0 = wk.dt * p.BD;
+      const int oh0 = wk.ht * p.BH, od0 = wk.dt * p.BD;
+      if (ptx_elect_one()) {
+        const uint32_t a16 = smem16 + (uint32_t)s * stage16, b16 = a16 + oper16;
         for (int pc = 0; pc < p.n_pieces; ++pc) {
           if (oh0 + (pc & (p.BH - 1)) >= p.out_h || od0 + (pc >> bh_shift) >= p.out_d) continue;
-          for (int j = 0; j < steps_per_line; ++j) {
-            umma<E::TF32>(tmem_base, make_desc_kmajor(a_addr + pc * (kTileM * p.PB) + j * 32, p.PB),
-                          make_desc_kmajor(b_addr + pc * (BN * p.PB) + j * 32, p.PB), idesc, first ? 0u : 1u);
-            first = 0u;
-          }
+          for (int j = 0; j < steps_per_line; ++j)
+            umma<E::TF32>(tmem_base, desc_const + (uint64_t)(a16 + (uint32_t)pc * a_piece16 + 2u * j),
+                          desc_const + (uint64_t)(b16 + (uint32_t)pc * b_piece16 + 2u * j), idesc, (uint32_t)(i | pc | j));
         }
         umma_commit(&empty_bar[s]);
         if (i == n_kb - 1) umma_commit(accum_bar);
@@ -518,11 +527,14 @@ tma_reduce_gemm_kernel(const __grid_constant__ MapArray map_array, const __grid_
 // whose positions beyond the output width read as zero, are used for both) and load nothing else.
 // Only super-tiles (I, J >= I) exist; inside a diagonal one the mirror block (2I+1, 2I) is not computed.
 // ---------------------------------------------------------------------------------------------
-constexpr int kStagesS = 3;
-constexpr int kSuperRows = 2 * kTileM;                       // 256
-constexpr int kSuperOperandBytes = kSuperRows * kRowBytes;   // 32 KB per operand and stage
-constexpr int kSuperStageBytes = 2 * kSuperOperandBytes;     // 64 KB
-constexpr int kSuperSmem = kStagesS * kSuperStageBytes + 1024 + 256;
+// Stage geometry (Params::st_*): in general 3 stages of [256 rows | 256 rows] x 128 B = 64 KB.  A factor with a
+// single (diagonal) super-tile never loads a column operand, and with a single 128-row tile only half of the
+// row operand: the same 192 KB then hold 6 stages of 32 KB or 12 of 16 KB.  These are the 1 x 1 layers with
+// A <= 256, whose K blocks are small (8-32 KB): with 3 of them in flight the kernel was bound by the TMA round
+// trip (Little: 24 KB / ~1.5 us per SM = 2.4 TB/s on the A = 64 layers).
+constexpr int kMaxStagesS = 12;
+constexpr int kSuperRing = 3 * 2 * 2 * kTileM * kRowBytes;   // 192 KB
+constexpr int kSuperSmem = kSuperRing + 1024 + 512;
 
 constexpr int kMaxOrdered = 1024;
 struct TileOrder {
@@ -538,11 +550,15 @@ kfc_super_kernel(const __grid_constant__ MapArray map_array, const __grid_consta
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                          ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesS * kSuperStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSuperRing);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kStagesS;
-  uint64_t* accum_bar = bars + 2 * kStagesS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStagesS + 1);
+  uint64_t* empty_bar = bars + kMaxStagesS;
+  uint64_t* accum_bar = bars + 2 * kMaxStagesS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStagesS + 1);
+  const int kStagesS = p.st_n;
+  const int kSuperStageBytes = p.st_bytes;
+  const int kSuperOperandBytes = p.st_a_bytes;
+  const int kSuperRows = p.st_rows;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -605,6 +621,10 @@ kfc_super_kernel(const __grid_constant__ MapArray map_array, const __grid_consta
 
   if (warp == 0) {
     // ================================= TMA producer ==========================================
+    // (Measured alternative: one elected lane issuing every box from warp-uniform code.  The instruction takes
+    // uniform registers, so per-lane operands cost an ELECT + R2UR.BROADCAST loop per box; yet the single-lane
+    // version was slower — sweep 18.0 -> 20.3 ms — because each issue stalls its thread for hundreds of cycles
+    // and the per-lane loops of the four unrolled slots overlap.)
     // boxes of one K block: per patch line (piece), per operand tile (A0, A1, B0, B1 as far as they exist
     // and are needed), per tap of the tile.  Lane l owns boxes l, l + 32, ...; everything that does not
     // depend on the patch position is computed once.
@@ -672,9 +692,10 @@ kfc_super_kernel(const __grid_constant__ MapArray map_array, const __grid_consta
 
     Walker wk;
     wk.init(p, kb_begin);
+    int s = -1;
+    uint32_t ph = 1u;  // flips to 0 at the first wrap below
     for (int i = 0; i < n_kb; ++i, wk.next(p)) {
-      const int s = i % kStagesS;
-      const uint32_t ph = (uint32_t)(i / kStagesS) & 1u;
+      if (++s == kStagesS || i == 0) { s = 0; ph ^= 1u; }  // (the stage count is a run-time value: no division per K block)
       mbar_wait(&empty_bar[s], ph ^ 1u);
       const int ow0 = wk.wt * p.BW, oh0 = wk.ht * p.BH, od0 = wk.dt * p.BD;
       if (lane == 0) {
@@ -696,57 +717,62 @@ kfc_super_kernel(const __grid_constant__ MapArray map_array, const __grid_consta
     }
   } else if (warp == 1) {
     // ================================= MMA issuer ============================================
-    constexpr uint32_t idesc256 = make_idesc(E::FMT, kTileM, 256);
-    constexpr uint32_t idesc128 = make_idesc(E::FMT, kTileM, 128);
-    const int steps_per_line = p.PB / 32;  // 32 bytes of K per instruction (16 fp16 / 8 tf32)
-    const int bh_shift = 31 - __clz(p.BH);
-    // taps beyond k_total leave rows of a tile unloaded: stale shared memory.  Their products land in rows /
-    // columns of the accumulator that the epilogue never reads, but they must be finite garbage-free for the
-    // rows that ARE read: rows only mix within their own (row, column) pair, so no masking is needed.
-    uint32_t first = 1u;
-    Walker wk;
-    wk.init(p, kb_begin);
-    for (int i = 0; i < n_kb; ++i, wk.next(p)) {
-      const int s = i % kStagesS;
-      const uint32_t ph = (uint32_t)(i / kStagesS) & 1u;
-      mbar_wait(&full_bar[s], ph);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(smem + s * kSuperStageBytes);
-        const uint32_t b_addr = diag ? a_addr : a_addr + kSuperOperandBytes;
+    // ONE thread runs the whole loop (waits, MMAs, commits).  tcgen05.mma is queued only one or two
+    // instructions deep, so whatever the issuing thread does between the last MMA of a K block and the first of
+    // the next (barrier wait, commit, loop control) is exposed as soon as it exceeds one MMA (128 cycles for
+    // N = 256, 64 for N = 128).  Measured with scripts/mma_pipe.cu (no data movement, 8 x N = 256 per stage =
+    // 1024 tensor cycles): whole-warp loop with an elected issuer 1246 cycles per stage, this form 1093; and
+    // issuing from an `if (lane == 0)` INSIDE a warp-wide loop makes the compiler broadcast every descriptor
+    // through R2UR (~350 cycles per MMA, the first version of this kernel).
+    if (lane == 0) {
+      constexpr uint32_t idesc256 = make_idesc(E::FMT, kTileM, 256);
+      constexpr uint32_t idesc128 = make_idesc(E::FMT, kTileM, 128);
+      const uint32_t idesc_row0 = n1 ? idesc256 : idesc128;
+      const int steps_per_line = p.PB / 32;  // 32 bytes of K per instruction (16 fp16 / 8 tf32)
+      const int bh_shift = 31 - __clz(p.BH);
+      // descriptors differ only in the 14-bit start-address field (units of 16 bytes; shared-memory addresses
+      // never carry out of it): constant part + offsets
+      const uint64_t desc_const = make_desc_kmajor(0, p.PB);
+      const uint32_t smem16 = smem_u32(smem) >> 4;
+      const uint32_t stage16 = (uint32_t)kSuperStageBytes >> 4;
+      const uint32_t oper16 = diag ? 0u : ((uint32_t)kSuperOperandBytes >> 4);
+      const uint32_t piece16 = (uint32_t)(kSuperRows * p.PB) >> 4, tile16 = (uint32_t)(kTileM * p.PB) >> 4;
+      const bool one_piece = p.n_pieces == 1;
+      Walker wk;
+      wk.init(p, kb_begin);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < n_kb; ++i) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a16 = smem16 + (uint32_t)s * stage16;
+        const uint32_t b16 = a16 + oper16;
         const int oh0 = wk.ht * p.BH, od0 = wk.dt * p.BD;
         for (int pc = 0; pc < p.n_pieces; ++pc) {
-          if (oh0 + (pc & (p.BH - 1)) >= p.out_h || od0 + (pc >> bh_shift) >= p.out_d) continue;
-          const uint32_t a_pc = a_addr + pc * (kSuperRows * p.PB);
-          const uint32_t b_pc = b_addr + pc * (kSuperRows * p.PB);
+          if (!one_piece && (oh0 + (pc & (p.BH - 1)) >= p.out_h || od0 + (pc >> bh_shift) >= p.out_d)) continue;
+          const uint32_t a_pc = a16 + (uint32_t)pc * piece16, b_pc = b16 + (uint32_t)pc * piece16;
           for (int j = 0; j < steps_per_line; ++j) {
+            // piece 0 of a K block is always valid: the very first MMA of the tile overwrites the accumulator
+            const uint32_t accumulate = (uint32_t)(i | pc | j);
+            const uint64_t a0 = desc_const + (uint64_t)(a_pc + 2u * j), b0 = desc_const + (uint64_t)(b_pc + 2u * j);
             // row tile 0 against both column tiles (or the only one)
-            if (n1)
-              umma<E::TF32>(tmem_base, make_desc_kmajor(a_pc + j * 32, p.PB), make_desc_kmajor(b_pc + j * 32, p.PB),
-                            idesc256, first ? 0u : 1u);
-            else
-              umma<E::TF32>(tmem_base, make_desc_kmajor(a_pc + j * 32, p.PB), make_desc_kmajor(b_pc + j * 32, p.PB),
-                            idesc128, first ? 0u : 1u);
+            umma<E::TF32>(tmem_base, a0, b0, idesc_row0, accumulate);
             if (m1) {
-              const uint32_t a1 = a_pc + kTileM * p.PB + j * 32;
+              const uint64_t a1 = a0 + (uint64_t)tile16;
               if (diag)  // the block (2I+1, 2I) is the mirror of (2I, 2I+1): only column tile 1
-                umma<E::TF32>(tmem_base + 256 + 128, make_desc_kmajor(a1, p.PB),
-                              make_desc_kmajor(b_pc + kTileM * p.PB + j * 32, p.PB), idesc128, first ? 0u : 1u);
-              else if (n1)
-                umma<E::TF32>(tmem_base + 256, make_desc_kmajor(a1, p.PB), make_desc_kmajor(b_pc + j * 32, p.PB),
-                              idesc256, first ? 0u : 1u);
+                umma<E::TF32>(tmem_base + 256 + 128, a1, b0 + (uint64_t)tile16, idesc128, accumulate);
               else
-                umma<E::TF32>(tmem_base + 256, make_desc_kmajor(a1, p.PB), make_desc_kmajor(b_pc + j * 32, p.PB),
-                              idesc128, first ? 0u : 1u);
+                umma<E::TF32>(tmem_base + 256, a1, b0, idesc_row0, accumulate);
             }
-            first = 0u;
           }
         }
         umma_commit(&empty_bar[s]);
         if (i == n_kb - 1) umma_commit(accum_bar);
+        if (++s == kStagesS) { s = 0; ph ^= 1u; }
+        if (!one_piece) wk.next(p);
       }
-      __syncwarp();
     }
+    __syncwarp();
   }
 
   // ================================= epilogue (all 8 warps) ====================================
@@ -1114,6 +1140,7 @@ struct Plan {
   bool tri = false;  // KFC: compute only the tiles on or above the diagonal
   bool super = false;  // KFC: 256 x 256 super-tiles (kfc_super_kernel)
   int s_tiles = 0;
+  int box_split = 1;          // super-tile kernel: TMA boxes of CB / box_split channels
   bool flat = false;          // KFC: flat-plane operand copies (flat_copy_kernel)
   bool flat_per_tap = false;  // one copy per tap (strided layers) instead of one per kernel column
   int flat_pitch = 0, flat_rows = 0;
@@ -1300,6 +1327,12 @@ static Plan make_plan(int op, const DevGeom& g, int dtype) {
   if (pl.flat) {
     if (!pl.super) { pl.flat = false; }
   }
+  if (pl.super && getenv("EINCONV_KFC_SPLIT")) {  // (measured: no gain; the producer issues uniformly now)
+    // boxes per K block of a typical CTA (both operands, two tiles each unless the factor is smaller)
+    const int tiles_cta = pl.s_tiles == 1 ? std::min(2, pl.m_tiles) : 4;
+    const int boxes = (pl.flat ? 1 : kRowBytes / pl.PB) * tiles_cta * std::min(pl.taps_per_tile, g.k_total);
+    while (pl.box_split < 4 && boxes * pl.box_split * 2 <= 32 && pl.CB / (pl.box_split * 2) >= 8) pl.box_split *= 2;
+  }
   if (pl.flat) {
     pl.per_tap = false; pl.x_direct = false;
     pl.n_copies = pl.flat_per_tap ? g.k_total : q.k[0];
@@ -1455,7 +1488,7 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   int flat_c0[kMaxMaps] = {0};
   if (pl.flat) {
     const int chans = g.groups * g.c_in_g;
-    const int box[5] = {pl.BW, 1, 1, pl.CB, 1};
+    const int box[5] = {pl.BW, 1, 1, pl.CB / pl.box_split, 1};
     const int est[5] = {1, 1, 1, 1, 1};
     const int plane = (int)pl.flat_plane;
     if (pl.flat_per_tap) {
@@ -1495,7 +1528,7 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
     for (int kw = 0; kw < q.k[0]; ++kw) {
       const void* base = copies_x + (long long)kw * pl.copy_x_bytes;
       const int extent[5] = {pl.Wp_x, q.in[1], q.in[2], g.groups * g.c_in_g, g.batch};
-      const int box[5] = {pl.BW, 1, 1, pl.CB, 1};
+      const int box[5] = {pl.BW, 1, 1, pl.CB / pl.box_split, 1};
       const int est[5] = {1, 1, 1, 1, 1};
       int st = encode_map(&host_maps[n_maps++], dtype, base, extent, box, est, pl.PB);
       if (st) return st;
@@ -1512,7 +1545,7 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
       const int Wext = direct ? q.in[0] : pl.Wp_x;
       res_margin[r] = direct ? 0 : A;
       const int extent[5] = {Wext, q.in[1], q.in[2], g.groups * g.c_in_g, g.batch};
-      const int box[5] = {pl.BW, 1, 1, pl.CB, 1};
+      const int box[5] = {pl.BW, 1, 1, pl.CB / pl.box_split, 1};
       const int est[5] = {1, 1, 1, 1, 1};
       int st = encode_map(&host_maps[n_maps++], dtype, base, extent, box, est, pl.PB, 0, direct ? x_batch_stride : 0);
       if (st) return st;
@@ -1548,6 +1581,14 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   p.tri = pl.tri ? 1 : 0;
   p.scale_dev = scale_dev;
   p.s_tiles = pl.s_tiles;
+  p.box_split = pl.box_split;
+  // stage geometry of the super-tile kernel
+  p.st_rows = 2 * kTileM; p.st_a_bytes = 2 * kTileM * kRowBytes; p.st_bytes = 2 * p.st_a_bytes; p.st_n = 3;
+  if (pl.super && pl.s_tiles == 1 && !getenv("EINCONV_KFC_NO_DEEP")) {
+    if (pl.m_tiles == 1) { p.st_rows = kTileM; p.st_a_bytes = kTileM * kRowBytes; }
+    p.st_bytes = p.st_a_bytes;            // no column operand: the only super-tile is diagonal
+    p.st_n = (3 * 4 * kTileM * kRowBytes) / p.st_bytes;  // 6 or 12
+  }
 #ifdef EINCONV_BRINGUP
   {
     const char* dbg = getenv("EINCONV_TMA_DEBUG");
@@ -1599,7 +1640,7 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
       const int pitch = direct ? q.in[0] : pl.Wp_x;
       const int clipped = std::max(1, std::min(pitch, q.out[0] + p.kw_c0[kw]));
       const int extent[5] = {clipped, q.in[1], q.in[2], g.groups * g.c_in_g, g.batch};
-      const int box[5] = {pl.BW, 1, 1, pl.CB, 1};
+      const int box[5] = {pl.BW, 1, 1, pl.CB / pl.box_split, 1};
       const int est[5] = {1, 1, 1, 1, 1};
       EINCONV_CHECK_ARG(n_maps < kMaxMaps, "kfc: too many tensor maps");
       p.kw_map_b[kw] = (signed char)n_maps;
