@@ -111,6 +111,26 @@ def test_c4_full_size_bf16():
     assert rel > 0.0  # a bf16 result cannot equal the fp64 truth bit for bit: guards a vacuous comparison
 
 
+@pytest.mark.parametrize("route", ["selfpack", "packed", "fused"])
+def test_c4_mid_size_every_slab_route(route, monkeypatch):
+    """A C4-like tensor small enough for a quick fp64 truth but long enough for several packing chunks:
+    the self-packing kernel (packed copies written by its own producer warps, chunk flags), the pre-packed
+    TMA route with contiguous K splits (the default deals k-blocks round-robin; test_c4_full_size_bf16 runs
+    that) and the fused shared-memory producers must agree with fp64."""
+    if route == "selfpack":
+        monkeypatch.setenv("EINCONV_WGRAD_SELFPACK", "1")
+    elif route == "packed":
+        monkeypatch.setenv("EINCONV_WGRAD_CONTIGUOUS_SPLITS", "1")   # the default route with the older k-block order
+    else:
+        monkeypatch.setenv("EINCONV_WGRAD_FUSED", "1")
+    torch.manual_seed(3)
+    x = (torch.rand(4, 64, 8, 40, 40) - 0.4).bfloat16().to(DEV)
+    v = (torch.rand(4, 64, 8, 40, 40) - 0.5).bfloat16().to(DEV)
+    gw = evaluator.conv_weight_vjp_raw(x, v, 3, 1, 1, 1, 1)
+    truth = _weight_vjp_truth_fp64(x, v, 3, 1)
+    rel_to_max(gw, truth, 2.0**-7, f"C4-like mid size, {route}")
+
+
 def test_c4_slice_against_the_c_oracle_bf16():
     """One sample, reduced depth/height of the C4 tensor against oracle/einconv_oracle.c (fp64, plain loops)."""
     torch.manual_seed(0)

@@ -839,6 +839,14 @@ CTMA_CASES = [
     ((2, 16, 11, 12), (64, 16, 3, 5), dict(padding=(1, 6), dilation=(1, 3))),  # dilated pairs, groups per row
     ((3, 16, 40), (64, 16, 3), dict(padding=1)),                             # N = 1
     ((2, 32, 9, 9), (128, 16, 3, 3), dict(padding=1, groups=2)),             # two conv groups of 64
+    # innermost extents that are multiples of 8: the weight VJP fills its slabs from the channels-first
+    # tensors with producer warps (no packed copies); 3 / 5 / 7 taps per kernel row: N = 192 / 256 MMAs
+    ((2, 64, 4, 8, 16), (64, 64, 3, 3, 3), dict(padding=1)),                 # C4 in small
+    ((2, 32, 10, 16), (128, 32, 3, 3), dict(padding=1)),                     # two cotangent blocks per tile
+    ((2, 24, 12, 24), (40, 24, 3, 3), dict(padding=(1, 2), dilation=(1, 2))),  # BN = 48, dilated
+    ((2, 16, 9, 16), (128, 8, 5, 5), dict(padding=2, groups=2)),             # 5 taps per row: units of 3 + 2
+    ((1, 8, 10, 24), (64, 8, 1, 7), dict(padding=(0, 3))),                   # 7 taps per row: units of 4 + 3
+    ((3, 72, 5, 8), (64, 72, 3, 3), dict(padding=0)),                        # two channel blocks, no padding
 ]
 CTMA_IDS = ["x".join(map(str, c[0])) + "-w" + "x".join(map(str, c[1])) for c in CTMA_CASES]
 
@@ -893,13 +901,19 @@ def test_conv_tma_forward_and_input_vjp(case, mode, ctma_weights, monkeypatch):
 
 @pytest.mark.parametrize("case", CTMA_CASES, ids=CTMA_IDS)
 @pytest.mark.parametrize("mode", ["bf16", "fp16", "tf32"])
-@pytest.mark.parametrize("taps_per_mma", ["auto", "pairs"])
+@pytest.mark.parametrize("taps_per_mma", ["auto", "pairs", "fused", "selfpack", "nb2"])
 def test_slab_weight_vjp(case, mode, taps_per_mma, monkeypatch):
     """csrc/wgrad_slab.cu (MN-major operands from the channels-last padded copies, tap pairs sharing one
     slab): max|d| <= 2^-7 (bf16) / 2^-10 (fp16) of max|ref| against the fp64 oracle on the same bits;
     fp32 tensors in TF32 mode run on scaled fp16 operand copies with the TF32 tolerance 1e-3."""
     if taps_per_mma == "pairs":
         monkeypatch.setenv("EINCONV_WGRAD_NO_QUAD", "1")
+    elif taps_per_mma == "fused":    # producer warps fill the slabs from the channels-first tensors (opt-in)
+        monkeypatch.setenv("EINCONV_WGRAD_FUSED", "1")
+    elif taps_per_mma == "selfpack":  # the kernel writes its own packed copies (forced on these small cases)
+        monkeypatch.setenv("EINCONV_WGRAD_SELFPACK", "1")
+    elif taps_per_mma == "nb2":      # two taps per unit (N = 128) where the dispatcher would take three or four
+        monkeypatch.setenv("EINCONV_WGRAD_NB", "2")
     dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "tf32": torch.float32}[mode]
     x, w, b, kw = _tc_inputs(case, dtype)
     N = x.dim() - 2
