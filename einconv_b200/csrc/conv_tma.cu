@@ -15,6 +15,18 @@
 // tap's MMA descriptor just starts `shift` rows further down.  Rows with o_d >= O_d (the wrap-around
 // columns of the padded grid) are computed and dropped by the epilogue.
 //
+// FUSED mode (opt-in, EINCONV_CTMA_FUSED=1; stride 1, innermost source rows that are multiples of 16 bytes):
+// no packed copy of the source exists.  Two groups of eight producer warps read the channels-first tensor
+// (16-byte loads of 4 fp32 / 8 16-bit positions of one channel), transpose blocks in registers (fp32:
+// register renaming, 16-bit: PRMT) and store 16-byte chunks of channels into the 128-byte-swizzled K-major
+// slab exactly where TMA would have put them; padding rows and lines outside the tensor are zeros.
+// Measured on C1 (profiles/r02_c1_fused_vs_packed.txt): kernel 39.5 us against 16.8 (pack) + 27.4 (TMA-fed
+// kernel) under ncu, 37.3 against 37.5 us per step in a graph -- no gain, and 2 x slower on wide layers
+// (256 -> 256 channels).  With the loads AND the stores removed the kernel still takes 28 us: the C1 kernel is
+// bound by its MMA issue rate (36 N = 64 MMAs of a stage take ~2100 cycles) and the 850 + 300 cycle bubbles of
+// a two-stage ring, not by how the slab is fed; the gather itself reaches ~3.5 TB/s chip-wide (64-byte
+// fragments of 8 channel planes per warp instruction) where TMA boxes reach twice that.
+//
 // Roles (192 threads, persistent CTAs, one per SM): warp 0 lane 0 issues TMA (A slabs, per-tap weight
 // tiles); warp 1 lane 0 issues tcgen05.mma (kind::tf32 / kind::f16, M = 128, N = BN <= 256, fp32
 // accumulators in TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1);
@@ -36,6 +48,8 @@ namespace ctma {
 using namespace ptx;
 
 constexpr int kThreads = 192;
+constexpr int kProducerWarps = 16;  // FUSED mode: warps 6..21 fill the A slabs from the channels-first source
+constexpr int kThreadsFused = kThreads + 32 * kProducerWarps;
 constexpr int kTileM = 128;
 constexpr int kMaxGroups = 128;
 constexpr int kMaxTpg = 64;
@@ -81,6 +95,17 @@ struct Params {
   // multiplies the accumulator by 1 / (s_src * s_w).  nullptr otherwise.
   const unsigned* absmax;
   long long* trace;  // bring-up only (EINCONV_CTMA_TRACE): clock64() stamps of CTA 0, 16 per tile
+  // FUSED mode: the channels-first source on the padded grid
+  struct Fill {
+    const void* src;
+    long long sample_stride, chan_stride;  // elements
+    long long sstride[kMaxDims];           // element stride of spatial dim d
+    int P[kMaxDims], S[kMaxDims], off[kMaxDims];
+    FastDiv P_div[kMaxDims], gw_div;
+    int groups_w;                          // S[N-1] / (positions per 16 bytes)
+    int ctot;
+    int debug;  // bring-up: 1 = no global loads (zeros), 2 = no shared stores, 4 = no row decode
+  } fill;
 };
 
 template <typename T> struct Elem;
@@ -122,10 +147,137 @@ __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint64_t a_base, ui
     if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(tile - tile_begin) * 16 + (slot)] = clock64(); \
   } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// FUSED producers (see the header): same scheme as wgrad_slab.cu's, for a K-major slab whose rows hold
+// 128 bytes of channels (32 fp32 / 64 16-bit).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ldg128_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  for (long long n = 0; !mbar_try_wait(bar, parity); ++n) {
+    __nanosleep(32);
+    if (n > 200000000ll) __trap();
+  }
+}
+__device__ __forceinline__ uint32_t word_of(const uint4& v, int i) {
+  return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+// Fill rows [0, n_rows) of the slab at `slab_addr` with padded rows [R0, R0 + n_rows) of channels
+// [chan0, chan0 + nch) (zero beyond nch) of the source.  ES = element size; a 16-byte load holds EPV = 16 / ES
+// positions of one channel, a 16-byte slab chunk EPV channels of one position.  A task moves 128 bytes:
+// 8 channels x EPV positions (fp32: two chunks per row, 16-bit: one), so that one round of a 256-thread
+// producer group covers a 32 KB slab.
+template <int ES>
+__device__ __forceinline__ void fill_slab(uint32_t slab_addr, int R0, int n_rows, const Params& p, int cb_bytes,
+                                          int chan0, int nch, int tid, int nthreads) {
+  constexpr int EPV = 16 / ES;
+  constexpr int CPT = 8 / EPV;  // chunks per task: 2 (fp32), 1 (16-bit)
+  const Params::Fill& f = p.fill;
+  const int N = p.n_dims;
+  const int Pw = f.P[N - 1], Sw = f.S[N - 1], offw = f.off[N - 1], gw = f.groups_w;
+  const int cols = max(1, (cb_bytes >> 4) / CPT);  // task columns per slab row: 4 / 8 for 128-byte rows
+  const int cshift = cols >= 8 ? 3 : (cols == 4 ? 2 : (cols == 2 ? 1 : 0));
+  // data groups line * gw + g touched by the rows, lines touched
+  const int ra = R0, rb = R0 + n_rows;
+  const int La = (int)f.P_div[N - 1].quot((uint32_t)ra), Lb = (int)f.P_div[N - 1].quot((uint32_t)(rb - 1));
+  const int wa = ra - La * Pw, wb = rb - 1 - Lb * Pw;
+  const int first = wa < offw ? La * gw : (wa < offw + Sw ? La * gw + (wa - offw) / EPV : (La + 1) * gw);
+  const int last = wb < offw ? Lb * gw - 1 : (wb < offw + Sw ? Lb * gw + (wb - offw) / EPV : Lb * gw + gw - 1);
+  const int n_groups = max(0, last - first + 1), n_lines = Lb - La + 1;
+  const int Tdata = n_groups << cshift, Ttot = Tdata + (n_lines << cshift);
+  const uint32_t swz_mask = 0x70u & (uint32_t)(cb_bytes - 16);  // address bits [4,7) ^= bits [7,10) (128 / 64 / 32 B)
+  for (int task = tid; task < Ttot; task += nthreads) {
+    const int c = task & (cols - 1);
+    const int t2 = task >> cshift;
+    if (task < Tdata) {
+      const int slot = first + t2;
+      const int L = (int)f.gw_div.quot((uint32_t)slot);
+      const int grp = slot - L * gw;
+      bool valid = true;
+      long long soff = 0;
+      uint32_t rem = (uint32_t)L;
+      for (int d = N - 2; d >= 0; --d) {
+        const uint32_t q = f.P_div[d].quot(rem);
+        const int sd = (int)(rem - q * (uint32_t)f.P[d]) - f.off[d];
+        rem = q;
+        valid = valid && (unsigned)sd < (unsigned)f.S[d];
+        soff += (long long)sd * f.sstride[d];
+      }
+      valid = valid && rem < (uint32_t)p.batch;
+      int nvalid = valid ? min(8, nch - c * 8) : 0;  // channels of this task that exist
+      if (f.debug & 1) nvalid = 0;
+      uint4 in[8];
+      const unsigned char* q = reinterpret_cast<const unsigned char*>(f.src) +
+                               ((long long)rem * f.sample_stride + (long long)(chan0 + c * 8) * f.chan_stride + soff +
+                                (long long)grp * EPV) * ES;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        in[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (j < nvalid) in[j] = ldg128_stream(q + (long long)j * f.chan_stride * ES);
+      }
+      const int r0 = L * Pw + offw + grp * EPV - R0;
+      // fp32: a quarter warp holds 4 task columns x 2 position groups whose rows are 4 apart; the odd group
+      // stores its second chunk first, so the eight 16-byte stores of a quarter hit eight different bank groups
+      const int flip = (ES == 4) ? (t2 & 1) : 0;
+#pragma unroll
+      for (int i = 0; i < EPV; ++i) {
+        const int rr = r0 + i;
+        if ((unsigned)rr < (unsigned)n_rows && !(f.debug & 2)) {
+          const uint32_t row_addr = slab_addr + (uint32_t)rr * (uint32_t)cb_bytes;
+          if constexpr (ES == 4) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int h = hh ^ flip;
+              const uint32_t a = row_addr + ((uint32_t)(c * 2 + h) << 4);
+              const uint32_t o0 = h ? word_of(in[4], i) : word_of(in[0], i), o1 = h ? word_of(in[5], i) : word_of(in[1], i);
+              const uint32_t o2 = h ? word_of(in[6], i) : word_of(in[2], i), o3 = h ? word_of(in[7], i) : word_of(in[3], i);
+              sts128(a ^ ((a >> 3) & swz_mask), o0, o1, o2, o3);
+            }
+          } else {
+            const uint32_t sel = (i & 1) ? 0x7632u : 0x5410u;
+            const uint32_t a = row_addr + ((uint32_t)c << 4);
+            sts128(a ^ ((a >> 3) & swz_mask), __byte_perm(word_of(in[0], i >> 1), word_of(in[1], i >> 1), sel),
+                   __byte_perm(word_of(in[2], i >> 1), word_of(in[3], i >> 1), sel),
+                   __byte_perm(word_of(in[4], i >> 1), word_of(in[5], i >> 1), sel),
+                   __byte_perm(word_of(in[6], i >> 1), word_of(in[7], i >> 1), sel));
+          }
+        }
+      }
+    } else {
+      // padding rows of line L: wp in [0, offw) and [offw + Sw, Pw)
+      const int L = La + (t2 - n_groups);
+      const int row_base = L * Pw - R0;
+      for (int wp = 0; wp < Pw; ++wp) {
+        if (wp == offw) wp += Sw;
+        if (wp >= Pw) break;
+        const int rr = row_base + wp;
+        if ((unsigned)rr < (unsigned)n_rows) {
+#pragma unroll
+          for (int h = 0; h < CPT; ++h) {
+            const uint32_t a = slab_addr + (uint32_t)rr * (uint32_t)cb_bytes + ((uint32_t)(c * CPT + h) << 4);
+            sts128(a ^ ((a >> 3) & swz_mask), 0u, 0u, 0u, 0u);
+          }
+        }
+      }
+    }
+  }
+}
+
 // T: operand type of the MMAs; TO: type of the destination and the bias (differs only for fp32 tensors on
 // scaled fp16 operands)
-template <typename T, typename TO = T>
-__global__ void __launch_bounds__(kThreads, 1)
+template <typename T, typename TO = T, bool FUSED = false>
+__global__ void __launch_bounds__(FUSED ? kThreadsFused : kThreads, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -138,12 +290,16 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.n_stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    // FUSED: the producers' arrival completes a stage, plus (streamed weights) the TMA warp's expect_tx arrival
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&bars->full[i], FUSED && !p.resident ? 2 : 1);
+      mbar_init(&bars->empty[i], 1);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
     for (int i = 0; i < kMaxWBars; ++i) mbar_init(&bars->w_full[i], 1);
     mbar_init(&bars->w_empty, 1);
     fence_barrier_init();
-    prefetch_tensormap(&map_a);
+    if constexpr (!FUSED) prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
   }
   // TMEM: two accumulators of BN fp32 columns (power of two >= 32)
@@ -161,13 +317,42 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int stages_per_tile = p.n_slices * p.n_groups;
   const int n_wbars = stages_per_tile <= kMaxWBars ? stages_per_tile : 1;
 
-  if (warp == 0) {
+  if (FUSED && warp >= 6) {
+    // ------------------------------------------------------------------ software producers (FUSED): A slabs
+    // Two groups of eight warps fill alternate stages, so that two rounds of loads (one per stage buffer) are
+    // in flight at once: a round is a full L2 / DRAM round trip, and the registers of the producers are the
+    // only staging memory.
+    constexpr int kGroupThreads = kProducerWarps * 32 / 2;
+    const int ptid = threadIdx.x - 6 * 32;
+    const int group = ptid / kGroupThreads, gtid = ptid - group * kGroupThreads;
+    long long sidx = 0;  // running stage number of this CTA
+    for (long long tile = tile_begin; tile < tile_end; ++tile) {
+      const int mtile = (int)(tile % p.n_mtiles);
+      const int g = (int)((tile / p.n_mtiles) / p.n_ntiles);
+      const int q0 = mtile * kTileM;
+      for (int s = 0; s < p.n_slices; ++s) {
+        for (int grp = 0; grp < p.n_groups; ++grp, ++sidx) {
+          if ((int)(sidx & 1) != group) continue;
+          const int st = (int)(sidx % p.n_stages);
+          const uint32_t ph = (uint32_t)((sidx / p.n_stages) & 1);
+          mbar_wait_backoff(&bars->empty[st], ph ^ 1);
+          fill_slab<(int)sizeof(T)>(smem_u32(ring + (size_t)st * p.stage_bytes), q0 + p.group_shift[grp], p.slab_rows, p,
+                                    p.cb_bytes, g * p.cs + s * p.cb_elems, min(p.cb_elems, p.cs - s * p.cb_elems), gtid,
+                                    kGroupThreads);
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          if (group == 0) asm volatile("bar.sync 2, %0;" ::"n"(kGroupThreads) : "memory");
+          else asm volatile("bar.sync 3, %0;" ::"n"(kGroupThreads) : "memory");
+          if (gtid == 0) mbar_arrive(&bars->full[st]);
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     // (the whole warp runs the loops and waits; one elected lane issues)
     int st = 0;
     uint32_t ph = 0, pw = 0;
     long long cur_class = -1;
-    const uint32_t stage_tx = (uint32_t)(p.slab_rows * p.cb_bytes) +
+    const uint32_t stage_tx = (FUSED ? 0u : (uint32_t)(p.slab_rows * p.cb_bytes)) +
                               (p.resident ? 0u : (uint32_t)(p.tpg * p.bn * p.cb_bytes));
     for (long long tile = tile_begin; tile < tile_end; ++tile) {
       const int mtile = (int)(tile % p.n_mtiles);
@@ -221,18 +406,21 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                           s * p.cb_elems, wrow0 + tap * p.np);
             }
           }
+          if (FUSED && p.resident) continue;  // nothing to load per stage: the producers own the ring
           mbar_wait(&bars->empty[st], ph ^ 1);
           if (sg < 2) CTMA_TRACE(1 + sg);
           {
             if (lane == 0) mbar_expect_tx(&bars->full[st], stage_tx);
             __syncwarp();
             unsigned char* stage = ring + (size_t)st * p.stage_bytes;
-            const int row0 = q0 + p.group_shift[grp];
-            const int col_a = g * p.cs + s * p.cb_elems;
-            const int n_boxes = p.slab_rows / p.box_rows;
-            for (int bx = lane; bx < n_boxes; bx += 32)
-              tma_load_2d(stage + (size_t)bx * p.box_rows * p.cb_bytes, &map_a, &bars->full[st], col_a,
-                          row0 + bx * p.box_rows);
+            if constexpr (!FUSED) {
+              const int row0 = q0 + p.group_shift[grp];
+              const int col_a = g * p.cs + s * p.cb_elems;
+              const int n_boxes = p.slab_rows / p.box_rows;
+              for (int bx = lane; bx < n_boxes; bx += 32)
+                tma_load_2d(stage + (size_t)bx * p.box_rows * p.cb_bytes, &map_a, &bars->full[st], col_a,
+                            row0 + bx * p.box_rows);
+            }
             if (!p.resident) {
               unsigned char* bt = stage + p.slab_bytes;
               for (int j = lane; j < p.tpg; j += 32)
@@ -297,7 +485,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       if (new_w) pw ^= 1;
     }
-  } else {
+  } else if (warp < 6) {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lanes 32 * quarter .. + 31 are visible to this warp
     const int etid = threadIdx.x - 64;
@@ -987,6 +1175,7 @@ static bool make_role(int op, const DevGeom& g, Role* r) {
 
 struct CPlan {
   bool ok = false;
+  bool fused = false;  // A slabs filled from the channels-first source by producer warps (no packed copy)
   int es;
   int cb_bytes, cb_elems, n_slices, cgp, cp;
   int bn, n_ntiles, np;
@@ -1038,11 +1227,14 @@ static int phase_index(const Role& r, int tap, int* n_phases_out) {
   return result;
 }
 
-static CPlan make_cplan(const Role& r, int dtype) {
+static CPlan make_cplan(const Role& r, int dtype, bool fused_ok = false) {
   CPlan pl;
   pl.es = (int)elem_size(dtype);
   if (dtype == EINCONV_F64) return pl;
   const int es = pl.es, N = r.n_dims;
+  // opt-in (EINCONV_CTMA_FUSED=1): measured equal to or slower than the packed route, see the header
+  pl.fused = fused_ok && !r.strided && ((long long)r.S[N - 1] * es) % 16 == 0 && getenv("EINCONV_CTMA_FUSED") &&
+             !getenv("EINCONV_CTMA_NO_FUSED");
   if (r.groups > 1 && ((long long)r.cs * es) % 16 != 0) return pl;  // TMA column start must be 16-byte aligned
   // channel slice: widest swizzle span among those with the least padding
   {
@@ -1129,15 +1321,23 @@ static CPlan make_cplan(const Role& r, int dtype) {
   // tap grouping: the trailing `level` dims of a group share one slab; one pipeline stage holds the
   // slab of a (slice, group) and, unless the weights are resident, the group's weight tiles
   // (strided: every tap is its own group — taps of different phases read different sub-images)
-  for (int level = r.strided ? 0 : N; level >= 0 && !pl.ok; --level) {
+  int level_max = r.strided ? 0 : N;
+  if (const char* e = getenv("EINCONV_CTMA_LEVEL")) level_max = std::min(level_max, std::max(0, atoi(e)));
+  for (int level = level_max; level >= 0 && !pl.ok; --level) {
     long long tpg = 1, span = 0;
     for (int d = N - level; d < N; ++d) {
       tpg *= r.K[d];
       span += (long long)r.dil[d] * (r.K[d] - 1) * pl.pitch[d];
     }
     if (tpg > kMaxTpg || pl.taps / tpg > kMaxGroups) continue;
-    const long long rows = (kTileM + span + pl.box_rows - 1) / pl.box_rows * pl.box_rows;
-    const long long slab = rows * pl.cb_bytes;  // multiple of 8 KB
+    if (getenv("EINCONV_CTMA_SMALL_BOXES")) {
+      // boxes of just enough rows for one box per lane (instead of 8 KB boxes): slabs without the rounding
+      const long long need = (kTileM + span + 7) / 8 * 8;
+      pl.box_rows = (int)((need + 31) / 32 + 7) / 8 * 8;
+    }
+    // TMA moves whole boxes; the producer warps of FUSED mode any number of rows (8-row swizzle atoms)
+    const long long rows = pl.fused ? (kTileM + span + 7) / 8 * 8 : (kTileM + span + pl.box_rows - 1) / pl.box_rows * pl.box_rows;
+    const long long slab = (rows * pl.cb_bytes + 1023) / 1024 * 1024;
     pl.level = level;
     pl.tpg = (int)tpg;
     pl.n_groups = pl.taps / pl.tpg;
@@ -1218,7 +1418,10 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
     wj.transpose = r.transpose;
     wj.total = (long long)r.groups * pl.taps * pl.np * pl.cgp;
     int st0;
-    if (CONVERT) {
+    if (pl.fused) {
+      // weights only (the source is read by the kernel's producer warps): a packing launch with no source rows
+      st0 = pack_channels_last(nullptr, xp, dtype, N, 0, 64, 64, r.S, pl.P, r.pad, stream, &wj);
+    } else if (CONVERT) {
       long long n_src = (long long)r.batch * r.groups * r.cs, n_w = (long long)r.groups * r.cs * r.cd;
       for (int d = 0; d < N; ++d) {
         n_src *= r.S[d];
@@ -1263,7 +1466,8 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
   }
   // ---- tensor maps
   CUtensorMap map_a, map_b;
-  int st = encode_2d(&map_a, dtype, xp, pl.xp_rows, pl.cp, pl.cb_elems, pl.box_rows, pl.cb_bytes);
+  memset(&map_a, 0, sizeof(map_a));
+  int st = pl.fused ? 0 : encode_2d(&map_a, dtype, xp, pl.xp_rows, pl.cp, pl.cb_elems, pl.box_rows, pl.cb_bytes);
   if (st) return st;
   st = encode_2d(&map_b, dtype, wp, (long long)r.groups * pl.taps * pl.np, pl.cgp, pl.cb_elems, pl.bn, pl.cb_bytes);
   if (st) return st;
@@ -1336,10 +1540,39 @@ static int run_t(const Role& r, const CPlan& pl, const void* src, const void* w,
     }
   }
 
+  if (pl.fused) {
+    Params::Fill& f = p.fill;
+    f.src = src;
+    f.ctot = r.groups * r.cs;
+    long long mul = 1;
+    for (int d = N - 1; d >= 0; --d) {
+      f.P[d] = (int)pl.P[d];
+      f.P_div[d] = FastDiv((uint32_t)pl.P[d]);
+      f.S[d] = r.S[d];
+      f.off[d] = r.pad[d];
+      f.sstride[d] = mul;
+      mul *= r.S[d];
+    }
+    f.chan_stride = mul;
+    f.sample_stride = mul * f.ctot;
+    f.groups_w = r.S[N - 1] / (16 / pl.es);
+    f.gw_div = FastDiv((uint32_t)std::max(1, f.groups_w));
+    f.debug = getenv("EINCONV_CTMA_FILL_DEBUG") ? atoi(getenv("EINCONV_CTMA_FILL_DEBUG")) : 0;
+  }
+  const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, num_sms());
+  if constexpr (!CONVERT) {
+    if (pl.fused) {
+      auto kernf = conv_tma_kernel<T, TO, true>;
+      cudaError_t ef = cudaFuncSetAttribute(kernf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+      if (ef != cudaSuccess) return cuda_fail(ef, "cudaFuncSetAttribute(conv_tma fused)");
+      kernf<<<grid, kThreadsFused, pl.smem, stream>>>(map_a, map_b, p);
+      EINCONV_CHECK_LAUNCH("conv_tma_kernel");
+      return EINCONV_OK;
+    }
+  }
   auto kern = conv_tma_kernel<T, TO>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tma)");
-  const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, num_sms());
   // (programmatic dependent launch was measured here: no gain, the GEMM's CTAs need the whole SM)
   long long* trace = nullptr;
   const int trace_tiles = 16;
@@ -1437,10 +1670,15 @@ int run(int op, const void* src, const void* w, const void* bias, void* dst, int
     set_error("conv_tma: unsupported geometry");
     return EINCONV_ERR_UNSUPPORTED;
   }
-  const CPlan pl = make_cplan(r, dtype);
+  CPlan pl = make_cplan(r, dtype);
   if (!pl.ok) {
     set_error("conv_tma: unsupported geometry");
     return EINCONV_ERR_UNSUPPORTED;
+  }
+  if (((uintptr_t)src % 16) == 0) {
+    // FUSED producers (same workspace layout; the packed source is simply not written)
+    const CPlan pf = make_cplan(r, dtype, true);
+    if (pf.ok && pf.fused && pf.xp_bytes == pl.xp_bytes && pf.wp_bytes == pl.wp_bytes) pl = pf;
   }
   if (!workspace || workspace_bytes_given < pl.xp_bytes + pl.wp_bytes + 1024) {
     set_error("conv_tma: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes_given,

@@ -91,6 +91,13 @@ int encode_tiled_raw(CUtensorMap* map, const void* base, int elem_bytes, int ran
                      const unsigned long long* strides_bytes, const unsigned* box, const unsigned* elem_strides);
 }  // namespace ctma
 
+// conv_dense.cu (1x1 convolutions as GEMMs on the channels-first tensors, no packed copies)
+namespace dense {
+bool supported(int op, const DevGeom& g, int dtype, int math);
+int run(int op, const void* src, const void* w, const void* bias, void* dst, int dtype, const DevGeom& g,
+        cudaStream_t stream);
+}  // namespace dense
+
 // wgrad_slab.cu (weight VJP from channels-last padded copies, MN-major tcgen05, stride 1, 16-bit)
 namespace wslab {
 bool supported(const DevGeom& g, int dtype);

@@ -742,12 +742,15 @@ static Plan make_plan(const DevGeom& g, int dtype) {
       }
     }
     if (!best_nb) continue;
+    const int kb_forced = getenv("EINCONV_WGRAD_KB") ? atoi(getenv("EINCONV_WGRAD_KB")) : 0;
     for (int kb : {256, 128, 64}) {
+      if (kb_forced && kb != kb_forced) continue;
       const long long rows = (kb + span + row_round - 1) / row_round * row_round;
       const long long v_early = best_nb > 1 ? (best_nb - 1) * q : 0;
       const long long v_rows = pl.fused ? (kb + v_early + 7) / 8 * 8 : (v_early ? kb + kBoxRows : kb);
       const long long stage = rows * kRowBytes + (long long)pl.n_vblocks * v_rows * kRowBytes;
       if (2 * stage > kSmemBudget) continue;
+      if (getenv("EINCONV_WGRAD_MIN3") && 3 * stage > kSmemBudget && kb > 64) continue;  // at least three stages
       pl.tpg = (int)tpg;
       pl.n_pairs = best_mmas;
       pl.nb = best_nb;

@@ -851,13 +851,19 @@ CTMA_CASES = [
 CTMA_IDS = ["x".join(map(str, c[0])) + "-w" + "x".join(map(str, c[1])) for c in CTMA_CASES]
 
 
-@pytest.fixture(params=["auto", "stream"])
+@pytest.fixture(params=["auto", "stream", "fused", "fused-stream"])
 def ctma_weights(request, monkeypatch):
-    """Weights resident in shared memory when they fit ("auto") or always streamed per stage."""
-    if request.param == "stream":
+    """Weights resident in shared memory when they fit ("auto") or always streamed per stage; "fused": the
+    A slabs are filled from the channels-first source by producer warps instead of TMA boxes of a packed
+    copy (opt-in route; applies where the innermost source rows are multiples of 16 bytes)."""
+    if "stream" in request.param:
         monkeypatch.setenv("EINCONV_CTMA_STREAM", "1")
     else:
         monkeypatch.delenv("EINCONV_CTMA_STREAM", raising=False)
+    if "fused" in request.param:
+        monkeypatch.setenv("EINCONV_CTMA_FUSED", "1")
+    else:
+        monkeypatch.delenv("EINCONV_CTMA_FUSED", raising=False)
     return request.param
 
 
@@ -931,6 +937,50 @@ def test_slab_weight_vjp(case, mode, taps_per_mma, monkeypatch):
     finally:
         evaluator.set_fp32_math("auto")
     _rel_to_max(got, want, {"bf16": 2.0**-7, "fp16": 2.0**-10, "tf32": 1e-3}[mode], f"slab wgrad {mode}")
+
+
+# ---- 1x1 convolutions: GEMMs on the channels-first tensors (csrc/conv_dense.cu), no packed copies ----------
+DENSE_CASES = [
+    ((2, 64, 16, 16), (64, 64, 1, 1)),       # one K block, N = 64
+    ((3, 72, 8, 12), (200, 72, 1, 1)),       # K = 72 (partial second block), N = 200 of 208 / 256 columns
+    ((2, 256, 8, 8), (520, 256, 1, 1)),      # four K blocks, three N tiles
+    ((1, 136, 40), (24, 136, 1)),            # N = 1 (1-d), partial position tile
+    ((2, 32, 4, 6, 8), (48, 32, 1, 1, 1)),   # N = 3: spatial dims collapse
+    ((5, 8, 24, 24), (16, 8, 1, 1)),         # K = 8: mostly zero-filled K block; 4.5 position tiles per sample
+]
+DENSE_IDS = ["x".join(map(str, c[0])) + "-w" + "x".join(map(str, c[1])) for c in DENSE_CASES]
+
+
+@pytest.mark.parametrize("case", DENSE_CASES, ids=DENSE_IDS)
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "tf32"])
+def test_dense_1x1_forward_and_input_vjp(case, mode):
+    """The dense rule's kernel: MN-major A operand fetched by TMA from the channels-first tensor, weights read
+    in place (K-major for the forward pass, MN-major for the input VJP).  Same tolerances as the other
+    tensor-core tests against the fp64 oracle on the same rounded inputs."""
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "tf32": torch.float32}[mode]
+    tol = {"bf16": 2.0**-7, "fp16": 2.0**-10, "tf32": 1e-3}[mode]
+    xs, ws = case
+    torch.manual_seed(4)
+    x = (torch.rand(*xs) - 0.3).to(dtype)
+    w = (torch.rand(*ws) - 0.5).to(dtype)
+    b = (torch.rand(ws[0]) - 0.5).to(dtype)
+    N = len(xs) - 2
+    want = direct.conv_forward(x.double().numpy(), w.double().numpy(), b.double().numpy(), stride=1, padding=0,
+                               dilation=1, groups=1)
+    v = (torch.rand(*want.shape) - 0.5).to(dtype)
+    want_gx = direct.conv_input_vjp(w.double().numpy(), v.double().numpy(), tuple(xs[2:]), stride=1, padding=0,
+                                    dilation=1, groups=1)
+    g = evaluator._geom(xs[0], 1, xs[1], ws[0], tuple(xs[2:]), tuple(ws[2:]), 1, 0, 1)[0]
+    evaluator.set_fp32_math("tf32" if mode == "tf32" else "auto")
+    try:
+        assert evaluator.selected_kernel(nat.OP_CONV_FWD, g, dtype) == "tcgen05_dense_conv_fwd"
+        assert evaluator.selected_kernel(nat.OP_CONV_INPUT_VJP, g, dtype) == "tcgen05_dense_conv_input_vjp"
+        got = convNd(x.to(DEV), w.to(DEV), b.to(DEV))
+        gx = evaluator.conv_input_vjp_raw(w.to(DEV), v.to(DEV), tuple(xs[2:]), 1, 0, 1, 1)
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, tol, f"dense 1x1 fwd {mode}")
+    _rel_to_max(gx, want_gx, tol, f"dense 1x1 input vjp {mode}")
 
 
 def test_conv_tma_is_used_by_autograd_and_matches_torch():
