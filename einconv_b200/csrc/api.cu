@@ -95,7 +95,7 @@ int make_dev_geom(const einconv_geom* g, DevGeom* out, bool need_c_out) {
 // ---------------------------------------------------------------------------------------------
 // kernel selection
 // ---------------------------------------------------------------------------------------------
-enum class Path { FFMA, DEPTHWISE, TENSOR, TMA, CONV_TMA, WGRAD_SLAB, DENSE };
+enum class Path { FFMA, DEPTHWISE, TENSOR, TMA, CONV_TMA, WGRAD_SLAB, DENSE, CONV_ROWS };
 
 static int resolve_math(int dtype, int math) {
   if (math == EINCONV_MATH_AUTO)
@@ -128,6 +128,8 @@ static Path select_path(int op, const DevGeom& g, int dtype, int math, int kerne
     // 1x1 / stride 1 / no padding (the simplifier's dense rule): a GEMM on the channels-first tensors themselves
     if ((op == EINCONV_OP_CONV_FWD || op == EINCONV_OP_CONV_INPUT_VJP) && dense::supported(op, g, dtype, m))
       return Path::DENSE;
+    // stride-1 2-d forward on fp32 tensors: MN-major operand from the channels-first tensor, kw taps in the epilogue
+    if (op == EINCONV_OP_CONV_FWD && crows::supported(op, g, dtype, m)) return Path::CONV_ROWS;
     // forward / input VJP: TMA-fed implicit GEMM over a zero-padded channels-last copy (stride 1)
     if ((op == EINCONV_OP_CONV_FWD || op == EINCONV_OP_CONV_INPUT_VJP) && ctma::supported(op, g, dtype, m))
       return Path::CONV_TMA;
@@ -284,6 +286,7 @@ const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype,
     case Path::TMA: return op == EINCONV_OP_KFC ? "tcgen05_tma_kfc" : "tcgen05_tma_wgrad";
     case Path::CONV_TMA: return op == EINCONV_OP_CONV_FWD ? "tcgen05_tma_conv_fwd" : "tcgen05_tma_conv_input_vjp";
     case Path::DENSE: return op == EINCONV_OP_CONV_FWD ? "tcgen05_dense_conv_fwd" : "tcgen05_dense_conv_input_vjp";
+    case Path::CONV_ROWS: return "tcgen05_rows_conv_fwd";
     case Path::WGRAD_SLAB: return "tcgen05_slab_wgrad";
     default: return "ffma_gather_gemm";
   }
@@ -324,6 +327,7 @@ static int64_t workspace_for(int op, DevGeom g, int dtype, int math, int kernels
   if (path == Path::TENSOR) return tc_workspace_bytes(op, g, dtype, resolve_math(dtype, math));
   if (path == Path::TMA) return tma::tma_workspace_bytes(op, g, dtype);
   if (path == Path::CONV_TMA) return ctma::workspace_bytes(op, g, dtype);
+  if (path == Path::CONV_ROWS) return crows::workspace_bytes(op, g, dtype, resolve_math(dtype, math));
   if (path == Path::WGRAD_SLAB) return wslab::workspace_bytes(g, dtype);
   switch (op) {
     case EINCONV_OP_KFAC_REDUCE: {
@@ -364,6 +368,9 @@ int einconv_conv_fwd(const void* x, const void* w, const void* bias, void* y, in
   switch (select_path(EINCONV_OP_CONV_FWD, g, dtype, math, kernels, al)) {
     case Path::DEPTHWISE: return dw_conv_fwd(x, w, bias, y, dtype, g, s);
     case Path::DENSE: return dense::run(EINCONV_OP_CONV_FWD, x, w, bias, y, dtype, g, s);
+    case Path::CONV_ROWS:
+      return crows::run(EINCONV_OP_CONV_FWD, x, w, bias, y, dtype, g, resolve_math(dtype, math), workspace,
+                        workspace_bytes, s);
     case Path::CONV_TMA:
       return ctma::run(EINCONV_OP_CONV_FWD, x, w, bias, y, dtype, g, workspace, workspace_bytes, s);
     case Path::TENSOR:

@@ -1,0 +1,517 @@
+// Stride-1 2-d convolutions straight from the channels-FIRST tensor: no packed copy, no one-hot pattern.
+//
+//   y[n, co, h, w] = sum_{ci, kh, kw} x[n, ci, h + kh - ph, w + kw - pw] * W[co, ci, kh, kw]
+//   (expressions/convNd_forward.py:48-55 with the index law i = o + k - p, conv_index_pattern.py:131-134)
+//
+// conv_tma.cu needs a zero-padded channels-LAST copy because its A operand has the channels contiguous; the
+// copy is a third of the C1 step and its N = 64 MMAs are shared-memory bound (36 of them take 2100 cycles).
+// Here the positions stay on the contiguous axis (MN-major A operand, tf32 through the 32-byte-atom swizzle,
+// see conv_dense.cu) and the two kinds of tap shift are taken apart:
+//   * kh (a shift by whole image rows) is a different TMA box of the same tensor: the slab of a tile holds
+//     image rows h0 - ph .. h0 + R + KH - 2 as blocks [K channels][BW positions of one row], and the A operand
+//     of tap row kh is the four consecutive blocks that start kh rows down.  Rows outside the image are TMA
+//     zero fill, which is the padding.
+//   * kw (a shift by single elements, which neither a TMA start coordinate nor a shared-memory descriptor can
+//     express: both move in 16-byte steps) is not applied to the operand at all.  The weights of the KW taps of
+//     a kernel row are stacked along N: one MMA of N = KW * BN computes, for UNSHIFTED input columns w',
+//         D_kw[h, w'][co] = sum_{kh, ci} x[ci, h + kh - ph, w'] W[co, ci, kh, kw]      for every kw at once,
+//     and the epilogue adds the KW accumulators of neighbouring columns, y[h, w] = sum_kw D_kw[h, w + kw - pw]:
+//     a TMEM lane is an input column, so the neighbours are neighbouring LANES and the sum is two warp
+//     shuffles per output.  Blocks of a row overlap by KW - 1 (rounded to 16 bytes) columns so that every
+//     output finds its neighbours inside one warp; columns outside the image are zero fill again.
+// The MMAs are N = 192 for a 3 x 3 kernel on 64 channels: tensor-bound (96 cycles) instead of shared-memory
+// bound, 24 per 128 columns instead of 72.
+//
+// Roles (320 threads, persistent CTAs): warp 0 TMA, warp 1 MMA issue, warps 2-9 epilogue.  The packed weights
+// Wp[kh][kw * BN + co][ci] (K-major, written by a small pre-pass) stay resident in shared memory.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "dispatch.cuh"
+#include "tc_ptx.cuh"
+
+namespace einconv {
+namespace crows {
+
+using namespace ptx;
+
+constexpr int kEpilogueWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpilogueWarps;
+constexpr int kMaxStages = 6;
+constexpr int kMaxKH = 8;
+constexpr int kSmemBudget = 216 * 1024;
+
+struct Params {
+  int batch, cs, cd;              // samples, source / destination channels
+  int H, W, OH, OW, KH, KW, ph, pw;
+  int bw, step, nb_w;             // block width (positions per 128 bytes), block step, blocks per image row
+  int R, nb_t, n_wtiles;          // tile = R rows x nb_t blocks (R * nb_t blocks = 128 rows of M); tiles per row
+  int n_htiles, n_ntiles, bn;     // row tiles per sample, destination-channel tiles, channels per tile (N = KW * bn)
+  long long total_tiles;
+  int kb_rows, n_kblocks;         // channel rows per stage (128 bytes of K for the weights), K blocks
+  int slab_blocks, block_bytes, stage_bytes, n_stages;
+  int w_tile_bytes, w_bytes;      // one [N rows][128 B] weight tile; all KH * n_kblocks of them
+  int mn_layout;
+  const void* bias;
+  void* dst;
+};
+
+struct Bars {
+  uint64_t full[kMaxStages], empty[kMaxStages];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t w_full;
+  uint32_t tmem_base;
+  float bias[256];
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// MN-major operand descriptor: see conv_dense.cu (layout 2: SWIZZLE_128B, 8-row K groups 1024 bytes apart;
+// layout 1: SWIZZLE_128B_BASE32B for 32-bit elements, 4-row K groups 512 bytes apart)
+__device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t start16, uint32_t lbo16, uint64_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)(start16 & 0x3FFF);
+  d |= (uint64_t)(lbo16 & 0x3FFF) << 16;
+  d |= (uint64_t)((layout == 1 ? 512 : 1024) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+template <typename T> struct Elem;
+template <> struct Elem<float> { static constexpr bool TF32 = true; static constexpr int FMT = 2; };
+template <> struct Elem<__nv_bfloat16> { static constexpr bool TF32 = false; static constexpr int FMT = 1; };
+template <> struct Elem<__half> { static constexpr bool TF32 = false; static constexpr int FMT = 0; };
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* w_region = smem;
+  unsigned char* ring = smem + p.w_bytes;
+  Bars* bars = reinterpret_cast<Bars*>(ring + (size_t)p.n_stages * p.stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ES = (int)sizeof(T);
+  constexpr int KSTEP = 32 / ES;  // K per MMA: 16 (16-bit) / 8 (tf32)
+  const int n_cols = p.KW * p.bn; // N of the MMAs = TMEM columns of one accumulator
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.n_stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], kEpilogueWarps); }
+    mbar_init(&bars->w_full, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)n_cols) tmem_cols <<= 1;
+  if (warp == 1) tmem_alloc(&bars->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  // tiles: index = ((ntile * batch + n) * n_htiles + htile) * n_wtiles + wtile; contiguous chunk per CTA
+  const long long tile_begin = p.total_tiles * blockIdx.x / gridDim.x;
+  const long long tile_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+  const long long per_ntile = (long long)p.batch * p.n_htiles * p.n_wtiles;
+  const int per_sample = p.n_htiles * p.n_wtiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one box per lane)
+    int st = 0;
+    uint32_t ph = 0;
+    int cur_ntile = -1;
+    const uint32_t stage_tx = (uint32_t)(p.slab_blocks * p.block_bytes);
+    for (long long tile = tile_begin; tile < tile_end; ++tile) {
+      const int ntile = (int)(tile / per_ntile);
+      const long long t2 = tile - (long long)ntile * per_ntile;
+      const int n = (int)(t2 / per_sample);
+      const int t3 = (int)(t2 - (long long)n * per_sample);
+      const int h0 = (t3 / p.n_wtiles) * p.R, wb0 = (t3 % p.n_wtiles) * p.nb_t;
+      if (ntile != cur_ntile) {
+        // (re)load the weights of this n-tile: KH * n_kblocks tiles of [n_cols rows][128 B of K]
+        // (only at the start of a CTA's chunk in practice; a second class would need the MMA warp to be done
+        // with the first: chunks are cut so that this cannot happen, see the host code)
+        cur_ntile = ntile;
+        const int n_wt = p.KH * p.n_kblocks;
+        if (lane == 0) mbar_expect_tx(&bars->w_full, (uint32_t)(n_wt * p.w_tile_bytes));
+        __syncwarp();
+        for (int i = lane; i < n_wt; i += 32) {
+          const int kh = i / p.n_kblocks, kb = i - kh * p.n_kblocks;
+          tma_load_2d(w_region + (size_t)i * p.w_tile_bytes, &map_b, &bars->w_full, kb * p.kb_rows,
+                      (ntile * p.KH + kh) * n_cols);
+        }
+      }
+      for (int kb = 0; kb < p.n_kblocks; ++kb) {
+        mbar_wait(&bars->empty[st], ph ^ 1);
+        if (lane == 0) mbar_expect_tx(&bars->full[st], stage_tx);
+        __syncwarp();
+        unsigned char* stage = ring + (size_t)st * p.stage_bytes;
+        for (int bx = lane; bx < p.slab_blocks; bx += 32) {
+          const int row = bx / p.nb_t, wb = wb0 + bx - row * p.nb_t;
+          tma_load_4d(stage + (size_t)bx * p.block_bytes, &map_a, &bars->full[st], wb * p.step, h0 - p.ph + row,
+                      kb * p.kb_rows, n);
+        }
+        __syncwarp();
+        if (++st == p.n_stages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc(Elem<T>::FMT, 128, n_cols) | (1u << 15);  // A MN-major, B K-major
+    const uint32_t ring16 = smem_u32(ring) >> 4, stage16 = (uint32_t)p.stage_bytes >> 4;
+    const uint32_t w16 = smem_u32(w_region) >> 4, wtile16 = (uint32_t)p.w_tile_bytes >> 4;
+    const uint32_t blk16 = (uint32_t)p.block_bytes >> 4;
+    const uint64_t kdesc = make_desc_kmajor(0, 128);
+    const uint32_t kMnStep16 = (uint32_t)(KSTEP * 128) >> 4;
+    const int ksteps = p.kb_rows / KSTEP;
+    const uint64_t layout = (uint64_t)p.mn_layout;
+    int st = 0;
+    uint32_t ph = 0, it = 0;
+    bool w_ready = false;
+    for (long long tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      if (!w_ready) {
+        mbar_wait(&bars->w_full, 0);
+        w_ready = true;
+      }
+      mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)n_cols;
+      for (int kb = 0; kb < p.n_kblocks; ++kb) {
+        mbar_wait(&bars->full[st], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a16 = ring16 + (uint32_t)st * stage16;
+          for (int kh = 0; kh < p.KH; ++kh) {
+            // tap row kh: the four blocks that start kh image rows into the slab
+            const uint64_t a_base = make_desc_mnmajor(a16 + (uint32_t)(kh * p.nb_t) * blk16, blk16, layout);
+            const uint64_t b_base = kdesc + (uint64_t)(w16 + (uint32_t)(kh * p.n_kblocks + kb) * wtile16);
+            for (int k = 0; k < ksteps; ++k)
+              umma<Elem<T>::TF32>(d_tmem, a_base + (uint64_t)((uint32_t)k * kMnStep16), b_base + (uint64_t)(2 * k), idesc,
+                                  (uint32_t)(kb | kh | k));
+          }
+          umma_commit(&bars->empty[st]);
+          if (kb + 1 == p.n_kblocks) umma_commit(&bars->tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++st == p.n_stages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int quarter = warp & 3;      // block `quarter` of the tile: TMEM lanes 32 * quarter .. + 31
+    const int half = (warp - 2) >> 2;  // 16-channel chunks half, half + 2, ..
+    const int etid = threadIdx.x - 64;
+    T* dst = reinterpret_cast<T*>(p.dst);
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    const int n_chunks = p.bn >> 4;
+    const long long plane = (long long)p.OH * p.OW;
+    const int r_local = quarter / p.nb_t, wb_local = quarter - r_local * p.nb_t;
+    uint32_t it = 0;
+    int cur_ntile = -1;
+    for (long long tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int ntile = (int)(tile / per_ntile);
+      const long long t2 = tile - (long long)ntile * per_ntile;
+      const int n = (int)(t2 / per_sample);
+      const int t3 = (int)(t2 - (long long)n * per_sample);
+      const int h = (t3 / p.n_wtiles) * p.R + r_local;
+      const int n0 = ntile * p.bn;
+      // this thread's input column (= output column) and the outputs its block owns: [lo, hi)
+      const int wb = (t3 % p.n_wtiles) * p.nb_t + wb_local;
+      const int col = wb * p.step + lane;
+      const int lo = wb == 0 ? 0 : wb * p.step + p.pw;
+      const int hi = wb + 1 >= p.nb_w ? p.OW : (wb + 1) * p.step + p.pw;
+      const bool col_ok = col >= lo && col < hi && col < p.OW && wb < p.nb_w;
+      if (bias && ntile != cur_ntile) {
+        cur_ntile = ntile;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
+        for (int c = etid; c < p.bn; c += 32 * kEpilogueWarps)
+          bars->bias[c] = n0 + c < p.cd ? (float)Cvt<T>::load(bias + n0 + c) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
+      }
+      const bool valid = col_ok && h < p.OH;
+      T* dst_row = dst + ((long long)n * p.cd + n0) * plane + (long long)h * p.OW + col;
+      mbar_wait_relaxed(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * (uint32_t)n_cols + ((uint32_t)(quarter * 32) << 16);
+      for (int ch = half; ch < n_chunks; ch += 2) {
+        const int c0 = ch << 4;
+        float y[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[j] = bias ? bars->bias[c0 + j] : 0.f;
+        for (int kw = 0; kw < p.KW; ++kw) {
+          uint32_t r[16];
+          tmem_ld16_nowait(taddr + (uint32_t)(kw * p.bn + c0), r);
+          tmem_ld_wait();
+          // y[w] += D_kw[w + kw - pw]: the value of lane + (kw - pw); lanes outside the warp are columns this
+          // block does not own outputs for, or padding (zero)
+          const int src = lane + kw - p.pw;
+          const bool src_ok = src >= 0 && src < 32;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float v = __shfl_sync(0xffffffffu, __uint_as_float(r[j]), src & 31);
+            y[j] += src_ok ? v : 0.f;
+          }
+        }
+        if (ch + 2 >= n_chunks) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+        }
+        if (valid) {
+          T* d0 = dst_row + (long long)c0 * plane;
+          if (n0 + c0 + 16 <= p.cd) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              Cvt<T>::store(d0, y[j]);
+              d0 += plane;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (n0 + c0 + j < p.cd) Cvt<T>::store(d0, y[j]);
+              d0 += plane;
+            }
+          }
+        }
+      }
+      if (half >= n_chunks) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// Wp[ntile][kh][kw * bn + c][ci] = W[ntile * bn + c][ci][kh][kw]   (zero where the channel does not exist)
+template <typename T>
+__global__ void __launch_bounds__(256) pack_rows_weights_kernel(const T* __restrict__ w, T* __restrict__ wp, int cd,
+                                                                int cs, int KH, int KW, int bn, int n_ntiles,
+                                                                int cs_pitch) {
+  const long long total = (long long)n_ntiles * KH * KW * bn * cs_pitch;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % cs_pitch);
+    long long r = idx / cs_pitch;
+    const int c = (int)(r % bn);
+    r /= bn;
+    const int kw = (int)(r % KW);
+    r /= KW;
+    const int kh = (int)(r % KH);
+    const int nt = (int)(r / KH);
+    const int co = nt * bn + c;
+    T v = T(0);
+    if (co < cd && ci < cs) v = w[(((long long)co * cs + ci) * KH + kh) * KW + kw];
+    wp[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeFn)ptr;
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* map, int dtype, const void* base, int rank, const cuuint64_t* dims,
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box, bool mn_major) {
+  EncodeFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return EINCONV_ERR_CUDA;
+  }
+  CUtensorMapDataType dt = dtype == EINCONV_F32    ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+                           : dtype == EINCONV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                   : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint32_t est[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, est,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  (mn_major && dtype == EINCONV_F32) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (conv_rows, rank %d) failed with CUresult %d", rank, (int)r);
+    return EINCONV_ERR_CUDA;
+  }
+  return EINCONV_OK;
+}
+
+struct Plan {
+  bool ok = false;
+  int es, bw, step, nb_w, R, nb_t, n_wtiles, bn, n_ntiles, n_cols, kb_rows, n_kblocks, cs_pitch;
+  int slab_blocks, block_bytes, stage_bytes, n_stages, w_tile_bytes, w_bytes, n_htiles;
+  long long wp_bytes;
+  size_t smem;
+};
+
+static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
+  Plan pl;
+  if (op != EINCONV_OP_CONV_FWD) return pl;
+  if (getenv("EINCONV_NO_CONV_ROWS")) return pl;
+  if (dtype == EINCONV_F64) return pl;
+  if (dtype == EINCONV_F32 && math != EINCONV_MATH_TF32) return pl;
+  if (g.n_dims != 2 || g.groups != 1 || g.batch == 0) return pl;
+  for (int d = 0; d < 2; ++d)
+    if (g.stride[d] != 1 || g.dil[d] != 1) return pl;
+  const int KH = g.k[0], KW = g.k[1], H = g.in[0], W = g.in[1];
+  if (KW < 2 || KW > 4 || KH > kMaxKH || g.pad[1] > KW - 1 || g.pad[0] > KH - 1) return pl;  // 1 x 1: conv_dense.cu
+  const int es = (int)elem_size(dtype);
+  pl.es = es;
+  if (((long long)W * es) % 16 != 0 || g.c_in_g == 0 || g.c_out_g == 0) return pl;
+  pl.bw = 128 / es;                                   // positions per 128-byte block: 32 (fp32) / 64 (16-bit)
+  const int halo = ((KW - 1) * es + 15) / 16 * 16 / es;  // overlap of neighbouring blocks, whole 16-byte units
+  pl.step = pl.bw - halo;
+  pl.nb_w = W <= pl.bw ? 1 : (W - pl.bw + pl.step - 1) / pl.step + 1;
+  // every output column must find its KW - 1 neighbours inside one block of 32 lanes: the lanes of a 64-column
+  // 16-bit block are two quarters, so the 16-bit route would need a cross-warp exchange: fp32 only for now
+  if (es != 4) return pl;
+  // tile = R image rows x nb_t blocks of a row, R * nb_t = 4 blocks (M = 128): fewest tiles, then the smallest
+  // slab ((R + KH - 1) * nb_t blocks: tall tiles re-read fewer halo rows and leave room for a third stage)
+  {
+    long long best = -1;
+    for (int nbt : {1, 2, 4}) {
+      const int R = 4 / nbt;
+      const long long tiles = (long long)((g.out[0] + R - 1) / R) * ((pl.nb_w + nbt - 1) / nbt);
+      const long long cost = tiles * 64 + (long long)(R + KH - 1) * nbt;
+      if (best < 0 || cost < best) {
+        best = cost;
+        pl.nb_t = nbt;
+        pl.R = R;
+      }
+    }
+    pl.n_wtiles = (pl.nb_w + pl.nb_t - 1) / pl.nb_t;
+  }
+  // destination channels per tile: N = KW * bn <= 256
+  const int bn_max = 256 / KW / 16 * 16;
+  pl.n_ntiles = (g.c_out_g + bn_max - 1) / bn_max;
+  pl.bn = ((g.c_out_g + pl.n_ntiles - 1) / pl.n_ntiles + 15) / 16 * 16;
+  pl.n_cols = KW * pl.bn;
+  pl.kb_rows = 128 / es;                              // 128 bytes of K per weight-tile row
+  pl.n_kblocks = (g.c_in_g + pl.kb_rows - 1) / pl.kb_rows;
+  pl.cs_pitch = pl.n_kblocks * pl.kb_rows;
+  pl.block_bytes = pl.kb_rows * 128;
+  pl.slab_blocks = (pl.R + KH - 1) * pl.nb_t;
+  pl.stage_bytes = pl.slab_blocks * pl.block_bytes;
+  pl.w_tile_bytes = (pl.n_cols * 128 + 1023) / 1024 * 1024;
+  pl.w_bytes = KH * pl.n_kblocks * pl.w_tile_bytes;
+  if (pl.w_bytes + 2 * pl.stage_bytes > kSmemBudget) return pl;
+  pl.n_stages = std::min(kMaxStages, (kSmemBudget - pl.w_bytes) / pl.stage_bytes);
+  pl.n_htiles = (g.out[0] + pl.R - 1) / pl.R;
+  pl.wp_bytes = ((long long)pl.n_ntiles * KH * pl.n_cols * pl.cs_pitch * es + 1023) / 1024 * 1024;
+  pl.smem = (size_t)pl.w_bytes + (size_t)pl.n_stages * pl.stage_bytes + sizeof(Bars) + 64;
+  // a CTA's chunk of tiles must stay inside one n-tile class (resident weights are loaded once)
+  if (pl.n_ntiles > 1) return pl;
+  pl.ok = true;
+  return pl;
+}
+
+bool supported(int op, const DevGeom& g, int dtype, int math) { return make_plan(op, g, dtype, math).ok; }
+
+int64_t workspace_bytes(int op, const DevGeom& g, int dtype, int math) {
+  const Plan pl = make_plan(op, g, dtype, math);
+  return pl.ok ? pl.wp_bytes + 1024 : 0;
+}
+
+template <typename T>
+static int run_t(const Plan& pl, const void* x, const void* w, const void* bias, void* y, int dtype, const DevGeom& g,
+                 void* workspace, cudaStream_t stream) {
+  const int es = pl.es;
+  uintptr_t base = ((uintptr_t)workspace + 1023) & ~(uintptr_t)1023;
+  T* wp = reinterpret_cast<T*>(base);
+  const int KH = g.k[0], KW = g.k[1];
+  {
+    const long long total = (long long)pl.n_ntiles * KH * KW * pl.bn * pl.cs_pitch;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 4 * num_sms());
+    pack_rows_weights_kernel<T><<<blocks, 256, 0, stream>>>((const T*)w, wp, g.c_out_g, g.c_in_g, KH, KW, pl.bn,
+                                                            pl.n_ntiles, pl.cs_pitch);
+    EINCONV_CHECK_LAUNCH("pack_rows_weights_kernel");
+  }
+  Params p{};
+  p.batch = g.batch;
+  p.cs = g.c_in_g;
+  p.cd = g.c_out_g;
+  p.H = g.in[0]; p.W = g.in[1]; p.OH = g.out[0]; p.OW = g.out[1];
+  p.KH = KH; p.KW = KW; p.ph = g.pad[0]; p.pw = g.pad[1];
+  p.bw = pl.bw; p.step = pl.step; p.nb_w = pl.nb_w; p.R = pl.R; p.nb_t = pl.nb_t; p.n_wtiles = pl.n_wtiles;
+  p.n_htiles = pl.n_htiles; p.n_ntiles = pl.n_ntiles; p.bn = pl.bn;
+  p.total_tiles = (long long)pl.n_ntiles * g.batch * pl.n_htiles * pl.n_wtiles;
+  p.kb_rows = pl.kb_rows; p.n_kblocks = pl.n_kblocks;
+  p.slab_blocks = pl.slab_blocks; p.block_bytes = pl.block_bytes; p.stage_bytes = pl.stage_bytes;
+  p.n_stages = pl.n_stages; p.w_tile_bytes = pl.w_tile_bytes; p.w_bytes = pl.w_bytes;
+  p.mn_layout = es == 4 ? 1 : 2;
+  p.bias = bias;
+  p.dst = y;
+
+  CUtensorMap map_a, map_b;
+  {
+    // source [n][ci][h][w]
+    cuuint64_t dims[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.cs, (cuuint64_t)p.batch};
+    cuuint64_t strides[3] = {(cuuint64_t)p.W * es, (cuuint64_t)p.W * p.H * es, (cuuint64_t)p.W * p.H * p.cs * es};
+    cuuint32_t box[4] = {(cuuint32_t)pl.bw, 1, (cuuint32_t)pl.kb_rows, 1};
+    int st = encode(&map_a, dtype, x, 4, dims, strides, box, true);
+    if (st) return st;
+  }
+  {
+    // packed weights [ntile * KH * n_cols rows][cs_pitch]
+    cuuint64_t dims[2] = {(cuuint64_t)pl.cs_pitch, (cuuint64_t)pl.n_ntiles * KH * pl.n_cols};
+    cuuint64_t strides[1] = {(cuuint64_t)pl.cs_pitch * es};
+    cuuint32_t box[2] = {(cuuint32_t)pl.kb_rows, (cuuint32_t)pl.n_cols};
+    int st = encode(&map_b, dtype, wp, 2, dims, strides, box, false);
+    if (st) return st;
+  }
+  auto kern = conv_rows_kernel<T>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_rows)");
+  const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, num_sms());
+  kern<<<grid, kThreads, pl.smem, stream>>>(map_a, map_b, p);
+  EINCONV_CHECK_LAUNCH("conv_rows_kernel");
+  return EINCONV_OK;
+}
+
+int run(int op, const void* x, const void* w, const void* bias, void* y, int dtype, const DevGeom& g, int math,
+        void* workspace, int64_t workspace_bytes_given, cudaStream_t stream) {
+  const Plan pl = make_plan(op, g, dtype, math);
+  if (!pl.ok) {
+    set_error("conv_rows: unsupported geometry");
+    return EINCONV_ERR_UNSUPPORTED;
+  }
+  if (!workspace || workspace_bytes_given < pl.wp_bytes + 1024) {
+    set_error("conv_rows: workspace too small");
+    return EINCONV_ERR_WORKSPACE;
+  }
+  switch (dtype) {
+    case EINCONV_F32: return run_t<float>(pl, x, w, bias, y, dtype, g, workspace, stream);
+    default: set_error("conv_rows: unsupported dtype"); return EINCONV_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace crows
+}  // namespace einconv

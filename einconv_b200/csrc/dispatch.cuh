@@ -98,6 +98,14 @@ int run(int op, const void* src, const void* w, const void* bias, void* dst, int
         cudaStream_t stream);
 }  // namespace dense
 
+// conv_rows.cu (stride-1 2-d forward from the channels-first tensor: kh as TMA boxes, kw in the epilogue)
+namespace crows {
+bool supported(int op, const DevGeom& g, int dtype, int math);
+int64_t workspace_bytes(int op, const DevGeom& g, int dtype, int math);
+int run(int op, const void* x, const void* w, const void* bias, void* y, int dtype, const DevGeom& g, int math,
+        void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+}  // namespace crows
+
 // wgrad_slab.cu (weight VJP from channels-last padded copies, MN-major tcgen05, stride 1, 16-bit)
 namespace wslab {
 bool supported(const DevGeom& g, int dtype);

@@ -58,7 +58,7 @@ def test_c1_full_batch_tf32_mode(tf32_mode):
     w = torch.rand(64, 64, 3, 3, device=DEV)
     b = torch.rand(64, device=DEV)
     g = evaluator._geom(32, 1, 64, 64, (56, 56), (3, 3), 1, 1, 1)[0]
-    assert evaluator.selected_kernel(nat.OP_CONV_FWD, g, torch.float32) == "tcgen05_tma_conv_fwd"
+    assert evaluator.selected_kernel(nat.OP_CONV_FWD, g, torch.float32) == "tcgen05_rows_conv_fwd"
     before = nat.launch_count()
     y = convNd(x, w, b, padding=1)
     assert nat.launch_count() > before

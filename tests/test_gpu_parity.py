@@ -983,6 +983,42 @@ def test_dense_1x1_forward_and_input_vjp(case, mode):
     _rel_to_max(gx, want_gx, tol, f"dense 1x1 input vjp {mode}")
 
 
+# ---- stride-1 2-d forward on fp32 tensors from the channels-first tensor (csrc/conv_rows.cu) -------------------
+ROWS_CASES = [
+    ((2, 64, 56, 56), (64, 64, 3, 3), dict(padding=1)),        # C1 geometry: two blocks per row, N = 192
+    ((2, 40, 20, 24), (48, 40, 3, 3), dict(padding=1)),        # one block per row (4 rows per tile), K = 40
+    ((1, 16, 9, 100), (80, 16, 3, 3), dict(padding=1)),        # four blocks per row, N = 240
+    ((2, 8, 12, 72), (16, 8, 3, 3), dict(padding=(1, 1))),     # three blocks -> four (one empty)
+    ((2, 24, 10, 32), (32, 24, 5, 4), dict(padding=(2, 1))),   # KW = 4 (N = 128), KH = 5, asymmetric result width
+    ((3, 32, 7, 28), (64, 32, 1, 2), dict(padding=(0, 1))),    # KH = 1, KW = 2
+    ((2, 16, 16, 40), (16, 16, 3, 3), dict(padding=0)),        # no padding: outputs narrower than the input
+    ((2, 70, 6, 44), (30, 70, 2, 3), dict(padding=(1, 2))),    # padding = KW - 1, three K blocks (70 channels)
+]
+ROWS_IDS = ["x".join(map(str, c[0])) + "-w" + "x".join(map(str, c[1])) for c in ROWS_CASES]
+
+
+@pytest.mark.parametrize("case", ROWS_CASES, ids=ROWS_IDS)
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_rows_forward_tf32(case, with_bias):
+    """kh taps as TMA boxes of whole image rows, kw taps summed over neighbouring TMEM lanes in the epilogue:
+    TF32 tolerance 1e-3 of max|ref| against the fp64 oracle."""
+    xs, ws, kw = case
+    torch.manual_seed(5)
+    x = torch.rand(*xs) - 0.3
+    w = torch.rand(*ws) - 0.5
+    b = torch.rand(ws[0]) - 0.5 if with_bias else None
+    want = direct.conv_forward(x.double().numpy(), w.double().numpy(), None if b is None else b.double().numpy(),
+                               stride=1, dilation=1, groups=1, **kw)
+    evaluator.set_fp32_math("tf32")
+    try:
+        g = evaluator._geom(xs[0], 1, xs[1], ws[0], tuple(xs[2:]), tuple(ws[2:]), 1, kw.get("padding", 0), 1)[0]
+        assert evaluator.selected_kernel(nat.OP_CONV_FWD, g, torch.float32) == "tcgen05_rows_conv_fwd"
+        got = convNd(x.to(DEV), w.to(DEV), None if b is None else b.to(DEV), **kw)
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, 1e-3, "rows fwd tf32")
+
+
 def test_conv_tma_is_used_by_autograd_and_matches_torch():
     torch.manual_seed(0)
     x = torch.randn(4, 32, 18, 18, device=DEV, dtype=torch.bfloat16, requires_grad=True)
