@@ -25,6 +25,7 @@
 // Roles (320 threads, persistent CTAs): warp 0 TMA, warp 1 MMA issue, warps 2-9 epilogue.  The packed weights
 // Wp[kh][kw * BN + co][ci] (K-major, written by a small pre-pass) stay resident in shared memory.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -36,7 +37,11 @@ namespace crows {
 
 using namespace ptx;
 
-constexpr int kEpilogueWarps = 8;
+#ifndef EINCONV_ROWS_EPI_WARPS
+#define EINCONV_ROWS_EPI_WARPS 8
+#endif
+constexpr int kEpilogueWarps = EINCONV_ROWS_EPI_WARPS;  // multiple of 4: kEpilogueWarps / 4 per TMEM lane quarter
+constexpr int kEpiParts = kEpilogueWarps / 4;
 constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 constexpr int kMaxStages = 6;
 constexpr int kMaxKH = 8;
@@ -55,7 +60,14 @@ struct Params {
   int mn_layout;
   const void* bias;
   void* dst;
+  long long* trace;  // bring-up only (EINCONV_ROWS_TRACE in an -DEINCONV_BRINGUP build): clock64 stamps of CTA 0
 };
+
+#define ROWS_TRACE(slot)                                                                             \
+  do {                                                                                               \
+    if (p.trace && blockIdx.x == 0 && lane == 0 && tile - tile_begin < 8)                            \
+      p.trace[(tile - tile_begin) * 16 + (slot)] = clock64();                                        \
+  } while (0)
 
 struct Bars {
   uint64_t full[kMaxStages], empty[kMaxStages];
@@ -153,6 +165,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(&bars->empty[st], ph ^ 1);
+        if (kb < 2) ROWS_TRACE(kb);
         if (lane == 0) mbar_expect_tx(&bars->full[st], stage_tx);
         __syncwarp();
         unsigned char* stage = ring + (size_t)st * p.stage_bytes;
@@ -184,12 +197,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(&bars->w_full, 0);
         w_ready = true;
       }
+      ROWS_TRACE(4);
       mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
+      ROWS_TRACE(5);
       const uint32_t d_tmem = tmem_base + acc * (uint32_t)n_cols;
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(&bars->full[st], ph);
         tc_fence_after();
+        if (kb < 2) ROWS_TRACE(6 + 2 * kb);
         if (elect_one()) {
           const uint32_t a16 = ring16 + (uint32_t)st * stage16;
           for (int kh = 0; kh < p.KH; ++kh) {
@@ -204,13 +220,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (kb + 1 == p.n_kblocks) umma_commit(&bars->tmem_full[acc]);
         }
         __syncwarp();
+        if (kb < 2) ROWS_TRACE(7 + 2 * kb);
         if (++st == p.n_stages) { st = 0; ph ^= 1; }
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int quarter = warp & 3;      // block `quarter` of the tile: TMEM lanes 32 * quarter .. + 31
-    const int half = (warp - 2) >> 2;  // 16-channel chunks half, half + 2, ..
+    const int half = (warp - 2) >> 2;  // 16-channel chunks half, half + kEpiParts, ..
     const int etid = threadIdx.x - 64;
     T* dst = reinterpret_cast<T*>(p.dst);
     const T* bias = reinterpret_cast<const T*>(p.bias);
@@ -242,10 +259,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       const bool valid = col_ok && h < p.OH;
       T* dst_row = dst + ((long long)n * p.cd + n0) * plane + (long long)h * p.OW + col;
+      if (warp == 2) ROWS_TRACE(10);
       mbar_wait_relaxed(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (warp == 2) ROWS_TRACE(11);
       const uint32_t taddr = tmem_base + acc * (uint32_t)n_cols + ((uint32_t)(quarter * 32) << 16);
-      for (int ch = half; ch < n_chunks; ch += 2) {
+      for (int ch = half; ch < n_chunks; ch += kEpiParts) {
         const int c0 = ch << 4;
         float y[16];
 #pragma unroll
@@ -264,7 +283,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             y[j] += src_ok ? v : 0.f;
           }
         }
-        if (ch + 2 >= n_chunks) {
+        if (ch + kEpiParts >= n_chunks) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
@@ -291,6 +310,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
       }
+      if (warp == 2) ROWS_TRACE(12);
     }
   }
 
@@ -491,8 +511,34 @@ static int run_t(const Plan& pl, const void* x, const void* w, const void* bias,
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_rows)");
   const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, num_sms());
+#ifdef EINCONV_BRINGUP  // allocates, synchronises and frees: never inside a product build
+  long long* trace = nullptr;
+  if (getenv("EINCONV_ROWS_TRACE")) {
+    cudaMalloc(&trace, 8 * 16 * sizeof(long long));
+    cudaMemset(trace, 0, 8 * 16 * sizeof(long long));
+    p.trace = trace;
+  }
+#endif
   kern<<<grid, kThreads, pl.smem, stream>>>(map_a, map_b, p);
   EINCONV_CHECK_LAUNCH("conv_rows_kernel");
+#ifdef EINCONV_BRINGUP
+  if (trace) {
+    long long h[8 * 16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(trace);
+    long long t0 = 0;
+    for (int i = 0; i < 8 * 16; ++i)
+      if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
+    fprintf(stderr, "conv_rows trace (cycles since first stamp)\n");
+    fprintf(stderr, "tile  P:st0   P:st1 | M:start M:tmem  M:full0 M:iss0  M:full1 M:iss1 | E:start E:full  E:done\n");
+    for (int t = 0; t < 8; ++t) {
+      fprintf(stderr, "%4d ", t);
+      for (int k : {0, 1, 4, 5, 6, 7, 8, 9, 10, 11, 12}) fprintf(stderr, "%7lld ", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
   return EINCONV_OK;
 }
 

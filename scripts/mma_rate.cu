@@ -24,7 +24,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
   return d;
 }
 
-template <int FMT, int N>
+// MN-major A operand: `layout` 2 = SWIZZLE_128B (16-bit), 1 = SWIZZLE_128B_BASE32B (tf32: K groups of 4 rows)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint64_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((layout == 1 ? 512 : 1024) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+// AMN: 0 = K-major A, 1 = MN-major A (4 blocks of [32 K rows][128 B of M], as conv_rows.cu / conv_dense.cu stage it)
+template <int FMT, int N, int AMN = 0>
 __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int per_commit, int two_acc, long long* out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
@@ -45,14 +57,16 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int per_commit,
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
   if (warp == 1) {
-    const uint64_t a = make_desc(smem_u32(smem)), b = make_desc(smem_u32(smem) + 128 * 128);
-    constexpr uint32_t idesc = make_idesc(FMT, 128, N);
+    const uint64_t a = AMN ? make_desc_mn(smem_u32(smem), 4096, FMT == 2 ? 1 : 2) : make_desc(smem_u32(smem));
+    const uint64_t b = make_desc(smem_u32(smem) + 128 * 128);
+    constexpr uint32_t idesc = make_idesc(FMT, 128, N) | (AMN ? (1u << 15) : 0u);
+    constexpr uint32_t a_step = AMN ? ((FMT == 2 ? 8 : 16) * 128) >> 4 : 2;  // one K step in 16-byte units
     long long t0 = clock64();
     uint32_t phase = 0;
     for (int i = 0; i < iters; ++i) {
       if (elect_one()) {
         const uint32_t d = tmem + ((two_acc && (i & 1)) ? 256u : 0u);
-        const uint64_t ad = a + 2 * (i & 3), bd = b + 2 * (i & 3);
+        const uint64_t ad = a + a_step * (i & (AMN && FMT != 2 ? 1 : 3)), bd = b + 2 * (i & 3);
         if (FMT == 2)
           asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"((uint32_t)(i > 1)) : "memory");
         else
@@ -77,14 +91,14 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int per_commit,
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-template <int FMT, int N>
+template <int FMT, int N, int AMN = 0>
 void run(const char* name, int two_acc, int grid) {
   long long* d;
   cudaMalloc(&d, grid * sizeof(long long));
   const int smem = (128 + 256) * 128 + 1024;
-  cudaFuncSetAttribute(rate_kernel<FMT, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(rate_kernel<FMT, N, AMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 4000;
-  rate_kernel<FMT, N><<<grid, 128, smem>>>(iters, 0, two_acc, d);
+  rate_kernel<FMT, N, AMN><<<grid, 128, smem>>>(iters, 0, two_acc, d);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[256];
   cudaMemcpy(h, d, grid * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -104,6 +118,15 @@ int main() {
     run<0, 256>("f16", 1, grid);
     run<2, 64>("tf32", 0, grid);
     run<0, 64>("f16", 0, grid);
+    run<2, 192>("tf32", 0, grid);
+    run<2, 192, 1>("tf32 A-MN", 0, grid);
+    run<2, 192, 1>("tf32 A-MN", 1, grid);
+    run<2, 64, 1>("tf32 A-MN", 0, grid);
+    run<2, 128, 1>("tf32 A-MN", 0, grid);
+    run<2, 256, 1>("tf32 A-MN", 0, grid);
+    run<0, 192, 1>("f16 A-MN", 0, grid);
+    run<0, 64, 1>("f16 A-MN", 0, grid);
+    run<0, 256, 1>("f16 A-MN", 0, grid);
   }
   return 0;
 }
