@@ -73,6 +73,9 @@ struct Bars {
   uint64_t full[kMaxStages], empty[kMaxStages];
   uint64_t tmem_full[2], tmem_empty[2];
   uint64_t w_full;
+  // CTA pair: the leader's MMA warp also needs the PEER's stage / weights / drained accumulator; the peer's
+  // (otherwise idle) MMA warp waits for its own barriers and relays each completion to these
+  uint64_t peer_full[kMaxStages], peer_tmem_empty[2], peer_w_full;
   uint32_t tmem_base;
   float bias[256];
 };
@@ -98,12 +101,81 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t start16, uint32_t
   return d;
 }
 
+// ---- CTA pair (cta_group::2) helpers -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// wait on a local barrier that a thread of the peer CTA arrives on
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                      uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
 template <typename T> struct Elem;
 template <> struct Elem<float> { static constexpr bool TF32 = true; static constexpr int FMT = 2; };
 template <> struct Elem<__nv_bfloat16> { static constexpr bool TF32 = false; static constexpr int FMT = 1; };
 template <> struct Elem<__half> { static constexpr bool TF32 = false; static constexpr int FMT = 0; };
 
-template <typename T>
+// PAIR: two CTAs of a cluster share every MMA (cta_group::2, M = 256): each holds its own 128-row A tile and
+// HALF of the weight rows, so the resident weights take half the shared memory (room for four stages instead of
+// two or three) and an MMA reads 4 + 3 KB per CTA instead of 4 + 6 (the one-CTA kernel sits at the shared-memory
+// bandwidth: its N = 192 MMAs take 121-136 cycles instead of 96).
+template <typename T, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ Params p) {
@@ -115,25 +187,46 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   constexpr int ES = (int)sizeof(T);
   constexpr int KSTEP = 32 / ES;  // K per MMA: 16 (16-bit) / 8 (tf32)
   const int n_cols = p.KW * p.bn; // N of the MMAs = TMEM columns of one accumulator
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int w_rows = PAIR ? n_cols / 2 : n_cols;  // weight rows this CTA holds of every tile
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.n_stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], kEpilogueWarps); }
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&bars->full[i], 1);
+      mbar_init(&bars->empty[i], 1);
+      mbar_init(&bars->peer_full[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);
+      mbar_init(&bars->tmem_empty[i], kEpilogueWarps);
+      mbar_init(&bars->peer_tmem_empty[i], 1);
+    }
     mbar_init(&bars->w_full, 1);
+    mbar_init(&bars->peer_w_full, 1);
     fence_barrier_init();
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
   }
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * (uint32_t)n_cols) tmem_cols <<= 1;
-  if (warp == 1) tmem_alloc(&bars->tmem_base, tmem_cols);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc2(&bars->tmem_base, tmem_cols);
+    else tmem_alloc(&bars->tmem_base, tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   // tiles: index = ((ntile * batch + n) * n_htiles + htile) * n_wtiles + wtile; contiguous chunk per CTA
-  const long long tile_begin = p.total_tiles * blockIdx.x / gridDim.x;
-  const long long tile_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+  // (PAIR: chunk of tile PAIRS per cluster; CTA `rank` takes tile 2 * pair + rank, which may lie past the end:
+  // its loads are then all zero fill and its stores masked)
+  const long long n_units = PAIR ? (p.total_tiles + 1) / 2 : p.total_tiles;
+  const long long n_workers = PAIR ? gridDim.x / 2 : gridDim.x, worker = PAIR ? blockIdx.x / 2 : blockIdx.x;
+  const long long unit_begin = n_units * worker / n_workers, unit_end = n_units * (worker + 1) / n_workers;
+  const long long tile_step = PAIR ? 2 : 1;
+  const long long tile_begin = PAIR ? 2 * unit_begin + rank : unit_begin;
+  const long long tile_end = PAIR ? 2 * unit_end + rank : unit_end;  // exclusive bound of the stepped loop
   const long long per_ntile = (long long)p.batch * p.n_htiles * p.n_wtiles;
   const int per_sample = p.n_htiles * p.n_wtiles;
 
@@ -143,10 +236,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t ph = 0;
     int cur_ntile = -1;
     const uint32_t stage_tx = (uint32_t)(p.slab_blocks * p.block_bytes);
-    for (long long tile = tile_begin; tile < tile_end; ++tile) {
+    for (long long tile = tile_begin; tile < tile_end; tile += tile_step) {
       const int ntile = (int)(tile / per_ntile);
       const long long t2 = tile - (long long)ntile * per_ntile;
-      const int n = (int)(t2 / per_sample);
+      const int n = (int)(t2 / per_sample);  // >= batch for the dummy tile of an odd count: zero fill
       const int t3 = (int)(t2 - (long long)n * per_sample);
       const int h0 = (t3 / p.n_wtiles) * p.R, wb0 = (t3 % p.n_wtiles) * p.nb_t;
       if (ntile != cur_ntile) {
@@ -155,12 +248,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // with the first: chunks are cut so that this cannot happen, see the host code)
         cur_ntile = ntile;
         const int n_wt = p.KH * p.n_kblocks;
-        if (lane == 0) mbar_expect_tx(&bars->w_full, (uint32_t)(n_wt * p.w_tile_bytes));
+        if (lane == 0) mbar_expect_tx(&bars->w_full, (uint32_t)(n_wt * w_rows * 128));
         __syncwarp();
         for (int i = lane; i < n_wt; i += 32) {
           const int kh = i / p.n_kblocks, kb = i - kh * p.n_kblocks;
           tma_load_2d(w_region + (size_t)i * p.w_tile_bytes, &map_b, &bars->w_full, kb * p.kb_rows,
-                      (ntile * p.KH + kh) * n_cols);
+                      (min(ntile, p.n_ntiles - 1) * p.KH + kh) * n_cols + (int)rank * w_rows);
         }
       }
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
@@ -178,9 +271,30 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++st == p.n_stages) { st = 0; ph ^= 1; }
       }
     }
+  } else if (warp == 1 && PAIR && rank == 1) {
+    // ------------------------------------------------------------------ peer CTA: relay completions to the leader
+    int st = 0;
+    uint32_t ph = 0, it = 0;
+    bool w_sent = false;
+    for (long long tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      if (!w_sent) {
+        mbar_wait(&bars->w_full, 0);
+        if (lane == 0) mbar_arrive_remote(&bars->peer_w_full, 0);
+        w_sent = true;
+      }
+      mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+      if (lane == 0) mbar_arrive_remote(&bars->peer_tmem_empty[acc], 0);
+      for (int kb = 0; kb < p.n_kblocks; ++kb) {
+        mbar_wait(&bars->full[st], ph);
+        if (lane == 0) mbar_arrive_remote(&bars->peer_full[st], 0);
+        __syncwarp();
+        if (++st == p.n_stages) { st = 0; ph ^= 1; }
+      }
+    }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc(Elem<T>::FMT, 128, n_cols) | (1u << 15);  // A MN-major, B K-major
+    // ------------------------------------------------------------------ MMA issuer (PAIR: the leader CTA)
+    const uint32_t idesc = make_idesc(Elem<T>::FMT, PAIR ? 256 : 128, n_cols) | (1u << 15);  // A MN-major, B K-major
     const uint32_t ring16 = smem_u32(ring) >> 4, stage16 = (uint32_t)p.stage_bytes >> 4;
     const uint32_t w16 = smem_u32(w_region) >> 4, wtile16 = (uint32_t)p.w_tile_bytes >> 4;
     const uint32_t blk16 = (uint32_t)p.block_bytes >> 4;
@@ -191,19 +305,22 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     int st = 0;
     uint32_t ph = 0, it = 0;
     bool w_ready = false;
-    for (long long tile = tile_begin; tile < tile_end; ++tile, ++it) {
+    for (long long tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       if (!w_ready) {
         mbar_wait(&bars->w_full, 0);
+        if constexpr (PAIR) mbar_wait_cluster(&bars->peer_w_full, 0);
         w_ready = true;
       }
       ROWS_TRACE(4);
       mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+      if constexpr (PAIR) mbar_wait_cluster(&bars->peer_tmem_empty[acc], acc_phase);
       tc_fence_after();
       ROWS_TRACE(5);
       const uint32_t d_tmem = tmem_base + acc * (uint32_t)n_cols;
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(&bars->full[st], ph);
+        if constexpr (PAIR) mbar_wait_cluster(&bars->peer_full[st], ph);
         tc_fence_after();
         if (kb < 2) ROWS_TRACE(6 + 2 * kb);
         if (elect_one()) {
@@ -212,12 +329,22 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // tap row kh: the four blocks that start kh image rows into the slab
             const uint64_t a_base = make_desc_mnmajor(a16 + (uint32_t)(kh * p.nb_t) * blk16, blk16, layout);
             const uint64_t b_base = kdesc + (uint64_t)(w16 + (uint32_t)(kh * p.n_kblocks + kb) * wtile16);
-            for (int k = 0; k < ksteps; ++k)
-              umma<Elem<T>::TF32>(d_tmem, a_base + (uint64_t)((uint32_t)k * kMnStep16), b_base + (uint64_t)(2 * k), idesc,
-                                  (uint32_t)(kb | kh | k));
+            for (int k = 0; k < ksteps; ++k) {
+              if constexpr (PAIR)
+                umma2<Elem<T>::TF32>(d_tmem, a_base + (uint64_t)((uint32_t)k * kMnStep16), b_base + (uint64_t)(2 * k), idesc,
+                                     (uint32_t)(kb | kh | k));
+              else
+                umma<Elem<T>::TF32>(d_tmem, a_base + (uint64_t)((uint32_t)k * kMnStep16), b_base + (uint64_t)(2 * k), idesc,
+                                    (uint32_t)(kb | kh | k));
+            }
           }
-          umma_commit(&bars->empty[st]);
-          if (kb + 1 == p.n_kblocks) umma_commit(&bars->tmem_full[acc]);
+          if constexpr (PAIR) {
+            umma_commit2(&bars->empty[st]);
+            if (kb + 1 == p.n_kblocks) umma_commit2(&bars->tmem_full[acc]);
+          } else {
+            umma_commit(&bars->empty[st]);
+            if (kb + 1 == p.n_kblocks) umma_commit(&bars->tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (kb < 2) ROWS_TRACE(7 + 2 * kb);
@@ -236,14 +363,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int r_local = quarter / p.nb_t, wb_local = quarter - r_local * p.nb_t;
     uint32_t it = 0;
     int cur_ntile = -1;
-    for (long long tile = tile_begin; tile < tile_end; ++tile, ++it) {
+    for (long long tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int ntile = (int)(tile / per_ntile);
       const long long t2 = tile - (long long)ntile * per_ntile;
       const int n = (int)(t2 / per_sample);
       const int t3 = (int)(t2 - (long long)n * per_sample);
       const int h = (t3 / p.n_wtiles) * p.R + r_local;
-      const int n0 = ntile * p.bn;
+      const int n0 = min(ntile, p.n_ntiles - 1) * p.bn;
       // this thread's input column (= output column) and the outputs its block owns: [lo, hi)
       const int wb = (t3 % p.n_wtiles) * p.nb_t + wb_local;
       const int col = wb * p.step + lane;
@@ -257,7 +384,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           bars->bias[c] = n0 + c < p.cd ? (float)Cvt<T>::load(bias + n0 + c) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
       }
-      const bool valid = col_ok && h < p.OH;
+      const bool valid = col_ok && h < p.OH && tile < p.total_tiles;
       T* dst_row = dst + ((long long)n * p.cd + n0) * plane + (long long)h * p.OW + col;
       if (warp == 2) ROWS_TRACE(10);
       mbar_wait_relaxed(&bars->tmem_full[acc], acc_phase);
@@ -316,9 +443,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory until the very end
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -386,6 +515,7 @@ static int encode(CUtensorMap* map, int dtype, const void* base, int rank, const
 
 struct Plan {
   bool ok = false;
+  bool pair = false;  // CTA pairs (cta_group::2): half of the weight rows per CTA
   int es, bw, step, nb_w, R, nb_t, n_wtiles, bn, n_ntiles, n_cols, kb_rows, n_kblocks, cs_pitch;
   int slab_blocks, block_bytes, stage_bytes, n_stages, w_tile_bytes, w_bytes, n_htiles;
   long long wp_bytes;
@@ -440,7 +570,10 @@ static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
   pl.block_bytes = pl.kb_rows * 128;
   pl.slab_blocks = (pl.R + KH - 1) * pl.nb_t;
   pl.stage_bytes = pl.slab_blocks * pl.block_bytes;
-  pl.w_tile_bytes = (pl.n_cols * 128 + 1023) / 1024 * 1024;
+  // measured on B200 (C1: 28.9 us against 24.2 us for one CTA per tile): the relay of the peer's barriers to the
+  // leader adds ~1000 cycles per tile, more than the halved weight reads save, so pairs are opt-in
+  pl.pair = (pl.n_cols / 2) % 8 == 0 && num_sms() % 2 == 0 && getenv("EINCONV_ROWS_PAIR") != nullptr;
+  pl.w_tile_bytes = ((pl.pair ? pl.n_cols / 2 : pl.n_cols) * 128 + 1023) / 1024 * 1024;
   pl.w_bytes = KH * pl.n_kblocks * pl.w_tile_bytes;
   if (pl.w_bytes + 2 * pl.stage_bytes > kSmemBudget) return pl;
   pl.n_stages = std::min(kMaxStages, (kSmemBudget - pl.w_bytes) / pl.stage_bytes);
@@ -503,14 +636,15 @@ static int run_t(const Plan& pl, const void* x, const void* w, const void* bias,
     // packed weights [ntile * KH * n_cols rows][cs_pitch]
     cuuint64_t dims[2] = {(cuuint64_t)pl.cs_pitch, (cuuint64_t)pl.n_ntiles * KH * pl.n_cols};
     cuuint64_t strides[1] = {(cuuint64_t)pl.cs_pitch * es};
-    cuuint32_t box[2] = {(cuuint32_t)pl.kb_rows, (cuuint32_t)pl.n_cols};
+    cuuint32_t box[2] = {(cuuint32_t)pl.kb_rows, (cuuint32_t)(pl.pair ? pl.n_cols / 2 : pl.n_cols)};
     int st = encode(&map_b, dtype, wp, 2, dims, strides, box, false);
     if (st) return st;
   }
-  auto kern = conv_rows_kernel<T>;
+  auto kern = pl.pair ? conv_rows_kernel<T, true> : conv_rows_kernel<T, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_rows)");
-  const unsigned grid = (unsigned)std::min<long long>(p.total_tiles, num_sms());
+  const unsigned grid = pl.pair ? 2u * (unsigned)std::min<long long>((p.total_tiles + 1) / 2, num_sms() / 2)
+                                : (unsigned)std::min<long long>(p.total_tiles, num_sms());
 #ifdef EINCONV_BRINGUP  // allocates, synchronises and frees: never inside a product build
   long long* trace = nullptr;
   if (getenv("EINCONV_ROWS_TRACE")) {
@@ -519,7 +653,24 @@ static int run_t(const Plan& pl, const void* x, const void* w, const void* bias,
     p.trace = trace;
   }
 #endif
-  kern<<<grid, kThreads, pl.smem, stream>>>(map_a, map_b, p);
+  if (pl.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t el = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, p);
+    if (el != cudaSuccess) return cuda_fail(el, "cudaLaunchKernelEx(conv_rows pair)");
+  } else {
+    kern<<<grid, kThreads, pl.smem, stream>>>(map_a, map_b, p);
+  }
   EINCONV_CHECK_LAUNCH("conv_rows_kernel");
 #ifdef EINCONV_BRINGUP
   if (trace) {
