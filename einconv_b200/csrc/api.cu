@@ -129,7 +129,8 @@ static Path select_path(int op, const DevGeom& g, int dtype, int math, int kerne
     if ((op == EINCONV_OP_CONV_FWD || op == EINCONV_OP_CONV_INPUT_VJP) && dense::supported(op, g, dtype, m))
       return Path::DENSE;
     // stride-1 2-d forward on fp32 tensors: MN-major operand from the channels-first tensor, kw taps in the epilogue
-    if (op == EINCONV_OP_CONV_FWD && crows::supported(op, g, dtype, m)) return Path::CONV_ROWS;
+    if ((op == EINCONV_OP_CONV_FWD || op == EINCONV_OP_CONV_INPUT_VJP) && crows::supported(op, g, dtype, m))
+      return Path::CONV_ROWS;
     // forward / input VJP: TMA-fed implicit GEMM over a zero-padded channels-last copy (stride 1)
     if ((op == EINCONV_OP_CONV_FWD || op == EINCONV_OP_CONV_INPUT_VJP) && ctma::supported(op, g, dtype, m))
       return Path::CONV_TMA;
@@ -286,7 +287,7 @@ const char* einconv_selected_kernel(int op, const einconv_geom* geom, int dtype,
     case Path::TMA: return op == EINCONV_OP_KFC ? "tcgen05_tma_kfc" : "tcgen05_tma_wgrad";
     case Path::CONV_TMA: return op == EINCONV_OP_CONV_FWD ? "tcgen05_tma_conv_fwd" : "tcgen05_tma_conv_input_vjp";
     case Path::DENSE: return op == EINCONV_OP_CONV_FWD ? "tcgen05_dense_conv_fwd" : "tcgen05_dense_conv_input_vjp";
-    case Path::CONV_ROWS: return "tcgen05_rows_conv_fwd";
+    case Path::CONV_ROWS: return op == EINCONV_OP_CONV_FWD ? "tcgen05_rows_conv_fwd" : "tcgen05_rows_conv_input_vjp";
     case Path::WGRAD_SLAB: return "tcgen05_slab_wgrad";
     default: return "ffma_gather_gemm";
   }
@@ -393,6 +394,9 @@ int einconv_conv_input_vjp(const void* w, const void* v, void* gx, int dtype,
   switch (select_path(EINCONV_OP_CONV_INPUT_VJP, g, dtype, math, kernels, al)) {
     case Path::DEPTHWISE: return dw_conv_input_vjp(w, v, gx, dtype, g, s);
     case Path::DENSE: return dense::run(EINCONV_OP_CONV_INPUT_VJP, v, w, nullptr, gx, dtype, g, s);
+    case Path::CONV_ROWS:
+      return crows::run(EINCONV_OP_CONV_INPUT_VJP, v, w, nullptr, gx, dtype, g, resolve_math(dtype, math), workspace,
+                        workspace_bytes, s);
     case Path::CONV_TMA:
       return ctma::run(EINCONV_OP_CONV_INPUT_VJP, v, w, nullptr, gx, dtype, g, workspace, workspace_bytes, s);
     default: return ffma_conv_input_vjp(w, v, gx, dtype, g, s);

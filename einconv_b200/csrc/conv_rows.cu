@@ -65,17 +65,14 @@ struct Params {
 
 #define ROWS_TRACE(slot)                                                                             \
   do {                                                                                               \
-    if (p.trace && blockIdx.x == 0 && lane == 0 && tile - tile_begin < 8)                            \
-      p.trace[(tile - tile_begin) * 16 + (slot)] = clock64();                                        \
+    if (p.trace && blockIdx.x < (PAIR ? 2 : 1) && lane == 0 && tile - tile_begin + rank < 8)         \
+      p.trace[(tile - tile_begin + rank) * 16 + (slot)] = clock64();                                 \
   } while (0)
 
 struct Bars {
   uint64_t full[kMaxStages], empty[kMaxStages];
   uint64_t tmem_full[2], tmem_empty[2];
   uint64_t w_full;
-  // CTA pair: the leader's MMA warp also needs the PEER's stage / weights / drained accumulator; the peer's
-  // (otherwise idle) MMA warp waits for its own barriers and relays each completion to these
-  uint64_t peer_full[kMaxStages], peer_tmem_empty[2], peer_w_full;
   uint32_t tmem_base;
   float bias[256];
 };
@@ -87,6 +84,30 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// CTA pair: the load lands in THIS CTA's shared memory, its bytes complete on the barrier `bar_cluster` (a
+// shared::cluster address, here the leader's barrier at the same offset)
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0,
+                                                 int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(p)), "r"(rank));
+  return raddr;
 }
 
 // MN-major operand descriptor: see conv_dense.cu (layout 2: SWIZZLE_128B, 8-row K groups 1024 bytes apart;
@@ -188,21 +209,22 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   constexpr int KSTEP = 32 / ES;  // K per MMA: 16 (16-bit) / 8 (tf32)
   const int n_cols = p.KW * p.bn; // N of the MMAs = TMEM columns of one accumulator
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+#ifdef EINCONV_BRINGUP
+  unsigned long long t_entry = 0;
+  if (p.trace && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
+#endif
   const int w_rows = PAIR ? n_cols / 2 : n_cols;  // weight rows this CTA holds of every tile
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(&bars->full[i], 1);
       mbar_init(&bars->empty[i], 1);
-      mbar_init(&bars->peer_full[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], kEpilogueWarps);
-      mbar_init(&bars->peer_tmem_empty[i], 1);
+      mbar_init(&bars->tmem_empty[i], PAIR ? 2 * kEpilogueWarps : kEpilogueWarps);  // PAIR: the leader's counts both CTAs
     }
     mbar_init(&bars->w_full, 1);
-    mbar_init(&bars->peer_w_full, 1);
     fence_barrier_init();
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
@@ -221,13 +243,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // tiles: index = ((ntile * batch + n) * n_htiles + htile) * n_wtiles + wtile; contiguous chunk per CTA
   // (PAIR: chunk of tile PAIRS per cluster; CTA `rank` takes tile 2 * pair + rank, which may lie past the end:
   // its loads are then all zero fill and its stores masked)
+  // (tile indices are 32-bit: the host rejects geometries with 2^30 tiles or more; the 64-bit divisions of the
+  // first version cost every warp ~700 cycles per tile)
   const long long n_units = PAIR ? (p.total_tiles + 1) / 2 : p.total_tiles;
   const long long n_workers = PAIR ? gridDim.x / 2 : gridDim.x, worker = PAIR ? blockIdx.x / 2 : blockIdx.x;
-  const long long unit_begin = n_units * worker / n_workers, unit_end = n_units * (worker + 1) / n_workers;
-  const long long tile_step = PAIR ? 2 : 1;
-  const long long tile_begin = PAIR ? 2 * unit_begin + rank : unit_begin;
-  const long long tile_end = PAIR ? 2 * unit_end + rank : unit_end;  // exclusive bound of the stepped loop
-  const long long per_ntile = (long long)p.batch * p.n_htiles * p.n_wtiles;
+  const int unit_begin = (int)(n_units * worker / n_workers), unit_end = (int)(n_units * (worker + 1) / n_workers);
+  const int tile_step = PAIR ? 2 : 1;
+  const int tile_begin = PAIR ? 2 * unit_begin + (int)rank : unit_begin;
+  const int tile_end = PAIR ? 2 * unit_end + (int)rank : unit_end;  // exclusive bound of the stepped loop
+  const int total_tiles = (int)p.total_tiles;
+  const int per_ntile = p.batch * p.n_htiles * p.n_wtiles;
   const int per_sample = p.n_htiles * p.n_wtiles;
 
   if (warp == 0) {
@@ -236,11 +261,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t ph = 0;
     int cur_ntile = -1;
     const uint32_t stage_tx = (uint32_t)(p.slab_blocks * p.block_bytes);
-    for (long long tile = tile_begin; tile < tile_end; tile += tile_step) {
-      const int ntile = (int)(tile / per_ntile);
-      const long long t2 = tile - (long long)ntile * per_ntile;
-      const int n = (int)(t2 / per_sample);  // >= batch for the dummy tile of an odd count: zero fill
-      const int t3 = (int)(t2 - (long long)n * per_sample);
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      const int ntile = tile / per_ntile;
+      const int t2 = tile - ntile * per_ntile;
+      const int n = t2 / per_sample;  // >= batch for the dummy tile of an odd count: zero fill
+      const int t3 = t2 - n * per_sample;
       const int h0 = (t3 / p.n_wtiles) * p.R, wb0 = (t3 % p.n_wtiles) * p.nb_t;
       if (ntile != cur_ntile) {
         // (re)load the weights of this n-tile: KH * n_kblocks tiles of [n_cols rows][128 B of K]
@@ -248,50 +273,42 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // with the first: chunks are cut so that this cannot happen, see the host code)
         cur_ntile = ntile;
         const int n_wt = p.KH * p.n_kblocks;
-        if (lane == 0) mbar_expect_tx(&bars->w_full, (uint32_t)(n_wt * w_rows * 128));
+        // PAIR: only the leader's barriers are waited on; they expect the bytes of both CTAs, and the peer's
+        // loads complete on them (cta_group::2), so nothing has to be relayed
+        if (lane == 0 && rank == 0) mbar_expect_tx(&bars->w_full, (uint32_t)((PAIR ? 2 : 1) * n_wt * w_rows * 128));
         __syncwarp();
         for (int i = lane; i < n_wt; i += 32) {
           const int kh = i / p.n_kblocks, kb = i - kh * p.n_kblocks;
-          tma_load_2d(w_region + (size_t)i * p.w_tile_bytes, &map_b, &bars->w_full, kb * p.kb_rows,
-                      (min(ntile, p.n_ntiles - 1) * p.KH + kh) * n_cols + (int)rank * w_rows);
+          const int row0 = (min(ntile, p.n_ntiles - 1) * p.KH + kh) * n_cols + (int)rank * w_rows;
+          if constexpr (PAIR)
+            tma_load_2d_pair(w_region + (size_t)i * p.w_tile_bytes, &map_b, mapa_u32(&bars->w_full, 0), kb * p.kb_rows,
+                             row0);
+          else
+            tma_load_2d(w_region + (size_t)i * p.w_tile_bytes, &map_b, &bars->w_full, kb * p.kb_rows, row0);
         }
       }
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(&bars->empty[st], ph ^ 1);
         if (kb < 2) ROWS_TRACE(kb);
-        if (lane == 0) mbar_expect_tx(&bars->full[st], stage_tx);
+        if (lane == 0 && rank == 0) mbar_expect_tx(&bars->full[st], (PAIR ? 2u : 1u) * stage_tx);
         __syncwarp();
         unsigned char* stage = ring + (size_t)st * p.stage_bytes;
+        const uint32_t full_leader = PAIR ? mapa_u32(&bars->full[st], 0) : 0u;
         for (int bx = lane; bx < p.slab_blocks; bx += 32) {
           const int row = bx / p.nb_t, wb = wb0 + bx - row * p.nb_t;
-          tma_load_4d(stage + (size_t)bx * p.block_bytes, &map_a, &bars->full[st], wb * p.step, h0 - p.ph + row,
-                      kb * p.kb_rows, n);
+          if constexpr (PAIR)
+            tma_load_4d_pair(stage + (size_t)bx * p.block_bytes, &map_a, full_leader, wb * p.step, h0 - p.ph + row,
+                             kb * p.kb_rows, n);
+          else
+            tma_load_4d(stage + (size_t)bx * p.block_bytes, &map_a, &bars->full[st], wb * p.step, h0 - p.ph + row,
+                        kb * p.kb_rows, n);
         }
         __syncwarp();
         if (++st == p.n_stages) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1 && PAIR && rank == 1) {
-    // ------------------------------------------------------------------ peer CTA: relay completions to the leader
-    int st = 0;
-    uint32_t ph = 0, it = 0;
-    bool w_sent = false;
-    for (long long tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
-      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      if (!w_sent) {
-        mbar_wait(&bars->w_full, 0);
-        if (lane == 0) mbar_arrive_remote(&bars->peer_w_full, 0);
-        w_sent = true;
-      }
-      mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
-      if (lane == 0) mbar_arrive_remote(&bars->peer_tmem_empty[acc], 0);
-      for (int kb = 0; kb < p.n_kblocks; ++kb) {
-        mbar_wait(&bars->full[st], ph);
-        if (lane == 0) mbar_arrive_remote(&bars->peer_full[st], 0);
-        __syncwarp();
-        if (++st == p.n_stages) { st = 0; ph ^= 1; }
-      }
-    }
+    // peer CTA: its MMAs are issued by the leader; this warp only allocates / frees the tensor memory
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (PAIR: the leader CTA)
     const uint32_t idesc = make_idesc(Elem<T>::FMT, PAIR ? 256 : 128, n_cols) | (1u << 15);  // A MN-major, B K-major
@@ -305,22 +322,20 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     int st = 0;
     uint32_t ph = 0, it = 0;
     bool w_ready = false;
-    for (long long tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       if (!w_ready) {
         mbar_wait(&bars->w_full, 0);
-        if constexpr (PAIR) mbar_wait_cluster(&bars->peer_w_full, 0);
         w_ready = true;
       }
       ROWS_TRACE(4);
-      mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
-      if constexpr (PAIR) mbar_wait_cluster(&bars->peer_tmem_empty[acc], acc_phase);
+      if constexpr (PAIR) mbar_wait_cluster(&bars->tmem_empty[acc], acc_phase ^ 1);  // peer warps arrive remotely
+      else mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       ROWS_TRACE(5);
       const uint32_t d_tmem = tmem_base + acc * (uint32_t)n_cols;
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(&bars->full[st], ph);
-        if constexpr (PAIR) mbar_wait_cluster(&bars->peer_full[st], ph);
         tc_fence_after();
         if (kb < 2) ROWS_TRACE(6 + 2 * kb);
         if (elect_one()) {
@@ -363,12 +378,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int r_local = quarter / p.nb_t, wb_local = quarter - r_local * p.nb_t;
     uint32_t it = 0;
     int cur_ntile = -1;
-    for (long long tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int ntile = (int)(tile / per_ntile);
-      const long long t2 = tile - (long long)ntile * per_ntile;
-      const int n = (int)(t2 / per_sample);
-      const int t3 = (int)(t2 - (long long)n * per_sample);
+      const int ntile = tile / per_ntile;
+      const int t2 = tile - ntile * per_ntile;
+      const int n = t2 / per_sample;
+      const int t3 = t2 - n * per_sample;
       const int h = (t3 / p.n_wtiles) * p.R + r_local;
       const int n0 = min(ntile, p.n_ntiles - 1) * p.bn;
       // this thread's input column (= output column) and the outputs its block owns: [lo, hi)
@@ -384,7 +399,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           bars->bias[c] = n0 + c < p.cd ? (float)Cvt<T>::load(bias + n0 + c) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
       }
-      const bool valid = col_ok && h < p.OH && tile < p.total_tiles;
+      const bool valid = col_ok && h < p.OH && tile < total_tiles;
       T* dst_row = dst + ((long long)n * p.cd + n0) * plane + (long long)h * p.OW + col;
       if (warp == 2) ROWS_TRACE(10);
       mbar_wait_relaxed(&bars->tmem_full[acc], acc_phase);
@@ -393,27 +408,38 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t taddr = tmem_base + acc * (uint32_t)n_cols + ((uint32_t)(quarter * 32) << 16);
       for (int ch = half; ch < n_chunks; ch += kEpiParts) {
         const int c0 = ch << 4;
+        // all KW accumulators of the chunk in flight before the one wait (the loads are ~150 cycles each when
+        // issued back to back with a wait in between: the epilogue, not the MMAs, then bounds a CTA pair)
+        uint32_t r[4][16];
+#pragma unroll
+        for (int kw = 0; kw < 4; ++kw)
+          if (kw < p.KW) tmem_ld16_nowait(taddr + (uint32_t)(kw * p.bn + c0), r[kw]);
+        tmem_ld_wait();
+        if (ch + kEpiParts >= n_chunks) {
+          // this warp's last read of the accumulator: hand it back before the shuffles and stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR && rank == 1) mbar_arrive_remote(&bars->tmem_empty[acc], 0);
+            else mbar_arrive(&bars->tmem_empty[acc]);
+          }
+        }
         float y[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) y[j] = bias ? bars->bias[c0 + j] : 0.f;
-        for (int kw = 0; kw < p.KW; ++kw) {
-          uint32_t r[16];
-          tmem_ld16_nowait(taddr + (uint32_t)(kw * p.bn + c0), r);
-          tmem_ld_wait();
-          // y[w] += D_kw[w + kw - pw]: the value of lane + (kw - pw); lanes outside the warp are columns this
-          // block does not own outputs for, or padding (zero)
-          const int src = lane + kw - p.pw;
-          const bool src_ok = src >= 0 && src < 32;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float v = __shfl_sync(0xffffffffu, __uint_as_float(r[j]), src & 31);
-            y[j] += src_ok ? v : 0.f;
+        for (int kw = 0; kw < 4; ++kw) {
+          if (kw < p.KW) {
+            // y[w] += D_kw[w + kw - pw]: the value of lane + (kw - pw); lanes outside the warp are columns this
+            // block does not own outputs for, or padding (zero)
+            const int src = lane + kw - p.pw;
+            const bool src_ok = src >= 0 && src < 32;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float v = __shfl_sync(0xffffffffu, __uint_as_float(r[kw][j]), src & 31);
+              y[j] += src_ok ? v : 0.f;
+            }
           }
-        }
-        if (ch + kEpiParts >= n_chunks) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
         }
         if (valid) {
           T* d0 = dst_row + (long long)c0 * plane;
@@ -435,7 +461,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (half >= n_chunks) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+        if (lane == 0) {
+          if (PAIR && rank == 1) mbar_arrive_remote(&bars->tmem_empty[acc], 0);
+          else mbar_arrive(&bars->tmem_empty[acc]);
+        }
       }
       if (warp == 2) ROWS_TRACE(12);
     }
@@ -443,6 +472,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+#ifdef EINCONV_BRINGUP
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 256) {
+    unsigned long long t_exit;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_exit));
+    p.trace[128 + 2 * blockIdx.x] = (long long)t_entry;
+    p.trace[129 + 2 * blockIdx.x] = (long long)t_exit;
+  }
+#endif
   if constexpr (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory until the very end
   if (warp == 1) {
     tc_fence_after();
@@ -452,10 +489,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // Wp[ntile][kh][kw * bn + c][ci] = W[ntile * bn + c][ci][kh][kw]   (zero where the channel does not exist)
+// flip (input VJP): Wp[ntile][kh][kw * bn + c][co] = W[co][ntile * bn + c][KH - 1 - kh][KW - 1 - kw]
 template <typename T>
 __global__ void __launch_bounds__(256) pack_rows_weights_kernel(const T* __restrict__ w, T* __restrict__ wp, int cd,
                                                                 int cs, int KH, int KW, int bn, int n_ntiles,
-                                                                int cs_pitch) {
+                                                                int cs_pitch, int flip) {
   const long long total = (long long)n_ntiles * KH * KW * bn * cs_pitch;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -469,7 +507,9 @@ __global__ void __launch_bounds__(256) pack_rows_weights_kernel(const T* __restr
     const int nt = (int)(r / KH);
     const int co = nt * bn + c;
     T v = T(0);
-    if (co < cd && ci < cs) v = w[(((long long)co * cs + ci) * KH + kh) * KW + kw];
+    if (co < cd && ci < cs)
+      v = flip ? w[(((long long)ci * cd + co) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)]
+               : w[(((long long)co * cs + ci) * KH + kh) * KW + kw];
     wp[idx] = v;
   }
 }
@@ -522,20 +562,40 @@ struct Plan {
   size_t smem;
 };
 
+// Both supported ops as a stride-1 forward convolution of a source [n][cs][SH][SW] into a destination
+// [n][cd][DH][DW].  The input VJP (expressions/convNd_input_vjp.py:52-60) is the forward convolution of the
+// cotangent with the weights flipped along every kernel axis and the channel roles swapped, padded by k - 1 - p.
+struct View {
+  int cs, cd, SH, SW, DH, DW, ph, pw;
+  bool flip;
+};
+static View make_view(int op, const DevGeom& g) {
+  View v;
+  if (op == EINCONV_OP_CONV_INPUT_VJP)
+    v = View{g.c_out_g, g.c_in_g, g.out[0], g.out[1], g.in[0], g.in[1], g.k[0] - 1 - g.pad[0], g.k[1] - 1 - g.pad[1], true};
+  else
+    v = View{g.c_in_g, g.c_out_g, g.in[0], g.in[1], g.out[0], g.out[1], g.pad[0], g.pad[1], false};
+  return v;
+}
+
 static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
   Plan pl;
-  if (op != EINCONV_OP_CONV_FWD) return pl;
+  if (op != EINCONV_OP_CONV_FWD && op != EINCONV_OP_CONV_INPUT_VJP) return pl;
   if (getenv("EINCONV_NO_CONV_ROWS")) return pl;
+  if (op == EINCONV_OP_CONV_INPUT_VJP && getenv("EINCONV_NO_CONV_ROWS_VJP")) return pl;
   if (dtype == EINCONV_F64) return pl;
   if (dtype == EINCONV_F32 && math != EINCONV_MATH_TF32) return pl;
   if (g.n_dims != 2 || g.groups != 1 || g.batch == 0) return pl;
   for (int d = 0; d < 2; ++d)
     if (g.stride[d] != 1 || g.dil[d] != 1) return pl;
-  const int KH = g.k[0], KW = g.k[1], H = g.in[0], W = g.in[1];
+  const View vw = make_view(op, g);
+  const int KH = g.k[0], KW = g.k[1], W = vw.SW;
   if (KW < 2 || KW > 4 || KH > kMaxKH || g.pad[1] > KW - 1 || g.pad[0] > KH - 1) return pl;  // 1 x 1: conv_dense.cu
+  // stride 1: every source element is covered, so the two sizes determine each other
+  if (vw.DH != vw.SH + 2 * vw.ph - KH + 1 || vw.DW != vw.SW + 2 * vw.pw - KW + 1) return pl;
   const int es = (int)elem_size(dtype);
   pl.es = es;
-  if (((long long)W * es) % 16 != 0 || g.c_in_g == 0 || g.c_out_g == 0) return pl;
+  if (((long long)W * es) % 16 != 0 || vw.cs == 0 || vw.cd == 0) return pl;
   pl.bw = 128 / es;                                   // positions per 128-byte block: 32 (fp32) / 64 (16-bit)
   const int halo = ((KW - 1) * es + 15) / 16 * 16 / es;  // overlap of neighbouring blocks, whole 16-byte units
   pl.step = pl.bw - halo;
@@ -549,7 +609,7 @@ static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
     long long best = -1;
     for (int nbt : {1, 2, 4}) {
       const int R = 4 / nbt;
-      const long long tiles = (long long)((g.out[0] + R - 1) / R) * ((pl.nb_w + nbt - 1) / nbt);
+      const long long tiles = (long long)((vw.DH + R - 1) / R) * ((pl.nb_w + nbt - 1) / nbt);
       const long long cost = tiles * 64 + (long long)(R + KH - 1) * nbt;
       if (best < 0 || cost < best) {
         best = cost;
@@ -561,11 +621,11 @@ static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
   }
   // destination channels per tile: N = KW * bn <= 256
   const int bn_max = 256 / KW / 16 * 16;
-  pl.n_ntiles = (g.c_out_g + bn_max - 1) / bn_max;
-  pl.bn = ((g.c_out_g + pl.n_ntiles - 1) / pl.n_ntiles + 15) / 16 * 16;
+  pl.n_ntiles = (vw.cd + bn_max - 1) / bn_max;
+  pl.bn = ((vw.cd + pl.n_ntiles - 1) / pl.n_ntiles + 15) / 16 * 16;
   pl.n_cols = KW * pl.bn;
   pl.kb_rows = 128 / es;                              // 128 bytes of K per weight-tile row
-  pl.n_kblocks = (g.c_in_g + pl.kb_rows - 1) / pl.kb_rows;
+  pl.n_kblocks = (vw.cs + pl.kb_rows - 1) / pl.kb_rows;
   pl.cs_pitch = pl.n_kblocks * pl.kb_rows;
   pl.block_bytes = pl.kb_rows * 128;
   pl.slab_blocks = (pl.R + KH - 1) * pl.nb_t;
@@ -577,11 +637,12 @@ static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
   pl.w_bytes = KH * pl.n_kblocks * pl.w_tile_bytes;
   if (pl.w_bytes + 2 * pl.stage_bytes > kSmemBudget) return pl;
   pl.n_stages = std::min(kMaxStages, (kSmemBudget - pl.w_bytes) / pl.stage_bytes);
-  pl.n_htiles = (g.out[0] + pl.R - 1) / pl.R;
+  pl.n_htiles = (vw.DH + pl.R - 1) / pl.R;
   pl.wp_bytes = ((long long)pl.n_ntiles * KH * pl.n_cols * pl.cs_pitch * es + 1023) / 1024 * 1024;
   pl.smem = (size_t)pl.w_bytes + (size_t)pl.n_stages * pl.stage_bytes + sizeof(Bars) + 64;
   // a CTA's chunk of tiles must stay inside one n-tile class (resident weights are loaded once)
   if (pl.n_ntiles > 1) return pl;
+  if ((long long)g.batch * pl.n_htiles * pl.n_wtiles >= (1ll << 30)) return pl;  // 32-bit tile indices in the kernel
   pl.ok = true;
   return pl;
 }
@@ -594,25 +655,32 @@ int64_t workspace_bytes(int op, const DevGeom& g, int dtype, int math) {
 }
 
 template <typename T>
-static int run_t(const Plan& pl, const void* x, const void* w, const void* bias, void* y, int dtype, const DevGeom& g,
-                 void* workspace, cudaStream_t stream) {
+static int run_t(int op, const Plan& pl, const void* x, const void* w, const void* bias, void* y, int dtype,
+                 const DevGeom& g, void* workspace, cudaStream_t stream) {
   const int es = pl.es;
+  const View vw = make_view(op, g);
   uintptr_t base = ((uintptr_t)workspace + 1023) & ~(uintptr_t)1023;
   T* wp = reinterpret_cast<T*>(base);
   const int KH = g.k[0], KW = g.k[1];
   {
     const long long total = (long long)pl.n_ntiles * KH * KW * pl.bn * pl.cs_pitch;
     const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 4 * num_sms());
-    pack_rows_weights_kernel<T><<<blocks, 256, 0, stream>>>((const T*)w, wp, g.c_out_g, g.c_in_g, KH, KW, pl.bn,
-                                                            pl.n_ntiles, pl.cs_pitch);
+#ifdef EINCONV_BRINGUP
+    if (getenv("EINCONV_ROWS_PACK_CARVE"))
+      cudaFuncSetAttribute(pack_rows_weights_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    static int calls = 0;
+    if (!(getenv("EINCONV_ROWS_SKIP_PACK") && calls++ > 0))
+#endif
+    pack_rows_weights_kernel<T><<<blocks, 256, 0, stream>>>((const T*)w, wp, vw.cd, vw.cs, KH, KW, pl.bn, pl.n_ntiles,
+                                                            pl.cs_pitch, vw.flip ? 1 : 0);
     EINCONV_CHECK_LAUNCH("pack_rows_weights_kernel");
   }
   Params p{};
   p.batch = g.batch;
-  p.cs = g.c_in_g;
-  p.cd = g.c_out_g;
-  p.H = g.in[0]; p.W = g.in[1]; p.OH = g.out[0]; p.OW = g.out[1];
-  p.KH = KH; p.KW = KW; p.ph = g.pad[0]; p.pw = g.pad[1];
+  p.cs = vw.cs;
+  p.cd = vw.cd;
+  p.H = vw.SH; p.W = vw.SW; p.OH = vw.DH; p.OW = vw.DW;
+  p.KH = KH; p.KW = KW; p.ph = vw.ph; p.pw = vw.pw;
   p.bw = pl.bw; p.step = pl.step; p.nb_w = pl.nb_w; p.R = pl.R; p.nb_t = pl.nb_t; p.n_wtiles = pl.n_wtiles;
   p.n_htiles = pl.n_htiles; p.n_ntiles = pl.n_ntiles; p.bn = pl.bn;
   p.total_tiles = (long long)pl.n_ntiles * g.batch * pl.n_htiles * pl.n_wtiles;
@@ -648,8 +716,8 @@ static int run_t(const Plan& pl, const void* x, const void* w, const void* bias,
 #ifdef EINCONV_BRINGUP  // allocates, synchronises and frees: never inside a product build
   long long* trace = nullptr;
   if (getenv("EINCONV_ROWS_TRACE")) {
-    cudaMalloc(&trace, 8 * 16 * sizeof(long long));
-    cudaMemset(trace, 0, 8 * 16 * sizeof(long long));
+    cudaMalloc(&trace, (8 * 16 + 512) * sizeof(long long));
+    cudaMemset(trace, 0, (8 * 16 + 512) * sizeof(long long));
     p.trace = trace;
   }
 #endif
@@ -674,10 +742,22 @@ static int run_t(const Plan& pl, const void* x, const void* w, const void* bias,
   EINCONV_CHECK_LAUNCH("conv_rows_kernel");
 #ifdef EINCONV_BRINGUP
   if (trace) {
-    long long h[8 * 16];
+    long long h[8 * 16 + 512];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(trace);
+    {
+      long long first = 0, last = 0;
+      for (unsigned c = 0; c < grid && c < 256; ++c) {
+        if (!first || h[128 + 2 * c] < first) first = h[128 + 2 * c];
+        if (h[129 + 2 * c] > last) last = h[129 + 2 * c];
+      }
+      fprintf(stderr, "conv_rows CTAs (globaltimer ns): first entry -> last exit %lld ns; per CTA entry offset / duration:\n",
+              last - first);
+      for (unsigned c = 0; c < grid && c < 256; ++c)
+        fprintf(stderr, "%u:%lld/%lld%s", c, h[128 + 2 * c] - first, h[129 + 2 * c] - h[128 + 2 * c], c % 8 == 7 ? "\n" : "  ");
+      fprintf(stderr, "\n");
+    }
     long long t0 = 0;
     for (int i = 0; i < 8 * 16; ++i)
       if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
@@ -705,7 +785,7 @@ int run(int op, const void* x, const void* w, const void* bias, void* y, int dty
     return EINCONV_ERR_WORKSPACE;
   }
   switch (dtype) {
-    case EINCONV_F32: return run_t<float>(pl, x, w, bias, y, dtype, g, workspace, stream);
+    case EINCONV_F32: return run_t<float>(op, pl, x, w, bias, y, dtype, g, workspace, stream);
     default: set_error("conv_rows: unsupported dtype"); return EINCONV_ERR_UNSUPPORTED;
   }
 }

@@ -5,7 +5,20 @@ sys.path.insert(0, '.')
 from einconv_b200 import evaluator
 from einconv_b200.functionals import convNd
 dev = 'cuda'
-def t(fn, n=20):
+_spin = None
+def spin(ms=300):
+    """sustained load first: a cold GPU sits at its idle clock (~1.2 GHz) for the first milliseconds of work, and
+    a 20-call measurement is over before it ramps (seen: 22.8 us per kernel cold, 13 us warm)"""
+    global _spin
+    if _spin is None: _spin = torch.rand(8192, 8192, device=dev)
+    s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    while True:
+        for _ in range(10): _spin @ _spin
+        e.record(); e.synchronize()
+        if s.elapsed_time(e) > ms: return
+def t(fn, n=200):
+    spin()
     for _ in range(5): fn()
     torch.cuda.synchronize()
     s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
@@ -13,7 +26,7 @@ def t(fn, n=20):
     for _ in range(n): fn()
     e.record(); e.synchronize()
     return s.elapsed_time(e) / n
-def tg(fn, n=20):
+def tg(fn, n=200):
     """graph replay: kernels back to back without the host"""
     for _ in range(3): fn()
     torch.cuda.synchronize()

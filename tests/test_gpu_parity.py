@@ -733,7 +733,9 @@ def test_tc_kernels_are_selected():
     lib = nat.lib()
     # stride 1: TMA-fed implicit GEMM over the padded channels-last copy (forward and input VJP)
     assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_conv_fwd"
-    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 0, nat.MATH_TF32, 0) == b"tcgen05_tma_conv_fwd"
+    # fp32 in TF32 mode, 2-d stride 1: the channels-first row kernel (csrc/conv_rows.cu, no packed copy);
+    # EINCONV_NO_CONV_ROWS=1 falls back to the TMA kernel over the channels-last copy
+    assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 0, nat.MATH_TF32, 0) == b"tcgen05_rows_conv_fwd"
     assert lib.einconv_selected_kernel(nat.OP_CONV_INPUT_VJP, g, 1, nat.MATH_AUTO, 0) == b"tcgen05_tma_conv_input_vjp"
     assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 0, nat.MATH_FP32, 0) == b"ffma_gather_gemm"
     assert lib.einconv_selected_kernel(nat.OP_CONV_FWD, g, 1, nat.MATH_AUTO, 1) == b"ffma_gather_gemm"
@@ -1017,6 +1019,30 @@ def test_rows_forward_tf32(case, with_bias):
     finally:
         evaluator.set_fp32_math("auto")
     _rel_to_max(got, want, 1e-3, "rows fwd tf32")
+
+
+@pytest.mark.parametrize("case", ROWS_CASES, ids=ROWS_IDS)
+def test_rows_input_vjp_tf32(case):
+    """The input VJP of the same geometries is the row kernel on the cotangent with flipped weights and
+    padding k - 1 - p (weights flipped by the packing pre-pass): TF32 tolerance 1e-3 of max|ref|."""
+    xs, ws, kw = case
+    pad = kw.get("padding", 0)
+    pad = (pad, pad) if isinstance(pad, int) else tuple(pad)
+    out = tuple(xs[2 + d] + 2 * pad[d] - ws[2 + d] + 1 for d in range(2))
+    torch.manual_seed(6)
+    w = torch.rand(*ws) - 0.5
+    v = torch.rand(xs[0], ws[0], *out) - 0.3
+    want = direct.conv_input_vjp(w.double().numpy(), v.double().numpy(), tuple(xs[2:]), stride=1, dilation=1,
+                                 groups=1, padding=pad)
+    evaluator.set_fp32_math("tf32")
+    try:
+        g = evaluator._geom(xs[0], 1, xs[1], ws[0], tuple(xs[2:]), tuple(ws[2:]), 1, pad, 1)[0]
+        if (out[1] * 4) % 16 == 0:  # the cotangent is the TMA source here: its rows must be 16-byte multiples
+            assert evaluator.selected_kernel(nat.OP_CONV_INPUT_VJP, g, torch.float32) == "tcgen05_rows_conv_input_vjp"
+        got = evaluator.conv_input_vjp(w.to(DEV), v.to(DEV), tuple(xs[2:]), padding=pad)
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, 1e-3, "rows input vjp tf32")
 
 
 def test_conv_tma_is_used_by_autograd_and_matches_torch():
