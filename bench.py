@@ -227,7 +227,7 @@ class UnfoldC2(Workload):
     bound = "hbm"
     shape = (16, 32, 16, 56, 56)
     kw = dict(kernel_size=3, dilation=2, padding=0, stride=2)
-    ncu_profiles = ("profiles/r01_unfold_c2_ncu_full_v10_tma.txt",)
+    ncu_profiles = ("profiles/r02_unfold_c2_ncu_full.txt",)
 
     def setup(self, device, seed=0):
         torch.manual_seed(seed)
@@ -295,7 +295,7 @@ class ConvFwdC1(Workload):
     bound = "tensor"
     dtype = "f32 (tf32 MMA, fp32 accumulate)"
     fp32_math = "tf32"
-    ncu_profiles = ("profiles/r01_conv_fwd_c1_ncu_full_v3.txt",)
+    ncu_profiles = ("profiles/r02_conv_rows_c1_ncu_full.txt",)  # main kernel; the 147 KB weight pre-pass is not in it
 
     def setup(self, device, seed=0):
         torch.manual_seed(seed)
@@ -347,8 +347,7 @@ class DepthwiseC3(Workload):
     metric = "depthwise fwd+input-VJP HBM GB/s"
     unit = "GB/s"
     bound = "hbm"
-    ncu_profiles = ("profiles/r01_depthwise_c3_ncu_full_v5_vec4_nr6.txt",)
-    traffic_launches = 2  # the step is two launches of the profiled kernel
+    ncu_profiles = ("profiles/r02_depthwise_c3_ncu_full.txt",)  # both kernels of the step
 
     def setup(self, device, seed=0):
         torch.manual_seed(seed)
@@ -417,8 +416,7 @@ class WeightVjpC4(Workload):
     bound = "tensor"
     dtype = "bf16"
     # main kernel + the two channels-last packing launches (x and v) that precede it in every call
-    ncu_profiles = ("profiles/r01_wgrad_c4_ncu_full_v3_quad.txt", "profiles/r01_pack_channels_last_c4_ncu_full_v3_vec4.txt",
-                    "profiles/r01_pack_channels_last_c4_ncu_full_v3_vec4.txt")
+    ncu_profiles = ("profiles/r02_wgrad_c4_ncu_full.txt",)  # two packs + slab kernel + finish
 
     def setup(self, device, seed=0):
         torch.manual_seed(seed)
@@ -701,13 +699,13 @@ def ncu_traffic(wl):
     for rel in wl.ncu_profiles:
         if not (ROOT / rel).exists():
             return None
-        seen = 0
+        seen = 0  # a summary holds one or more kernels (all of them launches of the step): read + write of each
         for line in (ROOT / rel).read_text().splitlines():
             parts = line.split()
-            if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and seen < 2:
+            if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 total += float(parts[1]) * scale.get(parts[2], 1.0)
                 seen += 1
-        if seen != 2:
+        if seen < 2 or seen % 2:
             return None
         sources.append(rel)
     if not sources:
