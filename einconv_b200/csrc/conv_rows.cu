@@ -272,6 +272,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // (only at the start of a CTA's chunk in practice; a second class would need the MMA warp to be done
         // with the first: chunks are cut so that this cannot happen, see the host code)
         cur_ntile = ntile;
+        // the packed weights are written by the preceding grid (launched with programmatic stream
+        // serialisation: everything above this line overlaps its tail); no-op without the attribute
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         const int n_wt = p.KH * p.n_kblocks;
         // PAIR: only the leader's barriers are waited on; they expect the bytes of both CTAs, and the peer's
         // loads complete on them (cta_group::2), so nothing has to be relayed
@@ -494,6 +497,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_rows_weights_kernel(const T* __restrict__ w, T* __restrict__ wp, int cd,
                                                                 int cs, int KH, int KW, int bn, int n_ntiles,
                                                                 int cs_pitch, int flip) {
+  // programmatic dependent launch: the row kernel may be scheduled now; it waits (griddepcontrol.wait) before
+  // its first read of wp
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long long total = (long long)n_ntiles * KH * KW * bn * cs_pitch;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -721,23 +727,32 @@ static int run_t(int op, const Plan& pl, const void* x, const void* w, const voi
     p.trace = trace;
   }
 #endif
-  if (pl.pair) {
+  {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
+    if (pl.pair) {
+      attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+      attr[n_attr].val.clusterDim.x = 2;
+      attr[n_attr].val.clusterDim.y = 1;
+      attr[n_attr].val.clusterDim.z = 1;
+      ++n_attr;
+    }
+    if (getenv("EINCONV_ROWS_PDL")) {
+      // overlap this kernel's launch, barrier / TMEM set-up and tensor-map fetch with the weight pre-pass
+      // (measured: no gain under graph replay, 22.6 us either way, so opt-in)
+      attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+      ++n_attr;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = n_attr;
     cudaError_t el = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, p);
-    if (el != cudaSuccess) return cuda_fail(el, "cudaLaunchKernelEx(conv_rows pair)");
-  } else {
-    kern<<<grid, kThreads, pl.smem, stream>>>(map_a, map_b, p);
+    if (el != cudaSuccess) return cuda_fail(el, "cudaLaunchKernelEx(conv_rows)");
   }
   EINCONV_CHECK_LAUNCH("conv_rows_kernel");
 #ifdef EINCONV_BRINGUP
