@@ -1113,6 +1113,101 @@ __global__ void __launch_bounds__(256) kfc_finish_tri_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Finish pass in OUTPUT space for kernels with several taps.  The factor is channel-major (a = ci * Kt + tap)
+// while tile rows are tap-major, so the tile-space kernel above writes every element as a lone 4-byte sector
+// (A = 4608: 139 us for 130 MB, 0.9 TB/s).  Here a CTA owns a pair of channel blocks (bi <= bj, BC channels
+// each) and ALL Kt x Kt taps: it gathers the BC x Kt x BC x Kt sub-block S[ci][t][ci2][t2] from the Kt^2 tile
+// fragments (64-byte runs, summed over the splits; fragments below the tile diagonal are read transposed from
+// their mirror tile), keeps it in shared memory, and writes whole rows of the factor: BC * Kt contiguous floats
+// per row for the block itself and, transposed out of shared memory, for its mirror image.
+// Shared-memory layout: addr(ci, t, ci2, t2) = (ci * Kt + t) * TS + ci2 * Kt + t2 with TS = BC * Kt + 1 (odd): the
+// direct fragment stores (lanes = ci2, stride Kt), the transposed fragment stores (lanes = ci, stride Kt * TS) and
+// the mirror reads (lanes = (ci, t), stride TS) are conflict-free for odd Kt.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int BC>
+__global__ void __launch_bounds__(256) kfc_finish_block_kernel(const float* __restrict__ partial, T* __restrict__ out,
+                                                               const __grid_constant__ Params p, float scale_host,
+                                                               int n_cblocks) {
+  extern __shared__ float fin_smem[];
+  const float scale = p.scale_dev ? scale_host * __ldg(p.scale_dev) : scale_host;
+  int bi = 0, bj = 0;
+  {
+    int rest = blockIdx.x, i = 0;
+    while (rest >= n_cblocks - i) {
+      rest -= n_cblocks - i;
+      ++i;
+    }
+    bi = i;
+    bj = i + rest;
+  }
+  const int grp = blockIdx.z;
+  const int Kt = p.k_total, tpt = p.taps_per_tile;
+  const int TS = BC * Kt + 1;
+  const long long A = (long long)p.c_in_g * Kt;
+  const long long tile = (long long)p.Mp * p.Np;
+  const float* base = partial + (long long)grp * p.k_splits * tile;
+  // tile-space coordinates of channel block b, tap t: tile (t / tpt) * c_blocks + cblock, row (t % tpt) * CB + cl
+  const int ci0 = bi * BC, cj0 = bj * BC;
+  const int cbl_i = ci0 / p.CB, cl_i = ci0 - cbl_i * p.CB;
+  const int cbl_j = cj0 / p.CB, cl_j = cj0 - cbl_j * p.CB;
+  constexpr int kItemsPerPass = 256 / BC;
+  const int sub = threadIdx.x / BC, ln = threadIdx.x % BC;
+  const int n_items = Kt * Kt * BC;
+  constexpr int U = 8;  // fragments in flight per thread (one split at small batches: latency, not bytes, is the cost)
+  for (int it0 = sub; it0 < n_items; it0 += U * kItemsPerPass) {
+    const float* src[U];
+    int dst[U];
+    float acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = it0 + u * kItemsPerPass;
+      src[u] = nullptr;
+      dst[u] = -1;
+      acc[u] = 0.f;
+      if (it < n_items) {
+        const int t = it / (Kt * BC);
+        const int rem = it - t * (Kt * BC);
+        const int t2 = rem / BC, rr = rem - t2 * BC;
+        const int tg = t / tpt, tl = t - tg * tpt, tg2 = t2 / tpt, tl2 = t2 - tg2 * tpt;
+        const int mt = tg * p.c_blocks + cbl_i, nt = tg2 * p.c_blocks + cbl_j;
+        const int row_i = tl * p.CB + cl_i, row_j = tl2 * p.CB + cl_j;  // first row / column of the fragment in its tile
+        const bool direct = mt <= nt;
+        // direct: row = ci = rr, lanes run over ci2; transposed (mirror tile (nt, mt)): row = ci2 = rr, lanes over ci
+        const int ci = direct ? rr : ln, ci2 = direct ? ln : rr;
+        dst[u] = (ci * Kt + t) * TS + ci2 * Kt + t2;
+        if (ci0 + ci < p.c_in_g && cj0 + ci2 < p.c_in_g)
+          src[u] = direct ? base + ((long long)mt * kTileM + row_i + rr) * p.Np + (long long)nt * kTileM + row_j + ln
+                          : base + ((long long)nt * kTileM + row_j + rr) * p.Np + (long long)mt * kTileM + row_i + ln;
+      }
+    }
+    for (int k = 0; k < p.k_splits; ++k) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (src[u]) acc[u] += __ldcs(src[u] + (long long)k * tile);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (dst[u] >= 0) fin_smem[dst[u]] = acc[u] * scale;
+  }
+  __syncthreads();
+  T* og = out + (long long)grp * A * A;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = BC * Kt;                      // rows of the block = (ci, t), columns = (ci2, t2)
+  const int rows_i = min(rows, (p.c_in_g - ci0) * Kt), rows_j = min(rows, (p.c_in_g - cj0) * Kt);
+  for (int r = warp; r < rows_i; r += 8) {
+    T* dst = og + ((long long)ci0 * Kt + r) * A + (long long)cj0 * Kt;
+    const float* srow = fin_smem + r * TS;
+    for (int c = lane; c < rows_j; c += 32) Cvt<T>::store(dst + c, srow[c]);
+  }
+  if (bi != bj) {
+    for (int r = warp; r < rows_j; r += 8) {     // mirror row (ci2, t2), columns (ci, t)
+      T* dst = og + ((long long)cj0 * Kt + r) * A + (long long)ci0 * Kt;
+      for (int c = lane; c < rows_i; c += 32) Cvt<T>::store(dst + c, fin_smem[c * TS + r]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host: tensor maps
 // ---------------------------------------------------------------------------------------------
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1708,6 +1803,37 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
   const long long total = (kfc ? Atot * Atot : (long long)g.c_out_g * Atot) * g.groups;
   auto run_finish = [&](auto* tag) -> int {
     using T = std::remove_pointer_t<decltype(tag)>;
+    if (kfc && pl.tri && g.k_total > 1 && !getenv("EINCONV_KFC_FINISH_TILE") && !getenv("EINCONV_KFC_FINISH_ELEMENTWISE")) {
+      // several taps: output-space blocks (whole factor rows) of BC channels
+      const int Kt = g.k_total;
+      auto smem_of = [&](int bc) { return (size_t)bc * Kt * ((size_t)bc * Kt + 1) * sizeof(float); };
+      auto ctas_of = [&](int bc) {
+        const long long nb = (g.c_in_g + bc - 1) / bc;
+        return nb * (nb + 1) / 2 * g.groups;
+      };
+      // measured at the 8-rank shard size (one split): BC = 16 A = 4608 139 -> 101 us; blocks of few channels
+      // leave too few CTAs (C = 64: 36 CTAs, 57 us against 10 us for the tile-space kernel), so the block kernel
+      // is used only where at least two CTAs per SM exist
+      int bc = 8;
+      if (const char* e = getenv("EINCONV_KFC_FINISH_BC")) bc = atoi(e) == 16 ? 16 : 8;
+      if (pl.CB % bc == 0 && smem_of(bc) <= 200 * 1024 && ctas_of(bc) >= 2ll * num_sms()) {
+        const int nb = (g.c_in_g + bc - 1) / bc;
+        dim3 grid((unsigned)(nb * (nb + 1) / 2), 1, (unsigned)g.groups);
+        const size_t smem = smem_of(bc);
+        cudaError_t e;
+        if (bc == 16) {
+          e = cudaFuncSetAttribute(kfc_finish_block_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(kfc_finish_block)");
+          kfc_finish_block_kernel<T, 16><<<grid, 256, smem, stream>>>(p.partial, (T*)out, p, (float)scale, nb);
+        } else {
+          e = cudaFuncSetAttribute(kfc_finish_block_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(kfc_finish_block)");
+          kfc_finish_block_kernel<T, 8><<<grid, 256, smem, stream>>>(p.partial, (T*)out, p, (float)scale, nb);
+        }
+        EINCONV_CHECK_LAUNCH("kfc_finish_block_kernel");
+        return EINCONV_OK;
+      }
+    }
     if (kfc && pl.tri && !getenv("EINCONV_KFC_FINISH_ELEMENTWISE")) {
       const long long n_tri = (long long)pl.m_tiles * (pl.m_tiles + 1) / 2 * g.groups;
       int rows = 8;  // rows per CTA: fewer when there are few tiles, so that >= ~4 CTAs per SM exist

@@ -1,4 +1,6 @@
-timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_benchmarked.py -q -x -k "rows_ or c1 or C1" 2>&1 | tail -2
-timeout 100 python scripts/time_conv_c1.py 2>&1 | head -2
-python scripts/time_conv_vjp.py 2>&1 | head -1
-EINCONV_ROWS_NO_PDL=1 timeout 100 python scripts/time_conv_c1.py 2>&1 | head -2
+python scripts/one_sweep.py 1 10
+python scripts/one_sweep.py 8 10
+EINCONV_KFC_FINISH_BC=16 python scripts/one_sweep.py 1 10
+EINCONV_KFC_FINISH_BC=16 python scripts/one_sweep.py 8 10
+ncu --metrics gpu__time_duration.sum --clock-control none --csv python scripts/one_layer_b32.py 2>/dev/null | grep -i "finish" | awk -F'","' '{print $5, $8, $NF}' | head -14
+ncu --metrics gpu__time_duration.sum --clock-control none --csv python scripts/one_layer_b32.py 256 2>/dev/null | grep -i "finish" | awk -F'","' '{print $5, $8, $NF}' | head -14
