@@ -120,4 +120,17 @@ int scaled_half_copy(const float* x, __half* y, long long n, void* header, cudaS
   return EINCONV_OK;
 }
 
+// first half of scaled_half_copy: header[0] = absmax bits; the consumer (flat_copy_kernel<.., CONVERT>) scales,
+// converts and writes header[1] = 1 / s^2 itself
+int absmax_header(const float* x, long long n, void* header, cudaStream_t stream) {
+  EINCONV_CHECK_ARG(((uintptr_t)x % 16) == 0, "absmax_header: misaligned tensor");
+  cudaError_t e = cudaMemsetAsync(header, 0, 8, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(absmax)");
+  if (n == 0) return EINCONV_OK;
+  const unsigned blocks = (unsigned)std::min<long long>((n / 4 + 255) / 256 + 1, 8ll * num_sms());
+  absmax_kernel<<<blocks, 256, 0, stream>>>(x, n, (unsigned*)header);
+  EINCONV_CHECK_LAUNCH("absmax_kernel");
+  return EINCONV_OK;
+}
+
 }  // namespace einconv

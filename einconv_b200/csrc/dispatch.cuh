@@ -49,6 +49,7 @@ int tc_kfc(const void* x, void* out, int dtype, const DevGeom& g, double scale, 
 
 // convert.cu
 int scaled_half_copy(const float* x, __half* y, long long n, void* header, cudaStream_t stream);
+int absmax_header(const float* x, long long n, void* header, cudaStream_t stream);  // header[0] only
 int launch_absmax(const float* x, long long n, unsigned* out_bits, cudaStream_t stream);
 int launch_absmax2(const float* a, long long na, const float* b, long long nb, unsigned* out_bits,
                    cudaStream_t stream);
@@ -61,7 +62,10 @@ int tma_run(int op, const void* x, const void* v, void* out, int dtype, const De
             void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype, int out_dtype, const DevGeom& g,
                       double scale, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
-                      const float* scale_dev = nullptr, long long x_batch_stride = 0);
+                      const float* scale_dev = nullptr, long long x_batch_stride = 0, const float* x_f32 = nullptr,
+                      const unsigned* absmax_bits = nullptr, float* inv_s2 = nullptr);
+// KFC plans whose kernel reads only the flat-plane copies of x (the copy pass may then convert fp32 -> scaled fp16)
+bool flat_reads_copies_only(int op, const DevGeom& g, int dtype);
 }  // namespace tma
 
 // conv_tma.cu (TMA-fed tcgen05 implicit GEMM for forward / input VJP, stride 1)

@@ -903,10 +903,22 @@ struct FlatCopyParams {
   long long planes;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256) flat_copy_kernel(const T* __restrict__ x, T* __restrict__ out,
-                                                        const __grid_constant__ FlatCopyParams fp) {
+// CONVERT: the source is the fp32 tensor itself and the copy is its power-of-two-scaled fp16 image (the scale
+// follows from the absmax bits written by absmax_kernel; this replaces scale_to_half_kernel + a 16-bit
+// flat_copy: one read of x instead of a read, a write and another read); thread 0 leaves 1 / s^2 for the finish.
+template <typename T, bool CONVERT>
+__global__ void __launch_bounds__(256) flat_copy_kernel(const void* __restrict__ x_any, T* __restrict__ out,
+                                                        const __grid_constant__ FlatCopyParams fp,
+                                                        const unsigned* __restrict__ absmax_bits,
+                                                        float* __restrict__ inv_s2) {
+  using S = std::conditional_t<CONVERT, float, T>;
+  const S* x = reinterpret_cast<const S*>(x_any);
   constexpr int A = 16 / sizeof(T);
+  float s = 1.f;
+  if constexpr (CONVERT) {
+    s = operand_scale(__ldg(absmax_bits));
+    if (blockIdx.x == 0 && threadIdx.x == 0) *inv_s2 = 1.f / (s * s);
+  }
   const int units = (int)(fp.plane_stride / A);
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long per_copy = fp.planes * units;
@@ -924,13 +936,18 @@ __global__ void __launch_bounds__(256) flat_copy_kernel(const T* __restrict__ x,
   }
   const int i = fp.per_tap ? r * fp.s_h + kh * fp.d_h - fp.p_h : r - fp.p_h;
   const bool row_ok = r < fp.rows && i >= 0 && i < fp.H;
-  const T* src = x + plane * ((long long)fp.W * fp.H) + (long long)(row_ok ? i : 0) * fp.W;
+  const S* src = x + plane * ((long long)fp.W * fp.H) + (long long)(row_ok ? i : 0) * fp.W;
   alignas(16) T vals[A];
 #pragma unroll
   for (int e = 0; e < A; ++e) {
     const int j = j0 + e;
     const int c = j * fp.s_w + kw * fp.d_w - fp.p_w;
-    vals[e] = (row_ok && j < fp.out_w && c >= 0 && c < fp.W) ? src[c] : T(0);
+    const bool ok = row_ok && j < fp.out_w && c >= 0 && c < fp.W;
+    if constexpr (CONVERT) {
+      vals[e] = ok ? (T)__half_as_ushort(__float2half_rn(__ldg(src + c) * s)) : T(0);
+    } else {
+      vals[e] = ok ? src[c] : T(0);
+    }
   }
   *reinterpret_cast<uint4*>(out + (long long)copy * fp.copy_stride + plane * fp.plane_stride + (long long)u * A) =
       *reinterpret_cast<const uint4*>(vals);
@@ -1510,9 +1527,13 @@ static int launch(const MapArray& maps, const Params& p, const Plan& pl, int gro
 
 int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype, int out_dtype, const DevGeom& g,
                       double scale, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
-                      const float* scale_dev, long long x_batch_stride) {
+                      const float* scale_dev, long long x_batch_stride, const float* x_f32,
+                      const unsigned* absmax_bits, float* inv_s2) {
   const Plan pl = make_plan(op, g, dtype);
   EINCONV_CHECK_ARG(pl.ok, "tma path not available for this geometry");
+  // fp32 source converted by the flat copy itself: only where nothing else reads x (see flat_reads_copies_only)
+  EINCONV_CHECK_ARG(!x_f32 || (pl.flat && dtype == EINCONV_F16 && absmax_bits && inv_s2),
+                    "converting flat copy needs the flat-plane fp16 plan");
   if (x_batch_stride > 0) {
     EINCONV_CHECK_ARG(pl.x_direct && pl.n_copies == 0 && (x_batch_stride * (long long)elem_size(dtype)) % 16 == 0,
                       "strided samples need a directly readable operand (16-byte multiples)");
@@ -1557,10 +1578,12 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
     fp.planes = (long long)g.batch * g.groups * g.c_in_g;
     const long long units = fp.planes * (fp.plane_stride / A) * fp.n_copies;
     const unsigned blocks = (unsigned)((units + 255) / 256);
-    if (es == 2)
-      flat_copy_kernel<uint16_t><<<blocks, 256, 0, stream>>>((const uint16_t*)x, (uint16_t*)copies_x, fp);
+    if (x_f32)
+      flat_copy_kernel<uint16_t, true><<<blocks, 256, 0, stream>>>(x_f32, (uint16_t*)copies_x, fp, absmax_bits, inv_s2);
+    else if (es == 2)
+      flat_copy_kernel<uint16_t, false><<<blocks, 256, 0, stream>>>(x, (uint16_t*)copies_x, fp, nullptr, nullptr);
     else
-      flat_copy_kernel<uint32_t><<<blocks, 256, 0, stream>>>((const uint32_t*)x, (uint32_t*)copies_x, fp);
+      flat_copy_kernel<uint32_t, false><<<blocks, 256, 0, stream>>>(x, (uint32_t*)copies_x, fp, nullptr, nullptr);
     EINCONV_CHECK_LAUNCH("flat_copy_kernel");
   }
   for (int i = 0; i < (pl.flat ? 0 : pl.n_copies); ++i) {
@@ -1853,6 +1876,11 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
     case EINCONV_F16: return run_finish((__half*)nullptr);
     default: set_error("tma path: unsupported output dtype %d", out_dtype); return EINCONV_ERR_UNSUPPORTED;
   }
+}
+
+bool flat_reads_copies_only(int op, const DevGeom& g, int dtype) {
+  const Plan pl = make_plan(op, g, dtype);
+  return pl.ok && pl.flat;
 }
 
 int tma_run(int op, const void* x, const void* v, void* out, int dtype, const DevGeom& g, double scale,

@@ -704,6 +704,32 @@ def test_tc_kfc(case, mode):
     _rel_to_max(got, want, 2.0**-7 if mode == "bf16" else 1e-3, f"tc kfc {mode}")
 
 
+@pytest.mark.parametrize("variant", ["default", "EINCONV_KFC_FINISH_BC=16", "EINCONV_KFC_FINISH_TILE=1",
+                                     "EINCONV_KFC_FUSED_CONVERT=1"])
+@pytest.mark.parametrize("shape,stride", [((2, 256, 7, 7), 1), ((3, 272, 9, 8), 1), ((2, 256, 14, 14), 2)])
+def test_kfc_finish_and_copy_variants_many_channels(variant, shape, stride, monkeypatch):
+    """Factors with many channels and several taps: the output-space finish kernel (blocks of 8 or 16 channels,
+    all taps gathered in shared memory, whole factor rows and their mirror written) against the tile-space
+    kernel, and the converting flat copy against scale_to_half + copy; every variant against the oracle
+    (1e-3 max|ref|: fp32 tensors in TF32 mode).  272 channels: a ragged last channel block."""
+    torch.manual_seed(3)
+    x = torch.rand(*shape) - 0.4
+    want = direct.kfc(x.double().numpy(), (3, 3), padding=1, stride=stride)
+    if variant != "default":
+        k, v = variant.split("=")
+        monkeypatch.setenv(k, v)
+    evaluator.clear_plan_cache()
+    evaluator.set_fp32_math("tf32")
+    try:
+        got = evaluator.kfc(x.to(DEV), (3, 3), padding=1, stride=stride)
+    finally:
+        evaluator.set_fp32_math("auto")
+        evaluator.clear_plan_cache()
+    _rel_to_max(got, want, 1e-3, f"kfc {variant} {shape}")
+    g = got.double().cpu().numpy()
+    assert np.array_equal(g, np.swapaxes(g, -1, -2)), "factor is not exactly symmetric"
+
+
 @pytest.mark.parametrize("magnitude", [1.0, 3.0e4, 2.0e-7])
 def test_kfc_scaled_fp16_operands_match_tf32_accuracy(magnitude, monkeypatch):
     """fp32 KFC in TF32 mode runs on fp16 copies scaled by a power of two (csrc/convert.cu): same
