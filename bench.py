@@ -963,6 +963,22 @@ def main():
                     max_err_rel_to_max=worst, tolerance=1e-3,
                     against="single-GPU evaluation of the concatenated batch of 256 on rank 0")
 
+    def factor_weak_scaling(strong_ms):
+        """Companion of the strong-scaling factor number (informational; BASELINE's config is the fixed batch of
+        256): every rank keeps a full batch of 256 (global batch 256 x N), same sweep, same all-reduce of every
+        factor.  Separates the cost of the exchange (all that weak scaling adds to the N = 1 sweep) from the
+        A x A work per factor that does not shrink with the per-rank batch under strong scaling."""
+        del_wl = FactorsC5(world, rank, global_batch=256 * world)
+        evaluator.set_fp32_math(del_wl.fp32_math)
+        del_wl.setup(device, seed=rank)
+        dist.barrier()
+        torch.cuda.synchronize(device)
+        times, _ = time_steps(del_wl, 5, 3, device)
+        ms = max_over_ranks(statistics.mean(times))
+        return dict(global_batch=256 * world, per_rank_batch=256, ms_per_step=ms, samples_per_s=256 * world / (ms * 1e-3),
+                    strong_samples_per_s=256 / (strong_ms * 1e-3),
+                    note="same 106 factors and the same NCCL exchange per step as the strong-scaling run")
+
     head = measure(args.workload, args.steps, args.warmup, sample_clocks=True)
     wl = head["wl"]
     exchange = factor_exchange_parity(wl) if (args.workload == "factors" and world > 1) else None
@@ -990,6 +1006,7 @@ def main():
                         entry[key] = r[key]
                 if name == "factors" and world > 1:
                     entry["exchange_parity"] = factor_exchange_parity(w2)
+                    entry["weak_scaling"] = factor_weak_scaling(r["ms"])
                 suite[name] = entry
                 del r, w2
             except Exception as e:  # keep the headline line even if a suite entry fails
