@@ -54,9 +54,10 @@ struct Params {
   int R, nb_t, n_wtiles;          // tile = R rows x nb_t blocks (R * nb_t blocks = 128 rows of M); tiles per row
   int n_htiles, n_ntiles, bn;     // row tiles per sample, destination-channel tiles, channels per tile (N = KW * bn)
   long long total_tiles;
-  int kb_rows, n_kblocks;         // channel rows per stage (128 bytes of K for the weights), K blocks
+  int kb_rows, n_kblocks;         // channel rows per pipeline stage of the source, K blocks
+  int wk_rows, n_wkblocks, ksplit;  // weight tiles hold 128 bytes of K per row (wk_rows channels = ksplit stages)
   int slab_blocks, block_bytes, stage_bytes, n_stages;
-  int w_tile_bytes, w_bytes;      // one [N rows][128 B] weight tile; all KH * n_kblocks of them
+  int w_tile_bytes, w_bytes;      // one [N rows][128 B] weight tile; all KH * n_wkblocks of them
   int mn_layout;
   const void* bias;
   void* dst;
@@ -275,19 +276,19 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // the packed weights are written by the preceding grid (launched with programmatic stream
         // serialisation: everything above this line overlaps its tail); no-op without the attribute
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        const int n_wt = p.KH * p.n_kblocks;
+        const int n_wt = p.KH * p.n_wkblocks;
         // PAIR: only the leader's barriers are waited on; they expect the bytes of both CTAs, and the peer's
         // loads complete on them (cta_group::2), so nothing has to be relayed
         if (lane == 0 && rank == 0) mbar_expect_tx(&bars->w_full, (uint32_t)((PAIR ? 2 : 1) * n_wt * w_rows * 128));
         __syncwarp();
         for (int i = lane; i < n_wt; i += 32) {
-          const int kh = i / p.n_kblocks, kb = i - kh * p.n_kblocks;
+          const int kh = i / p.n_wkblocks, kb = i - kh * p.n_wkblocks;
           const int row0 = (min(ntile, p.n_ntiles - 1) * p.KH + kh) * n_cols + (int)rank * w_rows;
           if constexpr (PAIR)
-            tma_load_2d_pair(w_region + (size_t)i * p.w_tile_bytes, &map_b, mapa_u32(&bars->w_full, 0), kb * p.kb_rows,
+            tma_load_2d_pair(w_region + (size_t)i * p.w_tile_bytes, &map_b, mapa_u32(&bars->w_full, 0), kb * p.wk_rows,
                              row0);
           else
-            tma_load_2d(w_region + (size_t)i * p.w_tile_bytes, &map_b, &bars->w_full, kb * p.kb_rows, row0);
+            tma_load_2d(w_region + (size_t)i * p.w_tile_bytes, &map_b, &bars->w_full, kb * p.wk_rows, row0);
         }
       }
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
@@ -346,7 +347,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int kh = 0; kh < p.KH; ++kh) {
             // tap row kh: the four blocks that start kh image rows into the slab
             const uint64_t a_base = make_desc_mnmajor(a16 + (uint32_t)(kh * p.nb_t) * blk16, blk16, layout);
-            const uint64_t b_base = kdesc + (uint64_t)(w16 + (uint32_t)(kh * p.n_kblocks + kb) * wtile16);
+            // weight tile of this stage's channels and, inside its 128-byte rows, the stage's part of K
+            const int wkb = kb / p.ksplit, part = kb - wkb * p.ksplit;
+            const uint64_t b_base = kdesc + (uint64_t)(w16 + (uint32_t)(kh * p.n_wkblocks + wkb) * wtile16 +
+                                                       (uint32_t)(part * p.kb_rows * ES) / 16u);
             for (int k = 0; k < ksteps; ++k) {
               if constexpr (PAIR)
                 umma2<Elem<T>::TF32>(d_tmem, a_base + (uint64_t)((uint32_t)k * kMnStep16), b_base + (uint64_t)(2 * k), idesc,
@@ -563,6 +567,7 @@ struct Plan {
   bool ok = false;
   bool pair = false;  // CTA pairs (cta_group::2): half of the weight rows per CTA
   int es, bw, step, nb_w, R, nb_t, n_wtiles, bn, n_ntiles, n_cols, kb_rows, n_kblocks, cs_pitch;
+  int wk_rows, n_wkblocks, ksplit;
   int slab_blocks, block_bytes, stage_bytes, n_stages, w_tile_bytes, w_bytes, n_htiles;
   long long wp_bytes;
   size_t smem;
@@ -630,17 +635,24 @@ static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
   pl.n_ntiles = (vw.cd + bn_max - 1) / bn_max;
   pl.bn = ((vw.cd + pl.n_ntiles - 1) / pl.n_ntiles + 15) / 16 * 16;
   pl.n_cols = KW * pl.bn;
-  pl.kb_rows = 128 / es;                              // 128 bytes of K per weight-tile row
+  pl.wk_rows = 128 / es;                              // 128 bytes of K per weight-tile row
+  pl.n_wkblocks = (vw.cs + pl.wk_rows - 1) / pl.wk_rows;
+  pl.cs_pitch = pl.n_wkblocks * pl.wk_rows;
+  // CTA pairs: measured slower on B200 (C1 28.6 us per call against 22.6 us): the MMAs reach their full rate but
+  // each SM is then bound by the epilogue's TMEM reads (see the kernel's header comment), so pairs are opt-in
+  pl.pair = (pl.n_cols / 2) % 8 == 0 && num_sms() % 2 == 0 && getenv("EINCONV_ROWS_PAIR") != nullptr;
+  pl.w_tile_bytes = ((pl.pair ? pl.n_cols / 2 : pl.n_cols) * 128 + 1023) / 1024 * 1024;
+  pl.w_bytes = KH * pl.n_wkblocks * pl.w_tile_bytes;
+  // source stages: a whole weight K block (32 fp32 channels) per stage; EINCONV_ROWS_KSPLIT=2 halves them (C1: four
+  // 16 KB stages instead of two of 32 KB next to the resident weights).  Measured neutral (24.5 us per call either
+  // way): the MMA warp is not waiting for loads
+  pl.ksplit = 1;
+  if (const char* e = getenv("EINCONV_ROWS_KSPLIT")) pl.ksplit = atoi(e) == 2 ? 2 : 1;
+  pl.kb_rows = pl.wk_rows / pl.ksplit;
   pl.n_kblocks = (vw.cs + pl.kb_rows - 1) / pl.kb_rows;
-  pl.cs_pitch = pl.n_kblocks * pl.kb_rows;
   pl.block_bytes = pl.kb_rows * 128;
   pl.slab_blocks = (pl.R + KH - 1) * pl.nb_t;
   pl.stage_bytes = pl.slab_blocks * pl.block_bytes;
-  // measured on B200 (C1: 28.9 us against 24.2 us for one CTA per tile): the relay of the peer's barriers to the
-  // leader adds ~1000 cycles per tile, more than the halved weight reads save, so pairs are opt-in
-  pl.pair = (pl.n_cols / 2) % 8 == 0 && num_sms() % 2 == 0 && getenv("EINCONV_ROWS_PAIR") != nullptr;
-  pl.w_tile_bytes = ((pl.pair ? pl.n_cols / 2 : pl.n_cols) * 128 + 1023) / 1024 * 1024;
-  pl.w_bytes = KH * pl.n_kblocks * pl.w_tile_bytes;
   if (pl.w_bytes + 2 * pl.stage_bytes > kSmemBudget) return pl;
   pl.n_stages = std::min(kMaxStages, (kSmemBudget - pl.w_bytes) / pl.stage_bytes);
   pl.n_htiles = (vw.DH + pl.R - 1) / pl.R;
@@ -691,6 +703,7 @@ static int run_t(int op, const Plan& pl, const void* x, const void* w, const voi
   p.n_htiles = pl.n_htiles; p.n_ntiles = pl.n_ntiles; p.bn = pl.bn;
   p.total_tiles = (long long)pl.n_ntiles * g.batch * pl.n_htiles * pl.n_wtiles;
   p.kb_rows = pl.kb_rows; p.n_kblocks = pl.n_kblocks;
+  p.wk_rows = pl.wk_rows; p.n_wkblocks = pl.n_wkblocks; p.ksplit = pl.ksplit;
   p.slab_blocks = pl.slab_blocks; p.block_bytes = pl.block_bytes; p.stage_bytes = pl.stage_bytes;
   p.n_stages = pl.n_stages; p.w_tile_bytes = pl.w_tile_bytes; p.w_bytes = pl.w_bytes;
   p.mn_layout = es == 4 ? 1 : 2;
@@ -710,7 +723,7 @@ static int run_t(int op, const Plan& pl, const void* x, const void* w, const voi
     // packed weights [ntile * KH * n_cols rows][cs_pitch]
     cuuint64_t dims[2] = {(cuuint64_t)pl.cs_pitch, (cuuint64_t)pl.n_ntiles * KH * pl.n_cols};
     cuuint64_t strides[1] = {(cuuint64_t)pl.cs_pitch * es};
-    cuuint32_t box[2] = {(cuuint32_t)pl.kb_rows, (cuuint32_t)(pl.pair ? pl.n_cols / 2 : pl.n_cols)};
+    cuuint32_t box[2] = {(cuuint32_t)pl.wk_rows, (cuuint32_t)(pl.pair ? pl.n_cols / 2 : pl.n_cols)};
     int st = encode(&map_b, dtype, wp, 2, dims, strides, box, false);
     if (st) return st;
   }

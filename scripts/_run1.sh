@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "finish_and_copy_variants" 2>&1 | tail -15
+timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_benchmarked.py -q -x -k "rows_ or c1 or C1" 2>&1 | tail -2

@@ -1025,6 +1025,28 @@ ROWS_CASES = [
 ROWS_IDS = ["x".join(map(str, c[0])) + "-w" + "x".join(map(str, c[1])) for c in ROWS_CASES]
 
 
+@pytest.mark.parametrize("variant", ["EINCONV_ROWS_PAIR=1", "EINCONV_ROWS_KSPLIT=2", "EINCONV_ROWS_PDL=1"])
+@pytest.mark.parametrize("case", ROWS_CASES[:5], ids=ROWS_IDS[:5])
+def test_rows_forward_variants(case, variant, monkeypatch):
+    """Opt-in variants of the row kernel (CTA pairs with cta_group::2 MMAs, half-size pipeline stages, programmatic
+    dependent launch) against the fp64 oracle, with bias."""
+    xs, ws, kw = case
+    torch.manual_seed(7)
+    x = torch.rand(*xs) - 0.3
+    w = torch.rand(*ws) - 0.5
+    b = torch.rand(ws[0]) - 0.5
+    want = direct.conv_forward(x.double().numpy(), w.double().numpy(), b.double().numpy(), stride=1, dilation=1,
+                               groups=1, **kw)
+    k, v = variant.split("=")
+    monkeypatch.setenv(k, v)
+    evaluator.set_fp32_math("tf32")
+    try:
+        got = convNd(x.to(DEV), w.to(DEV), b.to(DEV), **kw)
+    finally:
+        evaluator.set_fp32_math("auto")
+    _rel_to_max(got, want, 1e-3, f"rows fwd {variant}")
+
+
 @pytest.mark.parametrize("case", ROWS_CASES, ids=ROWS_IDS)
 @pytest.mark.parametrize("with_bias", [False, True])
 def test_rows_forward_tf32(case, with_bias):
