@@ -323,6 +323,31 @@ class ConvFwdC1(Workload):
     def work(self):
         return 2 * 32 * 64 * 64 * 9 * 56 * 56
 
+    def also(self, device, steps=10):
+        """The other calls BASELINE's metric names on the C1 shape, each timed like the step (one CUDA-graph replay
+        per step, L2 flushed, CUDA events): the input VJP in the same math mode and the bf16 forward
+        pass (8d: "also report bf16").  Same flop count as the forward pass."""
+        from einconv_b200 import evaluator
+
+        out = {}
+        v = torch.rand(32, 64, 56, 56, device=device)
+        xb, wb = self.x.bfloat16(), self.w.bfloat16()
+        cases = {
+            "input_vjp_f32_tf32": lambda: evaluator.conv_input_vjp(self.w, v, (56, 56), padding=1),
+            "fwd_bf16": lambda: self.fn(xb, wb, padding=1),
+        }
+        keep_graph, keep_launches = self.graph, getattr(self, "graph_launches", 0)
+        for name, body in cases.items():
+            self.graph = None
+            self.capture(body)
+            replay = self.graph.replay if self.graph is not None else body
+            times, _ = time_steps(self, steps, 3, device, step=replay)
+            ms = statistics.mean(times)
+            out[name] = dict(ms_per_step=ms, value=self.work() / (ms * 1e-3) / 1e12, unit="TFLOP/s",
+                             gpu_launches=getattr(self, "graph_launches", None))
+        self.graph, self.graph_launches = keep_graph, keep_launches
+        return out
+
     def bytes_algorithmic(self):
         return (2 * 32 * 64 * 56 * 56 + 64 * 64 * 9) * 4
 
@@ -900,6 +925,11 @@ def main():
             et, _ = time_steps(wl, min(steps, 10), 3, device, step=wl.eager_step)
             res["eager_ms_per_step"] = max_over_ranks(statistics.mean(et))
             res["plan_cache"] = evaluator.plan_cache_info()
+        if hasattr(wl, "also") and world == 1:
+            try:
+                res["also"] = wl.also(device)
+            except Exception as e:
+                res["also"] = dict(error=f"{type(e).__name__}: {e}")
 
         # ---- end to end through the public API with host buffers -------------------------------
         wl.e2e_setup(device)
@@ -1001,7 +1031,7 @@ def main():
                              ms_per_step=r["ms"], gpu_launches=r["launches"], dtype=w2.dtype,
                              scaling="strong" if name == "factors" else "weak",
                              roofline=r["roofline"], e2e=r["e2e"], cpu_baseline=r["cpu_baseline"])
-                for key in ("eager_ms_per_step", "plan_cache"):
+                for key in ("eager_ms_per_step", "plan_cache", "also"):
                     if key in r:
                         entry[key] = r[key]
                 if name == "factors" and world > 1:
@@ -1024,7 +1054,7 @@ def main():
             roofline=head["roofline"], cpu_baseline=head["cpu_baseline"], e2e=head["e2e"],
             gpu_launches=head["launches"], clocks=head["clocks"], suite=suite,
         )
-        for key in ("eager_ms_per_step", "plan_cache"):
+        for key in ("eager_ms_per_step", "plan_cache", "also"):
             if key in head:
                 line[key] = head[key]
         if exchange is not None:
