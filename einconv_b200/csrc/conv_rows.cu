@@ -22,6 +22,9 @@
 // The MMAs are N = 192 for a 3 x 3 kernel on 64 channels: tensor-bound (96 cycles) instead of shared-memory
 // bound, 24 per 128 columns instead of 72.
 //
+// 16-bit tensors: the same with blocks of 32 positions in 64-byte rows (SWIZZLE_64B), so that a block is still the
+// lanes of one warp.
+//
 // Roles (320 threads, persistent CTAs): warp 0 TMA, warp 1 MMA issue, warps 2-9 epilogue.  The packed weights
 // Wp[kh][kw * BN + co][ci] (K-major, written by a small pre-pass) stay resident in shared memory.
 #include <algorithm>
@@ -112,12 +115,13 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 }
 
 // MN-major operand descriptor: see conv_dense.cu (layout 2: SWIZZLE_128B, 8-row K groups 1024 bytes apart;
-// layout 1: SWIZZLE_128B_BASE32B for 32-bit elements, 4-row K groups 512 bytes apart)
+// layout 1: SWIZZLE_128B_BASE32B for 32-bit elements, 4-row K groups 512 bytes apart; layout 4: SWIZZLE_64B for
+// 16-bit elements in 64-byte rows = 32 positions, one warp's lanes, 8-row K groups 512 bytes apart)
 __device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t start16, uint32_t lbo16, uint64_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)(start16 & 0x3FFF);
   d |= (uint64_t)(lbo16 & 0x3FFF) << 16;
-  d |= (uint64_t)((layout == 1 ? 512 : 1024) >> 4) << 32;
+  d |= (uint64_t)((layout == 2 ? 1024 : 512) >> 4) << 32;  // 8 rows x 128 B; 4 rows x 128 B (base 32 B); 8 rows x 64 B
   d |= (uint64_t)1 << 46;
   d |= layout << 61;
   return d;
@@ -248,7 +252,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // first version cost every warp ~700 cycles per tile)
   const long long n_units = PAIR ? (p.total_tiles + 1) / 2 : p.total_tiles;
   const long long n_workers = PAIR ? gridDim.x / 2 : gridDim.x, worker = PAIR ? blockIdx.x / 2 : blockIdx.x;
-  const int unit_begin = (int)(n_units * worker / n_workers), unit_end = (int)(n_units * (worker + 1) / n_workers);
+  int unit_begin = (int)(n_units * worker / n_workers), unit_end = (int)(n_units * (worker + 1) / n_workers);
+  if (!PAIR && p.n_ntiles > 1) {
+    // several destination-channel classes (N = KW * bn <= 256 each): a CTA keeps the weights of ONE class resident,
+    // so the grid (a multiple of n_ntiles, see the host code) is cut into one group of CTAs per class
+    const int per_class = (int)(p.total_tiles / p.n_ntiles), wpc = (int)n_workers / p.n_ntiles;
+    const int cls = (int)worker / wpc, l = (int)worker - cls * wpc;
+    unit_begin = cls * per_class + (int)((long long)per_class * l / wpc);
+    unit_end = cls * per_class + (int)((long long)per_class * (l + 1) / wpc);
+  }
   const int tile_step = PAIR ? 2 : 1;
   const int tile_begin = PAIR ? 2 * unit_begin + (int)rank : unit_begin;
   const int tile_end = PAIR ? 2 * unit_end + (int)rank : unit_end;  // exclusive bound of the stepped loop
@@ -320,7 +332,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t w16 = smem_u32(w_region) >> 4, wtile16 = (uint32_t)p.w_tile_bytes >> 4;
     const uint32_t blk16 = (uint32_t)p.block_bytes >> 4;
     const uint64_t kdesc = make_desc_kmajor(0, 128);
-    const uint32_t kMnStep16 = (uint32_t)(KSTEP * 128) >> 4;
+    const uint32_t kMnStep16 = (uint32_t)(KSTEP * p.bw * ES) >> 4;  // KSTEP rows of one block
     const int ksteps = p.kb_rows / KSTEP;
     const uint64_t layout = (uint64_t)p.mn_layout;
     int st = 0;
@@ -554,7 +566,9 @@ static int encode(CUtensorMap* map, int dtype, const void* base, int rank, const
   cuuint32_t est[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, est,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  (mn_major && dtype == EINCONV_F32) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  !mn_major                ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : dtype == EINCONV_F32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                         : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (conv_rows, rank %d) failed with CUresult %d", rank, (int)r);
@@ -596,6 +610,7 @@ static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
   if (op == EINCONV_OP_CONV_INPUT_VJP && getenv("EINCONV_NO_CONV_ROWS_VJP")) return pl;
   if (dtype == EINCONV_F64) return pl;
   if (dtype == EINCONV_F32 && math != EINCONV_MATH_TF32) return pl;
+  if (dtype != EINCONV_F32 && getenv("EINCONV_ROWS_NO_16BIT")) return pl;
   if (g.n_dims != 2 || g.groups != 1 || g.batch == 0) return pl;
   for (int d = 0; d < 2; ++d)
     if (g.stride[d] != 1 || g.dil[d] != 1) return pl;
@@ -607,13 +622,10 @@ static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
   const int es = (int)elem_size(dtype);
   pl.es = es;
   if (((long long)W * es) % 16 != 0 || vw.cs == 0 || vw.cd == 0) return pl;
-  pl.bw = 128 / es;                                   // positions per 128-byte block: 32 (fp32) / 64 (16-bit)
+  pl.bw = 32;  // positions per block = the lanes of one warp: 128-byte rows (fp32) / 64-byte rows (16-bit, SWIZZLE_64B)
   const int halo = ((KW - 1) * es + 15) / 16 * 16 / es;  // overlap of neighbouring blocks, whole 16-byte units
   pl.step = pl.bw - halo;
   pl.nb_w = W <= pl.bw ? 1 : (W - pl.bw + pl.step - 1) / pl.step + 1;
-  // every output column must find its KW - 1 neighbours inside one block of 32 lanes: the lanes of a 64-column
-  // 16-bit block are two quarters, so the 16-bit route would need a cross-warp exchange: fp32 only for now
-  if (es != 4) return pl;
   // tile = R image rows x nb_t blocks of a row, R * nb_t = 4 blocks (M = 128): fewest tiles, then the smallest
   // slab ((R + KH - 1) * nb_t blocks: tall tiles re-read fewer halo rows and leave room for a third stage)
   {
@@ -640,7 +652,7 @@ static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
   pl.cs_pitch = pl.n_wkblocks * pl.wk_rows;
   // CTA pairs: measured slower on B200 (C1 28.6 us per call against 22.6 us): the MMAs reach their full rate but
   // each SM is then bound by the epilogue's TMEM reads (see the kernel's header comment), so pairs are opt-in
-  pl.pair = (pl.n_cols / 2) % 8 == 0 && num_sms() % 2 == 0 && getenv("EINCONV_ROWS_PAIR") != nullptr;
+  pl.pair = (pl.n_cols / 2) % 8 == 0 && num_sms() % 2 == 0 && pl.n_ntiles == 1 && getenv("EINCONV_ROWS_PAIR") != nullptr;
   pl.w_tile_bytes = ((pl.pair ? pl.n_cols / 2 : pl.n_cols) * 128 + 1023) / 1024 * 1024;
   pl.w_bytes = KH * pl.n_wkblocks * pl.w_tile_bytes;
   // source stages: a whole weight K block (32 fp32 channels) per stage; EINCONV_ROWS_KSPLIT=2 halves them (C1: four
@@ -650,7 +662,7 @@ static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
   if (const char* e = getenv("EINCONV_ROWS_KSPLIT")) pl.ksplit = atoi(e) == 2 ? 2 : 1;
   pl.kb_rows = pl.wk_rows / pl.ksplit;
   pl.n_kblocks = (vw.cs + pl.kb_rows - 1) / pl.kb_rows;
-  pl.block_bytes = pl.kb_rows * 128;
+  pl.block_bytes = pl.kb_rows * pl.bw * es;
   pl.slab_blocks = (pl.R + KH - 1) * pl.nb_t;
   pl.stage_bytes = pl.slab_blocks * pl.block_bytes;
   if (pl.w_bytes + 2 * pl.stage_bytes > kSmemBudget) return pl;
@@ -658,8 +670,9 @@ static Plan make_plan(int op, const DevGeom& g, int dtype, int math) {
   pl.n_htiles = (vw.DH + pl.R - 1) / pl.R;
   pl.wp_bytes = ((long long)pl.n_ntiles * KH * pl.n_cols * pl.cs_pitch * es + 1023) / 1024 * 1024;
   pl.smem = (size_t)pl.w_bytes + (size_t)pl.n_stages * pl.stage_bytes + sizeof(Bars) + 64;
-  // a CTA's chunk of tiles must stay inside one n-tile class (resident weights are loaded once)
-  if (pl.n_ntiles > 1) return pl;
+  // a CTA's chunk of tiles stays inside one n-tile class (resident weights are loaded once): one group of CTAs
+  // per class (the pair variant does not implement that: see pl.pair)
+  if (pl.n_ntiles > num_sms()) return pl;
   if ((long long)g.batch * pl.n_htiles * pl.n_wtiles >= (1ll << 30)) return pl;  // 32-bit tile indices in the kernel
   pl.ok = true;
   return pl;
@@ -706,7 +719,7 @@ static int run_t(int op, const Plan& pl, const void* x, const void* w, const voi
   p.wk_rows = pl.wk_rows; p.n_wkblocks = pl.n_wkblocks; p.ksplit = pl.ksplit;
   p.slab_blocks = pl.slab_blocks; p.block_bytes = pl.block_bytes; p.stage_bytes = pl.stage_bytes;
   p.n_stages = pl.n_stages; p.w_tile_bytes = pl.w_tile_bytes; p.w_bytes = pl.w_bytes;
-  p.mn_layout = es == 4 ? 1 : 2;
+  p.mn_layout = es == 4 ? 1 : 4;
   p.bias = bias;
   p.dst = y;
 
@@ -730,8 +743,9 @@ static int run_t(int op, const Plan& pl, const void* x, const void* w, const voi
   auto kern = pl.pair ? conv_rows_kernel<T, true> : conv_rows_kernel<T, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_rows)");
-  const unsigned grid = pl.pair ? 2u * (unsigned)std::min<long long>((p.total_tiles + 1) / 2, num_sms() / 2)
-                                : (unsigned)std::min<long long>(p.total_tiles, num_sms());
+  unsigned grid = pl.pair ? 2u * (unsigned)std::min<long long>((p.total_tiles + 1) / 2, num_sms() / 2)
+                          : (unsigned)std::min<long long>(p.total_tiles, num_sms());
+  if (pl.n_ntiles > 1) grid = grid / pl.n_ntiles * pl.n_ntiles;  // equal groups of CTAs per class (grid >= n_ntiles)
 #ifdef EINCONV_BRINGUP  // allocates, synchronises and frees: never inside a product build
   long long* trace = nullptr;
   if (getenv("EINCONV_ROWS_TRACE")) {
@@ -814,6 +828,8 @@ int run(int op, const void* x, const void* w, const void* bias, void* y, int dty
   }
   switch (dtype) {
     case EINCONV_F32: return run_t<float>(op, pl, x, w, bias, y, dtype, g, workspace, stream);
+    case EINCONV_BF16: return run_t<__nv_bfloat16>(op, pl, x, w, bias, y, dtype, g, workspace, stream);
+    case EINCONV_F16: return run_t<__half>(op, pl, x, w, bias, y, dtype, g, workspace, stream);
     default: set_error("conv_rows: unsupported dtype"); return EINCONV_ERR_UNSUPPORTED;
   }
 }

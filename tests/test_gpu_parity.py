@@ -1021,6 +1021,8 @@ ROWS_CASES = [
     ((3, 32, 7, 28), (64, 32, 1, 2), dict(padding=(0, 1))),    # KH = 1, KW = 2
     ((2, 16, 16, 40), (16, 16, 3, 3), dict(padding=0)),        # no padding: outputs narrower than the input
     ((2, 70, 6, 44), (30, 70, 2, 3), dict(padding=(1, 2))),    # padding = KW - 1, three K blocks (70 channels)
+    ((3, 32, 12, 40), (200, 32, 3, 3), dict(padding=1)),       # three destination-channel classes (N = 3 * 80 each)
+    ((2, 48, 9, 32), (100, 48, 3, 2), dict(padding=(1, 0))),   # KW = 2: one class of 112 would not fit, two of 64
 ]
 ROWS_IDS = ["x".join(map(str, c[0])) + "-w" + "x".join(map(str, c[1])) for c in ROWS_CASES]
 
@@ -1070,6 +1072,38 @@ def test_rows_forward_tf32(case, with_bias):
 
 
 @pytest.mark.parametrize("case", ROWS_CASES, ids=ROWS_IDS)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_rows_forward_and_input_vjp_16bit(case, dtype):
+    """16-bit tensors on the row kernel: blocks of 32 positions in 64-byte rows (MN-major operand through the
+    64-byte swizzle), so a block is still one warp's lanes.  Oracle in fp64 on the same rounded inputs; tolerance
+    2^-7 (bf16) / 2^-10 (fp16) of max|ref| for the rounded output."""
+    xs, ws, kw = case
+    if (xs[3] * 2) % 16:
+        pytest.skip("rows of the source are not 16-byte multiples in 16 bits")
+    pad = kw.get("padding", 0)
+    pad = (pad, pad) if isinstance(pad, int) else tuple(pad)
+    out = tuple(xs[2 + d] + 2 * pad[d] - ws[2 + d] + 1 for d in range(2))
+    tol = 2.0**-7 if dtype == torch.bfloat16 else 2.0**-10
+    torch.manual_seed(8)
+    x = (torch.rand(*xs) - 0.3).to(dtype)
+    w = (torch.rand(*ws) - 0.5).to(dtype)
+    b = (torch.rand(ws[0]) - 0.5).to(dtype)
+    v = (torch.rand(xs[0], ws[0], *out) - 0.3).to(dtype)
+    want = direct.conv_forward(x.double().numpy(), w.double().numpy(), b.double().numpy(), stride=1, dilation=1,
+                               groups=1, padding=pad)
+    want_gx = direct.conv_input_vjp(w.double().numpy(), v.double().numpy(), tuple(xs[2:]), stride=1, dilation=1,
+                                    groups=1, padding=pad)
+    g = evaluator._geom(xs[0], 1, xs[1], ws[0], tuple(xs[2:]), tuple(ws[2:]), 1, pad, 1)[0]
+    assert evaluator.selected_kernel(nat.OP_CONV_FWD, g, dtype) == "tcgen05_rows_conv_fwd"
+    got = convNd(x.to(DEV), w.to(DEV), b.to(DEV), padding=pad)
+    _rel_to_max(got, want, tol, f"rows fwd {dtype}")
+    if (out[1] * 2) % 16 == 0 and ws[0] <= 100:
+        assert evaluator.selected_kernel(nat.OP_CONV_INPUT_VJP, g, dtype) == "tcgen05_rows_conv_input_vjp"
+    gx = evaluator.conv_input_vjp(w.to(DEV), v.to(DEV), tuple(xs[2:]), padding=pad)
+    _rel_to_max(gx, want_gx, tol, f"rows input vjp {dtype}")
+
+
+@pytest.mark.parametrize("case", ROWS_CASES, ids=ROWS_IDS)
 def test_rows_input_vjp_tf32(case):
     """The input VJP of the same geometries is the row kernel on the cotangent with flipped weights and
     padding k - 1 - p (weights flipped by the packing pre-pass): TF32 tolerance 1e-3 of max|ref|."""
@@ -1085,7 +1119,9 @@ def test_rows_input_vjp_tf32(case):
     evaluator.set_fp32_math("tf32")
     try:
         g = evaluator._geom(xs[0], 1, xs[1], ws[0], tuple(xs[2:]), tuple(ws[2:]), 1, pad, 1)[0]
-        if (out[1] * 4) % 16 == 0:  # the cotangent is the TMA source here: its rows must be 16-byte multiples
+        # the cotangent is the TMA source here: its rows must be 16-byte multiples, and the flipped weights of all
+        # C_out source channels must fit in shared memory (not for the 200-channel case)
+        if (out[1] * 4) % 16 == 0 and ws[0] <= 100:
             assert evaluator.selected_kernel(nat.OP_CONV_INPUT_VJP, g, torch.float32) == "tcgen05_rows_conv_input_vjp"
         got = evaluator.conv_input_vjp(w.to(DEV), v.to(DEV), tuple(xs[2:]), padding=pad)
     finally:
