@@ -201,7 +201,9 @@ template <> struct Elem<__half> { static constexpr bool TF32 = false; static con
 // HALF of the weight rows, so the resident weights take half the shared memory (room for four stages instead of
 // two or three) and an MMA reads 4 + 3 KB per CTA instead of 4 + 6 (the one-CTA kernel sits at the shared-memory
 // bandwidth: its N = 192 MMAs take 121-136 cycles instead of 96).
-template <typename T, bool PAIR>
+// KWS > 0: kernel width and left padding along W known at compile time (KWS, PWS): the epilogue's exchange becomes
+// shuffles by constant distances and the tap of the column itself needs none; KWS = 0: both read from Params.
+template <typename T, bool PAIR, int KWS, int PWS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ Params p) {
@@ -429,10 +431,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int c0 = ch << 4;
         // all KW accumulators of the chunk in flight before the one wait (the loads are ~150 cycles each when
         // issued back to back with a wait in between: the epilogue, not the MMAs, then bounds a CTA pair)
+        constexpr bool SPEC = KWS > 0;
+        const int kw_n = SPEC ? KWS : p.KW, pw_v = SPEC ? PWS : p.pw;
         uint32_t r[4][16];
 #pragma unroll
         for (int kw = 0; kw < 4; ++kw)
-          if (kw < p.KW) tmem_ld16_nowait(taddr + (uint32_t)(kw * p.bn + c0), r[kw]);
+          if (kw < kw_n) tmem_ld16_nowait(taddr + (uint32_t)(kw * p.bn + c0), r[kw]);
         tmem_ld_wait();
         if (ch + kEpiParts >= n_chunks) {
           // this warp's last read of the accumulator: hand it back before the shuffles and stores
@@ -448,15 +452,37 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int j = 0; j < 16; ++j) y[j] = bias ? bars->bias[c0 + j] : 0.f;
 #pragma unroll
         for (int kw = 0; kw < 4; ++kw) {
-          if (kw < p.KW) {
+          if (kw < kw_n) {
             // y[w] += D_kw[w + kw - pw]: the value of lane + (kw - pw); lanes outside the warp are columns this
             // block does not own outputs for, or padding (zero)
-            const int src = lane + kw - p.pw;
-            const bool src_ok = src >= 0 && src < 32;
+            if constexpr (SPEC) {
+              const int delta = kw - PWS;  // a constant after unrolling
+              if (delta == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float v = __shfl_sync(0xffffffffu, __uint_as_float(r[kw][j]), src & 31);
-              y[j] += src_ok ? v : 0.f;
+                for (int j = 0; j < 16; ++j) y[j] += __uint_as_float(r[kw][j]);
+              } else if (delta > 0) {
+                const bool ok = lane + delta < 32;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float v = __shfl_down_sync(0xffffffffu, __uint_as_float(r[kw][j]), (unsigned)delta);
+                  y[j] += ok ? v : 0.f;
+                }
+              } else {
+                const bool ok = lane + delta >= 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float v = __shfl_up_sync(0xffffffffu, __uint_as_float(r[kw][j]), (unsigned)(-delta));
+                  y[j] += ok ? v : 0.f;
+                }
+              }
+            } else {
+              const int src = lane + kw - pw_v;
+              const bool src_ok = src >= 0 && src < 32;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float v = __shfl_sync(0xffffffffu, __uint_as_float(r[kw][j]), src & 31);
+                y[j] += src_ok ? v : 0.f;
+              }
             }
           }
         }
@@ -740,7 +766,9 @@ static int run_t(int op, const Plan& pl, const void* x, const void* w, const voi
     int st = encode(&map_b, dtype, wp, 2, dims, strides, box, false);
     if (st) return st;
   }
-  auto kern = pl.pair ? conv_rows_kernel<T, true> : conv_rows_kernel<T, false>;
+  const bool spec31 = KW == 3 && vw.pw == 1 && !getenv("EINCONV_ROWS_NO_SPEC");
+  auto kern = spec31 ? (pl.pair ? conv_rows_kernel<T, true, 3, 1> : conv_rows_kernel<T, false, 3, 1>)
+                     : (pl.pair ? conv_rows_kernel<T, true, 0, 0> : conv_rows_kernel<T, false, 0, 0>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_rows)");
   unsigned grid = pl.pair ? 2u * (unsigned)std::min<long long>((p.total_tiles + 1) / 2, num_sms() / 2)
