@@ -201,6 +201,31 @@ template <> struct Elem<__half> { static constexpr bool TF32 = false; static con
 // HALF of the weight rows, so the resident weights take half the shared memory (room for four stages instead of
 // two or three) and an MMA reads 4 + 3 KB per CTA instead of 4 + 6 (the one-CTA kernel sits at the shared-memory
 // bandwidth: its N = 192 MMAs take 121-136 cycles instead of 96).
+// Position of a CTA's current tile, advanced without divisions (a tile index costs three integer divisions, ~500
+// cycles per tile on the epilogue's critical path): class `ntile` is fixed for a CTA, (n, ht, wt) step through
+// samples x row tiles x column tiles.  n >= batch marks the dummy tile past the end (CTA pairs, odd tile count).
+struct TilePos {
+  int ntile, n, ht, wt;
+  __device__ __forceinline__ void init(int tile, int per_ntile, int per_sample, int n_wtiles, int n_ntiles) {
+    ntile = min(tile / per_ntile, n_ntiles - 1);
+    const int t2 = tile - ntile * per_ntile;
+    n = t2 / per_sample;
+    const int t3 = t2 - n * per_sample;
+    ht = t3 / n_wtiles;
+    wt = t3 - ht * n_wtiles;
+  }
+  __device__ __forceinline__ void advance(int steps, int n_htiles, int n_wtiles) {
+    for (int s = 0; s < steps; ++s)
+      if (++wt == n_wtiles) {
+        wt = 0;
+        if (++ht == n_htiles) {
+          ht = 0;
+          ++n;
+        }
+      }
+  }
+};
+
 // KWS > 0: kernel width and left padding along W known at compile time (KWS, PWS): the epilogue's exchange becomes
 // shuffles by constant distances and the tap of the column itself needs none; KWS = 0: both read from Params.
 template <typename T, bool PAIR, int KWS, int PWS>
@@ -276,12 +301,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t ph = 0;
     int cur_ntile = -1;
     const uint32_t stage_tx = (uint32_t)(p.slab_blocks * p.block_bytes);
-    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-      const int ntile = tile / per_ntile;
-      const int t2 = tile - ntile * per_ntile;
-      const int n = t2 / per_sample;  // >= batch for the dummy tile of an odd count: zero fill
-      const int t3 = t2 - n * per_sample;
-      const int h0 = (t3 / p.n_wtiles) * p.R, wb0 = (t3 % p.n_wtiles) * p.nb_t;
+    TilePos pos;
+    pos.init(tile_begin, per_ntile, per_sample, p.n_wtiles, p.n_ntiles);
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, pos.advance(tile_step, p.n_htiles, p.n_wtiles)) {
+      const int ntile = pos.ntile;
+      const int n = pos.n;  // >= batch for the dummy tile of an odd count: zero fill
+      const int h0 = pos.ht * p.R, wb0 = pos.wt * p.nb_t;
       if (ntile != cur_ntile) {
         // (re)load the weights of this n-tile: KH * n_kblocks tiles of [n_cols rows][128 B of K]
         // (only at the start of a CTA's chunk in practice; a second class would need the MMA warp to be done
@@ -399,16 +424,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int r_local = quarter / p.nb_t, wb_local = quarter - r_local * p.nb_t;
     uint32_t it = 0;
     int cur_ntile = -1;
-    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
+    TilePos pos;
+    pos.init(tile_begin, per_ntile, per_sample, p.n_wtiles, p.n_ntiles);
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it, pos.advance(tile_step, p.n_htiles, p.n_wtiles)) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int ntile = tile / per_ntile;
-      const int t2 = tile - ntile * per_ntile;
-      const int n = t2 / per_sample;
-      const int t3 = t2 - n * per_sample;
-      const int h = (t3 / p.n_wtiles) * p.R + r_local;
-      const int n0 = min(ntile, p.n_ntiles - 1) * p.bn;
+      const int ntile = pos.ntile;
+      const int n = pos.n;
+      const int h = pos.ht * p.R + r_local;
+      const int n0 = ntile * p.bn;
       // this thread's input column (= output column) and the outputs its block owns: [lo, hi)
-      const int wb = (t3 % p.n_wtiles) * p.nb_t + wb_local;
+      const int wb = pos.wt * p.nb_t + wb_local;
       const int col = wb * p.step + lane;
       const int lo = wb == 0 ? 0 : wb * p.step + p.pw;
       const int hi = wb + 1 >= p.nb_w ? p.OW : (wb + 1) * p.step + p.pw;
