@@ -1,8 +1,5 @@
 N=$1
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-$TR --master-port 29511 scripts/multi_sweep.py 16 64 256 1024 2>&1 | grep "ms per sweep"
-NCCL_MAX_CTAS=8 $TR --master-port 29512 scripts/multi_sweep.py 64 2>&1 | grep "ms per sweep"
-NCCL_MAX_CTAS=4 $TR --master-port 29513 scripts/multi_sweep.py 64 2>&1 | grep "ms per sweep"
-NCCL_MIN_CTAS=32 $TR --master-port 29514 scripts/multi_sweep.py 64 2>&1 | grep "ms per sweep"
-NCCL_ALGO=Ring $TR --master-port 29515 scripts/multi_sweep.py 64 2>&1 | grep "ms per sweep"
-NCCL_ALGO=NVLS $TR --master-port 29516 scripts/multi_sweep.py 64 2>&1 | grep "ms per sweep"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r8_bench_n$N.json 2> gpurun_out/r8_bench_n$N.err
+tail -c 300 gpurun_out/r8_bench_n$N.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 3 --warmup 1 > gpurun_out/r8_benchref_n$N.json 2> gpurun_out/r8_benchref_n$N.err
+tail -c 200 gpurun_out/r8_benchref_n$N.json
