@@ -1,4 +1,3 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_benchmarked.py -q -k "rows_ or c1 or C1" 2>&1 | tail -2
-timeout 100 python scripts/time_conv_c1.py 2>&1 | head -3
-EINCONV_ROWS_PAIR=1 timeout 100 python scripts/time_conv_c1.py 2>&1 | head -3
-python scripts/time_conv_vjp.py | head -1
+python -m pytest tests -m gpu -x -q > gpurun_out/r9_gpu_all.log 2>&1; tail -3 gpurun_out/r9_gpu_all.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+(time python bench.py) > gpurun_out/r9_bench.json 2> gpurun_out/r9_bench.err; tail -4 gpurun_out/r9_bench.err
