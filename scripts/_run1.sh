@@ -1,3 +1,6 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r9_gpu_all.log 2>&1; tail -3 gpurun_out/r9_gpu_all.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-(time python bench.py) > gpurun_out/r9_bench.json 2> gpurun_out/r9_bench.err; tail -4 gpurun_out/r9_bench.err
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_benchmarked.py -q -x -n 2 -k "kfc or factor or Factor or sweep" 2>&1 | tail -3
+python scripts/one_sweep.py 1 10
+python scripts/one_sweep.py 8 10
+EINCONV_KFC_FUSED_CONVERT=1 python scripts/one_sweep.py 1 10
+EINCONV_KFC_FUSED_CONVERT=1 python scripts/one_sweep.py 8 10
+EINCONV_KFC_FLAT_PER_ELEMENT=1 python scripts/one_sweep.py 1 10
