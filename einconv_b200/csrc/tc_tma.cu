@@ -1169,6 +1169,22 @@ __global__ void __launch_bounds__(256) kfc_finish_block_kernel(const float* __re
   const int cbl_j = cj0 / p.CB, cl_j = cj0 - cbl_j * p.CB;
   constexpr int kItemsPerPass = 256 / BC;
   const int sub = threadIdx.x / BC, ln = threadIdx.x % BC;
+  // per (t, t2) fragment: offset of its first element in a split's partial matrix (x), shared-memory base
+  // t * TS + t2 and the orientation bit (y).  Built once per CTA: the divisions and 64-bit products of this index
+  // arithmetic, done per loaded element, made the first version issue-bound (ncu: 74 % issue-active, 130
+  // instructions per 4-byte load).
+  int2* tbl = reinterpret_cast<int2*>(fin_smem + (size_t)BC * Kt * TS);
+  for (int pr = threadIdx.x; pr < Kt * Kt; pr += 256) {
+    const int t = pr / Kt, t2 = pr - t * Kt;
+    const int tg = t / tpt, tl = t - tg * tpt, tg2 = t2 / tpt, tl2 = t2 - tg2 * tpt;
+    const int mt = tg * p.c_blocks + cbl_i, nt = tg2 * p.c_blocks + cbl_j;
+    const int row_i = tl * p.CB + cl_i, row_j = tl2 * p.CB + cl_j;  // first row / column of the fragment in its tile
+    const bool direct = mt <= nt;  // else: read transposed from the mirror tile (nt, mt)
+    const int off = direct ? (mt * kTileM + row_i) * p.Np + nt * kTileM + row_j
+                           : (nt * kTileM + row_j) * p.Np + mt * kTileM + row_i;
+    tbl[pr] = make_int2(off, (t * TS + t2) | (direct ? (1 << 30) : 0));
+  }
+  __syncthreads();
   const int n_items = Kt * Kt * BC;
   constexpr int U = 8;  // fragments in flight per thread (one split at small batches: latency, not bytes, is the cost)
   for (int it0 = sub; it0 < n_items; it0 += U * kItemsPerPass) {
@@ -1182,19 +1198,13 @@ __global__ void __launch_bounds__(256) kfc_finish_block_kernel(const float* __re
       dst[u] = -1;
       acc[u] = 0.f;
       if (it < n_items) {
-        const int t = it / (Kt * BC);
-        const int rem = it - t * (Kt * BC);
-        const int t2 = rem / BC, rr = rem - t2 * BC;
-        const int tg = t / tpt, tl = t - tg * tpt, tg2 = t2 / tpt, tl2 = t2 - tg2 * tpt;
-        const int mt = tg * p.c_blocks + cbl_i, nt = tg2 * p.c_blocks + cbl_j;
-        const int row_i = tl * p.CB + cl_i, row_j = tl2 * p.CB + cl_j;  // first row / column of the fragment in its tile
-        const bool direct = mt <= nt;
-        // direct: row = ci = rr, lanes run over ci2; transposed (mirror tile (nt, mt)): row = ci2 = rr, lanes over ci
+        const int pr = it / BC, rr = it - pr * BC;  // BC is a power of two
+        const int2 e = tbl[pr];
+        const bool direct = (e.y >> 30) & 1;
+        // direct: row = ci = rr, lanes run over ci2; transposed: row = ci2 = rr, lanes over ci
         const int ci = direct ? rr : ln, ci2 = direct ? ln : rr;
-        dst[u] = (ci * Kt + t) * TS + ci2 * Kt + t2;
-        if (ci0 + ci < p.c_in_g && cj0 + ci2 < p.c_in_g)
-          src[u] = direct ? base + ((long long)mt * kTileM + row_i + rr) * p.Np + (long long)nt * kTileM + row_j + ln
-                          : base + ((long long)nt * kTileM + row_j + rr) * p.Np + (long long)mt * kTileM + row_i + ln;
+        dst[u] = ci * Kt * TS + ci2 * Kt + (e.y & 0x3fffffff);
+        if (ci0 + ci < p.c_in_g && cj0 + ci2 < p.c_in_g) src[u] = base + e.x + rr * p.Np + ln;
       }
     }
     for (int k = 0; k < p.k_splits; ++k) {
@@ -1829,7 +1839,9 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
     if (kfc && pl.tri && g.k_total > 1 && !getenv("EINCONV_KFC_FINISH_TILE") && !getenv("EINCONV_KFC_FINISH_ELEMENTWISE")) {
       // several taps: output-space blocks (whole factor rows) of BC channels
       const int Kt = g.k_total;
-      auto smem_of = [&](int bc) { return (size_t)bc * Kt * ((size_t)bc * Kt + 1) * sizeof(float); };
+      auto smem_of = [&](int bc) {  // block + fragment table
+        return (size_t)bc * Kt * ((size_t)bc * Kt + 1) * sizeof(float) + (size_t)Kt * Kt * 8 + 8;
+      };
       auto ctas_of = [&](int bc) {
         const long long nb = (g.c_in_g + bc - 1) / bc;
         return nb * (nb + 1) / 2 * g.groups;
@@ -1839,7 +1851,8 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
       // is used only where at least two CTAs per SM exist
       int bc = 8;
       if (const char* e = getenv("EINCONV_KFC_FINISH_BC")) bc = atoi(e) == 16 ? 16 : 8;
-      if (pl.CB % bc == 0 && smem_of(bc) <= 200 * 1024 && ctas_of(bc) >= 2ll * num_sms()) {
+      if (pl.CB % bc == 0 && smem_of(bc) <= 200 * 1024 && ctas_of(bc) >= 2ll * num_sms() &&
+          (long long)pl.Mp * pl.Np < (1ll << 31)) {  // 32-bit fragment offsets
         const int nb = (g.c_in_g + bc - 1) / bc;
         dim3 grid((unsigned)(nb * (nb + 1) / 2), 1, (unsigned)g.groups);
         const size_t smem = smem_of(bc);
