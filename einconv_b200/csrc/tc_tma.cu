@@ -901,6 +901,8 @@ struct FlatCopyParams {
   int k_w;                // kernel width (tap -> (kh, kw))
   int s_h, s_w, d_h, d_w, p_h, p_w, out_w;
   long long planes;
+  uint32_t per_copy32;        // planes * units of one plane (the launch checks that it fits)
+  FastDiv units_div, upr_div; // units per plane, units per row
 };
 
 // CONVERT: the source is the fp32 tensor itself and the copy is its power-of-two-scaled fp16 image (the scale
@@ -919,16 +921,15 @@ __global__ void __launch_bounds__(256) flat_copy_kernel(const void* __restrict__
     s = operand_scale(__ldg(absmax_bits));
     if (blockIdx.x == 0 && threadIdx.x == 0) *inv_s2 = 1.f / (s * s);
   }
+  // blockIdx.y = copy; (plane, unit) from a 32-bit index with magic-number divisions (the 64-bit divisions of the
+  // first version were most of this issue-bound kernel's instructions)
   const int units = (int)(fp.plane_stride / A);
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long per_copy = fp.planes * units;
-  if (idx >= per_copy * fp.n_copies) return;
-  const int copy = (int)(idx / per_copy);
-  const long long rem = idx - (long long)copy * per_copy;
-  const long long plane = rem / units;
-  const int u = (int)(rem - plane * units);
-  const int q0 = u * A;
-  const int r = q0 / fp.pitch, j0 = q0 - r * fp.pitch;  // pitch is a multiple of A: one unit stays in one row
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= fp.per_copy32) return;
+  const int copy = blockIdx.y;
+  const uint32_t plane = fp.units_div.quot(idx);
+  const int u = (int)(idx - plane * (uint32_t)units);
+  const int r = (int)fp.upr_div.quot((uint32_t)u), j0 = (u - r * (fp.pitch / A)) * A;  // one unit stays in one row
   int kh = 0, kw = copy;
   if (fp.per_tap) {
     kh = copy / fp.k_w;
@@ -949,8 +950,8 @@ __global__ void __launch_bounds__(256) flat_copy_kernel(const void* __restrict__
       vals[e] = ok ? src[c] : T(0);
     }
   }
-  *reinterpret_cast<uint4*>(out + (long long)copy * fp.copy_stride + plane * fp.plane_stride + (long long)u * A) =
-      *reinterpret_cast<const uint4*>(vals);
+  *reinterpret_cast<uint4*>(out + (long long)copy * fp.copy_stride + (long long)plane * fp.plane_stride +
+                            (long long)u * A) = *reinterpret_cast<const uint4*>(vals);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1586,8 +1587,12 @@ int tma_run_typed_out(int op, const void* x, const void* v, void* out, int dtype
     fp.s_h = q.stride[1]; fp.s_w = q.stride[0]; fp.d_h = q.dil[1]; fp.d_w = q.dil[0];
     fp.p_h = q.pad[1]; fp.p_w = q.pad[0]; fp.out_w = q.out[0];
     fp.planes = (long long)g.batch * g.groups * g.c_in_g;
-    const long long units = fp.planes * (fp.plane_stride / A) * fp.n_copies;
-    const unsigned blocks = (unsigned)((units + 255) / 256);
+    const long long per_copy = fp.planes * (fp.plane_stride / A);
+    EINCONV_CHECK_ARG(per_copy < (1ll << 31), "kfc: flat copy of more than 2^31 units");
+    fp.per_copy32 = (uint32_t)per_copy;
+    fp.units_div = FastDiv((uint32_t)(fp.plane_stride / A));
+    fp.upr_div = FastDiv((uint32_t)(fp.pitch / A));
+    const dim3 blocks((unsigned)((per_copy + 255) / 256), (unsigned)fp.n_copies);
     if (x_f32)
       flat_copy_kernel<uint16_t, true><<<blocks, 256, 0, stream>>>(x_f32, (uint16_t*)copies_x, fp, absmax_bits, inv_s2);
     else if (es == 2)
