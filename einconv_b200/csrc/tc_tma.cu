@@ -970,7 +970,8 @@ __global__ void __launch_bounds__(256) shift_copy_kernel(const T* __restrict__ x
   const int units = Wp / A;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * units) return;
-  const long long row = idx / units;
+  // 32-bit division where the index fits (a 64-bit one is ~100 instructions of this 30-instruction kernel)
+  const long long row = idx < (1ll << 32) ? (long long)((uint32_t)idx / (uint32_t)units) : idx / units;
   const int u = (int)(idx - row * units);
   const T* src = x + row * W;
   alignas(16) T vals[A];
