@@ -1,4 +1,2 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r10_gpu_all.log 2>&1; tail -2 gpurun_out/r10_gpu_all.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python bench.py > gpurun_out/r10_bench_n1.json 2> gpurun_out/r10_bench_n1.err; tail -2 gpurun_out/r10_bench_n1.err
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r10_benchref_n1.json 2> gpurun_out/r10_benchref_n1.err; tail -c 300 gpurun_out/r10_benchref_n1.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2i_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2i_ncu_bench.log 2>&1
+ls -la gpurun_out/r2i_*
