@@ -567,17 +567,17 @@ __global__ void __launch_bounds__(256) pack_rows_weights_kernel(const T* __restr
   // programmatic dependent launch: the row kernel may be scheduled now; it waits (griddepcontrol.wait) before
   // its first read of wp
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const long long total = (long long)n_ntiles * KH * KW * bn * cs_pitch;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(idx % cs_pitch);
-    long long r = idx / cs_pitch;
-    const int c = (int)(r % bn);
-    r /= bn;
-    const int kw = (int)(r % KW);
-    r /= KW;
-    const int kh = (int)(r % KH);
-    const int nt = (int)(r / KH);
+  // 32-bit indices (resident weights are at most a few hundred KB: the host checks total < 2^31)
+  const unsigned total = (unsigned)n_ntiles * KH * KW * bn * cs_pitch;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % (unsigned)cs_pitch);
+    unsigned r = idx / (unsigned)cs_pitch;
+    const int c = (int)(r % (unsigned)bn);
+    r /= (unsigned)bn;
+    const int kw = (int)(r % (unsigned)KW);
+    r /= (unsigned)KW;
+    const int kh = (int)(r % (unsigned)KH);
+    const int nt = (int)(r / (unsigned)KH);
     const int co = nt * bn + c;
     T v = T(0);
     if (co < cd && ci < cs)
