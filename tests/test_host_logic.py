@@ -385,3 +385,25 @@ def test_call_plan_cache_hits_and_keys():
     assert evaluator.plan_cache_info()["size"] == size
     assert isinstance(a.kernel, str) and a.kernel
     evaluator.clear_plan_cache()
+
+
+def test_bench_profiles_exist_and_parse():
+    """Every ncu summary bench.py cites for `roofline.traffic` is committed under profiles/ and yields a positive
+    byte count (read + write of every kernel in the file)."""
+    import importlib.util
+    import pathlib
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location("bench_for_test", root / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    seen = 0
+    for name, cls in bench.WORKLOADS.items():
+        wl = cls() if name != "factors" else cls(1, 0)
+        assert wl.ncu_profiles, name
+        for rel in wl.ncu_profiles:
+            assert (root / rel).exists(), rel
+        t = bench.ncu_traffic(wl)
+        assert t is not None and t["bytes"] > 0, name
+        seen += 1
+    assert seen == 5
